@@ -1,0 +1,343 @@
+// Dynamics stage, one CTA per scene: pedestrian waypoints + beeps + solver step + gait
+// (ImgEnv::_step_ped_normal, img_env.cpp:304-359), then robot kinematics and the hand-over of robot
+// poses to the pedestrian solver (ImgEnv::_step_robot, img_env.cpp:388-419).
+// Solvers: ORCA / ERVO in orca.cuh; SFM (libpedsim) below, following
+//   Tscene::moveAgents ped_scene.cpp:167-182, Tagent::computeForces ped_agent.cpp:498-507,
+//   desiredForce :236-306, socialForce :316-404, obstacleForce :411-429, lookaheadForce :439-480,
+//   move :519-571, Twaypoint::getForce ped_waypoint.cpp:81-135, Tobstacle::closestPoint
+//   ped_obstacle.cpp:90-105, Tvector::lineIntersection ped_vector.cpp, adapter pedscene.h:18-93.
+#pragma once
+#include "state.cuh"
+#include "kin.cuh"
+#include "orca.cuh"
+
+#define DYN_THREADS 128
+
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 v3(double x, double y, double z = 0) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(double f, V3 a) { return v3(f * a.x, f * a.y, f * a.z); }
+__device__ __forceinline__ V3 operator*(V3 a, double f) { return v3(f * a.x, f * a.y, f * a.z); }
+__device__ __forceinline__ V3 operator/(V3 a, double d) { double f = 1 / d; return v3(f * a.x, f * a.y, f * a.z); }   // scaled(1/divisor)
+__device__ __forceinline__ double lensq(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+__device__ __forceinline__ double len(V3 a) { if (a.x == 0 && a.y == 0 && a.z == 0) return 0; return sqrt(lensq(a)); }
+__device__ __forceinline__ V3 normalized(V3 a) { double l = len(a); if (l == 0) return v3(0, 0, 0); return v3(a.x / l, a.y / l, a.z / l); }
+__device__ __forceinline__ double dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// sfm state record: p.xyz, v.xyz, vmax, dest, lastdest, deque_front, in_tree, pad
+#define SFM_REC 12
+
+struct SfmForces { V3 desired, social, obstacle, lookahead; };
+
+// Tagent::computeForces for agent `self` (reads the pre-move state of all agents)
+__device__ inline SfmForces sfm_forces(const Dev& d, int s, int self, double* rec_self, const double* recs, int n_agents) {
+    const Cfg& c = d.c;
+    SfmForces F;
+    V3 p = v3(rec_self[0], rec_self[1], rec_self[2]);
+    V3 vself = v3(rec_self[3], rec_self[4], rec_self[5]);
+    double vmax = rec_self[6];
+    // ---- desiredForce (waypoint bookkeeping mutates dest/lastdest/front) ----
+    V3 desiredDirection = v3(0, 0, 0);
+    int dest = (int)rec_self[7], lastdest = (int)rec_self[8], front = (int)rec_self[9];
+    int nwp = 0;
+    const double* wp = nullptr;
+    if (self < c.P) { nwp = 1 + d.traj_len[s * c.P + self]; wp = d.sfm_wp + ((size_t)(s * c.P + self) * (1 + c.max_traj)) * 3; }
+    if (dest < 0 && nwp > 0) { dest = front; front = (front + 1) % nwp; }   // pop_front + push_back (BEHAVIOR_CIRCULAR)
+    bool reached = false;
+    if (dest >= 0) {
+        // both branches (temporary TYPE_POINT waypoint / TYPE_NORMAL) evaluate the same expression
+        V3 diff = v3(wp[3 * dest] - p.x, wp[3 * dest + 1] - p.y, 0);
+        reached = len(diff) < wp[3 * dest + 2];
+        desiredDirection = normalized(diff);
+    }
+    if (dest >= 0 && reached) { lastdest = dest; dest = -1; }
+    rec_self[7] = dest; rec_self[8] = lastdest; rec_self[9] = front;
+    F.desired = normalized(desiredDirection) * vmax;
+    // ---- neighbours: every agent currently held by the quadtree (SFM visibility) ----
+    // lookaheadForce
+    const double pi = 3.14159265;
+    int lookforwardcount = 0;
+    V3 soc = v3(0, 0, 0);
+    for (int o = 0; o < n_agents; o++) {
+        const double* ro = recs + (size_t)o * SFM_REC;
+        if (ro[10] == 0.0) continue;      // not in the tree -> never returned by getNeighbors
+        if (o == self) continue;
+        V3 op = v3(ro[0], ro[1], ro[2]), ov = v3(ro[3], ro[4], ro[5]);
+        {
+            double distancex = op.x - p.x, distancey = op.y - p.y;
+            double dist2 = (distancex * distancex + distancey * distancey);
+            if (dist2 < 400) {
+                double at2v = atan2(-desiredDirection.x, -desiredDirection.y);
+                double at2d = atan2(-distancex, -distancey);
+                double at2v2 = atan2(-ov.x, -ov.y);
+                double sa = at2d - at2v;
+                if (sa > pi) sa -= 2 * pi;
+                if (sa < -pi) sa += 2 * pi;
+                double vv = at2v - at2v2;
+                if (vv > pi) vv -= 2 * pi;
+                if (vv < -pi) vv += 2 * pi;
+                if (fabs(vv) > 2.5) {
+                    if ((sa < 0) && (sa > -0.3)) lookforwardcount--;
+                    if ((sa > 0) && (sa < 0.3)) lookforwardcount++;
+                }
+            }
+        }
+        {   // socialForce (Moussaid-Helbing 2009 constants)
+            const double lambdaImportance = 2.0, gamma = 0.35, n = 2, n_prime = 3;
+            V3 diff = op - p;
+            if (lensq(diff) > 64.0) continue;
+            V3 diffDirection = normalized(diff);
+            V3 velDiff = vself - ov;
+            V3 interactionVector = lambdaImportance * velDiff + diffDirection;
+            double interactionLength = len(interactionVector);
+            V3 interactionDirection = interactionVector / interactionLength;
+            double angleThis = atan2(interactionDirection.y, interactionDirection.x);
+            double angleOther = atan2(diffDirection.y, diffDirection.x);
+            double theta = angleOther - angleThis;
+            if (theta > M_PI) theta -= 2 * M_PI;
+            else if (theta <= -M_PI) theta += 2 * M_PI;
+            int thetaSign = (theta == 0) ? (0) : (int)(theta / fabs(theta));
+            double B = gamma * interactionLength;
+            double forceVelocityAmount = -exp(-len(diff) / B - (n_prime * B * theta) * (n_prime * B * theta));
+            double forceAngleAmount = -thetaSign * exp(-len(diff) / B - (n * B * theta) * (n * B * theta));
+            V3 forceVelocity = forceVelocityAmount * interactionDirection;
+            V3 forceAngle = forceAngleAmount * v3(-interactionDirection.y, interactionDirection.x, 0);
+            soc = soc + (forceVelocity + forceAngle);
+        }
+    }
+    V3 lf = v3(0, 0, 0);
+    if (lookforwardcount < 0) { lf.x = 0.5f * desiredDirection.y; lf.y = 0.5f * -desiredDirection.x; }
+    if (lookforwardcount > 0) { lf.x = 0.5f * -desiredDirection.y; lf.y = 0.5f * desiredDirection.x; }
+    F.lookahead = lf;
+    F.social = soc;
+    // ---- obstacleForce: closest obstacle segment only ----
+    V3 minDiff = v3(0, 0, 0);
+    double minDistanceSquared = INFINITY;
+    int nob = d.sfm_nobs[s];
+    for (int o = 0; o < nob; o++) {
+        const double* sg = d.sfm_obs + ((size_t)s * c.max_obs + o) * 4;
+        V3 startPoint = v3(sg[0], sg[1]), endPoint = v3(sg[2], sg[3]);
+        V3 relativeEndPoint = endPoint - startPoint;
+        V3 relativePoint = p - startPoint;
+        double lambda = dot3(relativePoint, relativeEndPoint) / lensq(relativeEndPoint);
+        V3 closest;
+        if (lambda <= 0) closest = startPoint;
+        else if (lambda >= 1) closest = endPoint;
+        else closest = startPoint + lambda * relativeEndPoint;
+        V3 diff = p - closest;
+        double distanceSquared = lensq(diff);
+        if (distanceSquared < minDistanceSquared) { minDistanceSquared = distanceSquared; minDiff = diff; }
+    }
+    double distance = sqrt(minDistanceSquared) - 0.2;    // agentRadius
+    double forceAmount = exp(-distance / 0.8);            // obstacleForceSigma
+    F.obstacle = forceAmount * normalized(minDiff);
+    return F;
+}
+
+// Tagent::move (without the tree notification)
+__device__ inline void sfm_move(const Dev& d, int s, double* rec, const SfmForces& F, double h) {
+    const Cfg& c = d.c;
+    V3 p = v3(rec[0], rec[1], rec[2]), v = v3(rec[3], rec[4], rec[5]);
+    double vmax = rec[6];
+    V3 p_desired = p + v * h;
+    int nob = d.sfm_nobs[s];
+    for (int o = 0; o < nob; o++) {
+        const double* sg = d.sfm_obs + ((size_t)s * c.max_obs + o) * 4;
+        double s1x = p_desired.x - p.x, s1y = p_desired.y - p.y;
+        double s2x = sg[2] - sg[0], s2y = sg[3] - sg[1];
+        double ss = (-s1y * (p.x - sg[0]) + s1x * (p.y - sg[1])) / (-s2x * s1y + s1x * s2y);
+        double tt = (s2x * (p.y - sg[1]) - s2y * (p.x - sg[0])) / (-s2x * s1y + s1x * s2y);
+        if (ss >= 0 && ss <= 1 && tt >= 0 && tt <= 1) {
+            V3 inter = v3(p.x + (tt * s1x), p.y + (tt * s1y), 0);
+            p_desired = inter - normalized(v * h) * 0.1;
+        }
+    }
+    p = p_desired;
+    V3 a = 1.0 * F.desired + 2.1 * F.social + 1.0 * F.obstacle + 1.0 * F.lookahead + v3(0, 0, 0);
+    v = 0.5 * v + a * h;
+    if (len(v) > vmax) v = normalized(v) * vmax;
+    rec[0] = p.x; rec[1] = p.y; rec[2] = p.z; rec[3] = v.x; rec[4] = v.y; rec[5] = v.z;
+}
+
+__device__ __forceinline__ double beep_uniform(unsigned long long seed, unsigned long long step, int s, int r) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (step * 1315423911ull + (unsigned long long)s * 2654435761ull + r + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// PedAgent::update_bbox, agent.cpp:696-735
+__device__ inline void ped_gait(const Dev& d, int pi, int p) {
+    if (d.ped_shape[p] != 2) return;
+    const double step_len = 0.3;
+    const double* sz = d.ped_size + 6 * p;
+    double x = PDF(d, PD_X, pi), y = PDF(d, PD_Y, pi), lx = PDF(d, PD_LX, pi), ly = PDF(d, PD_LY, pi);
+    double move_dist = sqrt((x - lx) * (x - lx) + (y - ly) * (y - ly));
+    int state = (int)PDF(d, PD_GAIT, pi);
+    double rem = PDF(d, PD_REM, pi);
+    int last_state = state;
+    state = (int)((move_dist + rem) / step_len + last_state);
+    rem = move_dist + rem - (state - last_state) * step_len;
+    state %= 7;
+    PDF(d, PD_LGAIT, pi) = last_state; PDF(d, PD_GAIT, pi) = state; PDF(d, PD_REM, pi) = rem;
+    if (state == 0 || state == 4) {
+        PDF(d, PD_LLX, pi) = sz[0]; PDF(d, PD_LLY, pi) = sz[1]; PDF(d, PD_LLZ, pi) = 0;
+        PDF(d, PD_RLX, pi) = sz[3]; PDF(d, PD_RLY, pi) = sz[4]; PDF(d, PD_RLZ, pi) = 0;
+    } else if (state == 1 || state == 3) { PDF(d, PD_LLX, pi) = -step_len / 2; PDF(d, PD_RLX, pi) = step_len / 2; }
+    else if (state == 2) { PDF(d, PD_LLX, pi) = -step_len; PDF(d, PD_RLX, pi) = step_len; }
+    else if (state == 5) { PDF(d, PD_LLX, pi) = step_len / 2; PDF(d, PD_RLX, pi) = -step_len / 2; }
+    else if (state == 6) { PDF(d, PD_LLX, pi) = step_len; PDF(d, PD_RLX, pi) = -step_len; }
+}
+
+// grid = S CTAs. actions [S][R][3] float32 (v, w, v_y); alive [S][R] or NULL (-> library dones)
+__global__ void __launch_bounds__(DYN_THREADS) k_dynamics(Dev d, const float* actions, const uint8_t* alive, int ped_yaw_mode) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const Cfg& c = d.c;
+    const int s = blockIdx.x, tid = threadIdx.x;
+    V2* pos = reinterpret_cast<V2*>(dsm);
+    V2* vel = pos + c.NA;
+    V2* nvel = vel + c.NA;
+    V2* beep_p = nvel + c.NA;
+    float* beep_r = reinterpret_cast<float*>(beep_p + c.R);
+    unsigned long long step = d.step_no[s];
+
+    if (c.P > 0 && c.scene_type != 0) {
+        // beeps (img_env.cpp:323-342): robots' PRE-step poses
+        for (int j = tid; j < c.R; j += DYN_THREADS) {
+            int idx = s * c.R + j;
+            bool is_beep = false;
+            bool al = alive ? alive[idx] != 0 : RBF(d, RB_DONE, idx) == 0.0;
+            float v_y = al ? actions[(size_t)idx * 3 + 2] : 0.f;
+            if (beep_uniform(c.seed, step, s, j) < c.ped_ca_p) {
+                if ((double)v_y > 0) {
+                    beep_p[j] = v2((float)RBF(d, RB_X, idx), (float)RBF(d, RB_Y, idx));
+                    beep_r[j] = (float)c.beep_r;
+                    is_beep = true;
+                }
+            }
+            if (!is_beep) { beep_p[j] = v2(0.f, 0.f); beep_r[j] = 0.f; }
+            RBF(d, RB_BEEP, idx) = is_beep ? 1.0 : 0.0;
+        }
+        if (c.scene_type == 2 || c.scene_type == 3) {
+            for (int a = tid; a < c.NA; a += DYN_THREADS) {
+                pos[a] = v2(d.rvo_pos[((size_t)s * c.NA + a) * 2], d.rvo_pos[((size_t)s * c.NA + a) * 2 + 1]);
+                vel[a] = v2(d.rvo_vel[((size_t)s * c.NA + a) * 2], d.rvo_vel[((size_t)s * c.NA + a) * 2 + 1]);
+            }
+            __syncthreads();
+            ObstView ob;
+            ob.verts = d.rvo_verts + (size_t)s * d.max_verts * 8;
+            ob.nodes = d.rvo_nodes + (size_t)s * d.max_verts * 3;
+            ob.root = d.rvo_counts[2 * s + 1];
+            for (int a = tid; a < c.NA; a += DYN_THREADS) {
+                V2 pref = v2(0.f, 0.f);
+                float maxSpeed = 0.6f;
+                if (a < c.P) {
+                    int pi = s * c.P + a;
+                    // waypoint cycling (img_env.cpp:306-319, agent.cpp:823-843); an index past the end of
+                    // trajectory_ is an out-of-bounds read in the node -> treated as "not arrived"
+                    int ti = (int)PDF(d, PD_TIDX, pi), tl = d.traj_len[pi];
+                    const double* tr = d.traj + ((size_t)pi * c.max_traj) * 3;
+                    double x = PDF(d, PD_X, pi), y = PDF(d, PD_Y, pi);
+                    if (ti < tl) {
+                        double gx = tr[3 * ti], gy = tr[3 * ti + 1];
+                        if ((gx - x) * (gx - x) + (gy - y) * (gy - y) < 0.04) ti += 1;
+                    }
+                    PDF(d, PD_TIDX, pi) = ti;
+                    const double* g = tr + 3 * (ti % tl);
+                    V2 goalVector = v2((float)g[0], (float)g[1]) - pos[a];     // rvoscene.h:37-44
+                    if (absSq(goalVector) > 1.0f) goalVector = normalize(goalVector);
+                    pref = goalVector;
+                    maxSpeed = (float)d.ped_maxspeed[a];
+                }
+                nvel[a] = orca_new_velocity(a, c.NA, pos, vel, pref, maxSpeed, (float)c.step_hz, ob, c.scene_type == 3, c.R, beep_p, beep_r);
+            }
+            __syncthreads();
+            for (int a = tid; a < c.NA; a += DYN_THREADS) {   // Agent::update
+                V2 nv = nvel[a];
+                V2 np = pos[a] + nv * (float)c.step_hz;
+                d.rvo_pos[((size_t)s * c.NA + a) * 2] = np.x; d.rvo_pos[((size_t)s * c.NA + a) * 2 + 1] = np.y;
+                d.rvo_vel[((size_t)s * c.NA + a) * 2] = nv.x; d.rvo_vel[((size_t)s * c.NA + a) * 2 + 1] = nv.y;
+                if (a < c.P) {   // getNewPosAndVel + set_position + update_bbox (img_env.cpp:344-358)
+                    int pi = s * c.P + a;
+                    PDF(d, PD_LX, pi) = PDF(d, PD_X, pi); PDF(d, PD_LY, pi) = PDF(d, PD_Y, pi); PDF(d, PD_LYAW, pi) = PDF(d, PD_YAW, pi);
+                    PDF(d, PD_X, pi) = (double)np.x; PDF(d, PD_Y, pi) = (double)np.y;
+                    PDF(d, PD_VX, pi) = (double)nv.x; PDF(d, PD_VY, pi) = (double)nv.y;
+                    if (ped_yaw_mode == 1) PDF(d, PD_YAW, pi) = 0.0;
+                    else if (ped_yaw_mode == 2) PDF(d, PD_YAW, pi) = atan2((double)nv.y, (double)nv.x);
+                    ped_gait(d, pi, a);
+                }
+            }
+        } else if (c.scene_type == 1) {
+            double* recs = d.sfm + (size_t)s * c.NA * SFM_REC;
+            // waypoint cycling of the PedAgent wrapper still runs (unused by the SFM adapter's step)
+            for (int a = tid; a < c.P; a += DYN_THREADS) {
+                int pi = s * c.P + a;
+                int ti = (int)PDF(d, PD_TIDX, pi), tl = d.traj_len[pi];
+                const double* tr = d.traj + ((size_t)pi * c.max_traj) * 3;
+                double x = PDF(d, PD_X, pi), y = PDF(d, PD_Y, pi);
+                if (ti < tl) {
+                    double gx = tr[3 * ti], gy = tr[3 * ti + 1];
+                    if ((gx - x) * (gx - x) + (gy - y) * (gy - y) < 0.04) ti += 1;
+                }
+                PDF(d, PD_TIDX, pi) = ti;
+            }
+            // phase 1: forces from the pre-move state (kept in registers), phase 2: move
+            SfmForces F[4];   // NA <= 4 * DYN_THREADS
+            int k = 0;
+            for (int a = tid; a < c.NA && k < 4; a += DYN_THREADS, k++) F[k] = sfm_forces(d, s, a, recs + (size_t)a * SFM_REC, recs, c.NA);
+            __syncthreads();
+            k = 0;
+            for (int a = tid; a < c.NA && k < 4; a += DYN_THREADS, k++) {
+                double* rec = recs + (size_t)a * SFM_REC;
+                sfm_move(d, s, rec, F[k], c.step_hz);
+                // Ttree::moveAgent with the never-split root leaf [0,10]x[10,20] (pedscene.h:19,
+                // ped_tree.cpp:124-130): an agent outside the box is re-inserted, then erased.
+                bool outside = (rec[0] < 0) || (rec[0] > 10) || (rec[1] < 10) || (rec[1] > 20);
+                if (outside) rec[10] = 0.0;
+                if (a < c.P) {
+                    int pi = s * c.P + a;
+                    PDF(d, PD_LX, pi) = PDF(d, PD_X, pi); PDF(d, PD_LY, pi) = PDF(d, PD_Y, pi); PDF(d, PD_LYAW, pi) = PDF(d, PD_YAW, pi);
+                    PDF(d, PD_X, pi) = rec[0]; PDF(d, PD_Y, pi) = rec[1];
+                    PDF(d, PD_VX, pi) = rec[3]; PDF(d, PD_VY, pi) = rec[4];
+                    if (ped_yaw_mode == 1) PDF(d, PD_YAW, pi) = 0.0;
+                    else if (ped_yaw_mode == 2) PDF(d, PD_YAW, pi) = atan2(rec[4], rec[3]);
+                    ped_gait(d, pi, a);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- robots (img_env.cpp:388-419) ----
+    for (int j = tid; j < c.R; j += DYN_THREADS) {
+        int idx = s * c.R + j;
+        bool al = alive ? alive[idx] != 0 : RBF(d, RB_DONE, idx) == 0.0;
+        if (al) {
+            RobotKin rk;
+            rk.x = RBF(d, RB_X, idx); rk.y = RBF(d, RB_Y, idx); rk.yaw = RBF(d, RB_YAW, idx);
+            rk.gx = RBF(d, RB_GX, idx); rk.gy = RBF(d, RB_GY, idx);
+            rk.l0v = RBF(d, RB_L0V, idx); rk.l0w = RBF(d, RB_L0W, idx); rk.l1v = RBF(d, RB_L1V, idx); rk.l1w = RBF(d, RB_L1W, idx);
+            rk.vx = RBF(d, RB_VX, idx); rk.vy = RBF(d, RB_VY, idx);
+            const float* ac = actions + (size_t)idx * 3;
+            robot_cmd(rk, d.lim_v[j], d.lim_w[j], c.ktype, c.step_hz, c.control_hz, (double)ac[0], (double)ac[1], (double)ac[2]);
+            RBF(d, RB_X, idx) = rk.x; RBF(d, RB_Y, idx) = rk.y; RBF(d, RB_YAW, idx) = rk.yaw;
+            RBF(d, RB_L0V, idx) = rk.l0v; RBF(d, RB_L0W, idx) = rk.l0w; RBF(d, RB_L1V, idx) = rk.l1v; RBF(d, RB_L1W, idx) = rk.l1w;
+            RBF(d, RB_VX, idx) = rk.vx; RBF(d, RB_VY, idx) = rk.vy;
+            RBF(d, RB_ARR, idx) = rk.arrive ? 1.0 : 0.0;
+        }
+        if (c.relation == 1 && c.P > 0) {   // setRobotPos
+            int a = c.P + j;
+            if (c.scene_type == 2 || c.scene_type == 3) {
+                d.rvo_pos[((size_t)s * c.NA + a) * 2] = (float)RBF(d, RB_X, idx); d.rvo_pos[((size_t)s * c.NA + a) * 2 + 1] = (float)RBF(d, RB_Y, idx);
+                d.rvo_vel[((size_t)s * c.NA + a) * 2] = (float)RBF(d, RB_VX, idx); d.rvo_vel[((size_t)s * c.NA + a) * 2 + 1] = (float)RBF(d, RB_VY, idx);
+            } else if (c.scene_type == 1) {
+                double* rec = d.sfm + ((size_t)s * c.NA + a) * SFM_REC;
+                rec[0] = RBF(d, RB_X, idx); rec[1] = RBF(d, RB_Y, idx); rec[2] = 1.0;   // pedscene.h:53-56
+            }
+        }
+    }
+    if (tid == 0) d.step_no[s] = step + 1;
+}
+
+inline size_t dyn_smem_bytes(const Cfg& c) { return (size_t)c.NA * 3 * 8 + (size_t)c.R * 12 + 64; }

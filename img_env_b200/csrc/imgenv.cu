@@ -1,0 +1,556 @@
+// libimgenv_b200.so — host side of the C ABI declared in include/imgenv.h.
+// Replaces EnvService::{init_env,reset_env,step_env,end_ep} (img_env.cpp:716-755) and the Python
+// _get_states post-processing (yaml_env.py:446-481).  Compiled for sm_100a only; there is no CPU
+// fallback: every entry point fails loudly if CUDA is unavailable.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <limits>
+#include <string>
+#include <vector>
+#include "../../include/imgenv.h"
+#include "state.cuh"
+#include "kin.cuh"
+#include "view.cuh"
+#include "dyn.cuh"
+#include "host_tables.h"
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct imgenv {
+    Dev d;
+    int device = 0;
+    std::vector<void*> allocs;
+    std::vector<double> robot_desc;   // [R][25] float32-widened
+    std::vector<int> ped_shape;
+    bool outputs_bound = false;
+    int ped_yaw_mode = 0;
+    // reset staging (pinned host + device)
+    double* st_h = nullptr; double* st_d = nullptr; size_t st_doubles = 0;
+    int* sti_h = nullptr; int* sti_d = nullptr; size_t st_ints = 0;
+    float* stf_h = nullptr; float* stf_d = nullptr; size_t st_floats = 0;
+    float* act_d = nullptr; uint8_t* alive_d = nullptr;
+    size_t view_smem = 0, dyn_smem = 0;
+};
+
+template <class T> static int dalloc(imgenv* h, T** p, size_t n, int fill_byte = 0) {
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CK(cudaMalloc(&q, bytes));
+    CK(cudaMemset(q, fill_byte, bytes));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+template <class T> static int dupload(imgenv* h, const T** p, const std::vector<T>& v) {
+    T* q = nullptr;
+    if (dalloc(h, &q, v.size())) return -1;
+    if (!v.empty()) CK(cudaMemcpy(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *p = q;
+    return 0;
+}
+
+extern "C" const char* imgenv_last_error(void) { return g_err.c_str(); }
+extern "C" const char* imgenv_version(void) { return "img_env_b200 0.1 (sm_100a)"; }
+// host-only helpers exported for CPU-side table checks (tests/test_tables.py)
+extern "C" void imgenv_f16_lut(uint16_t* out256) { ht::f16_lut(out256); }
+extern "C" int imgenv_cubic_tables(int src, int dst, short* need_idx, int* ns, short* tap, short* coef) {
+    std::vector<short> n, t, c;
+    ht::cubic_tables(src, dst, n, t, c);
+    *ns = (int)n.size();
+    memcpy(need_idx, n.data(), n.size() * 2); memcpy(tap, t.data(), t.size() * 2); memcpy(coef, c.data(), c.size() * 2);
+    return 0;
+}
+extern "C" double imgenv_yaw_from_quaternion(double x, double y, double z, double w) { return ht::yaw_from_quaternion(x, y, z, w); }
+extern "C" int imgenv_set_ped_yaw_mode(imgenv_t* h, int mode) { if (!h) return fail("null handle"); h->ped_yaw_mode = mode; return 0; }
+
+__global__ void k_init_state(Dev d) {
+    size_t wpp = (size_t)d.c.H * d.c.Wb;
+    size_t n = wpp * d.c.S;
+    size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = t0; i < n; i += stride) d.occ_all[i] = d.static_occ[i % wpp];
+    size_t pc = (((size_t)d.c.H * d.c.W + 3) & ~(size_t)3) * d.c.S;
+    for (size_t i = t0; i < pc; i += stride) { d.rmin[i] = RMIN_EMPTY; d.flags[i] = 0; }
+    size_t nr = (size_t)d.c.S * d.c.R;
+    for (size_t i = t0; i < nr; i += stride) {
+        d.rb[(size_t)RB_PREVD * nr + i] = nan("");
+        d.rb[(size_t)RB_MIND * nr + i] = INFINITY;
+    }
+    size_t na = (size_t)d.c.S * d.c.NA;
+    if (d.c.scene_type == 1)
+        for (size_t i = t0; i < na; i += stride) {
+            double* rec = d.sfm + i * SFM_REC;
+            rec[6] = 1.2;      // Tagent(): vmax ~ N(1.2, 0.2) from a process-global engine (ped_agent.cpp:43-44); overridable via set_internal
+            rec[7] = -1; rec[8] = -1; rec[9] = 0;
+            rec[10] = 1.0;     // every agent is inserted into the quadtree by addAgent (ped_scene.cpp:69-75)
+            if ((int)(i % d.c.NA) < d.c.P) rec[6] = d.ped_maxspeed[i % d.c.NA];   // setVmax (pedscene.h:66)
+        }
+}
+
+extern "C" int imgenv_destroy(imgenv_t* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->st_h) cudaFreeHost(h->st_h);
+    if (h->sti_h) cudaFreeHost(h->sti_h);
+    if (h->stf_h) cudaFreeHost(h->stf_h);
+    delete h;
+    return 0;
+}
+
+static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid, int32_t H, int32_t W, const double* robot_desc,
+                       const double* ped_desc, const double* robot_size_last) {
+    Cfg& c = h->d.c;
+    using ht::f32;
+    c.S = cfg->num_scenes; c.R = cfg->num_robots; c.P = cfg->num_peds;
+    c.scene_type = c.P > 0 ? cfg->scene_type : 0;
+    c.relation = cfg->relation_ped_robo;
+    c.NA = (c.scene_type != 0) ? c.P + (c.relation == 1 ? c.R : 0) : 0;
+    c.H = H; c.W = W; c.Wb = (W + 31) / 32;
+    c.res = f32(cfg->view_resolution);
+    double vwid = f32(cfg->view_width), vhei = f32(cfg->view_height);
+    c.vw = (int)(vwid / c.res); c.vh = (int)(vhei / c.res);       // agent.cpp:82-83
+    c.vwb = (c.vw + 31) / 32;
+    c.step_hz = f32(cfg->step_hz); c.control_hz = 0.05;            // agent.cpp:89
+    c.state_dim = cfg->state_dim; c.use_laser = cfg->use_laser != 0; c.range_total = cfg->range_total;
+    c.ktype = cfg->robot_ktype;
+    c.beep_r = f32(cfg->beep_r); c.ped_ca_p = f32(cfg->ped_ca_p);
+    c.view_max_dist = f32(cfg->view_max_dist);
+    c.view_base = tf_from_pose(vhei / 2, vwid / 2, 3.14159);      // agent.cpp:84-87
+    c.base_view = tf_inv(c.view_base);
+    c.img = cfg->image_size; c.max_ped = cfg->max_ped; c.ped_vec_dim = cfg->ped_vec_dim;
+    c.pvs_len = 1 + c.max_ped * c.ped_vec_dim;
+    c.ped_image_r = cfg->ped_image_r; c.ped_res = 6.0 / cfg->ped_image_size; c.laser_max = cfg->laser_max;
+    c.laser_norm = cfg->laser_norm;
+    c.max_obs = std::max(cfg->max_obstacles, 1); c.max_traj = std::max(cfg->max_traj, 1);
+    c.seed = cfg->seed;
+    if (c.vh != c.vw) return fail("imgenv_create: only square view maps are supported");
+    if (cfg->ped_image_size != cfg->image_size) return fail("imgenv_create: ped_image_size must equal image_size");
+    if (c.ped_vec_dim != 7) return fail("imgenv_create: ped_vec_dim must be 7 (yaml_env.py:399-408)");
+    if (c.state_dim < 3 || c.state_dim > 5) return fail("imgenv_create: state_dim must be 3, 4 or 5");
+    if (c.R < 1 || c.R > 4096 || c.P < 0 || c.P > 4096 || c.S < 1) return fail("imgenv_create: bad S/R/P");
+    if (c.range_total > 4000 || c.range_total < 1) return fail("imgenv_create: range_total out of range");
+    if (c.scene_type == 1 && c.NA > 4 * DYN_THREADS) return fail("imgenv_create: too many SFM agents per scene");
+    if (c.scene_type < 0 || c.scene_type > 3) return fail("imgenv_create: unknown scene type");
+
+    // ---- static tables ----
+    std::vector<short> need_idx, tap, coef;
+    ht::cubic_tables(c.vw, c.img, need_idx, tap, coef);
+    c.ns = (int)need_idx.size();
+    h->robot_desc.assign(robot_desc, robot_desc + 25 * (size_t)c.R);
+    std::vector<int> type_of(c.R, -1);
+    std::vector<ht::TypeTables> types;
+    std::vector<Limiter> lv(c.R), lw(c.R);
+    for (int r = 0; r < c.R; r++) {
+        double* dsc = h->robot_desc.data() + 25 * (size_t)r;
+        for (int k = 1; k < 7; k++) dsc[k] = f32(dsc[k]);
+        for (int L = 0; L < 2; L++) {
+            const double* q = dsc + 7 + 9 * L;
+            Limiter m;
+            m.has_v = q[0] != 0; m.has_a = q[1] != 0; m.has_j = q[2] != 0;
+            m.min_v = f32(q[3]); m.max_v = f32(q[4]); m.min_a = f32(q[5]); m.max_a = f32(q[6]);
+            // SpeedLimiter(msg) copies min_jerk into max_jerk and leaves min_jerk uninitialised
+            // (speed_limit.cpp:56-65); we take min_jerk for both.
+            m.min_j = f32(q[7]); m.max_j = f32(q[7]);
+            (L == 0 ? lv : lw)[r] = m;
+        }
+        for (int t = 0; t < (int)types.size() && type_of[r] < 0; t++) {
+            int r0 = -1;
+            for (int q = 0; q < r; q++) if (type_of[q] == t) { r0 = q; break; }
+            const double* a = h->robot_desc.data() + 25 * (size_t)r0;
+            bool same = robot_size_last[r0] == robot_size_last[r];
+            for (int k = 0; k < 7; k++) same = same && a[k] == dsc[k];
+            if (same) type_of[r] = t;
+        }
+        if (type_of[r] < 0) {
+            types.emplace_back();
+            std::string e = ht::build_type(c, dsc, f32(cfg->view_angle_begin), f32(cfg->view_angle_end), f32(cfg->view_min_dist),
+                                           f32(cfg->view_max_dist), types.back());
+            if (!e.empty()) return fail("imgenv_create: " + e);
+            types.back().t.size_last = robot_size_last[r];
+            type_of[r] = (int)types.size() - 1;
+        }
+    }
+    c.n_types = (int)types.size();
+    std::vector<double> lattice; std::vector<short> ray_end, spans; std::vector<unsigned short> khi, klo; std::vector<uint32_t> own_mask;
+    std::vector<RobotType> rts;
+    for (auto& T : types) {
+        T.t.pts_off = (int)lattice.size() / 2; lattice.insert(lattice.end(), T.lattice.begin(), T.lattice.end());
+        T.t.ray_off = (int)ray_end.size() / 2; ray_end.insert(ray_end.end(), T.ray_end.begin(), T.ray_end.end());
+        T.t.span_off = (int)spans.size(); spans.insert(spans.end(), T.spans.begin(), T.spans.end());
+        T.t.khi_off = (int)khi.size(); khi.insert(khi.end(), T.khi.begin(), T.khi.end()); klo.insert(klo.end(), T.klo.begin(), T.klo.end());
+        T.t.own_mask_off = (int)own_mask.size(); own_mask.insert(own_mask.end(), T.own_mask.begin(), T.own_mask.end());
+        T.t.n_own = 0; T.t.own_off = 0;
+        rts.push_back(T.t);
+    }
+    // pedestrians
+    std::vector<int> pshape(c.P), poff(2 * (size_t)c.P, 0), pn(2 * (size_t)c.P, 0);
+    std::vector<double> psize(6 * (size_t)c.P), pmax(c.P), prr(c.P);
+    std::vector<float> prw(c.P);
+    for (int p = 0; p < c.P; p++) {
+        const double* q = ped_desc + 8 * (size_t)p;
+        pshape[p] = (int)q[0];
+        for (int k = 0; k < 6; k++) psize[6 * p + k] = f32(q[1 + k]);
+        pmax[p] = f32(q[7]);
+        prw[p] = (float)q[3];                                     // PedInfo.r_ = sizes_[2] (img_env.cpp:582)
+        char buf[64]; snprintf(buf, sizeof buf, "%.2f", (double)prw[p]); prr[p] = atof(buf);   // python round(rt.r_, 2)
+        std::vector<double> a, b;
+        if (pshape[p] == 0) ht::lattice_circle(psize[6 * p], psize[6 * p + 1], psize[6 * p + 2], a);
+        else if (pshape[p] == 2) { ht::lattice_circle(0, 0, psize[6 * p + 2], a); ht::lattice_circle(0, 0, psize[6 * p + 5], b); }
+        poff[2 * p] = (int)lattice.size() / 2; pn[2 * p] = (int)a.size() / 2; lattice.insert(lattice.end(), a.begin(), a.end());
+        poff[2 * p + 1] = (int)lattice.size() / 2; pn[2 * p + 1] = (int)b.size() / 2; lattice.insert(lattice.end(), b.begin(), b.end());
+    }
+    h->ped_shape = pshape;
+    std::vector<uint16_t> lut(256); ht::f16_lut(lut.data());
+    std::vector<uint8_t> g(grid, grid + (size_t)H * W);
+    std::vector<uint32_t> socc((size_t)H * c.Wb, 0u);
+    for (int i = 0; i < H; i++) for (int j = 0; j < W; j++) if (grid[(size_t)i * W + j] < 250) socc[(size_t)i * c.Wb + (j >> 5)] |= 1u << (j & 31);
+    std::vector<int> own_dummy(1, 0);
+
+    Dev& d = h->d;
+#define UP(field, vec) if (dupload(h, &d.field, vec)) return -1;
+    UP(grid, g) UP(static_occ, socc) UP(types, rts) UP(type_of, type_of) UP(lattice_xy, lattice) UP(ray_end, ray_end)
+    UP(fov_spans, spans) UP(khi, khi) UP(klo, klo) UP(own_mask, own_mask) UP(need_idx, need_idx) UP(cubic_tap, tap)
+    UP(cubic_coef, coef) UP(f16_lut, lut) UP(lim_v, lv) UP(lim_w, lw) UP(ped_shape, pshape) UP(ped_size, psize)
+    UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(own_cells, own_dummy)
+#undef UP
+    size_t S = c.S;
+    size_t pc = ((size_t)H * W + 3) & ~(size_t)3;
+    d.max_verts = 16 * c.max_obs + 16;
+#define AL(field, n) if (dalloc(h, &d.field, (size_t)(n))) return -1;
+    AL(occ_all, S * H * c.Wb) AL(flags, S * pc) AL(rmin, S * pc)
+    AL(rb, (size_t)RB_FIELDS * S * c.R) AL(pd, (size_t)PD_FIELDS * S * c.P)
+    AL(traj, S * c.P * c.max_traj * 3) AL(traj_len, S * c.P) AL(obs, S * c.max_obs * 8) AL(n_obs, S) AL(step_no, S)
+    AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 3)
+    AL(rvo_counts, S * 2) AL(sfm, S * c.NA * SFM_REC) AL(sfm_obs, S * c.max_obs * 4) AL(sfm_nobs, S)
+    AL(sfm_wp, S * c.P * (1 + c.max_traj) * 3)
+#undef AL
+    if (dalloc(h, &h->act_d, S * c.R * 3)) return -1;
+    if (dalloc(h, &h->alive_d, S * c.R)) return -1;
+    {   // rvo root = -1 (no obstacle tree) until the first reset
+        std::vector<int> rc(2 * S, 0);
+        for (size_t s = 0; s < S; s++) rc[2 * s + 1] = -1;
+        CK(cudaMemcpy(d.rvo_counts, rc.data(), rc.size() * 4, cudaMemcpyHostToDevice));
+    }
+    // reset staging: per scene doubles = obs 8*max_obs + robots 5*R + peds 5*P + traj 3*max_traj*P + sfm segs 4*max_obs
+    h->st_doubles = S * ((size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 3 * (size_t)c.max_traj * c.P + 4 * c.max_obs) + 8;
+    h->st_ints = S * ((size_t)4 + c.P + 3 * (size_t)d.max_verts) + 8;
+    h->st_floats = S * ((size_t)8 * d.max_verts) + 8;
+    CK(cudaMallocHost((void**)&h->st_h, h->st_doubles * 8)); if (dalloc(h, &h->st_d, h->st_doubles)) return -1;
+    CK(cudaMallocHost((void**)&h->sti_h, h->st_ints * 4)); if (dalloc(h, &h->sti_d, h->st_ints)) return -1;
+    CK(cudaMallocHost((void**)&h->stf_h, h->st_floats * 4)); if (dalloc(h, &h->stf_d, h->st_floats)) return -1;
+
+    h->view_smem = view_smem_bytes(c);
+    h->dyn_smem = dyn_smem_bytes(c);
+    if (h->view_smem > 227 * 1024) return fail("imgenv_create: view kernel needs too much shared memory for this configuration");
+    CK(cudaFuncSetAttribute(k_view<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
+    CK(cudaFuncSetAttribute(k_view<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
+    if (h->dyn_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_dynamics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
+    k_init_state<<<1184, 256>>>(d);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int imgenv_create(const imgenv_config* cfg, const uint8_t* grid, int32_t H, int32_t W, const double* robot_desc,
+                             const double* ped_desc, const double* robot_size_last, int32_t device, imgenv_t** out) {
+    if (!cfg || !grid || !out || !robot_desc || !robot_size_last) return fail("imgenv_create: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("imgenv_create: no CUDA device (this library has no CPU path)");
+    CK(cudaSetDevice(device));
+    imgenv* h = new imgenv();
+    memset(&h->d, 0, sizeof(Dev));
+    h->device = device;
+    if (create_impl(h, cfg, grid, H, W, robot_desc, ped_desc, robot_size_last)) { std::string e = g_err; imgenv_destroy(h); g_err = e; return -1; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int imgenv_bind_outputs(imgenv_t* h, const imgenv_outputs* o) {
+    if (!h || !o) return fail("imgenv_bind_outputs: null argument");
+    if (!o->vector_states || !o->sensor_maps || !o->is_collisions || !o->is_arrives || !o->lasers || !o->ped_vector_states ||
+        !o->ped_maps || !o->step_ds || !o->ped_min_dists) return fail("imgenv_bind_outputs: every output pointer is required");
+    Dev& d = h->d;
+    d.o_vec = o->vector_states; d.o_sensor = o->sensor_maps; d.o_coll = o->is_collisions; d.o_arr = o->is_arrives;
+    d.o_laser = o->lasers; d.o_pvs = o->ped_vector_states; d.o_pmap = o->ped_maps; d.o_stepd = o->step_ds; d.o_mind = o->ped_min_dists;
+    h->outputs_bound = true;
+    return 0;
+}
+
+// staged reset record layout (per listed scene), doubles:
+//   obs[max_obs][8] | robots[R][5] x,y,yaw,gx,gy | peds[P][5] x,y,yaw,gx,gy | traj[P][max_traj][3] | segs[max_obs][4]
+// ints: scene_id, n_obs, n_segs, n_verts, root | traj_len[P] | nodes[max_verts][3]   floats: verts[max_verts][8]
+__global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, const float* stf, size_t dper, size_t iper, size_t fper) {
+    const Cfg& c = d.c;
+    int sl = blockIdx.x;
+    if (sl >= n) return;
+    const double* D = st + dper * sl; const int* I = sti + iper * sl; const float* Fp = stf + fper * sl;
+    int s = I[0];
+    const double* obs = D; const double* rob = obs + 8 * (size_t)c.max_obs; const double* ped = rob + 5 * (size_t)c.R;
+    const double* traj = ped + 5 * (size_t)c.P; const double* segs = traj + 3 * (size_t)c.max_traj * c.P;
+    const int* tl = I + 5; const int* nodes = tl + c.P;
+    for (int k = threadIdx.x; k < 8 * c.max_obs; k += blockDim.x) d.obs[(size_t)s * c.max_obs * 8 + k] = obs[k];
+    for (int k = threadIdx.x; k < 4 * c.max_obs; k += blockDim.x) d.sfm_obs[(size_t)s * c.max_obs * 4 + k] = segs[k];
+    if (threadIdx.x == 0) {
+        d.n_obs[s] = I[1]; d.sfm_nobs[s] = I[2]; d.rvo_counts[2 * s] = I[3]; d.rvo_counts[2 * s + 1] = I[4]; d.step_no[s] = 0;
+    }
+    for (int k = threadIdx.x; k < 8 * d.max_verts; k += blockDim.x) d.rvo_verts[(size_t)s * d.max_verts * 8 + k] = Fp[k];
+    for (int k = threadIdx.x; k < 3 * d.max_verts; k += blockDim.x) d.rvo_nodes[(size_t)s * d.max_verts * 3 + k] = nodes[k];
+    for (int j = threadIdx.x; j < c.R; j += blockDim.x) {
+        int idx = s * c.R + j;
+        const double* q = rob + 5 * j;
+        // init_pose (agent.cpp:133-142), set_goal (:144-154), flag reset (img_env.cpp:269-273)
+        RBF(d, RB_X, idx) = q[0]; RBF(d, RB_Y, idx) = q[1]; RBF(d, RB_YAW, idx) = q[2];
+        RBF(d, RB_L0V, idx) = 0; RBF(d, RB_L0W, idx) = 0;
+        RBF(d, RB_GX, idx) = q[3]; RBF(d, RB_GY, idx) = q[4]; RBF(d, RB_GYAW, idx) = q[2];
+        RBF(d, RB_COLL, idx) = 0; RBF(d, RB_ARR, idx) = 0; RBF(d, RB_DONE, idx) = 0;
+        RBF(d, RB_PREVD, idx) = nan("");                                    // yaml_env.py:225
+        if (c.relation == 1 && c.NA > 0) {                                  // setRobotPos(..., 0.0, 0.0) img_env.cpp:278-281
+            int a = c.P + j;
+            if (c.scene_type == 2 || c.scene_type == 3) {
+                d.rvo_pos[((size_t)s * c.NA + a) * 2] = (float)q[0]; d.rvo_pos[((size_t)s * c.NA + a) * 2 + 1] = (float)q[1];
+                d.rvo_vel[((size_t)s * c.NA + a) * 2] = 0.f; d.rvo_vel[((size_t)s * c.NA + a) * 2 + 1] = 0.f;
+            } else if (c.scene_type == 1) {
+                double* rec = d.sfm + ((size_t)s * c.NA + a) * SFM_REC;
+                rec[0] = q[0]; rec[1] = q[1]; rec[2] = 1.0;
+            }
+        }
+    }
+    for (int p = threadIdx.x; p < c.P; p += blockDim.x) {
+        int pi = s * c.P + p;
+        const double* q = ped + 5 * p;
+        PDF(d, PD_X, pi) = q[0]; PDF(d, PD_Y, pi) = q[1]; PDF(d, PD_YAW, pi) = q[2];
+        PDF(d, PD_TIDX, pi) = 0;
+        d.traj_len[pi] = tl[p];
+        for (int k = 0; k < 3 * c.max_traj; k++) d.traj[(size_t)pi * c.max_traj * 3 + k] = traj[(size_t)p * c.max_traj * 3 + k];
+        if (c.scene_type == 2 || c.scene_type == 3) {                       // setPedPos (velocity is NOT reset by the node)
+            d.rvo_pos[((size_t)s * c.NA + p) * 2] = (float)q[0]; d.rvo_pos[((size_t)s * c.NA + p) * 2 + 1] = (float)q[1];
+        } else if (c.scene_type == 1) {
+            double* rec = d.sfm + ((size_t)s * c.NA + p) * SFM_REC;
+            rec[0] = q[0]; rec[1] = q[1]; rec[2] = 0.0;                     // setPosition(x, y, 0)
+            // setWayPoint (pedscene.h:38-47): clearWaypoints, then goal (r=1) + trajectory (r = z);
+            // addWaypoint leaves destination = waypoints.front() without popping it
+            rec[7] = 0; rec[8] = -1; rec[9] = 0;
+            double* wp = d.sfm_wp + (size_t)pi * (1 + c.max_traj) * 3;
+            wp[0] = q[3]; wp[1] = q[4]; wp[2] = 1.0;
+            for (int k = 0; k < tl[p]; k++) { wp[3 + 3 * k] = traj[((size_t)p * c.max_traj + k) * 3]; wp[4 + 3 * k] = traj[((size_t)p * c.max_traj + k) * 3 + 1]; wp[5 + 3 * k] = traj[((size_t)p * c.max_traj + k) * 3 + 2]; }
+        }
+    }
+}
+
+static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int is_reset, cudaStream_t st) {
+    Dev& d = h->d; const Cfg& c = d.c;
+    k_stamp_agents<<<n_scenes * (c.R + c.P), 128, 0, st>>>(d, d_scene_ids, 0);
+    k_view<false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
+    k_stamp_agents<<<n_scenes * (c.R + c.P), 128, 0, st>>>(d, d_scene_ids, 1);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, const int32_t* n_obs, const double* obs,
+                            const double* robots, const double* peds, const int32_t* traj_len, const double* traj,
+                            int32_t ignore_obstacle, void* stream) {
+    if (!h) return fail("imgenv_reset: null handle");
+    if (!h->outputs_bound) return fail("imgenv_reset: outputs not bound (imgenv_bind_outputs)");
+    Dev& d = h->d; const Cfg& c = d.c;
+    if (n < 1 || n > c.S) return fail("imgenv_reset: bad scene count");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaStreamSynchronize(st));   // staging buffers are reused
+    using ht::f32;
+    size_t dper = (size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 3 * (size_t)c.max_traj * c.P + 4 * c.max_obs;
+    size_t iper = (size_t)5 + c.P + 3 * (size_t)d.max_verts;
+    size_t fper = (size_t)8 * d.max_verts;
+    memset(h->st_h, 0, dper * n * 8); memset(h->sti_h, 0, iper * n * 4); memset(h->stf_h, 0, fper * n * 4);
+    for (int sl = 0; sl < n; sl++) {
+        int s = scene_ids ? scene_ids[sl] : sl;
+        if (s < 0 || s >= c.S) return fail("imgenv_reset: scene id out of range");
+        double* D = h->st_h + dper * sl; int* I = h->sti_h + iper * sl; float* Fp = h->stf_h + fper * sl;
+        double* o_obs = D; double* o_rob = o_obs + 8 * (size_t)c.max_obs; double* o_ped = o_rob + 5 * (size_t)c.R;
+        double* o_traj = o_ped + 5 * (size_t)c.P; double* o_seg = o_traj + 3 * (size_t)c.max_traj * c.P;
+        int no = n_obs ? n_obs[sl] : 0;
+        if (no < 0 || no > c.max_obs) return fail("imgenv_reset: too many obstacles for max_obstacles");
+        I[0] = s; I[1] = no;
+        std::vector<ht::RvoObst> robst; int nseg = 0;
+        for (int k = 0; k < no; k++) {
+            const double* q = obs + ((size_t)sl * c.max_obs + k) * 11;
+            double* o = o_obs + 8 * k;
+            int shape = (int)q[0];
+            o[0] = shape; for (int m = 0; m < 4; m++) o[1 + m] = f32(q[1 + m]);
+            o[5] = q[5]; o[6] = q[6]; o[7] = ht::yaw_from_quaternion(q[7], q[8], q[9], q[10]);   // img_env.cpp:180-185
+            // get_corners (agent.cpp:626-651) -> pedscene->addObs (img_env.cpp:188-192)
+            Tf2 t = tf_from_pose(o[5], o[6], o[7]);
+            double pax, pay, pbx, pby;
+            if (shape == 0) { tf_apply(t, o[1] - o[3], o[2] - o[3], pax, pay); tf_apply(t, o[1] + o[3], o[2] + o[3], pbx, pby); }
+            else { tf_apply(t, o[1], o[3], pax, pay); tf_apply(t, o[2], o[4], pbx, pby); }
+            if (!ignore_obstacle) {
+                double* sg = o_seg + 4 * nseg; sg[0] = pax; sg[1] = pay; sg[2] = pbx; sg[3] = pby; nseg++;   // pedscene.h:23-27
+                ht::F2 v[4] = {ht::f2((float)pax, (float)pay), ht::f2((float)pax, (float)pby), ht::f2((float)pbx, (float)pby), ht::f2((float)pbx, (float)pay)};
+                ht::rvo_add_obstacle(robst, v, 4);                                                         // rvoscene.h:19-26
+            }
+        }
+        I[2] = nseg;
+        std::vector<ht::RvoNode> nodes;
+        int root = -1;
+        if (c.scene_type == 2 || c.scene_type == 3) {   // processObstacles (KdTree.cpp:119-128)
+            std::vector<int> list(robst.size());
+            for (size_t k = 0; k < list.size(); k++) list[k] = (int)k;
+            root = ht::rvo_build_tree(robst, nodes, list);
+            if ((int)robst.size() > d.max_verts || (int)nodes.size() > d.max_verts) return fail("imgenv_reset: obstacle k-d tree exceeds max_verts");
+            for (size_t k = 0; k < robst.size(); k++) {
+                float* v = Fp + 8 * k;
+                v[0] = robst[k].px; v[1] = robst[k].py; v[2] = robst[k].dx; v[3] = robst[k].dy; v[4] = (float)robst[k].convex;
+                v[5] = (float)robst[k].next; v[6] = (float)robst[k].prev; v[7] = 0;
+            }
+            int* nd = I + 5 + c.P;
+            for (size_t k = 0; k < nodes.size(); k++) { nd[3 * k] = nodes[k].obstacle; nd[3 * k + 1] = nodes[k].left; nd[3 * k + 2] = nodes[k].right; }
+        }
+        I[3] = (int)robst.size(); I[4] = root;
+        for (int j = 0; j < c.R; j++) {
+            const double* q = robots + ((size_t)sl * c.R + j) * 8;
+            double* o = o_rob + 5 * j;
+            o[0] = q[0]; o[1] = q[1]; o[2] = ht::yaw_from_quaternion(q[2], q[3], q[4], q[5]); o[3] = q[6]; o[4] = q[7];
+        }
+        for (int p = 0; p < c.P; p++) {
+            const double* q = peds + ((size_t)sl * c.P + p) * 8;
+            double* o = o_ped + 5 * p;
+            o[0] = q[0]; o[1] = q[1]; o[2] = ht::yaw_from_quaternion(q[2], q[3], q[4], q[5]); o[3] = q[6]; o[4] = q[7];
+            int tl = traj_len ? traj_len[(size_t)sl * c.P + p] : 0;
+            if (tl < 1 || tl > c.max_traj) return fail("imgenv_reset: pedestrian trajectory length must be in [1, max_traj]");
+            I[5 + p] = tl;
+            for (int k = 0; k < 3 * tl; k++) o_traj[(size_t)p * c.max_traj * 3 + k] = traj[((size_t)sl * c.P + p) * c.max_traj * 3 + k];
+        }
+    }
+    CK(cudaMemcpyAsync(h->st_d, h->st_h, dper * n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->sti_d, h->sti_h, iper * n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->stf_d, h->stf_h, fper * n * 4, cudaMemcpyHostToDevice, st));
+    // the scene-id list lives at the head of each int record; build a compact list after the records
+    int* ids_h = h->sti_h + iper * n;   // (st_ints has S*(...)+8 >= iper*n + n only if checked)
+    if (iper * (size_t)n + n > h->st_ints) return fail("imgenv_reset: staging overflow");
+    for (int sl = 0; sl < n; sl++) ids_h[sl] = h->sti_h[iper * sl];
+    int* ids_d = h->sti_d + iper * n;
+    CK(cudaMemcpyAsync(ids_d, ids_h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    k_stamp_objects<<<n * c.max_obs, 128, 0, st>>>(d, ids_d, 1);     // remove the previous episode's objects
+    k_apply_reset<<<n, 128, 0, st>>>(d, n, h->st_d, h->sti_d, h->stf_d, dper, iper, fper);
+    k_stamp_objects<<<n * c.max_obs, 128, 0, st>>>(d, ids_d, 0);     // obs.draw(obs_map_, 0, ...) img_env.cpp:187
+    if (launch_observe(h, ids_d, n, 1, st)) return -1;                 // view_agent(); get_states() img_env.cpp:285-286
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int imgenv_launches_per_step(const imgenv_t*) { return 4; }
+
+extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d_alive, void* stream) {
+    if (!h) return fail("imgenv_step: null handle");
+    if (!h->outputs_bound) return fail("imgenv_step: outputs not bound (imgenv_bind_outputs)");
+    if (!d_actions) return fail("imgenv_step: null actions");
+    Dev& d = h->d; const Cfg& c = d.c;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_dynamics<<<c.S, DYN_THREADS, h->dyn_smem, st>>>(d, d_actions, d_alive, h->ped_yaw_mode);
+    return launch_observe(h, nullptr, c.S, 0, st);
+}
+
+extern "C" int imgenv_step_host(imgenv_t* h, const float* h_actions, const uint8_t* h_alive, void* stream) {
+    if (!h || !h_actions) return fail("imgenv_step_host: null argument");
+    const Cfg& c = h->d.c;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h->act_d, h_actions, (size_t)c.S * c.R * 3 * 4, cudaMemcpyHostToDevice, st));
+    if (h_alive) CK(cudaMemcpyAsync(h->alive_d, h_alive, (size_t)c.S * c.R, cudaMemcpyHostToDevice, st));
+    return imgenv_step(h, h->act_d, h_alive ? h->alive_d : nullptr, st);
+}
+
+extern "C" int imgenv_end_episode(imgenv_t* h, int32_t) { return h ? 0 : fail("imgenv_end_episode: null handle"); }
+extern "C" int imgenv_solver_agents(const imgenv_t* h) { return h ? h->d.c.NA : 0; }
+extern "C" int imgenv_view_dims(const imgenv_t* h, int32_t* vh, int32_t* vw) {
+    if (!h) return fail("null handle");
+    *vh = h->d.c.vh; *vw = h->d.c.vw;
+    return 0;
+}
+extern "C" int64_t imgenv_algorithmic_bytes_per_robot_step(const imgenv_t* h) {
+    // outputs written once + action/alive read + robot state read-modify-write
+    const Cfg& c = h->d.c;
+    return (int64_t)c.img * c.img * 2 + 3ll * c.img * c.img * 4 + 4ll * c.range_total + 4ll * c.state_dim + 4ll * c.pvs_len + 10 + 13 + 2 * 104;
+}
+
+extern "C" int imgenv_get_internal(imgenv_t* h, double* robot, double* ped, double* solver) {
+    if (!h) return fail("null handle");
+    Dev& d = h->d; const Cfg& c = d.c;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    size_t nr = (size_t)c.S * c.R, np = (size_t)c.S * c.P;
+    if (robot) {
+        std::vector<double> rb((size_t)RB_FIELDS * nr);
+        CK(cudaMemcpy(rb.data(), d.rb, rb.size() * 8, cudaMemcpyDeviceToHost));
+        const int map[16] = {RB_X, RB_Y, RB_YAW, RB_GX, RB_GY, RB_GYAW, RB_L0V, RB_L0W, RB_L1V, RB_L1W, RB_VX, RB_VY, RB_COLL, RB_ARR, RB_BEEP, RB_PREVD};
+        for (size_t i = 0; i < nr; i++) for (int k = 0; k < 16; k++) robot[16 * i + k] = rb[(size_t)map[k] * nr + i];
+    }
+    if (ped && np) {
+        std::vector<double> pd((size_t)PD_FIELDS * np);
+        CK(cudaMemcpy(pd.data(), d.pd, pd.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < np; i++) for (int k = 0; k < PD_FIELDS; k++) ped[(size_t)PD_FIELDS * i + k] = pd[(size_t)k * np + i];
+    }
+    if (solver && c.NA) {
+        size_t na = (size_t)c.S * c.NA;
+        if (c.scene_type == 2 || c.scene_type == 3) {
+            std::vector<float> p(2 * na), v(2 * na);
+            CK(cudaMemcpy(p.data(), d.rvo_pos, p.size() * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(v.data(), d.rvo_vel, v.size() * 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < na; i++) { solver[4 * i] = p[2 * i]; solver[4 * i + 1] = p[2 * i + 1]; solver[4 * i + 2] = v[2 * i]; solver[4 * i + 3] = v[2 * i + 1]; }
+        } else if (c.scene_type == 1) {
+            CK(cudaMemcpy(solver, d.sfm, na * SFM_REC * 8, cudaMemcpyDeviceToHost));
+        }
+    }
+    return 0;
+}
+
+extern "C" int imgenv_set_internal(imgenv_t* h, const double* robot, const double* ped, const double* solver) {
+    if (!h) return fail("null handle");
+    Dev& d = h->d; const Cfg& c = d.c;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    size_t nr = (size_t)c.S * c.R, np = (size_t)c.S * c.P;
+    if (robot) {
+        std::vector<double> rb((size_t)RB_FIELDS * nr);
+        CK(cudaMemcpy(rb.data(), d.rb, rb.size() * 8, cudaMemcpyDeviceToHost));
+        const int map[16] = {RB_X, RB_Y, RB_YAW, RB_GX, RB_GY, RB_GYAW, RB_L0V, RB_L0W, RB_L1V, RB_L1W, RB_VX, RB_VY, RB_COLL, RB_ARR, RB_BEEP, RB_PREVD};
+        for (size_t i = 0; i < nr; i++) for (int k = 0; k < 16; k++) rb[(size_t)map[k] * nr + i] = robot[16 * i + k];
+        CK(cudaMemcpy(d.rb, rb.data(), rb.size() * 8, cudaMemcpyHostToDevice));
+    }
+    if (ped && np) {
+        std::vector<double> pd((size_t)PD_FIELDS * np);
+        for (size_t i = 0; i < np; i++) for (int k = 0; k < PD_FIELDS; k++) pd[(size_t)k * np + i] = ped[(size_t)PD_FIELDS * i + k];
+        CK(cudaMemcpy(d.pd, pd.data(), pd.size() * 8, cudaMemcpyHostToDevice));
+    }
+    if (solver && c.NA) {
+        size_t na = (size_t)c.S * c.NA;
+        if (c.scene_type == 2 || c.scene_type == 3) {
+            std::vector<float> p(2 * na), v(2 * na);
+            for (size_t i = 0; i < na; i++) { p[2 * i] = (float)solver[4 * i]; p[2 * i + 1] = (float)solver[4 * i + 1]; v[2 * i] = (float)solver[4 * i + 2]; v[2 * i + 1] = (float)solver[4 * i + 3]; }
+            CK(cudaMemcpy(d.rvo_pos, p.data(), p.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d.rvo_vel, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+        } else if (c.scene_type == 1) {
+            CK(cudaMemcpy(d.sfm, solver, na * SFM_REC * 8, cudaMemcpyHostToDevice));
+        }
+    }
+    return 0;
+}
+
+extern "C" int imgenv_debug_view_maps(imgenv_t* h, uint8_t* host_out, void* stream) {
+    if (!h || !host_out) return fail("imgenv_debug_view_maps: null argument");
+    Dev d = h->d; const Cfg& c = d.c;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t n = (size_t)c.S * c.R * c.vh * c.vw;
+    uint8_t* buf = nullptr;
+    CK(cudaMalloc((void**)&buf, n));
+    d.dbg_view = buf;
+    k_stamp_agents<<<c.S * (c.R + c.P), 128, 0, st>>>(d, nullptr, 0);
+    k_view<true><<<c.S * c.R, VIEW_THREADS, h->view_smem, st>>>(d, nullptr, 0);
+    k_stamp_agents<<<c.S * (c.R + c.P), 128, 0, st>>>(d, nullptr, 1);
+    cudaError_t e = cudaMemcpyAsync(host_out, buf, n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(std::string("imgenv_debug_view_maps: ") + cudaGetErrorString(e));
+    return 0;
+}

@@ -1,0 +1,134 @@
+// Device-resident state of one handle (S scenes on one GPU) and the static per-config tables.
+// Layout notes (DESIGN.md "Data layout in HBM"):
+//   * one static occupancy grid (u8, H x W) + its 1-bit "value < 250" plane shared by all scenes
+//     (L2-resident: 0.5-54 MB), instead of the reference's R full-map clones per step
+//     (img_env.cpp:623);
+//   * per scene: a 1-bit plane occ_all = static | reset objects | pedestrians | robots, a u8 flag
+//     plane and a u16 "lowest robot id" plane; footprints are stamped/unstamped each step
+//     (O(footprint) work, never O(map));
+//   * robots / pedestrians as SoA of doubles ([S][R], [S][P]).
+#pragma once
+#include <stdint.h>
+#include "tfmath.cuh"
+
+// flag plane bits
+#define F_OBJ 1u      // reset object wrote 0 here   (img_env.cpp:187)
+#define F_RIGHT 2u    // right leg (overwrites 0)    (agent.cpp:757-772)
+#define F_LEFT 4u     // left leg                    (agent.cpp:742-756)
+#define F_CIRC 8u     // circle pedestrian           (img_env.cpp:599-601)
+#define F_ROBOT 16u   // some robot footprint
+#define F_MULTI 32u   // footprints of >= 2 different robots
+#define RMIN_EMPTY 0xFFFFu
+
+#define MAX_SPANS 2
+#define RB_FIELDS 18   // doubles per robot
+#define PD_FIELDS 20   // doubles per pedestrian
+
+// per-robot SoA field ids (double)
+enum { RB_X = 0, RB_Y, RB_YAW, RB_GX, RB_GY, RB_GYAW, RB_L0V, RB_L0W, RB_L1V, RB_L1W, RB_VX, RB_VY,
+       RB_COLL, RB_ARR, RB_BEEP, RB_PREVD, RB_MIND, RB_DONE };
+// per-ped SoA field ids (double)
+enum { PD_X = 0, PD_Y, PD_YAW, PD_LX, PD_LY, PD_LYAW, PD_VX, PD_VY, PD_GAIT, PD_LGAIT, PD_REM,
+       PD_LLX, PD_LLY, PD_LLZ, PD_RLX, PD_RLY, PD_RLZ, PD_TIDX, PD_PAD0, PD_PAD1 };
+
+struct Limiter {
+    int has_v, has_a, has_j;
+    double min_v, max_v, min_a, max_a, min_j, max_j;
+};
+
+// One robot "type" = identical shape/sensor description (deduplicated on the host).
+struct RobotType {
+    int n_pts;            // footprint lattice points (agent.cpp:18-62)
+    int pts_off;          // offset into lattice_xy (double2 units)
+    int n_own;            // own-footprint cells in the view raster (static: base2view is pose independent)
+    int own_off;          // offset into own_cells (int: row*vw+col)
+    int org_x, org_y;     // laser origin cell (agent.cpp:366-369)
+    int ray_off;          // offset into ray_end (short2 units), range_total entries
+    int span_off;         // offset into fov_spans (vh * MAX_SPANS * 2 shorts)
+    int zone_r0, zone_r1, zone_c0, zone_c1;  // view-raster box where the robot's own footprint may be the only stamp
+    int khi_off;          // offset into khi/klo tables (ns*ns entries)
+    int own_mask_off;     // offset into own_mask (ns*ns bits, u32 words)
+    double size_last;     // python: robots[i].size[-1]
+    double sensor_x, sensor_y;
+};
+
+struct Cfg {
+    // geometry
+    int S, R, P, NA;         // NA = solver agents = P + (relation ? R : 0)
+    int H, W, Wb;            // grid rows, cols, u32 words per bit-plane row
+    int vh, vw, vwb;         // view raster rows/cols, words per row
+    double res;              // view resolution == grid resolution (float32 widened)
+    double step_hz, control_hz;   // period (float32 widened), 0.05
+    int state_dim, use_laser, range_total, ktype, scene_type, relation;
+    double beep_r, ped_ca_p;
+    double view_max_dist;
+    Tf2 view_base, base_view;     // tf_view_base_, tf_base_view_
+    // python side
+    int img, ns;                  // output image side (48), needed source rows/cols (144)
+    int max_ped, ped_vec_dim, pvs_len;
+    double ped_image_r, ped_res, laser_max;
+    int laser_norm;
+    int max_obs, max_traj;
+    unsigned long long seed;
+    int n_types;
+};
+
+struct Dev {
+    Cfg c;
+    // static, shared
+    const uint8_t* grid;          // [H][W]
+    const uint32_t* static_occ;   // [H][Wb]  bit = grid < 250
+    const RobotType* types;       // [n_types]
+    const int* type_of;           // [R]
+    const double* lattice_xy;     // packed (x,y) pairs
+    const int* own_cells;
+    const short* ray_end;         // (x2,y2) pairs
+    const short* fov_spans;       // per type: [vh][MAX_SPANS][2] (c0,c1 exclusive), -1 = none
+    const unsigned short* khi;    // per type [ns*ns]: highest ray index touching the needed pixel (0xFFFF none)
+    const unsigned short* klo;    //                   lowest
+    const uint32_t* own_mask;     // per type: bit per needed pixel = own footprint cell
+    const short* need_idx;        // [ns] source row/col index of the k-th needed row/col
+    const short* cubic_tap;       // [img][4] index into need_idx space (0..ns-1) of the 4 taps
+    const short* cubic_coef;      // [img][4] fixed-point weights (x2048)
+    const uint16_t* f16_lut;      // [256] half(x/255)
+    const Limiter* lim_v; const Limiter* lim_w;   // [R]
+    // pedestrian footprints
+    const int* ped_shape;         // [P]
+    const double* ped_size;       // [P][6] (float32 widened)
+    const double* ped_maxspeed;   // [P]
+    const double* ped_r_round;    // [P] python round(r_,2)
+    const float* ped_r_wire;      // [P] float32 r_ = sizes_[2]
+    const int* ped_pts_off;       // [P][2] lattice offsets (body or left leg, right leg)
+    const int* ped_pts_n;         // [P][2]
+    // per scene planes
+    uint32_t* occ_all;            // [S][H][Wb]
+    uint8_t* flags;               // [S][H][W]
+    unsigned short* rmin;         // [S][H][W]
+    // dynamic state
+    double* rb;                   // [RB_FIELDS][S*R]
+    double* pd;                   // [PD_FIELDS][S*P]
+    double* traj;                 // [S][P][max_traj][3]
+    int* traj_len;                // [S][P]
+    double* obs;                  // [S][max_obs][8]: shape, size[4], x, y, yaw
+    int* n_obs;                   // [S]
+    unsigned long long* step_no;  // [S]
+    // solver state
+    float* rvo_pos; float* rvo_vel;         // [S][NA][2]
+    float* rvo_verts;                       // [S][max_verts][8]: px,py,dx,dy,convex,next,prev,0
+    int* rvo_nodes;                         // [S][max_verts][3]: obstacle, left, right
+    int* rvo_counts;                        // [S][2]: n_verts, root(-1 none)
+    int max_verts;
+    double* sfm;                            // [S][NA][12]
+    double* sfm_obs;                        // [S][max_obs][4] segment ax,ay,bx,by
+    int* sfm_nobs;                          // [S]
+    double* sfm_wp;                         // [S][P][1+max_traj][3] waypoints x,y,r
+    int* sfm_tree;                          // [S][...] quadtree emulation (see sfm.cuh)
+    int sfm_tree_stride;
+    // outputs
+    float* o_vec; uint16_t* o_sensor; int8_t* o_coll; uint8_t* o_arr; float* o_laser;
+    float* o_pvs; float* o_pmap; float* o_stepd; float* o_mind;
+    uint8_t* dbg_view;            // optional [S][R][vh][vw]
+};
+
+__host__ __device__ inline double& RBF(const Dev& d, int f, int idx) { return d.rb[(size_t)f * d.c.S * d.c.R + idx]; }
+__host__ __device__ inline double& PDF(const Dev& d, int f, int idx) { return d.pd[(size_t)f * d.c.S * d.c.P + idx]; }

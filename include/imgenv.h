@@ -1,0 +1,128 @@
+/*
+ * imgenv.h — C ABI of libimgenv_b200.so: the B200-native replacement for the img_env
+ * per-step simulation hot path.
+ *
+ * What it replaces in the reference (DRL-Navigation/img_env):
+ *   - the four ROS1 services of the scene node      src/img_env/src/img_env.cpp:716-755
+ *       init_image_env  (InitEnv.srv)   -> imgenv_create
+ *       reset_image_env (ResetEnv.srv)  -> imgenv_reset
+ *       step_image_env  (StepEnv.srv)   -> imgenv_step
+ *       ep_end_image_env(EndEp.srv)     -> imgenv_end_episode (no-op: EpRes logging is out of scope)
+ *   - AND the Python post-processing of the reply   envs/env/yaml_env.py:392-481
+ *       (_get_states/_draw_ped_map/_trans_cv2_sensor_map/_norm_lasers), so the nine ImageState
+ *       fields (envs/state/state.py:4-28) are produced on the device.
+ *
+ * One handle = one GPU = S independent scenes sharing one configuration (the reference runs
+ * one ROS node per scene, create_launch.py:25-34).  Plain pointers and sizes only; no torch
+ * types.  All device work is enqueued on the caller's cudaStream_t (passed as void*; NULL =
+ * legacy default stream) and is stream-ordered: no host synchronisation inside step.
+ * The handle is not thread-safe.  Every entry point returns 0 on success, <0 on error;
+ * imgenv_last_error() returns the message of the last failure on the calling thread.
+ */
+#ifndef IMGENV_H_
+#define IMGENV_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct imgenv imgenv_t;
+
+enum { IMGENV_SCENE_EMPTY = 0, IMGENV_SCENE_PEDSCENE = 1, IMGENV_SCENE_RVO = 2, IMGENV_SCENE_ERVO = 3 };
+enum { IMGENV_SHAPE_CIRCLE = 0, IMGENV_SHAPE_RECTANGLE = 1, IMGENV_SHAPE_LEG = 2 };
+enum { IMGENV_KTYPE_DIFF = 0, IMGENV_KTYPE_OMNI = 1 };
+
+/* InitEnv.srv scalars (float32 on the ROS wire: the library rounds them through float exactly
+ * like the node sees them) + the cfg keys only yaml_env.py consumes. */
+typedef struct imgenv_config {
+    double view_resolution, view_width, view_height;   /* cfg view_map.{resolution,width,height} */
+    double step_hz;                                     /* cfg control_hz: a PERIOD in seconds     */
+    int32_t state_dim;                                  /* 3, 4 or 5 (agent.cpp:156-184)           */
+    int32_t use_laser, range_total;
+    double view_angle_begin, view_angle_end, view_min_dist, view_max_dist;
+    double beep_r, ped_ca_p;                            /* never filled by the reference's Python: 0 */
+    int32_t relation_ped_robo;
+    /* python side (yaml_env.py:133-181) */
+    int32_t image_size, ped_image_size;                 /* 48, 48 (square)                          */
+    int32_t max_ped, ped_vec_dim;                       /* ped_vector_states is [1 + ped_vec_dim*max_ped] */
+    double ped_image_r, laser_max;
+    int32_t laser_norm;
+    /* batch shape */
+    int32_t num_scenes, num_robots, num_peds;           /* S, R, P per scene                        */
+    int32_t scene_type;                                 /* IMGENV_SCENE_*  (cfg ped_sim.type)      */
+    int32_t robot_ktype;                                /* IMGENV_KTYPE_*  (cfg robot_type)        */
+    int32_t max_obstacles;                              /* reset objects per scene (cfg object.total) */
+    int32_t max_traj;                                   /* waypoints per pedestrian (1 or 2 from reset_helper.py:337-342) */
+    uint64_t seed;                                      /* beep Bernoulli draws (img_env.cpp:327 uses glibc rand()) */
+} imgenv_config;
+
+/* Device pointers the library WRITES every reset/step (caller-owned, e.g. torch tensors; bound
+ * once with imgenv_bind_outputs).  Rows of robots whose view is frozen (already collided /
+ * arrived: agent.cpp:358-360) keep sensor_maps/lasers/is_collisions untouched, as the node
+ * re-sends its stale buffers (img_env.cpp:553-565).  Layouts are C-contiguous. */
+typedef struct imgenv_outputs {
+    float*    vector_states;      /* [S,R,state_dim]   AgentState.state (float32 on the wire)     */
+    uint16_t* sensor_maps;        /* [S,R,48,48] IEEE binary16: cubic-resized view_map / 255       */
+    int8_t*   is_collisions;      /* [S,R] 0 none, 1 obstacle, 2 pedestrian, 3 robot               */
+    uint8_t*  is_arrives;         /* [S,R]                                                          */
+    float*    lasers;             /* [S,R,range_total]  (/laser_max when laser_norm)               */
+    float*    ped_vector_states;  /* [S,R,1+ped_vec_dim*max_ped]                                    */
+    float*    ped_maps;           /* [S,R,3,48,48]                                                  */
+    float*    step_ds;            /* [S,R]                                                          */
+    float*    ped_min_dists;      /* [S,R]  +inf until a pedestrian exists                          */
+} imgenv_outputs;
+
+/* robot_desc[R][25]: shape, size[4], sensor_cfg[2], speed_limiter_v[9], speed_limiter_w[9]
+ *   (limiter = has_velocity, has_acceleration, has_jerk, min_v, max_v, min_a, max_a, min_j, max_j;
+ *    Agent.msg / SpeedLimiter.msg, built by reset_helper.py:374-393)
+ * ped_desc[P][8]:    shape, size[6], max_speed                       (reset_helper.py:395-412)
+ * robot_size_last[R]: cfg robot.size[i][-1] as the python double yaml_env.py:407 adds to ped_r
+ * grid: the occupancy PNG already decoded (cv2.imread GRAYSCALE) and resized to the view
+ *   resolution as grid_map.cpp:28-38 does; H rows (world x), W cols (world y). */
+int imgenv_create(const imgenv_config* cfg, const uint8_t* grid, int32_t H, int32_t W,
+                  const double* robot_desc, const double* ped_desc, const double* robot_size_last,
+                  int32_t device, imgenv_t** out);
+int imgenv_destroy(imgenv_t* h);
+int imgenv_bind_outputs(imgenv_t* h, const imgenv_outputs* out);
+
+/* ResetEnv.srv for n scenes (host arrays, float64; poses as x,y,qx,qy,qz,qw like geometry_msgs/Pose).
+ *   scene_ids[n]; n_obs[n]; obs[n][max_obstacles][11] = shape,size[4],x,y,q[4]
+ *   robots[n][R][8] = x,y,q[4],goal_x,goal_y ;  peds[n][P][8] likewise
+ *   traj_len[n][P] ; traj[n][P][max_traj][3]   (Agent.msg trajectory, reset_helper.py:337-342)
+ * Runs the node's _reset (img_env.cpp:162-292) incl. view_agent + get_states, then the Python
+ * _get_states; outputs of those scenes are written to the bound tensors. */
+int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, const int32_t* n_obs, const double* obs,
+                 const double* robots, const double* peds, const int32_t* traj_len, const double* traj,
+                 int32_t ignore_obstacle, void* stream);
+
+/* StepEnv.srv for all S scenes. d_actions[S][R][3] = v, w, v_y(beep) float32 DEVICE pointer;
+ * d_alive[S][R] uint8 DEVICE pointer, or NULL to use the library's own dones bookkeeping
+ * (yaml_env.py:319-331,373-377: alive = not (collided or arrived) after the previous call). */
+int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d_alive, void* stream);
+/* Same call with HOST buffers (pinned or pageable): copies in, steps, leaves outputs on device. */
+int imgenv_step_host(imgenv_t* h, const float* h_actions, const uint8_t* h_alive, void* stream);
+int imgenv_end_episode(imgenv_t* h, int32_t scene_id);
+
+/* Internal state in/out for single-step parity tests. Host arrays.
+ *   robot[S][R][16]: x,y,yaw, gx,gy,gyaw, last0 v,w, last1 v,w, vx,vy, is_collision,is_arrive,beep, prev_goal_dist(NaN=None)
+ *   ped[S][P][20]:   x,y,yaw, lx,ly,lyaw, vx,vy, gait state,last_state,remaining, lleg xyz, rleg xyz, traj_idx, 0,0
+ *   solver: RVO/ERVO [S][P+R'][4] float64 holding px,py,vx,vy ; SFM [S][P+R'][12]
+ *           (p.xyz, v.xyz, vmax, dest, lastdest, deque_front, in_tree, 0)   R' = R if relation_ped_robo==1 else 0 */
+int imgenv_get_internal(imgenv_t* h, double* robot, double* ped, double* solver);
+int imgenv_set_internal(imgenv_t* h, const double* robot, const double* ped, const double* solver);
+/* Debug raster: the 400x400 view_map_ of every robot as the node would send it (u8 [S][R][vh][vw]). */
+int imgenv_debug_view_maps(imgenv_t* h, uint8_t* host_out, void* stream);
+/* ped_min_dists persistence (NearbyPed, reset_helper.py:85-99) and dones are library state. */
+int imgenv_solver_agents(const imgenv_t* h);   /* P + R' */
+int imgenv_view_dims(const imgenv_t* h, int32_t* vh, int32_t* vw);
+/* Number of kernel launches one imgenv_step enqueues (for bench.py's gpu_launches claim). */
+int imgenv_launches_per_step(const imgenv_t* h);
+/* Algorithmic HBM bytes one robot-step must move (SURVEY.md §8d formula for this config). */
+int64_t imgenv_algorithmic_bytes_per_robot_step(const imgenv_t* h);
+const char* imgenv_last_error(void);
+const char* imgenv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMGENV_H_ */

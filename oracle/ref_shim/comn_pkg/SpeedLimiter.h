@@ -1,0 +1,2 @@
+#pragma once
+#include <comn_pkg/msgs.h>

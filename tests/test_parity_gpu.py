@@ -1,0 +1,110 @@
+"""GPU parity: the CUDA path (through the C ABI) against the UNMODIFIED reference node
+(oracle/_ref, built from /root/reference by oracle/Makefile; the prebuilt .so travels to the GPU
+box) + the restated Python post-processing, single-step on identical pre-step state
+(SURVEY.md Appendix C)."""
+import numpy as np
+import pytest
+
+from helpers import base_cfg, build_spec, compare_state, make_reset, random_actions
+
+pytestmark = pytest.mark.gpu
+
+
+def _to_np(out, s):
+    return {k: v[s].detach().cpu().numpy() for k, v in out.items()}
+
+
+def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False, n_obj=None, lo=2.5, hi=8.5,
+                 check_view=True):
+    import torch
+    from img_env_b200.lib import BatchedSim
+    from oracle.pyref import RefEnv, PyPost, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref/libimgenv_ref.so not built")
+    spec = build_spec(cfg, opt_in_beep=opt_in_beep)
+    R = spec["R"]
+    rng = np.random.default_rng(seed)
+    sim = BatchedSim(spec, num_scenes=S, ped_yaw_mode=1)
+    refs = [RefEnv(spec) for _ in range(S)]
+    posts = [PyPost(spec) for _ in range(S)]
+    resets = [make_reset(spec, rng, n_obj=n_obj, lo=lo, hi=hi) for _ in range(S)]
+    out = sim.reset(resets)
+    torch.cuda.synchronize()
+    errs = []
+    for s in range(S):
+        st = refs[s].reset(resets[s]); posts[s].on_reset()
+        want = posts[s].get_states(st)
+        errs += compare_state(_to_np(out, s), want, spec, where="reset scene %d: " % s)
+        if check_view:
+            vm = sim.debug_view_maps()
+            nb = int((vm[s] != st["view_map"]).sum())
+            if nb:
+                errs.append("reset scene %d: %d view_map pixels differ" % (s, nb))
+    assert not errs, "\n".join(errs[:20])
+    dones = np.zeros((S, R), np.int64)
+    for t in range(steps):
+        acts = np.stack([random_actions(R, rng, beep=beep) for _ in range(S)])
+        alive = (dones == 0).astype(np.uint8)
+        if sync:   # put the product into the node's exact pre-step state
+            rbs, pds, svs = [], [], []
+            for s in range(S):
+                rb, pd = refs[s].get_internal()
+                rb = rb.copy()
+                td = posts[s].tmp_distances
+                rb[:, 15] = td if td is not None else np.nan
+                rbs.append(rb); pds.append(pd)
+                if sim.solver_agents:
+                    a = refs[s].rvo_get() if spec["scene_type"] in ("rvoscene", "ervoscene") else refs[s].sfm_get()
+                    svs.append(a.astype(np.float64))
+            sim.set_internal(np.stack(rbs), np.stack(pds) if spec["P"] else None, np.stack(svs) if svs else None)
+        out = sim.step(torch.from_numpy(acts).cuda(), torch.from_numpy(alive).cuda())
+        torch.cuda.synchronize()
+        vm = sim.debug_view_maps() if check_view else None
+        for s in range(S):
+            frozen_before = np.array([refs[s].get_internal()[0][j, 12] != 0 or refs[s].get_internal()[0][j, 13] != 0 for j in range(R)])
+            st = refs[s].step(acts[s] * alive[s][:, None], alive[s])
+            want = posts[s].get_states(st)
+            errs += compare_state(_to_np(out, s), want, spec, where="step %d scene %d: " % (t, s))
+            rb_ref, pd_ref = refs[s].get_internal()
+            rb, pd, sv = sim.get_internal()
+            if not np.allclose(rb[s][:, :12], rb_ref[:, :12], rtol=1e-4, atol=1e-6):
+                errs.append("step %d scene %d: robot internal state differs" % (t, s))
+            if spec["P"] and not np.allclose(pd[s][:, [0, 1, 6, 7, 8, 10, 11, 12, 14, 15, 17]], pd_ref[:, [0, 1, 6, 7, 8, 10, 11, 12, 14, 15, 17]], rtol=1e-4, atol=1e-5):
+                errs.append("step %d scene %d: pedestrian state differs\n%s\n%s" % (t, s, pd[s][:, :8], pd_ref[:, :8]))
+            if check_view:
+                # frozen robots keep a stale view in the node; the debug raster is recomputed -> skip them
+                now_frozen = (rb_ref[:, 12] != 0) | (rb_ref[:, 13] != 0)
+                for j in range(R):
+                    if frozen_before[j]:
+                        continue
+                    nb = int((vm[s, j] != st["view_map"][j]).sum())
+                    if nb:
+                        errs.append("step %d scene %d robot %d: %d view_map pixels differ" % (t, s, j, nb))
+                del now_frozen
+            dones[s] = np.clip(np.clip(want["is_collisions"], -1, 1) + want["is_arrives"], 0, 1)
+        assert not errs, "\n".join(errs[:20])
+    sim.close()
+
+
+def test_c1_single_robot_static():
+    run_lockstep(base_cfg(R=1, P=0, n_obj=4), seed=1, steps=6)
+
+
+def test_c2_eight_robots():
+    run_lockstep(base_cfg(R=8, P=0, n_obj=0), seed=2, steps=6, lo=4.0, hi=7.0)
+
+
+def test_c3_orca_20_peds():
+    run_lockstep(base_cfg(R=1, P=20, scene="rvoscene", n_obj=4, max_ped=20), seed=3, steps=6)
+
+
+def test_ervo_beeps():
+    run_lockstep(base_cfg(R=3, P=12, scene="ervoscene", n_obj=3, max_ped=12), seed=4, steps=6, beep=True, opt_in_beep=True)
+
+
+def test_crowded_collisions_multi_scene():
+    run_lockstep(base_cfg(R=6, P=10, scene="rvoscene", n_obj=6, max_ped=10), seed=5, steps=8, S=3, lo=4.0, hi=7.0)
+
+
+def test_circle_peds_rect_robot_state5():
+    run_lockstep(base_cfg(R=2, P=5, scene="rvoscene", ped_shape="circle", robot_shape="rectangle", state_dim=5, n_obj=2), seed=6, steps=5)
