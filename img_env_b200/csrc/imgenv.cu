@@ -33,6 +33,8 @@ struct imgenv {
     float* stf_h = nullptr; float* stf_d = nullptr; size_t st_floats = 0;
     float* act_d = nullptr; uint8_t* alive_d = nullptr;
     size_t view_smem = 0, dyn_smem = 0;
+    // optional per-kernel CUDA-event timing (bench.py roofline): 5 events per profiled step
+    std::vector<cudaEvent_t> evs; int prof_max = 0, prof_n = 0;
 };
 
 template <class T> static int dalloc(imgenv* h, T** p, size_t n, int fill_byte = 0) {
@@ -340,11 +342,14 @@ __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, co
     }
 }
 
-static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int is_reset, cudaStream_t st) {
+static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int is_reset, cudaStream_t st, cudaEvent_t* ev = nullptr) {
     Dev& d = h->d; const Cfg& c = d.c;
     k_stamp_agents<<<n_scenes * (c.R + c.P), 128, 0, st>>>(d, d_scene_ids, 0);
+    if (ev) cudaEventRecord(ev[2], st);
     k_view<false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
+    if (ev) cudaEventRecord(ev[3], st);
     k_stamp_agents<<<n_scenes * (c.R + c.P), 128, 0, st>>>(d, d_scene_ids, 1);
+    if (ev) cudaEventRecord(ev[4], st);
     CK(cudaGetLastError());
     return 0;
 }
@@ -448,8 +453,51 @@ extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d
     if (!d_actions) return fail("imgenv_step: null actions");
     Dev& d = h->d; const Cfg& c = d.c;
     cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t* ev = nullptr;
+    if (h->prof_n < h->prof_max) { ev = h->evs.data() + 5 * (size_t)h->prof_n; h->prof_n++; }
+    if (ev) cudaEventRecord(ev[0], st);
     k_dynamics<<<c.S, DYN_THREADS, h->dyn_smem, st>>>(d, d_actions, d_alive, h->ped_yaw_mode);
-    return launch_observe(h, nullptr, c.S, 0, st);
+    if (ev) cudaEventRecord(ev[1], st);
+    return launch_observe(h, nullptr, c.S, 0, st, ev);
+}
+
+// Per-kernel device timing for bench.py: events are recorded on the launching stream around each of the
+// four kernels of the next `max_steps` imgenv_step calls.
+extern "C" int imgenv_profile_begin(imgenv_t* h, int max_steps) {
+    if (!h) return fail("null handle");
+    for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
+    h->evs.assign(5 * (size_t)max_steps, nullptr);
+    for (auto& e : h->evs) CK(cudaEventCreate(&e));
+    h->prof_max = max_steps; h->prof_n = 0;
+    return 0;
+}
+// ms[4] = mean duration of k_dynamics, k_stamp_agents(stamp), k_view, k_stamp_agents(unstamp); returns #steps
+extern "C" int imgenv_profile_end(imgenv_t* h, float* ms) {
+    if (!h) return fail("null handle");
+    CK(cudaDeviceSynchronize());
+    for (int k = 0; k < 4; k++) ms[k] = 0.f;
+    for (int i = 0; i < h->prof_n; i++)
+        for (int k = 0; k < 4; k++) { float t = 0; CK(cudaEventElapsedTime(&t, h->evs[5 * i + k], h->evs[5 * i + k + 1])); ms[k] += t; }
+    int n = h->prof_n;
+    for (int k = 0; k < 4 && n; k++) ms[k] /= n;
+    for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
+    h->evs.clear(); h->prof_max = 0; h->prof_n = 0;
+    return n;
+}
+
+// Clears is_collision_/is_arrive_ of every robot (what ImgEnv::_reset does at img_env.cpp:272-273) without
+// moving anything, so a throughput run never benefits from Agent::view's early-out (agent.cpp:358-360).
+__global__ void k_revive(Dev d) {
+    size_t n = (size_t)d.c.S * d.c.R;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) { d.rb[(size_t)RB_COLL * n + i] = 0; d.rb[(size_t)RB_ARR * n + i] = 0; d.rb[(size_t)RB_DONE * n + i] = 0; }
+}
+extern "C" int imgenv_revive(imgenv_t* h, void* stream) {
+    if (!h) return fail("null handle");
+    size_t n = (size_t)h->d.c.S * h->d.c.R;
+    k_revive<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->d);
+    CK(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int imgenv_step_host(imgenv_t* h, const float* h_actions, const uint8_t* h_alive, void* stream) {

@@ -187,6 +187,17 @@ class BatchedSim:
                                               self._stream()))
         return self.out
 
+    def revive(self):
+        self._check(self.lib.imgenv_revive(self.h, self._stream()))
+
+    def profile_begin(self, max_steps):
+        self._check(self.lib.imgenv_profile_begin(self.h, int(max_steps)))
+
+    def profile_end(self):
+        ms = (C.c_float * 4)()
+        n = self.lib.imgenv_profile_end(self.h, ms)
+        return n, dict(k_dynamics=ms[0], k_stamp=ms[1], k_view=ms[2], k_unstamp=ms[3])
+
     def get_internal(self):
         rb = np.zeros((self.S, self.R, 16)); pd = np.zeros((self.S, max(self.P, 1), 20))
         na = self.solver_agents
