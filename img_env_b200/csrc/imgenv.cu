@@ -238,7 +238,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     }
     // reset staging: per scene doubles = obs 8*max_obs + robots 5*R + peds 5*P + traj 3*max_traj*P + sfm segs 4*max_obs
     h->st_doubles = S * ((size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 3 * (size_t)c.max_traj * c.P + 4 * c.max_obs) + 8;
-    h->st_ints = S * ((size_t)4 + c.P + 3 * (size_t)d.max_verts) + 8;
+    h->st_ints = S * ((size_t)5 + c.P + 3 * (size_t)d.max_verts) + S + 8;
     h->st_floats = S * ((size_t)8 * d.max_verts) + 8;
     CK(cudaMallocHost((void**)&h->st_h, h->st_doubles * 8)); if (dalloc(h, &h->st_d, h->st_doubles)) return -1;
     CK(cudaMallocHost((void**)&h->sti_h, h->st_ints * 4)); if (dalloc(h, &h->sti_d, h->st_ints)) return -1;
