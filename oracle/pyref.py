@@ -22,27 +22,44 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = None
+_LIBS = {}
 
 
 def ref_lib_path():
     return os.path.join(_HERE, "_ref", "libimgenv_ref.so")
 
 
+def port_lib_path():
+    return os.path.join(_HERE, "liboracle_port.so")
+
+
 def have_ref():
     return os.path.exists(ref_lib_path())
 
 
-def _lib():
-    global _LIB
-    if _LIB is None:
-        lib = C.CDLL(ref_lib_path())
-        lib.ref_create.restype = C.c_void_p
-        for name in ("ref_destroy", "ref_get_states", "ref_get_internal", "ref_set_internal", "ref_rvo_get",
-                     "ref_rvo_set", "ref_rvo_get_obstacles", "ref_sfm_get", "ref_sfm_set_pv", "ref_get_map"):
-            getattr(lib, name).restype = None
-        _LIB = lib
-    return _LIB
+def have_port():
+    return os.path.exists(port_lib_path())
+
+
+class _Prefixed:
+    """lib.ref_xxx / lib.port_xxx -> .xxx"""
+
+    def __init__(self, lib, prefix):
+        self._lib, self._prefix = lib, prefix
+
+    def __getattr__(self, name):
+        return getattr(self._lib, self._prefix + name)
+
+
+def _lib(prefix="ref_"):
+    if prefix not in _LIBS:
+        lib = C.CDLL(ref_lib_path() if prefix == "ref_" else port_lib_path())
+        getattr(lib, prefix + "create").restype = C.c_void_p
+        for name in ("destroy", "get_states", "get_internal", "set_internal", "rvo_get",
+                     "rvo_set", "rvo_get_obstacles", "sfm_get", "sfm_set_pv", "get_map"):
+            getattr(lib, prefix + name).restype = None
+        _LIBS[prefix] = _Prefixed(lib, prefix)
+    return _LIBS[prefix]
 
 
 def _p(a, t):
@@ -56,16 +73,18 @@ def _dbl(a):
 class RefEnv:
     """One scene of the reference node (one ROS node == one scene in the reference)."""
 
+    PREFIX = "ref_"
+
     def __init__(self, spec):
-        self.lib = _lib()
+        self.lib = _lib(self.PREFIX)
         self.spec = spec
-        self.h = C.c_void_p(self.lib.ref_create())
+        self.h = C.c_void_p(self.lib.create())
         self.R, self.P = spec["R"], spec["P"]
         sc = _dbl(spec["scalars"])
         grid = np.ascontiguousarray(spec["grid"], dtype=np.uint8)
         rd = _dbl(spec["robot_desc"]).reshape(self.R, 25)
         pd = _dbl(spec["ped_desc"]).reshape(self.P, 8) if self.P else np.zeros((0, 8))
-        rc = self.lib.ref_init(self.h, _p(sc, C.c_double), C.c_double(spec["global_resolution"]),
+        rc = self.lib.init(self.h, _p(sc, C.c_double), C.c_double(spec["global_resolution"]),
                                _p(grid, C.c_uint8), grid.shape[0], grid.shape[1], spec["raw_h"], spec["raw_w"],
                                self.R, _p(rd, C.c_double), spec["robot_ktype"].encode(),
                                self.P, _p(pd, C.c_double), spec["scene_type"].encode())
@@ -77,7 +96,7 @@ class RefEnv:
 
     def __del__(self):
         try:
-            self.lib.ref_destroy(self.h)
+            self.lib.destroy(self.h)
         except Exception:
             pass
 
@@ -92,7 +111,7 @@ class RefEnv:
         for i in range(self.P):
             flat.append(np.asarray(traj[i][: tl[i]], dtype=np.float64).reshape(-1, 3))
         flat = _dbl(np.concatenate(flat, 0)) if flat else np.zeros((0, 3))
-        rc = self.lib.ref_reset(self.h, obs.shape[0], _p(obs, C.c_double), _p(robots, C.c_double), _p(peds, C.c_double),
+        rc = self.lib.reset(self.h, obs.shape[0], _p(obs, C.c_double), _p(robots, C.c_double), _p(peds, C.c_double),
                                 _p(tl, C.c_int), _p(flat, C.c_double), None, None, int(rs.get("ignore_obstacle", 0)))
         if rc != 0:
             raise RuntimeError("ref_reset failed")
@@ -101,67 +120,76 @@ class RefEnv:
     def step(self, actions, alive):
         a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.R, 3)
         al = np.ascontiguousarray(alive, dtype=np.uint8).reshape(self.R)
-        rc = self.lib.ref_step(self.h, _p(a, C.c_float), _p(al, C.c_uint8))
+        rc = self.lib.step(self.h, _p(a, C.c_float), _p(al, C.c_uint8))
         if rc != 0:
             raise RuntimeError("ref_step failed")
         return self.get_states()
 
     def get_states(self):
         R, P = self.R, self.P
-        vs = self.lib.ref_view_size(self.h)
+        vs = self.lib.view_size(self.h)
         side = int(round(math.sqrt(vs)))
-        nl = self.lib.ref_laser_size(self.h)
+        nl = self.lib.laser_size(self.h)
         out = dict(view_map=np.zeros((R, vs), np.uint8), state=np.zeros((R, self.state_dim), np.float32),
                    laser=np.zeros((R, nl), np.float32), is_collision=np.zeros(R, np.int8),
                    is_arrive=np.zeros(R, np.uint8), pedinfo=np.zeros((R, P, 5), np.float32))
-        self.lib.ref_get_states(self.h, _p(out["view_map"], C.c_uint8), _p(out["state"], C.c_float),
+        self.lib.get_states(self.h, _p(out["view_map"], C.c_uint8), _p(out["state"], C.c_float),
                                 _p(out["laser"], C.c_float), _p(out["is_collision"], C.c_int8),
                                 _p(out["is_arrive"], C.c_uint8), _p(out["pedinfo"], C.c_float))
-        vw = int(round(self.spec["scalars"][1] / np.float32(self.spec["scalars"][0])))
+        vw = int(float(np.float32(self.spec["scalars"][1])) / float(np.float32(self.spec["scalars"][0])))   # agent.cpp:82
         out["view_map"] = out["view_map"].reshape(R, vs // max(vw, 1), -1) if vs else out["view_map"]
         del side
         return out
 
     def get_internal(self):
         rb = np.zeros((self.R, 16)); pd = np.zeros((self.P, 20))
-        self.lib.ref_get_internal(self.h, _p(rb, C.c_double), _p(pd, C.c_double))
+        self.lib.get_internal(self.h, _p(rb, C.c_double), _p(pd, C.c_double))
         return rb, pd
 
     def set_internal(self, rb=None, pd=None):
         rb = _dbl(rb) if rb is not None else None
         pd = _dbl(pd) if pd is not None else None
-        self.lib.ref_set_internal(self.h, _p(rb, C.c_double), _p(pd, C.c_double))
+        self.lib.set_internal(self.h, _p(rb, C.c_double), _p(pd, C.c_double))
 
     def rvo_get(self):
-        n = self.lib.ref_rvo_num_agents(self.h)
+        n = self.lib.rvo_num_agents(self.h)
         a = np.zeros((n, 4), np.float32)
-        self.lib.ref_rvo_get(self.h, _p(a, C.c_float))
+        self.lib.rvo_get(self.h, _p(a, C.c_float))
         return a
 
     def rvo_set(self, a):
         a = np.ascontiguousarray(a, dtype=np.float32)
-        self.lib.ref_rvo_set(self.h, _p(a, C.c_float))
+        self.lib.rvo_set(self.h, _p(a, C.c_float))
 
     def rvo_obstacles(self):
-        n = self.lib.ref_rvo_num_obstacles(self.h)
+        n = self.lib.rvo_num_obstacles(self.h)
         v = np.zeros((n, 8), np.float32)
-        self.lib.ref_rvo_get_obstacles(self.h, _p(v, C.c_float))
+        self.lib.rvo_get_obstacles(self.h, _p(v, C.c_float))
         return v
 
     def sfm_get(self):
-        n = self.lib.ref_sfm_num_agents(self.h)
+        n = self.lib.sfm_num_agents(self.h)
         a = np.zeros((n, 12))
-        self.lib.ref_sfm_get(self.h, _p(a, C.c_double))
+        self.lib.sfm_get(self.h, _p(a, C.c_double))
         return a
 
     def sfm_set_pv(self, a):
         a = _dbl(a)
-        self.lib.ref_sfm_set_pv(self.h, _p(a, C.c_double))
+        self.lib.sfm_set_pv(self.h, _p(a, C.c_double))
 
     def get_map(self, which):
         m = np.zeros((self.H, self.W), np.uint8)
-        self.lib.ref_get_map(self.h, which, _p(m, C.c_uint8))
+        self.lib.get_map(self.h, which, _p(m, C.c_uint8))
         return m
+
+
+class PortEnv(RefEnv):
+    """Same interface on top of oracle/liboracle_port.so (our own CPU restatement, oracle/port/)."""
+    PREFIX = "port_"
+
+    def sfm_set(self, a):
+        a = _dbl(a)
+        self.lib.sfm_set(self.h, _p(a, C.c_double))
 
 
 # ---------------------------------------------------------------------------------------------

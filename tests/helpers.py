@@ -121,3 +121,20 @@ def compare_state(got, want, spec, where="", frozen=None):
     wm = want["ped_min_dists"]
     chk(np.allclose(got["ped_min_dists"].astype(np.float64), wm, rtol=1e-4, atol=1e-5, equal_nan=True), "ped_min_dists differ")
     return msgs
+
+
+STATE_KEYS = ["vector_states", "sensor_maps", "is_collisions", "is_arrives", "lasers", "ped_vector_states", "ped_maps", "step_ds",
+              "ped_min_dists"]
+
+
+def load_golden(name):
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    return dict(np.load(path, allow_pickle=False))
+
+
+def golden_reset_request(g):
+    return {k[len("reset_"):]: g[k] for k in g if k.startswith("reset_")}
+
+
+def golden_state(g, prefix):
+    return {k: g["%s_%s" % (prefix, k)] for k in STATE_KEYS}

@@ -108,3 +108,22 @@ def test_crowded_collisions_multi_scene():
 
 def test_circle_peds_rect_robot_state5():
     run_lockstep(base_cfg(R=2, P=5, scene="rvoscene", ped_shape="circle", robot_shape="rectangle", state_dim=5, n_obj=2), seed=6, steps=5)
+
+
+def test_c5_sfm():
+    run_lockstep(base_cfg(R=4, P=6, scene="pedscene", n_obj=3), seed=7, steps=6, lo=3.0, hi=8.0)
+
+
+def test_sfm_many_agents_in_tree_bounds():
+    # y in [10, 20] keeps agents inside the quadtree root box (pedscene.h:19): neighbours stay visible
+    cfg = base_cfg(R=4, P=12, scene="pedscene", n_obj=2, max_ped=12, map_px=220)
+    run_lockstep(cfg, seed=8, steps=6, lo=3.0, hi=17.0)
+
+
+def test_omni_and_limiters():
+    cfg = base_cfg(R=3, P=0, n_obj=3, robot_type="omni", control_hz=0.25)
+    cfg["speed_limiter_v"] = dict(has_velocity_limits=True, has_acceleration_limits=True, has_jerk_limits=False, min_velocity=0,
+                                  max_velocity=0.5, min_acceleration=-1.6, max_acceleration=1.0, min_jerk=0, max_jerk=0)
+    cfg["speed_limiter_w"] = dict(has_velocity_limits=True, has_acceleration_limits=True, has_jerk_limits=False, min_velocity=-0.8,
+                                  max_velocity=0.8, min_acceleration=-0.6, max_acceleration=2, min_jerk=0, max_jerk=0)
+    run_lockstep(cfg, seed=9, steps=8, beep=True)
