@@ -48,6 +48,13 @@ def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False
         if sync:   # put the product into the node's exact pre-step state
             rbs, pds, svs = [], [], []
             for s in range(S):
+                if t == 0 and spec["scene_type"] == "pedscene" and spec["P"]:
+                    # libpedsim's socialForce takes sign(theta) of an angle that is pure rounding noise (~1e-16)
+                    # while all relative velocities are exactly zero, i.e. only on the very first step of a
+                    # process (velocities are never reset, pedscene.h:34-36).  Start from generic velocities.
+                    a0 = refs[s].sfm_get()
+                    a0[:, 3:5] = rng.uniform(-0.3, 0.3, (a0.shape[0], 2))
+                    refs[s].sfm_set_pv(a0)
                 rb, pd = refs[s].get_internal()
                 rb = rb.copy()
                 td = posts[s].tmp_distances
