@@ -1,0 +1,90 @@
+"""ImageEnv: the reference's Gym-style environment (envs/env/yaml_env.py:52-390) on top of the CUDA
+library. Same constructor argument (the yaml cfg dict), same reset()/step(actions)/end_ep() surface
+and attributes; `env_num` scenes of the cfg are simulated by ONE env object on one GPU (the reference
+needs one ROS node + one ImageEnv per scene), so State arrays carry S*R robots, scene-major."""
+import numpy as np
+
+from ..lib import BatchedSim
+from ..spec import build_spec
+from .action import ContinuousAction
+from .reset_helper import EnvPos, NearbyPed
+from .state import ImageState
+
+
+class ImageEnv:
+    def __init__(self, cfg: dict, num_scenes=None, device=0, numpy_state=False, map_dir=None):
+        import torch
+        self.torch = torch
+        self.cfg = cfg
+        self._init_static_param(cfg)
+        self.num_scenes = int(num_scenes if num_scenes is not None else cfg.get("batch_scenes", 1))
+        self.numpy_state = numpy_state
+        self.env_pose = [EnvPos(cfg) for _ in range(self.num_scenes)]
+        self.nearby_ped = NearbyPed(self.robot_total * self.num_scenes)
+        self.spec = build_spec(cfg, map_dir=map_dir, opt_in_beep=bool(cfg.get("opt_in_beep", False)))
+        self.sim = BatchedSim(self.spec, num_scenes=self.num_scenes, device=device, seed=int(cfg.get("seed", 0)),
+                              ped_yaw_mode=int(cfg.get("ped_yaw_mode", 1)))
+        self.dones = None
+        self._act = torch.zeros(self.num_scenes, self.robot_total, 3, dtype=torch.float32, device=self.sim.device)
+
+    def _init_static_param(self, cfg):     # yaml_env.py:133-181 (only the keys the hot path consumes)
+        self.test = cfg.get("test", False)
+        self.env_name = cfg.get("env_name", "img_env")
+        self.env_type = cfg.get("env_type", "robot_nav")
+        self.robot_type = cfg["robot_type"]
+        self.image_size = tuple(cfg["image_size"]); self.ped_image_size = tuple(cfg["ped_image_size"])
+        self.state_dim = cfg["state_dim"]; self.laser_max = cfg["laser_max"]; self.control_hz = cfg["control_hz"]
+        self.robot_total = cfg["robot"]["total"]; self.ped_total = cfg["ped_sim"]["total"]
+        self.max_ped = cfg["max_ped"]; self.ped_vec_dim = cfg["ped_vec_dim"]; self.ped_image_r = cfg["ped_image_r"]
+        self.laser_norm = cfg.get("laser_norm", True)
+        self.node_id = str(cfg.get("node_id", 0))
+
+    def __len__(self):
+        return self.num_scenes * self.robot_total
+
+    def _state(self):
+        o = self.sim.out
+        n = len(self)
+        flat = {k: v.reshape((n,) + tuple(v.shape[2:])) for k, v in o.items()}
+        if self.numpy_state:                # reference dtypes (yaml_env.py:472-481)
+            self.torch.cuda.synchronize()
+            f = {k: v.cpu().numpy() for k, v in flat.items()}
+            return ImageState(f["vector_states"].astype(np.float64), f["sensor_maps"], f["is_collisions"].astype(np.int64),
+                              f["is_arrives"].astype(bool), f["lasers"].astype(np.float64), f["ped_vector_states"], f["ped_maps"],
+                              f["step_ds"].astype(np.float64), f["ped_min_dists"].astype(np.float64))
+        return ImageState(**flat)
+
+    def reset(self, scene_ids=None, **kwargs):
+        ids = list(range(self.num_scenes)) if scene_ids is None else list(scene_ids)
+        self.sim.reset([self.env_pose[s].reset() for s in ids], scene_ids=ids)
+        state = self._state()
+        if scene_ids is None or self.dones is None:
+            self.dones = self.torch.zeros(len(self), dtype=self.torch.int64, device=self.sim.device)
+        return state
+
+    def step(self, actions):
+        """actions: list of ContinuousAction (len S*R) or a float tensor/array [S*R, 2|3] of (v, w[, beep])."""
+        torch = self.torch
+        if isinstance(actions, (list, tuple)) and len(actions) and isinstance(actions[0], ContinuousAction):
+            a = np.array([[x.v, x.w, x.beep] for x in actions], dtype=np.float32)
+            self._act.copy_(torch.from_numpy(a).view_as(self._act), non_blocking=True)
+        else:
+            t = torch.as_tensor(actions, dtype=torch.float32, device=self.sim.device).reshape(self.num_scenes, self.robot_total, -1)
+            self._act.zero_(); self._act[..., : t.shape[-1]] = t
+        self.sim.step(self._act, None)     # alive = library dones (yaml_env.py:319-331)
+        state = self._state()
+        if self.numpy_state:
+            rewards = state.is_arrives.astype(np.int64) - state.is_collisions
+            dones = np.clip(np.clip(state.is_collisions, -1, 1) + state.is_arrives, 0, 1)
+            self.dones = dones
+            return state, rewards, dones.copy(), {"dones_info": np.zeros_like(dones)}
+        coll = state.is_collisions.to(torch.int64); arr = state.is_arrives.to(torch.int64)
+        rewards = arr - coll                                            # yaml_env.py:373
+        self.dones = (coll.clamp(-1, 1) + arr).clamp(0, 1)               # yaml_env.py:374-376
+        return state, rewards, self.dones.clone(), {"dones_info": torch.zeros_like(self.dones)}
+
+    def end_ep(self, robot_res=None):
+        return True                        # EpRes logging is out of scope
+
+    def close(self):
+        self.sim.close()

@@ -1,0 +1,55 @@
+"""GPU: the Gym-style API (make_env / ImageEnv.reset / step) runs the reference's test.yaml scenario
+through the CUDA library and returns the nine ImageState fields with the reference's shapes."""
+import os
+import random
+
+import numpy as np
+import pytest
+import yaml
+
+from helpers import ROOT, base_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg():
+    sampler = yaml.load(open(os.path.join(ROOT, "tests", "golden", "cfg", "test.yaml")), Loader=yaml.FullLoader)
+    cfg = base_cfg(R=1, P=4, scene="rvoscene", n_obj=4)
+    cfg.update(sampler)
+    cfg["discrete_action"] = True
+    cfg["discrete_actions"] = [[0.0, -0.9], [0.2, 0.0], [0.6, 0.3], [0.4, 0.9]]
+    cfg["wrapper"] = ["VelActionWrapper", "TimeLimitWrapper", "SensorsPaperRewardWrapper"]   # unknown names are skipped (next rows)
+    return cfg
+
+
+def test_make_env_reset_step_shapes():
+    import torch
+    from img_env_b200.envs import make_env
+    random.seed(3)
+    env = make_env(_cfg(), num_scenes=3)
+    s = env.reset()
+    assert len(s) == 3
+    assert tuple(s.sensor_maps.shape) == (3, 48, 48) and s.sensor_maps.dtype == torch.float16
+    assert tuple(s.ped_maps.shape) == (3, 3, 48, 48) and tuple(s.lasers.shape) == (3, 1000)
+    assert tuple(s.ped_vector_states.shape) == (3, 71) and float(s.ped_vector_states[0, 0]) == 4.0
+    assert torch.all(s.step_ds == 0)
+    d0 = torch.linalg.norm(s.vector_states[:, :2], dim=1)
+    for t in range(5):
+        s, r, done, info = env.step(torch.tensor([2, 1, 3]))
+        assert r.shape == done.shape == (3,) and "dones_info" in info
+    d1 = torch.linalg.norm(s.vector_states[:, :2], dim=1)
+    assert torch.isfinite(s.lasers).all() and float(s.lasers.max()) <= 1.0 + 1e-6
+    assert not torch.equal(d0, d1)
+    env.close()
+
+
+def test_numpy_state_has_reference_dtypes():
+    from img_env_b200.envs import ImageEnv, ContinuousAction
+    random.seed(4)
+    env = ImageEnv(_cfg(), num_scenes=1, numpy_state=True)
+    s = env.reset()
+    assert s.vector_states.dtype == np.float64 and s.sensor_maps.dtype == np.float16 and s.is_collisions.dtype == np.int64
+    assert s.is_arrives.dtype == bool and s.lasers.dtype == np.float64 and s.ped_maps.dtype == np.float32
+    s, r, d, info = env.step([ContinuousAction(0.3, 0.1)])
+    assert r.shape == (1,) and d.dtype == np.int64
+    env.close()
