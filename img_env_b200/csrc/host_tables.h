@@ -62,7 +62,7 @@ struct TypeTables {
     std::vector<short> ray_end;
     std::vector<short> spans;
     std::vector<unsigned short> khi, klo;
-    std::vector<uint32_t> own_mask;
+    std::vector<uint32_t> own_mask, tile_fov;
 };
 
 // desc: shape, size[4], sensor_cfg[2] (already float32-widened)
@@ -110,6 +110,16 @@ inline std::string build_type(const Cfg& c, const double* desc, double view_angl
                 T.spans[(i * MAX_SPANS + nsp) * 2] = (short)j; in = true;
             } else if (!ok && in) { T.spans[(i * MAX_SPANS + nsp) * 2 + 1] = (short)j; nsp++; in = false; }
         }
+    }
+    {   // 32x32 view tiles that contain at least one FOV pixel
+        int th = (c.vh + 31) / 32, tw = c.vwb;
+        T.tile_fov.assign(((size_t)th * tw + 31) / 32, 0u);
+        for (int i = 0; i < c.vh; i++)
+            for (int sp = 0; sp < MAX_SPANS; sp++) {
+                int c0 = T.spans[(i * MAX_SPANS + sp) * 2], c1 = T.spans[(i * MAX_SPANS + sp) * 2 + 1];
+                if (c0 < 0) continue;
+                for (int wj = c0 >> 5; wj <= (c1 - 1) >> 5; wj++) { int t = (i >> 5) * tw + wj; T.tile_fov[t >> 5] |= 1u << (t & 31); }
+            }
     }
     // own footprint cells in the view raster: draw(view_map_, 100, "view_map", bbox_) agent.cpp:503
     size_t npx = (size_t)c.vh * c.vw;

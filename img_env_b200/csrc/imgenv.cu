@@ -75,6 +75,13 @@ __global__ void k_init_state(Dev d) {
     for (size_t i = t0; i < n; i += stride) d.occ_all[i] = d.static_occ[i % wpp];
     size_t pc = (((size_t)d.c.H * d.c.W + 3) & ~(size_t)3) * d.c.S;
     for (size_t i = t0; i < pc; i += stride) { d.rmin[i] = RMIN_EMPTY; d.flags[i] = 0; }
+    size_t nb = (size_t)d.c.Hc * d.c.Wb;
+    for (size_t i = t0; i < nb * d.c.S; i += stride) {       // coarse[s][I][J] = popcount of the static bits of the block
+        size_t b = i % nb; int I = (int)(b / d.c.Wb), J = (int)(b % d.c.Wb);
+        unsigned cnt = 0;
+        for (int rr = 32 * I; rr < min(32 * I + 32, d.c.H); rr++) cnt += __popc(d.static_occ[(size_t)rr * d.c.Wb + J]);
+        d.coarse[i] = cnt;
+    }
     size_t nr = (size_t)d.c.S * d.c.R;
     for (size_t i = t0; i < nr; i += stride) {
         d.rb[(size_t)RB_PREVD * nr + i] = nan("");
@@ -110,7 +117,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     c.scene_type = c.P > 0 ? cfg->scene_type : 0;
     c.relation = cfg->relation_ped_robo;
     c.NA = (c.scene_type != 0) ? c.P + (c.relation == 1 ? c.R : 0) : 0;
-    c.H = H; c.W = W; c.Wb = (W + 31) / 32;
+    c.H = H; c.W = W; c.Wb = (W + 31) / 32; c.Hc = (H + 31) / 32;
     c.res = f32(cfg->view_resolution);
     double vwid = f32(cfg->view_width), vhei = f32(cfg->view_height);
     c.vw = (int)(vwid / c.res); c.vh = (int)(vhei / c.res);       // agent.cpp:82-83
@@ -129,6 +136,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     c.max_obs = std::max(cfg->max_obstacles, 1); c.max_traj = std::max(cfg->max_traj, 1);
     c.seed = cfg->seed;
     if (c.vh != c.vw) return fail("imgenv_create: only square view maps are supported");
+    if (c.vh > 1022) return fail("imgenv_create: view raster larger than 1022x1022 cells is not supported");
     if (cfg->ped_image_size != cfg->image_size) return fail("imgenv_create: ped_image_size must equal image_size");
     if (c.ped_vec_dim != 7) return fail("imgenv_create: ped_vec_dim must be 7 (yaml_env.py:399-408)");
     if (c.state_dim < 3 || c.state_dim > 5) return fail("imgenv_create: state_dim must be 3, 4 or 5");
@@ -176,7 +184,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         }
     }
     c.n_types = (int)types.size();
-    std::vector<double> lattice; std::vector<short> ray_end, spans; std::vector<unsigned short> khi, klo; std::vector<uint32_t> own_mask;
+    std::vector<double> lattice; std::vector<short> ray_end, spans; std::vector<unsigned short> khi, klo; std::vector<uint32_t> own_mask, tile_fov;
     std::vector<RobotType> rts;
     for (auto& T : types) {
         T.t.pts_off = (int)lattice.size() / 2; lattice.insert(lattice.end(), T.lattice.begin(), T.lattice.end());
@@ -184,6 +192,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         T.t.span_off = (int)spans.size(); spans.insert(spans.end(), T.spans.begin(), T.spans.end());
         T.t.khi_off = (int)khi.size(); khi.insert(khi.end(), T.khi.begin(), T.khi.end()); klo.insert(klo.end(), T.klo.begin(), T.klo.end());
         T.t.own_mask_off = (int)own_mask.size(); own_mask.insert(own_mask.end(), T.own_mask.begin(), T.own_mask.end());
+        T.t.tile_off = (int)tile_fov.size(); tile_fov.insert(tile_fov.end(), T.tile_fov.begin(), T.tile_fov.end());
         T.t.n_own = 0; T.t.own_off = 0;
         rts.push_back(T.t);
     }
@@ -213,16 +222,18 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
 
     Dev& d = h->d;
 #define UP(field, vec) if (dupload(h, &d.field, vec)) return -1;
-    UP(grid, g) UP(static_occ, socc) UP(types, rts) UP(type_of, type_of) UP(lattice_xy, lattice) UP(ray_end, ray_end)
+    std::vector<uint32_t> kpack(khi.size());
+    for (size_t k = 0; k < khi.size(); k++) kpack[k] = (uint32_t)khi[k] | ((uint32_t)klo[k] << 16);
+    UP(kpack, kpack) UP(grid, g) UP(static_occ, socc) UP(types, rts) UP(type_of, type_of) UP(lattice_xy, lattice) UP(ray_end, ray_end)
     UP(fov_spans, spans) UP(khi, khi) UP(klo, klo) UP(own_mask, own_mask) UP(need_idx, need_idx) UP(cubic_tap, tap)
     UP(cubic_coef, coef) UP(f16_lut, lut) UP(lim_v, lv) UP(lim_w, lw) UP(ped_shape, pshape) UP(ped_size, psize)
-    UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(own_cells, own_dummy)
+    UP(tile_fov, tile_fov) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(own_cells, own_dummy)
 #undef UP
     size_t S = c.S;
     size_t pc = ((size_t)H * W + 3) & ~(size_t)3;
     d.max_verts = 16 * c.max_obs + 16;
 #define AL(field, n) if (dalloc(h, &d.field, (size_t)(n))) return -1;
-    AL(occ_all, S * H * c.Wb) AL(flags, S * pc) AL(rmin, S * pc)
+    AL(occ_all, S * H * c.Wb) AL(flags, S * pc) AL(rmin, S * pc) AL(coarse, S * c.Hc * c.Wb)
     AL(rb, (size_t)RB_FIELDS * S * c.R) AL(pd, (size_t)PD_FIELDS * S * c.P)
     AL(traj, S * c.P * c.max_traj * 3) AL(traj_len, S * c.P) AL(obs, S * c.max_obs * 8) AL(n_obs, S) AL(step_no, S)
     AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 3)

@@ -47,7 +47,8 @@ struct RobotType {
     int span_off;         // offset into fov_spans (vh * MAX_SPANS * 2 shorts)
     int zone_r0, zone_r1, zone_c0, zone_c1;  // view-raster box where the robot's own footprint may be the only stamp
     int khi_off;          // offset into khi/klo tables (ns*ns entries)
-    int own_mask_off;     // offset into own_mask (ns*ns bits, u32 words)
+    int own_mask_off;     // offset into own_mask (vh*vw bits, u32 words)
+    int tile_off;         // offset into tile_fov (u32 words): bit per 32x32 view tile that contains FOV pixels
     double size_last;     // python: robots[i].size[-1]
     double sensor_x, sensor_y;
 };
@@ -55,7 +56,7 @@ struct RobotType {
 struct Cfg {
     // geometry
     int S, R, P, NA;         // NA = solver agents = P + (relation ? R : 0)
-    int H, W, Wb;            // grid rows, cols, u32 words per bit-plane row
+    int H, W, Wb, Hc;        // grid rows, cols, u32 words per bit-plane row, 32-row blocks
     int vh, vw, vwb;         // view raster rows/cols, words per row
     double res;              // view resolution == grid resolution (float32 widened)
     double step_hz, control_hz;   // period (float32 widened), 0.05
@@ -86,7 +87,9 @@ struct Dev {
     const short* fov_spans;       // per type: [vh][MAX_SPANS][2] (c0,c1 exclusive), -1 = none
     const unsigned short* khi;    // per type [ns*ns]: highest ray index touching the needed pixel (0xFFFF none)
     const unsigned short* klo;    //                   lowest
-    const uint32_t* own_mask;     // per type: bit per needed pixel = own footprint cell
+    const uint32_t* kpack;        // khi | klo << 16 (one load per pixel)
+    const uint32_t* own_mask;     // per type: bit per view pixel = own footprint cell
+    const uint32_t* tile_fov;     // per type: bit per 32x32 view tile (row-major, vwb per row) with any FOV pixel
     const short* need_idx;        // [ns] source row/col index of the k-th needed row/col
     const short* cubic_tap;       // [img][4] index into need_idx space (0..ns-1) of the 4 taps
     const short* cubic_coef;      // [img][4] fixed-point weights (x2048)
@@ -104,6 +107,7 @@ struct Dev {
     uint32_t* occ_all;            // [S][H][Wb]
     uint8_t* flags;               // [S][H][W]
     unsigned short* rmin;         // [S][H][W]
+    uint32_t* coarse;             // [S][Hc][Wb] number of set occ_all bits per 32x32-cell block (0 = block is free)
     // dynamic state
     double* rb;                   // [RB_FIELDS][S*R]
     double* pd;                   // [PD_FIELDS][S*P]

@@ -63,6 +63,7 @@ __device__ __forceinline__ void stamp_cell(const Dev& d, int s, int cx, int cy, 
     size_t ci = (size_t)cx * d.c.W + cy;
     size_t po = (size_t)s * plane_cells(d.c);
     uint32_t* occ = d.occ_all + (size_t)s * d.c.H * d.c.Wb + (size_t)cx * d.c.Wb + (cy >> 5);
+    uint32_t* cz = d.coarse + (size_t)s * d.c.Hc * d.c.Wb + (size_t)(cx >> 5) * d.c.Wb + (cy >> 5);
     uint32_t bit = 1u << (cy & 31);
     if (mode < 8) {
         if (mode == 0) {
@@ -73,7 +74,7 @@ __device__ __forceinline__ void stamp_cell(const Dev& d, int s, int cx, int cy, 
         } else {
             flag_or(d.flags + po, ci, mode == 1 ? F_CIRC : mode == 2 ? F_LEFT : mode == 3 ? F_RIGHT : F_OBJ);
         }
-        atomicOr(occ, bit);
+        if (!(atomicOr(occ, bit) & bit)) atomicAdd(cz, 1u);     // first setter of the bit maintains the block count
     } else {
         int m = mode - 8;
         if (m == 0) { d.rmin[po + ci] = RMIN_EMPTY; flag_clear(d.flags + po, ci, F_ROBOT | F_MULTI); }
@@ -81,7 +82,7 @@ __device__ __forceinline__ void stamp_cell(const Dev& d, int s, int cx, int cy, 
         // restore the occupancy bit to static | object (dynamic stamps never survive a step)
         bool base = (d.static_occ[(size_t)cx * d.c.Wb + (cy >> 5)] & bit) != 0;
         if (m != 4) base = base || (d.flags[po + ci] & F_OBJ);
-        if (!base) atomicAnd(occ, ~bit);
+        if (!base && (atomicAnd(occ, ~bit) & bit)) atomicSub(cz, 1u);
     }
 }
 
@@ -213,6 +214,39 @@ __device__ __forceinline__ int ray_touch(int ox, int oy, int ex, int ey, int pr,
     }
 }
 
+// Shared-memory plan (bytes for the canonical 400x400 view / 1000 rays / 48x48 outputs):
+//   region A  occ raster 400*13*4 = 20.8 KB   (phases B-C)   | later: ped map winners + pedestrian scratch (phase G)
+//   region B  boundary-cell list 24 KB        (phase C)       | later: horizontal resize buffer 144*48*4 = 27.6 KB (phase F)
+//   pix       144*144 u8 = 20.7 KB            (phases D-F)
+//   hitkey    range_total*4, ray end cells range_total*4, needed-line indices
+#define BL_CAP 2048          // boundary cells kept in shared memory; more -> per-ray marching fallback
+#define BL2_CAP 256          // cells touched by many rays (close to the origin): processed warp-cooperatively
+#define BL_HEAVY 24
+#define NOHIT 0xFFFFFFFFu
+
+#define HB_COLS 16           // output columns per vertical-pass block (bounds the horizontal buffer)
+struct ViewLayout { size_t sh, regA, regB, pix, hitkey, rays, need, spans, total; };
+__host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
+    ViewLayout L;
+    size_t off = 0;
+    L.sh = off; off += (sizeof(ViewShared) + 15) & ~(size_t)15;
+    size_t occ = (size_t)c.vh * c.vwb * 4 * (c.use_laser ? 1 : 2);
+    size_t pedb = (size_t)c.img * c.img * 4 + (size_t)((c.P + 1) & ~1) * 8 + (size_t)c.P * 16 + (size_t)c.P * 4 + 16;
+    L.regA = off; off += ((occ > pedb ? occ : pedb) + 15) & ~(size_t)15;
+    size_t bl = (size_t)(BL_CAP + BL2_CAP) * 4, hb = (size_t)c.ns * HB_COLS * 4;
+    L.regB = off; off += ((bl > hb ? bl : hb) + 15) & ~(size_t)15;
+    L.pix = off; off += ((size_t)c.ns * ((c.ns + 15) / 16) * 4 + 15) & ~(size_t)15;      // 2 bits per needed pixel, rows padded to words
+    L.hitkey = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
+    L.rays = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
+    L.need = off; off += ((size_t)c.ns * 2 + 15) & ~(size_t)15;
+    L.spans = off; off += ((size_t)c.vh * 8 + 15) & ~(size_t)15;
+    L.total = off + 16;
+    return L;
+}
+inline size_t view_smem_bytes(const Cfg& c) { return view_layout(c).total; }
+
+__device__ __forceinline__ unsigned hit_key(int i, int x, int y) { return ((unsigned)i << 22) | ((unsigned)x << 11) | (unsigned)y; }
+
 template <bool DEBUG_FULL>
 __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_ids, int is_reset) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -222,21 +256,26 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
     const int s = scene_ids ? scene_ids[sl] : sl;
     const int idx = s * c.R + r;
     const RobotType ty = d.types[d.type_of[r]];
+    const ViewLayout L = view_layout(c);
+    const int vwb = c.vwb, vh = c.vh, vw = c.vw;
 
-    // ---- shared memory carve-up ----
-    unsigned char* sp = smem_raw;
-    ViewShared* sh = reinterpret_cast<ViewShared*>(sp); sp += (sizeof(ViewShared) + 15) & ~15;
-    uint32_t* occ = reinterpret_cast<uint32_t*>(sp); sp += (size_t)c.vh * c.vwb * 4;
-    uint32_t* known = reinterpret_cast<uint32_t*>(sp); if (!c.use_laser) sp += (size_t)c.vh * c.vwb * 4;
-    unsigned short* hitpos = reinterpret_cast<unsigned short*>(sp); sp += ((size_t)c.range_total * 2 + 15) & ~15;
-    short* hitx = reinterpret_cast<short*>(sp); sp += ((size_t)c.range_total * 2 + 15) & ~15;
-    short* hity = reinterpret_cast<short*>(sp); sp += ((size_t)c.range_total * 2 + 15) & ~15;
-    uint8_t* pix = sp; sp += ((size_t)c.ns * c.ns + 15) & ~15;
-    int* hbuf = reinterpret_cast<int*>(sp); sp += (size_t)c.ns * c.img * 4;
-    int* winner = reinterpret_cast<int*>(sp); sp += (size_t)c.img * c.img * 4;
-    double* pkey = reinterpret_cast<double*>(sp); sp += (size_t)((c.P + 1) & ~1) * 8;
-    float* pobs = reinterpret_cast<float*>(sp); sp += (size_t)c.P * 4 * 4;
-    int* prank = reinterpret_cast<int*>(sp); sp += (size_t)c.P * 4;
+    ViewShared* sh = reinterpret_cast<ViewShared*>(smem_raw + L.sh);
+    uint32_t* occ = reinterpret_cast<uint32_t*>(smem_raw + L.regA);
+    uint32_t* known = occ + (size_t)vh * vwb;                               // only when !use_laser
+    uint32_t* blist = reinterpret_cast<uint32_t*>(smem_raw + L.regB);
+    uint32_t* blist2 = blist + BL_CAP;
+    int* hbuf = reinterpret_cast<int*>(smem_raw + L.regB);
+    uint32_t* pix = reinterpret_cast<uint32_t*>(smem_raw + L.pix);     // 2-bit codes: 0 -> 0, 1 -> 100, 2 -> 200, 3 -> 255
+    const int pixw = (c.ns + 15) / 16;
+    short* spans = reinterpret_cast<short*>(smem_raw + L.spans);
+    unsigned* hitkey = reinterpret_cast<unsigned*>(smem_raw + L.hitkey);
+    short* rend = reinterpret_cast<short*>(smem_raw + L.rays);
+    short* need = reinterpret_cast<short*>(smem_raw + L.need);
+    // phase G aliases of region A
+    int* winner = reinterpret_cast<int*>(smem_raw + L.regA);
+    double* pkey = reinterpret_cast<double*>(smem_raw + L.regA + (((size_t)c.img * c.img * 4 + 15) & ~(size_t)15));
+    float* pobs = reinterpret_cast<float*>(pkey + ((c.P + 1) & ~1));
+    int* prank = reinterpret_cast<int*>(pobs + 4 * (size_t)c.P);
 
     if (tid == 0) {
         double x = RBF(d, RB_X, idx), y = RBF(d, RB_Y, idx), yaw = RBF(d, RB_YAW, idx);
@@ -250,16 +289,25 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         sh->cy = llrint((A.oy / c.res) * FX_ONE) + (1ll << 31);
         // Agent::view early-out (agent.cpp:358-360): stale view_map_/hits_/is_collision_ are re-sent
         sh->frozen = (RBF(d, RB_COLL, idx) != 0.0) || (RBF(d, RB_ARR, idx) != 0.0);
-        sh->coll_key = 0;
+        sh->coll_key = 0;      // reused as boundary-list counters below
+        sh->red[0] = 0; sh->red[1] = 0; sh->red[2] = 0;
     }
-    for (int k = tid; k < c.img * c.img; k += VIEW_THREADS) winner[k] = -1;
+    {   // static tables into shared memory
+        const short* g_rend = d.ray_end + 2 * (size_t)ty.ray_off;
+        for (int k = tid; k < 2 * c.range_total; k += VIEW_THREADS) rend[k] = g_rend[k];
+        for (int k = tid; k < c.ns; k += VIEW_THREADS) need[k] = d.need_idx[k];
+        const short* g_spans = d.fov_spans + (size_t)ty.span_off;
+        for (int k = tid; k < 4 * vh; k += VIEW_THREADS) spans[k] = g_spans[k];
+        for (int k = tid; k < c.ns * pixw; k += VIEW_THREADS) pix[k] = 0u;
+        for (int k = tid; k < c.range_total; k += VIEW_THREADS) hitkey[k] = NOHIT;
+    }
     __syncthreads();
     const bool frozen = DEBUG_FULL ? false : sh->frozen != 0;
 
     if (!frozen) {
         // ---- Phase A: collision code = code of the LAST colliding lattice point (agent.cpp:294-326)
+        int best = 0;
         if (!DEBUG_FULL) {
-            int best = 0;
             const double* pts = d.lattice_xy + 2 * (size_t)ty.pts_off;
             for (int k = tid; k < ty.n_pts; k += VIEW_THREADS) {
                 double wx, wy;
@@ -271,136 +319,236 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 }
             }
             for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-            if (lane == 0) sh->red[warp] = best;
         }
-        // zero the raster while the reduction settles
-        for (int k = tid; k < c.vh * c.vwb; k += VIEW_THREADS) { occ[k] = 0; if (!c.use_laser) known[k] = 0; }
+        // ---- Phase B: egocentric occupancy raster (agent.cpp:373-404), 1 bit per view cell:
+        // zero <=> in FOV && in map && global value < 250.  FOV = static column spans per row; the pixel ->
+        // world cell map is affine and evaluated in 2^-32-cell fixed point with an exact fp64 fallback inside
+        // a guard band around the rounding boundary.
+        // The raster is produced in 32x32-pixel tiles: a tile whose world footprint (bounding box of its four
+        // corner cells + 1 cell margin) only touches 32x32-cell blocks with a zero occupancy count
+        // (Dev::coarse, maintained by the stamp kernels) is all-free and is skipped.
+        const uint32_t* occ_all = d.occ_all + (size_t)s * c.H * c.Wb;
+        const uint32_t* coarse = d.coarse + (size_t)s * c.Hc * c.Wb;
+        const unsigned H = c.H, W = c.W, Wb = c.Wb;
+        const int n_trow = (vh + 31) >> 5, n_tiles = n_trow * vwb;
+        int* n_active = &sh->red[2];
+        unsigned short* tile_list = reinterpret_cast<unsigned short*>(blist);     // region B is free until phase C
+        for (int q = tid; q < vh * vwb; q += VIEW_THREADS) { occ[q] = 0u; if (!c.use_laser) known[q] = 0u; }
+        for (int t = tid; t < n_tiles; t += VIEW_THREADS) {
+            if (!((d.tile_fov[ty.tile_off + (t >> 5)] >> (t & 31)) & 1u)) continue;
+            bool active = !c.use_laser;          // the "known" plane needs every FOV pixel
+            if (!active) {
+                const int ti = t / vwb, tj = t - ti * vwb;
+                const int i0 = ti * 32, i1 = min(i0 + 31, vh - 1), j0 = tj * 32, j1 = min(j0 + 31, vw - 1);
+                int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int ii = (k & 1) ? i1 : i0, jj = (k & 2) ? j1 : j0;
+                    const int cx = (int)((sh->cx + (long long)ii * sh->ax + (long long)jj * sh->bx) >> 32);
+                    const int cy = (int)((sh->cy + (long long)ii * sh->ay + (long long)jj * sh->by) >> 32);
+                    xmin = min(xmin, cx); xmax = max(xmax, cx); ymin = min(ymin, cy); ymax = max(ymax, cy);
+                }
+                xmin = max(xmin - 1, 0); ymin = max(ymin - 1, 0); xmax = min(xmax + 1, (int)H - 1); ymax = min(ymax + 1, (int)W - 1);
+                for (int bi = xmin >> 5; bi <= (xmax >> 5) && !active; bi++)
+                    for (int bj = ymin >> 5; bj <= (ymax >> 5); bj++)
+                        if (__ldg(coarse + (unsigned)bi * Wb + bj)) { active = true; break; }
+            }
+            if (active) { const int ti = t / vwb; tile_list[atomicAdd(n_active, 1)] = (unsigned short)((ti << 8) | (t - ti * vwb)); }
+        }
+        if (!DEBUG_FULL && lane == 0) atomicMax(&sh->coll_key, best);
+        __syncthreads();
+        {
+            const int n_items = sh->red[2] * 32;
+            const long long lbx = sh->cx + (long long)lane * sh->bx, lby = sh->cy + (long long)lane * sh->by;
+            const long long bx32 = sh->bx * 32, by32 = sh->by * 32;
+#pragma unroll 2
+            for (int item = warp; item < n_items; item += VIEW_THREADS / 32) {
+                const int t = tile_list[item >> 5];
+                const int wj = t & 255;
+                const int i = (t >> 8) * 32 + (item & 31);
+                if (i >= vh) continue;
+                const int a0 = spans[i * 4 + 0], a1 = spans[i * 4 + 1], b0 = spans[i * 4 + 2], b1 = spans[i * 4 + 3];
+                const int j = wj * 32 + lane;
+                const bool in_fov = (j >= a0 && j < a1) || (j >= b0 && j < b1);     // empty spans are (-1,-1)
+                bool o = false, kn = false;
+                if (in_fov) {
+                    const long long tx = lbx + (long long)i * sh->ax + (long long)wj * bx32;
+                    const long long tyy = lby + (long long)i * sh->ay + (long long)wj * by32;
+                    int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
+                    const unsigned lx = (unsigned)tx, ly = (unsigned)tyy;
+                    if (lx + FX_GUARD < 2 * FX_GUARD || ly + FX_GUARD < 2 * FX_GUARD) {
+                        double wx, wy;   // exact path: map2world, tf multiply, world2map
+                        tf_apply(sh->view_world, i * c.res, j * c.res, wx, wy);
+                        cx = world2cell(wx, c.res); cy = world2cell(wy, c.res);
+                    }
+                    if ((unsigned)cx < H && (unsigned)cy < W) {
+                        kn = true;
+                        o = (__ldg(occ_all + (unsigned)cx * Wb + ((unsigned)cy >> 5)) >> (cy & 31)) & 1u;
+                        if (o && i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1)
+                            o = global_value(d, s, r, cx, cy) < 250;   // exclude the robot's own stamp
+                    }
+                }
+                const unsigned wo = __ballot_sync(0xffffffffu, o);
+                if (!c.use_laser) { const unsigned wk = __ballot_sync(0xffffffffu, kn); if (lane == 0) known[i * vwb + wj] = wk; }
+                if (lane == 0) occ[i * vwb + wj] = wo;
+            }
+        }
         __syncthreads();
         if (!DEBUG_FULL && tid == 0) {
-            int best = 0;
-            for (int k = 0; k < VIEW_THREADS / 32; k++) best = max(best, sh->red[k]);
-            int code = best & 3;
+            int code = sh->coll_key & 3;
             RBF(d, RB_COLL, idx) = (double)code;
-            sh->coll_key = code;
         }
 
-        // ---- Phase B: egocentric occupancy raster (agent.cpp:373-404), 1 bit per view cell.
-        // zero <=> in FOV && in map && global value < 250.  The FOV test depends only on the pixel
-        // (static spans); the pixel -> world cell map is affine: evaluated in 2^-32-cell fixed point
-        // with an exact fp64 fallback inside a guard band around the rounding boundary.
-        const short* spans = d.fov_spans + (size_t)ty.span_off;
-        const uint32_t* occ_all = d.occ_all + (size_t)s * c.H * c.Wb;
-        for (int i = warp; i < c.vh; i += VIEW_THREADS / 32) {
-            long long rowx = sh->cx + (long long)i * sh->ax, rowy = sh->cy + (long long)i * sh->ay;
-            for (int sp_i = 0; sp_i < MAX_SPANS; sp_i++) {
-                int c0 = spans[(i * MAX_SPANS + sp_i) * 2], c1 = spans[(i * MAX_SPANS + sp_i) * 2 + 1];
-                if (c0 < 0) continue;
-                for (int j0 = c0 & ~31; j0 < c1; j0 += 32) {
-                    int j = j0 + lane;
-                    bool o = false, kn = false;
-                    if (j >= c0 && j < c1) {
-                        long long tx = rowx + (long long)j * sh->bx, tyy = rowy + (long long)j * sh->by;
-                        int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
-                        unsigned lx = (unsigned)tx, ly = (unsigned)tyy;
-                        if (lx + FX_GUARD < 2 * FX_GUARD || ly + FX_GUARD < 2 * FX_GUARD) {
-                            double wx, wy;   // exact path: map2world, tf multiply, world2map
-                            tf_apply(sh->view_world, i * c.res, j * c.res, wx, wy);
-                            cx = world2cell(wx, c.res); cy = world2cell(wy, c.res);
-                        }
-                        if ((unsigned)cx < (unsigned)c.H && (unsigned)cy < (unsigned)c.W) {
-                            kn = true;
-                            o = (occ_all[(size_t)cx * c.Wb + (cy >> 5)] >> (cy & 31)) & 1u;
-                            if (o && i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1)
-                                o = global_value(d, s, r, cx, cy) < 250;   // exclude the robot's own stamp
-                        }
-                    }
-                    unsigned wo = __ballot_sync(0xffffffffu, o);
-                    unsigned wk = __ballot_sync(0xffffffffu, kn);
-                    if (lane == 0) {
-                        // a word may be shared by two spans of the same row: OR (same warp, sequential)
-                        occ[i * c.vwb + (j0 >> 5)] |= wo;
-                        if (!c.use_laser) known[i * c.vwb + (j0 >> 5)] |= wk;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- Phase C: laser rays (agent.cpp:405-438, 511-624): one thread per ray marches the bit raster
-        const short* rend = d.ray_end + 2 * (size_t)ty.ray_off;
+        // ---- Phase C: first occupied cell of every laser ray (agent.cpp:405-438, 511-624).
+        // A ray's hit cell always has a free 8-neighbour (its predecessor on the ray), so only the boundary
+        // cells of the raster can be hits.  For each boundary cell the (static) interval of ray indices whose
+        // integer line walk passes through it is scanned with the closed-form touch test and the ray keeps
+        // the minimum step (atomicMin on step<<22|cell).  Dense rasters overflow the list -> marching fallback.
+        const int ox = ty.org_x, oy = ty.org_y;
+        const uint32_t* kpack = d.kpack + (size_t)ty.khi_off;
         if (c.use_laser) {
-            for (int k = tid; k < c.range_total; k += VIEW_THREADS) {
-                int x1 = ty.org_x, y1 = ty.org_y, x2 = rend[2 * k], y2 = rend[2 * k + 1];
-                int w = x2 - x1, h = y2 - y1;
-                int dx = w > 0 ? 1 : -1, dy = h > 0 ? 1 : -1;
-                w = abs(w); h = abs(h);
-                int hp = 0xFFFF, hx = -1, hy = -1;
-                int x = x1, y = y1, f;
-                if (w > h) {
-                    f = 2 * h - w;
-                    for (int i = 0; x != x2; x += dx, i++) {
-                        if ((unsigned)x >= (unsigned)c.vh || (unsigned)y >= (unsigned)c.vw) break;
-                        if ((occ[x * c.vwb + (y >> 5)] >> (y & 31)) & 1u) { hp = i; hx = x; hy = y; break; }
-                        if (f < 0) f += 2 * h; else { y += dy; f += 2 * (h - w); }
+            int* n_list = &sh->red[0]; int* n_list2 = &sh->red[1];
+            for (int q = tid; q < vh * 16 * ((vwb + 15) / 16); q += VIEW_THREADS) {
+                const int wpr = 16 * ((vwb + 15) / 16);                  // words per row rounded up to 16: shift/mask indexing
+                const int i = (wpr == 16) ? (q >> 4) : q / wpr, wj = (wpr == 16) ? (q & 15) : q - i * wpr;
+                if (wj >= vwb) continue;
+                const unsigned O = occ[i * vwb + wj];
+                if (!O) continue;
+                unsigned all8 = 0xffffffffu;
+                for (int di = -1; di <= 1; di++) {
+                    const int ii = i + di;
+                    unsigned m = 0, ml = 0, mr = 0;      // outside the raster counts as free (conservative superset)
+                    if (ii >= 0 && ii < vh) {
+                        m = occ[ii * vwb + wj];
+                        ml = wj > 0 ? occ[ii * vwb + wj - 1] : 0u;
+                        mr = wj + 1 < vwb ? occ[ii * vwb + wj + 1] : 0u;
                     }
-                } else {
-                    f = 2 * w - h;
-                    for (int i = 0; y != y2; y += dy, i++) {
-                        if ((unsigned)x >= (unsigned)c.vh || (unsigned)y >= (unsigned)c.vw) break;
-                        if ((occ[x * c.vwb + (y >> 5)] >> (y & 31)) & 1u) { hp = i; hx = x; hy = y; break; }
-                        if (f < 0) f += 2 * w; else { x += dx; f += 2 * (w - h); }
-                    }
+                    const unsigned left = (m << 1) | (ml >> 31), right = (m >> 1) | (mr << 31);
+                    all8 &= left & right;
+                    if (di != 0) all8 &= m;
                 }
-                hitpos[k] = (unsigned short)hp; hitx[k] = (short)hx; hity[k] = (short)hy;
-                if (!DEBUG_FULL) {
-                    double hit = 6;   // agent.cpp:513
-                    if (hp != 0xFFFF) {
-                        double x0 = x1 * c.res, y0 = y1 * c.res, xc = hx * c.res, yc = hy * c.res;
-                        hit = sqrt((x0 - xc) * (x0 - xc) + (y0 - yc) * (y0 - yc));
-                    }
-                    float wire = (float)hit;                         // AgentState.laser is float32[]
-                    d.o_laser[(size_t)idx * c.range_total + k] =
-                        c.laser_norm ? (float)((double)wire / c.laser_max) : wire;   // yaml_env.py:440-444
+                unsigned bnd = O & ~all8;
+                if (i == ox && (oy >> 5) == wj) bnd |= O & (1u << (oy & 31));   // an occupied origin hits every ray at step 0
+                while (bnd) {
+                    const int b = __ffs(bnd) - 1; bnd &= bnd - 1;
+                    const int col = wj * 32 + b;
+                    if (col >= vw) break;
+                    const int full = i * vw + col;
+                    const unsigned kp = __ldg(kpack + full);
+                    const int kh = kp & 0xFFFF;
+                    if (kh == 0xFFFF) continue;                                  // no ray passes through this cell
+                    const int nr = kh - (int)(kp >> 16) + 1;
+                    if (nr > BL_HEAVY) { int p = atomicAdd(n_list2, 1); if (p < BL2_CAP) blist2[p] = (unsigned)full; }
+                    else { int p = atomicAdd(n_list, 1); if (p < BL_CAP) blist[p] = (unsigned)full; }
                 }
             }
-        }
-        __syncthreads();
-
-        // ---- Phase D/E: final view_map_ value of every pixel the cubic resize reads (or of the whole
-        // raster in debug mode): last-writer-wins over rays in index order evaluated per pixel from the
-        // highest ray downwards (static khi/klo tables), then the robot's own footprint (value 100,
-        // agent.cpp:503) unless the cell is 0.
-        const unsigned short* khi = d.khi + (size_t)ty.khi_off;
-        const unsigned short* klo = d.klo + (size_t)ty.khi_off;
-        const uint32_t* own_mask = d.own_mask + (size_t)ty.own_mask_off;
-        const int npx = DEBUG_FULL ? c.vh * c.vw : c.ns * c.ns;
-        for (int q = tid; q < npx; q += VIEW_THREADS) {
-            int pr, pc;
-            if (DEBUG_FULL) { pr = q / c.vw; pc = q % c.vw; }
-            else { pr = d.need_idx[q / c.ns]; pc = d.need_idx[q % c.ns]; }
-            int full = pr * c.vw + pc;
-            int val = 200;
-            if (c.use_laser) {
-                int kh = khi[full];
-                if (kh != 0xFFFF) {
-                    int kl = klo[full];
-                    for (int k = kh; k >= kl; k--) {
-                        int i = ray_touch(ty.org_x, ty.org_y, rend[2 * k], rend[2 * k + 1], pr, pc);
-                        if (i < 0) continue;
-                        int hp = hitpos[k];
-                        if (i < hp) { val = 255; break; }
-                        if (i == hp) { val = 0; break; }
-                        if (pr != hitx[k] && pc != hity[k]) { val = 200; break; }   // shadow write (agent.cpp:557-558)
+            __syncthreads();
+            const int nl = sh->red[0], nl2 = sh->red[1];
+            if (nl <= BL_CAP && nl2 <= BL2_CAP) {
+                for (int q = tid; q < nl; q += VIEW_THREADS) {
+                    const int full = blist[q], pr = full / vw, pc = full - pr * vw;
+                    const unsigned kp = __ldg(kpack + full);
+                    const int kh = kp & 0xFFFF, kl = kp >> 16;
+                    for (int k = kl; k <= kh; k++) {
+                        const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
+                        if (i >= 0) atomicMin(&hitkey[k], hit_key(i, pr, pc));
+                    }
+                }
+                for (int q = warp; q < nl2; q += VIEW_THREADS / 32) {
+                    const int full = blist2[q], pr = full / vw, pc = full - pr * vw;
+                    const unsigned kp = __ldg(kpack + full);
+                    const int kh = kp & 0xFFFF, kl = kp >> 16;
+                    for (int k = kl + lane; k <= kh; k += 32) {
+                        const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
+                        if (i >= 0) atomicMin(&hitkey[k], hit_key(i, pr, pc));
                     }
                 }
             } else {
-                bool o = (occ[pr * c.vwb + (pc >> 5)] >> (pc & 31)) & 1u;
-                bool kn = (known[pr * c.vwb + (pc >> 5)] >> (pc & 31)) & 1u;
-                val = o ? 0 : (kn ? 255 : 200);
+                // fallback: one thread per ray marches the bit raster with the reference's integer line walk
+                for (int k = tid; k < c.range_total; k += VIEW_THREADS) {
+                    int x1 = ox, y1 = oy, x2 = rend[2 * k], y2 = rend[2 * k + 1];
+                    int w = x2 - x1, h = y2 - y1;
+                    const int dx = w > 0 ? 1 : -1, dy = h > 0 ? 1 : -1;
+                    w = abs(w); h = abs(h);
+                    int x = x1, y = y1, f;
+                    unsigned key = NOHIT;
+                    if (w > h) {
+                        f = 2 * h - w;
+                        for (int i = 0; x != x2; x += dx, i++) {
+                            if ((unsigned)x >= (unsigned)vh || (unsigned)y >= (unsigned)vw) break;
+                            if ((occ[x * vwb + (y >> 5)] >> (y & 31)) & 1u) { key = hit_key(i, x, y); break; }
+                            if (f < 0) f += 2 * h; else { y += dy; f += 2 * (h - w); }
+                        }
+                    } else {
+                        f = 2 * w - h;
+                        for (int i = 0; y != y2; y += dy, i++) {
+                            if ((unsigned)x >= (unsigned)vh || (unsigned)y >= (unsigned)vw) break;
+                            if ((occ[x * vwb + (y >> 5)] >> (y & 31)) & 1u) { key = hit_key(i, x, y); break; }
+                            if (f < 0) f += 2 * w; else { x += dx; f += 2 * (w - h); }
+                        }
+                    }
+                    hitkey[k] = key;
+                }
             }
-            if (val != 0 && ((own_mask[full >> 5] >> (full & 31)) & 1u)) val = 100;
-            if (DEBUG_FULL) { if (d.dbg_view) d.dbg_view[(size_t)idx * c.vh * c.vw + full] = (uint8_t)val; }
-            else pix[q] = (uint8_t)val;
+            __syncthreads();
+            if (!DEBUG_FULL) {
+                for (int k = tid; k < c.range_total; k += VIEW_THREADS) {
+                    const unsigned key = hitkey[k];
+                    double hit = 6;   // agent.cpp:513
+                    if (key != NOHIT) {
+                        const int hx = (key >> 11) & 2047, hy = key & 2047;
+                        double x0 = ox * c.res, y0 = oy * c.res, xc = hx * c.res, yc = hy * c.res;
+                        hit = sqrt((x0 - xc) * (x0 - xc) + (y0 - yc) * (y0 - yc));
+                    }
+                    const float wire = (float)hit;                         // AgentState.laser is float32[]
+                    d.o_laser[(size_t)idx * c.range_total + k] = c.laser_norm ? (float)((double)wire / c.laser_max) : wire;   // yaml_env.py:440-444
+                }
+            }
+        }
+
+        // ---- Phase D/E: final view_map_ value of every pixel the cubic resize reads (or of the whole
+        // raster in debug mode): last-writer-wins over rays in index order, evaluated per pixel from the
+        // highest touching ray downwards, then the robot's own footprint (value 100, agent.cpp:503).
+        // kpack = highest | lowest<<16 touching ray; the highest one touches by construction, so only its
+        // step index is needed; the full touch test runs only on the (rare) fall-through candidates.
+        const uint32_t* own_mask = d.own_mask + (size_t)ty.own_mask_off;
+        const int nrows = DEBUG_FULL ? vh : c.ns, ncols = DEBUG_FULL ? vw : c.ns;
+        for (int rr = warp; rr < nrows; rr += VIEW_THREADS / 32) {
+            const int pr = DEBUG_FULL ? rr : need[rr];
+            for (int cc = lane; cc < ncols; cc += 32) {
+                const int pc = DEBUG_FULL ? cc : need[cc];
+                const int full = pr * vw + pc;
+                int val = 200;
+                if (c.use_laser) {
+                    const unsigned kp = __ldg(kpack + full);
+                    const int kh = kp & 0xFFFF;
+                    if (kh != 0xFFFF) {
+                        const int kl = kp >> 16;
+                        const int w0 = abs((int)rend[2 * kh] - ox), h0 = abs((int)rend[2 * kh + 1] - oy);
+                        int i = w0 > h0 ? abs(pr - ox) : abs(pc - oy);
+                        for (int k = kh;;) {
+                            const unsigned key = hitkey[k];
+                            const int hp = (int)(key >> 22);
+                            if (i < hp) { val = 255; break; }
+                            if (i == hp) { val = 0; break; }
+                            if (pr != (int)((key >> 11) & 2047) && pc != (int)(key & 2047)) { val = 200; break; }   // shadow write (agent.cpp:557-558)
+                            do { k--; i = k >= kl ? ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc) : 0; } while (k >= kl && i < 0);
+                            if (k < kl) break;
+                        }
+                    }
+                } else {
+                    const bool o = (occ[pr * vwb + (pc >> 5)] >> (pc & 31)) & 1u;
+                    const bool kn = (known[pr * vwb + (pc >> 5)] >> (pc & 31)) & 1u;
+                    val = o ? 0 : (kn ? 255 : 200);
+                }
+                if (val != 0 && pr >= ty.zone_r0 && pr <= ty.zone_r1 && pc >= ty.zone_c0 && pc <= ty.zone_c1 &&
+                    ((own_mask[full >> 5] >> (full & 31)) & 1u)) val = 100;
+                if (DEBUG_FULL) { if (d.dbg_view) d.dbg_view[(size_t)idx * vh * vw + full] = (uint8_t)val; }
+                else {
+                    const unsigned code = val == 0 ? 0u : val == 100 ? 1u : val == 200 ? 2u : 3u;
+                    if (code) atomicOr(&pix[rr * pixw + (cc >> 4)], code << (2 * (cc & 15)));
+                }
+            }
         }
         __syncthreads();
 
@@ -408,30 +556,46 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             // ---- Phase F: cv2.resize(INTER_CUBIC) 400->48 (yaml_env.py:433-434), OpenCV's own path:
             // horizontal pass in int32 with 11-bit weights, vertical pass as an fp32 FMA chain with
             // weights * 2^-22, round-half-even, saturate; then float16(x)/255 via a host-built table.
-            for (int q = tid; q < c.ns * c.img; q += VIEW_THREADS) {
-                int rr = q / c.img, oc = q % c.img;
-                const short* tp = d.cubic_tap + 4 * oc; const short* cf = d.cubic_coef + 4 * oc;
-                const uint8_t* row = pix + rr * c.ns;
-                hbuf[q] = row[tp[0]] * cf[0] + row[tp[1]] * cf[1] + row[tp[2]] * cf[2] + row[tp[3]] * cf[3];
-            }
-            __syncthreads();
+            // Done in blocks of HB_COLS output columns to bound the int32 buffer.
             const float scale = 1.f / (2048.f * 2048.f);
-            for (int q = tid; q < c.img * c.img; q += VIEW_THREADS) {
-                int orow = q / c.img, oc = q % c.img;
-                const short* tp = d.cubic_tap + 4 * orow; const short* cf = d.cubic_coef + 4 * orow;
-                float b0 = cf[0] * scale, b1 = cf[1] * scale, b2 = cf[2] * scale, b3 = cf[3] * scale;
-                float s0 = (float)hbuf[tp[0] * c.img + oc], s1 = (float)hbuf[tp[1] * c.img + oc];
-                float s2 = (float)hbuf[tp[2] * c.img + oc], s3 = (float)hbuf[tp[3] * c.img + oc];
-                float v = fmaf(s0, b0, fmaf(s1, b1, fmaf(s2, b2, s3 * b3)));
-                int iv = __float2int_rn(v);
-                iv = min(255, max(0, iv));
-                d.o_sensor[(size_t)idx * c.img * c.img + q] = d.f16_lut[iv];
+            for (int cb = 0; cb < c.img; cb += HB_COLS) {
+                const int nc = min(HB_COLS, c.img - cb);
+                for (int q = tid; q < c.ns * HB_COLS; q += VIEW_THREADS) {
+                    const int rr = q / HB_COLS, ocl = q % HB_COLS;
+                    if (ocl >= nc) continue;
+                    const short* tp = d.cubic_tap + 4 * (cb + ocl); const short* cf = d.cubic_coef + 4 * (cb + ocl);
+                    const uint32_t* row = pix + rr * pixw;
+                    int acc = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int n = tp[k];
+                        const unsigned code = (row[n >> 4] >> (2 * (n & 15))) & 3u;
+                        acc += (int)((0xFFC86400u >> (8 * code)) & 0xFFu) * cf[k];
+                    }
+                    hbuf[rr * HB_COLS + ocl] = acc;
+                }
+                __syncthreads();
+                for (int q = tid; q < c.img * HB_COLS; q += VIEW_THREADS) {
+                    const int orow = q / HB_COLS, ocl = q % HB_COLS;
+                    if (ocl >= nc) continue;
+                    const short* tp = d.cubic_tap + 4 * orow; const short* cf = d.cubic_coef + 4 * orow;
+                    const float b0 = cf[0] * scale, b1 = cf[1] * scale, b2 = cf[2] * scale, b3 = cf[3] * scale;
+                    const float s0 = (float)hbuf[tp[0] * HB_COLS + ocl], s1 = (float)hbuf[tp[1] * HB_COLS + ocl];
+                    const float s2 = (float)hbuf[tp[2] * HB_COLS + ocl], s3 = (float)hbuf[tp[3] * HB_COLS + ocl];
+                    const float v = fmaf(s0, b0, fmaf(s1, b1, fmaf(s2, b2, s3 * b3)));
+                    int iv = __float2int_rn(v);
+                    iv = min(255, max(0, iv));
+                    d.o_sensor[(size_t)idx * c.img * c.img + orow * c.img + cb + ocl] = d.f16_lut[iv];
+                }
+                __syncthreads();
             }
         }
     }
     if (DEBUG_FULL) return;
+    __syncthreads();     // region A (raster) is dead from here on: reuse it for the pedestrian observation
 
     // ---- Phase G: state vector + pedestrian observation (img_env.cpp:547-587, yaml_env.py:392-481)
+    for (int k = tid; k < c.img * c.img; k += VIEW_THREADS) winner[k] = -1;
     if (tid == 0) {
         double st[5];
         robot_state_vec(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx), RBF(d, RB_GX, idx), RBF(d, RB_GY, idx),
@@ -495,22 +659,11 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
     if (tid == 0) d.o_mind[idx] = (float)RBF(d, RB_MIND, idx);
     float* pm = d.o_pmap + (size_t)idx * 3 * c.img * c.img;
     const int npm = c.img * c.img;
-    for (int q = tid; q < 3 * npm; q += VIEW_THREADS) {
-        int ch = q / npm, cell = q % npm;
-        int wv = winner[cell];
-        float v = 0.f;
-        if (wv >= 0) { int j = wv & 0xFFFF; v = ch == 0 ? 1.0f : pobs[4 * j + 1 + ch]; }
-        pm[q] = v;
-    }
-}
-
-inline size_t view_smem_bytes(const Cfg& c) {
-    size_t b = (sizeof(ViewShared) + 15) & ~15;
-    b += (size_t)c.vh * c.vwb * 4 * (c.use_laser ? 1 : 2);
-    b += 3 * (((size_t)c.range_total * 2 + 15) & ~15);
-    b += ((size_t)c.ns * c.ns + 15) & ~15;
-    b += (size_t)c.ns * c.img * 4;
-    b += (size_t)c.img * c.img * 4;
-    b += (size_t)((c.P + 1) & ~1) * 8 + (size_t)c.P * 16 + (size_t)c.P * 4;
-    return b + 64;
+    for (int ch = 0; ch < 3; ch++)
+        for (int cell = tid; cell < npm; cell += VIEW_THREADS) {
+            int wv = winner[cell];
+            float v = 0.f;
+            if (wv >= 0) { int j = wv & 0xFFFF; v = ch == 0 ? 1.0f : pobs[4 * j + 1 + ch]; }
+            pm[ch * npm + cell] = v;
+        }
 }
