@@ -11,7 +11,7 @@
 #include "kin.cuh"
 #include "orca.cuh"
 
-#define DYN_THREADS 128
+#define DYN_THREADS 64
 
 struct V3 { double x, y, z; };
 __device__ __forceinline__ V3 v3(double x, double y, double z = 0) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -191,129 +191,146 @@ __device__ inline void ped_gait(const Dev& d, int pi, int p) {
     else if (state == 6) { PDF(d, PD_LLX, pi) = step_len; PDF(d, PD_RLX, pi) = -step_len; }
 }
 
-// grid = S CTAs. actions [S][R][3] float32 (v, w, v_y); alive [S][R] or NULL (-> library dones)
-__global__ void __launch_bounds__(DYN_THREADS) k_dynamics(Dev d, const float* actions, const uint8_t* alive, int ped_yaw_mode) {
+// The dynamics stage runs as two kernels so that a scene's agents spread over several CTAs:
+//   k_dyn_solve : grid = S * nblk CTAs; every CTA loads the scene's agents (pre-step pos/vel) into shared
+//                 memory and solves its slice of DYN_THREADS agents (ORCA/ERVO new velocity, or the SFM forces),
+//                 writing only scratch (new velocities / forces) and per-agent waypoint bookkeeping;
+//   k_dyn_apply : grid = S * nblk CTAs; Agent::update / Tagent::move, pedestrian pose + gait, then the robots
+//                 (limiter, cmd, arrival) and setRobotPos.
+// actions [S][R][3] float32 (v, w, v_y); alive [S][R] or NULL (-> library dones)
+__device__ __forceinline__ bool robot_alive(const Dev& d, const uint8_t* alive, int idx) {
+    return alive ? alive[idx] != 0 : RBF(d, RB_DONE, idx) == 0.0;
+}
+__device__ __forceinline__ int dyn_nblk(const Cfg& c) { int n = c.NA > c.R ? c.NA : c.R; return (n + DYN_THREADS - 1) / DYN_THREADS; }
+
+__global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* actions, const uint8_t* alive) {
     extern __shared__ __align__(16) unsigned char dsm[];
     const Cfg& c = d.c;
-    const int s = blockIdx.x, tid = threadIdx.x;
+    const int nblk = dyn_nblk(c);
+    const int s = blockIdx.x / nblk, blk = blockIdx.x % nblk, tid = threadIdx.x;
+    if (!(c.P > 0 && c.scene_type != 0)) return;
     V2* pos = reinterpret_cast<V2*>(dsm);
     V2* vel = pos + c.NA;
-    V2* nvel = vel + c.NA;
-    V2* beep_p = nvel + c.NA;
+    V2* beep_p = vel + c.NA;
     float* beep_r = reinterpret_cast<float*>(beep_p + c.R);
-    unsigned long long step = d.step_no[s];
-
-    if (c.P > 0 && c.scene_type != 0) {
-        // beeps (img_env.cpp:323-342): robots' PRE-step poses
-        for (int j = tid; j < c.R; j += DYN_THREADS) {
-            int idx = s * c.R + j;
-            bool is_beep = false;
-            bool al = alive ? alive[idx] != 0 : RBF(d, RB_DONE, idx) == 0.0;
-            float v_y = al ? actions[(size_t)idx * 3 + 2] : 0.f;
-            if (beep_uniform(c.seed, step, s, j) < c.ped_ca_p) {
-                if ((double)v_y > 0) {
-                    beep_p[j] = v2((float)RBF(d, RB_X, idx), (float)RBF(d, RB_Y, idx));
-                    beep_r[j] = (float)c.beep_r;
-                    is_beep = true;
-                }
-            }
-            if (!is_beep) { beep_p[j] = v2(0.f, 0.f); beep_r[j] = 0.f; }
-            RBF(d, RB_BEEP, idx) = is_beep ? 1.0 : 0.0;
+    const unsigned long long step = d.step_no[s];
+    // beeps (img_env.cpp:323-342): robots' PRE-step poses; recomputed identically by every CTA of the scene
+    for (int j = tid; j < c.R; j += DYN_THREADS) {
+        int idx = s * c.R + j;
+        bool is_beep = false;
+        float v_y = robot_alive(d, alive, idx) ? actions[(size_t)idx * 3 + 2] : 0.f;
+        if (beep_uniform(c.seed, step, s, j) < c.ped_ca_p && (double)v_y > 0) {
+            beep_p[j] = v2((float)RBF(d, RB_X, idx), (float)RBF(d, RB_Y, idx));
+            beep_r[j] = (float)c.beep_r;
+            is_beep = true;
         }
-        if (c.scene_type == 2 || c.scene_type == 3) {
-            for (int a = tid; a < c.NA; a += DYN_THREADS) {
-                pos[a] = v2(d.rvo_pos[((size_t)s * c.NA + a) * 2], d.rvo_pos[((size_t)s * c.NA + a) * 2 + 1]);
-                vel[a] = v2(d.rvo_vel[((size_t)s * c.NA + a) * 2], d.rvo_vel[((size_t)s * c.NA + a) * 2 + 1]);
+        if (!is_beep) { beep_p[j] = v2(0.f, 0.f); beep_r[j] = 0.f; }
+        if (blk == 0) RBF(d, RB_BEEP, idx) = is_beep ? 1.0 : 0.0;
+    }
+    const int a = blk * DYN_THREADS + tid;
+    if (c.scene_type == 2 || c.scene_type == 3) {
+        for (int k = tid; k < c.NA; k += DYN_THREADS) {
+            pos[k] = v2(d.rvo_pos[((size_t)s * c.NA + k) * 2], d.rvo_pos[((size_t)s * c.NA + k) * 2 + 1]);
+            vel[k] = v2(d.rvo_vel[((size_t)s * c.NA + k) * 2], d.rvo_vel[((size_t)s * c.NA + k) * 2 + 1]);
+        }
+        __syncthreads();
+        if (a >= c.NA) return;
+        ObstView ob;
+        ob.verts = d.rvo_verts + (size_t)s * d.max_verts * 8;
+        ob.nodes = d.rvo_nodes + (size_t)s * d.max_verts * 3;
+        ob.root = d.rvo_counts[2 * s + 1];
+        V2 pref = v2(0.f, 0.f);
+        float maxSpeed = 0.6f;
+        if (a < c.P) {
+            int pi = s * c.P + a;
+            // waypoint cycling (img_env.cpp:306-319, agent.cpp:823-843); an index past the end of
+            // trajectory_ is an out-of-bounds read in the node -> treated as "not arrived"
+            int ti = (int)PDF(d, PD_TIDX, pi), tl = d.traj_len[pi];
+            const double* tr = d.traj + ((size_t)pi * c.max_traj) * 3;
+            double x = PDF(d, PD_X, pi), y = PDF(d, PD_Y, pi);
+            if (ti < tl) {
+                double gx = tr[3 * ti], gy = tr[3 * ti + 1];
+                if ((gx - x) * (gx - x) + (gy - y) * (gy - y) < 0.04) ti += 1;
             }
-            __syncthreads();
-            ObstView ob;
-            ob.verts = d.rvo_verts + (size_t)s * d.max_verts * 8;
-            ob.nodes = d.rvo_nodes + (size_t)s * d.max_verts * 3;
-            ob.root = d.rvo_counts[2 * s + 1];
-            for (int a = tid; a < c.NA; a += DYN_THREADS) {
-                V2 pref = v2(0.f, 0.f);
-                float maxSpeed = 0.6f;
-                if (a < c.P) {
-                    int pi = s * c.P + a;
-                    // waypoint cycling (img_env.cpp:306-319, agent.cpp:823-843); an index past the end of
-                    // trajectory_ is an out-of-bounds read in the node -> treated as "not arrived"
-                    int ti = (int)PDF(d, PD_TIDX, pi), tl = d.traj_len[pi];
-                    const double* tr = d.traj + ((size_t)pi * c.max_traj) * 3;
-                    double x = PDF(d, PD_X, pi), y = PDF(d, PD_Y, pi);
-                    if (ti < tl) {
-                        double gx = tr[3 * ti], gy = tr[3 * ti + 1];
-                        if ((gx - x) * (gx - x) + (gy - y) * (gy - y) < 0.04) ti += 1;
-                    }
-                    PDF(d, PD_TIDX, pi) = ti;
-                    const double* g = tr + 3 * (ti % tl);
-                    V2 goalVector = v2((float)g[0], (float)g[1]) - pos[a];     // rvoscene.h:37-44
-                    if (absSq(goalVector) > 1.0f) goalVector = normalize(goalVector);
-                    pref = goalVector;
-                    maxSpeed = (float)d.ped_maxspeed[a];
-                }
-                nvel[a] = orca_new_velocity(a, c.NA, pos, vel, pref, maxSpeed, (float)c.step_hz, ob, c.scene_type == 3, c.R, beep_p, beep_r);
+            PDF(d, PD_TIDX, pi) = ti;
+            const double* g = tr + 3 * (ti % tl);
+            V2 goalVector = v2((float)g[0], (float)g[1]) - pos[a];     // rvoscene.h:37-44
+            if (absSq(goalVector) > 1.0f) goalVector = normalize(goalVector);
+            pref = goalVector;
+            maxSpeed = (float)d.ped_maxspeed[a];
+        }
+        V2 nv = orca_new_velocity(a, c.NA, pos, vel, pref, maxSpeed, (float)c.step_hz, ob, c.scene_type == 3, c.R, beep_p, beep_r);
+        d.rvo_nvel[((size_t)s * c.NA + a) * 2] = nv.x; d.rvo_nvel[((size_t)s * c.NA + a) * 2 + 1] = nv.y;
+    } else if (c.scene_type == 1) {
+        if (a >= c.NA) return;
+        double* recs = d.sfm + (size_t)s * c.NA * SFM_REC;
+        if (a < c.P) {   // waypoint cycling of the PedAgent wrapper still runs (unused by the SFM adapter's step)
+            int pi = s * c.P + a;
+            int ti = (int)PDF(d, PD_TIDX, pi), tl = d.traj_len[pi];
+            const double* tr = d.traj + ((size_t)pi * c.max_traj) * 3;
+            double x = PDF(d, PD_X, pi), y = PDF(d, PD_Y, pi);
+            if (ti < tl) {
+                double gx = tr[3 * ti], gy = tr[3 * ti + 1];
+                if ((gx - x) * (gx - x) + (gy - y) * (gy - y) < 0.04) ti += 1;
             }
-            __syncthreads();
-            for (int a = tid; a < c.NA; a += DYN_THREADS) {   // Agent::update
-                V2 nv = nvel[a];
-                V2 np = pos[a] + nv * (float)c.step_hz;
-                d.rvo_pos[((size_t)s * c.NA + a) * 2] = np.x; d.rvo_pos[((size_t)s * c.NA + a) * 2 + 1] = np.y;
-                d.rvo_vel[((size_t)s * c.NA + a) * 2] = nv.x; d.rvo_vel[((size_t)s * c.NA + a) * 2 + 1] = nv.y;
-                if (a < c.P) {   // getNewPosAndVel + set_position + update_bbox (img_env.cpp:344-358)
-                    int pi = s * c.P + a;
-                    PDF(d, PD_LX, pi) = PDF(d, PD_X, pi); PDF(d, PD_LY, pi) = PDF(d, PD_Y, pi); PDF(d, PD_LYAW, pi) = PDF(d, PD_YAW, pi);
-                    PDF(d, PD_X, pi) = (double)np.x; PDF(d, PD_Y, pi) = (double)np.y;
-                    PDF(d, PD_VX, pi) = (double)nv.x; PDF(d, PD_VY, pi) = (double)nv.y;
-                    if (ped_yaw_mode == 1) PDF(d, PD_YAW, pi) = 0.0;
-                    else if (ped_yaw_mode == 2) PDF(d, PD_YAW, pi) = atan2((double)nv.y, (double)nv.x);
-                    ped_gait(d, pi, a);
-                }
+            PDF(d, PD_TIDX, pi) = ti;
+        }
+        SfmForces F = sfm_forces(d, s, a, recs + (size_t)a * SFM_REC, recs, c.NA);
+        double* o = d.sfm_force + ((size_t)s * c.NA + a) * 12;
+        o[0] = F.desired.x; o[1] = F.desired.y; o[2] = F.desired.z; o[3] = F.social.x; o[4] = F.social.y; o[5] = F.social.z;
+        o[6] = F.obstacle.x; o[7] = F.obstacle.y; o[8] = F.obstacle.z; o[9] = F.lookahead.x; o[10] = F.lookahead.y; o[11] = F.lookahead.z;
+    }
+}
+
+__global__ void __launch_bounds__(DYN_THREADS) k_dyn_apply(Dev d, const float* actions, const uint8_t* alive, int ped_yaw_mode) {
+    const Cfg& c = d.c;
+    const int nblk = dyn_nblk(c);
+    const int s = blockIdx.x / nblk, blk = blockIdx.x % nblk, tid = threadIdx.x;
+    const int a = blk * DYN_THREADS + tid;
+    if (c.P > 0 && c.scene_type != 0 && a < c.NA) {
+        if (c.scene_type == 2 || c.scene_type == 3) {   // Agent::update
+            const size_t o = ((size_t)s * c.NA + a) * 2;
+            V2 nv = v2(d.rvo_nvel[o], d.rvo_nvel[o + 1]);
+            V2 np = v2(d.rvo_pos[o], d.rvo_pos[o + 1]) + nv * (float)c.step_hz;
+            d.rvo_pos[o] = np.x; d.rvo_pos[o + 1] = np.y;
+            d.rvo_vel[o] = nv.x; d.rvo_vel[o + 1] = nv.y;
+            if (a < c.P) {   // getNewPosAndVel + set_position + update_bbox (img_env.cpp:344-358)
+                int pi = s * c.P + a;
+                PDF(d, PD_LX, pi) = PDF(d, PD_X, pi); PDF(d, PD_LY, pi) = PDF(d, PD_Y, pi); PDF(d, PD_LYAW, pi) = PDF(d, PD_YAW, pi);
+                PDF(d, PD_X, pi) = (double)np.x; PDF(d, PD_Y, pi) = (double)np.y;
+                PDF(d, PD_VX, pi) = (double)nv.x; PDF(d, PD_VY, pi) = (double)nv.y;
+                if (ped_yaw_mode == 1) PDF(d, PD_YAW, pi) = 0.0;
+                else if (ped_yaw_mode == 2) PDF(d, PD_YAW, pi) = atan2((double)nv.y, (double)nv.x);
+                ped_gait(d, pi, a);
             }
         } else if (c.scene_type == 1) {
-            double* recs = d.sfm + (size_t)s * c.NA * SFM_REC;
-            // waypoint cycling of the PedAgent wrapper still runs (unused by the SFM adapter's step)
-            for (int a = tid; a < c.P; a += DYN_THREADS) {
+            double* rec = d.sfm + ((size_t)s * c.NA + a) * SFM_REC;
+            const double* f = d.sfm_force + ((size_t)s * c.NA + a) * 12;
+            SfmForces F;
+            F.desired = v3(f[0], f[1], f[2]); F.social = v3(f[3], f[4], f[5]); F.obstacle = v3(f[6], f[7], f[8]); F.lookahead = v3(f[9], f[10], f[11]);
+            sfm_move(d, s, rec, F, c.step_hz);
+            // Ttree::moveAgent with the never-split root leaf [0,10]x[10,20] (pedscene.h:19,
+            // ped_tree.cpp:124-130): an agent outside the box is re-inserted, then erased.
+            bool outside = (rec[0] < 0) || (rec[0] > 10) || (rec[1] < 10) || (rec[1] > 20);
+            if (outside) rec[10] = 0.0;
+            if (a < c.P) {
                 int pi = s * c.P + a;
-                int ti = (int)PDF(d, PD_TIDX, pi), tl = d.traj_len[pi];
-                const double* tr = d.traj + ((size_t)pi * c.max_traj) * 3;
-                double x = PDF(d, PD_X, pi), y = PDF(d, PD_Y, pi);
-                if (ti < tl) {
-                    double gx = tr[3 * ti], gy = tr[3 * ti + 1];
-                    if ((gx - x) * (gx - x) + (gy - y) * (gy - y) < 0.04) ti += 1;
-                }
-                PDF(d, PD_TIDX, pi) = ti;
-            }
-            // phase 1: forces from the pre-move state (kept in registers), phase 2: move
-            SfmForces F[4];   // NA <= 4 * DYN_THREADS
-            int k = 0;
-            for (int a = tid; a < c.NA && k < 4; a += DYN_THREADS, k++) F[k] = sfm_forces(d, s, a, recs + (size_t)a * SFM_REC, recs, c.NA);
-            __syncthreads();
-            k = 0;
-            for (int a = tid; a < c.NA && k < 4; a += DYN_THREADS, k++) {
-                double* rec = recs + (size_t)a * SFM_REC;
-                sfm_move(d, s, rec, F[k], c.step_hz);
-                // Ttree::moveAgent with the never-split root leaf [0,10]x[10,20] (pedscene.h:19,
-                // ped_tree.cpp:124-130): an agent outside the box is re-inserted, then erased.
-                bool outside = (rec[0] < 0) || (rec[0] > 10) || (rec[1] < 10) || (rec[1] > 20);
-                if (outside) rec[10] = 0.0;
-                if (a < c.P) {
-                    int pi = s * c.P + a;
-                    PDF(d, PD_LX, pi) = PDF(d, PD_X, pi); PDF(d, PD_LY, pi) = PDF(d, PD_Y, pi); PDF(d, PD_LYAW, pi) = PDF(d, PD_YAW, pi);
-                    PDF(d, PD_X, pi) = rec[0]; PDF(d, PD_Y, pi) = rec[1];
-                    PDF(d, PD_VX, pi) = rec[3]; PDF(d, PD_VY, pi) = rec[4];
-                    if (ped_yaw_mode == 1) PDF(d, PD_YAW, pi) = 0.0;
-                    else if (ped_yaw_mode == 2) PDF(d, PD_YAW, pi) = atan2(rec[4], rec[3]);
-                    ped_gait(d, pi, a);
-                }
+                PDF(d, PD_LX, pi) = PDF(d, PD_X, pi); PDF(d, PD_LY, pi) = PDF(d, PD_Y, pi); PDF(d, PD_LYAW, pi) = PDF(d, PD_YAW, pi);
+                PDF(d, PD_X, pi) = rec[0]; PDF(d, PD_Y, pi) = rec[1];
+                PDF(d, PD_VX, pi) = rec[3]; PDF(d, PD_VY, pi) = rec[4];
+                if (ped_yaw_mode == 1) PDF(d, PD_YAW, pi) = 0.0;
+                else if (ped_yaw_mode == 2) PDF(d, PD_YAW, pi) = atan2(rec[4], rec[3]);
+                ped_gait(d, pi, a);
             }
         }
     }
-    __syncthreads();
-    // ---- robots (img_env.cpp:388-419) ----
-    for (int j = tid; j < c.R; j += DYN_THREADS) {
+    // ---- robots (img_env.cpp:388-419). Robot j is handled by the thread that (if the robots are solver
+    // agents) also updated solver agent P + j, so the solver write above is ordered before the overwrite below.
+    const bool robots_in_solver = c.relation == 1 && c.NA > 0;
+    const int j = robots_in_solver ? a - c.P : a;
+    if (j >= 0 && j < c.R) {
         int idx = s * c.R + j;
-        bool al = alive ? alive[idx] != 0 : RBF(d, RB_DONE, idx) == 0.0;
-        if (al) {
+        if (robot_alive(d, alive, idx)) {
             RobotKin rk;
             rk.x = RBF(d, RB_X, idx); rk.y = RBF(d, RB_Y, idx); rk.yaw = RBF(d, RB_YAW, idx);
             rk.gx = RBF(d, RB_GX, idx); rk.gy = RBF(d, RB_GY, idx);
@@ -326,18 +343,18 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dynamics(Dev d, const float* ac
             RBF(d, RB_VX, idx) = rk.vx; RBF(d, RB_VY, idx) = rk.vy;
             RBF(d, RB_ARR, idx) = rk.arrive ? 1.0 : 0.0;
         }
-        if (c.relation == 1 && c.P > 0) {   // setRobotPos
-            int a = c.P + j;
+        if (robots_in_solver) {   // setRobotPos
+            int ag = c.P + j;
             if (c.scene_type == 2 || c.scene_type == 3) {
-                d.rvo_pos[((size_t)s * c.NA + a) * 2] = (float)RBF(d, RB_X, idx); d.rvo_pos[((size_t)s * c.NA + a) * 2 + 1] = (float)RBF(d, RB_Y, idx);
-                d.rvo_vel[((size_t)s * c.NA + a) * 2] = (float)RBF(d, RB_VX, idx); d.rvo_vel[((size_t)s * c.NA + a) * 2 + 1] = (float)RBF(d, RB_VY, idx);
+                d.rvo_pos[((size_t)s * c.NA + ag) * 2] = (float)RBF(d, RB_X, idx); d.rvo_pos[((size_t)s * c.NA + ag) * 2 + 1] = (float)RBF(d, RB_Y, idx);
+                d.rvo_vel[((size_t)s * c.NA + ag) * 2] = (float)RBF(d, RB_VX, idx); d.rvo_vel[((size_t)s * c.NA + ag) * 2 + 1] = (float)RBF(d, RB_VY, idx);
             } else if (c.scene_type == 1) {
-                double* rec = d.sfm + ((size_t)s * c.NA + a) * SFM_REC;
+                double* rec = d.sfm + ((size_t)s * c.NA + ag) * SFM_REC;
                 rec[0] = RBF(d, RB_X, idx); rec[1] = RBF(d, RB_Y, idx); rec[2] = 1.0;   // pedscene.h:53-56
             }
         }
     }
-    if (tid == 0) d.step_no[s] = step + 1;
+    if (blk == 0 && tid == 0) d.step_no[s] += 1;
 }
 
-inline size_t dyn_smem_bytes(const Cfg& c) { return (size_t)c.NA * 3 * 8 + (size_t)c.R * 12 + 64; }
+inline size_t dyn_smem_bytes(const Cfg& c) { return (size_t)c.NA * 2 * 8 + (size_t)c.R * 12 + 64; }

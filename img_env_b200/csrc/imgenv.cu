@@ -142,7 +142,6 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     if (c.state_dim < 3 || c.state_dim > 5) return fail("imgenv_create: state_dim must be 3, 4 or 5");
     if (c.R < 1 || c.R > 4096 || c.P < 0 || c.P > 4096 || c.S < 1) return fail("imgenv_create: bad S/R/P");
     if (c.range_total > 4000 || c.range_total < 1) return fail("imgenv_create: range_total out of range");
-    if (c.scene_type == 1 && c.NA > 4 * DYN_THREADS) return fail("imgenv_create: too many SFM agents per scene");
     if (c.scene_type < 0 || c.scene_type > 3) return fail("imgenv_create: unknown scene type");
 
     // ---- static tables ----
@@ -236,7 +235,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     AL(occ_all, S * H * c.Wb) AL(flags, S * pc) AL(rmin, S * pc) AL(coarse, S * c.Hc * c.Wb)
     AL(rb, (size_t)RB_FIELDS * S * c.R) AL(pd, (size_t)PD_FIELDS * S * c.P)
     AL(traj, S * c.P * c.max_traj * 3) AL(traj_len, S * c.P) AL(obs, S * c.max_obs * 8) AL(n_obs, S) AL(step_no, S)
-    AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 3)
+    AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_nvel, S * c.NA * 2) AL(sfm_force, c.scene_type == 1 ? S * c.NA * 12 : 1) AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 3)
     AL(rvo_counts, S * 2) AL(sfm, S * c.NA * SFM_REC) AL(sfm_obs, S * c.max_obs * 4) AL(sfm_nobs, S)
     AL(sfm_wp, S * c.P * (1 + c.max_traj) * 3)
 #undef AL
@@ -260,7 +259,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     if (h->view_smem > 227 * 1024) return fail("imgenv_create: view kernel needs too much shared memory for this configuration");
     CK(cudaFuncSetAttribute(k_view<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
     CK(cudaFuncSetAttribute(k_view<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
-    if (h->dyn_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_dynamics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
+    if (h->dyn_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_dyn_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
     k_init_state<<<1184, 256>>>(d);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
@@ -456,7 +455,7 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     return 0;
 }
 
-extern "C" int imgenv_launches_per_step(const imgenv_t*) { return 4; }
+extern "C" int imgenv_launches_per_step(const imgenv_t* h) { return (h && h->d.c.NA > 0) ? 5 : 4; }
 
 extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d_alive, void* stream) {
     if (!h) return fail("imgenv_step: null handle");
@@ -467,7 +466,11 @@ extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d
     cudaEvent_t* ev = nullptr;
     if (h->prof_n < h->prof_max) { ev = h->evs.data() + 5 * (size_t)h->prof_n; h->prof_n++; }
     if (ev) cudaEventRecord(ev[0], st);
-    k_dynamics<<<c.S, DYN_THREADS, h->dyn_smem, st>>>(d, d_actions, d_alive, h->ped_yaw_mode);
+    {
+        const int nmax = c.NA > c.R ? c.NA : c.R, nblk = (nmax + DYN_THREADS - 1) / DYN_THREADS;
+        if (c.NA > 0) k_dyn_solve<<<c.S * nblk, DYN_THREADS, h->dyn_smem, st>>>(d, d_actions, d_alive);
+        k_dyn_apply<<<c.S * nblk, DYN_THREADS, 0, st>>>(d, d_actions, d_alive, h->ped_yaw_mode);
+    }
     if (ev) cudaEventRecord(ev[1], st);
     return launch_observe(h, nullptr, c.S, 0, st, ev);
 }
@@ -596,20 +599,30 @@ extern "C" int imgenv_set_internal(imgenv_t* h, const double* robot, const doubl
     return 0;
 }
 
-extern "C" int imgenv_debug_view_maps(imgenv_t* h, uint8_t* host_out, void* stream) {
-    if (!h || !host_out) return fail("imgenv_debug_view_maps: null argument");
+extern "C" int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* stats_out, void* stream);
+extern "C" int imgenv_debug_view_maps(imgenv_t* h, uint8_t* host_out, void* stream) { return imgenv_debug_view_maps2(h, host_out, nullptr, stream); }
+
+// Same, plus per-robot kernel statistics (int32 [S][R][4]: active raster tiles, boundary cells, heavy cells,
+// 1 if the per-ray marching fallback ran). Either output may be NULL.
+extern "C" int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* stats_out, void* stream) {
+    if (!h) return fail("imgenv_debug_view_maps: null argument");
     Dev d = h->d; const Cfg& c = d.c;
     cudaStream_t st = (cudaStream_t)stream;
     size_t n = (size_t)c.S * c.R * c.vh * c.vw;
     uint8_t* buf = nullptr;
-    CK(cudaMalloc((void**)&buf, n));
-    d.dbg_view = buf;
+    int* sbuf = nullptr;
+    if (host_out) CK(cudaMalloc((void**)&buf, n));
+    if (stats_out) { CK(cudaMalloc((void**)&sbuf, (size_t)c.S * c.R * 16)); CK(cudaMemsetAsync(sbuf, 0, (size_t)c.S * c.R * 16, st)); }
+    d.dbg_view = buf; d.dbg_stats = sbuf;
     k_stamp_agents<<<c.S * (c.R + c.P), 128, 0, st>>>(d, nullptr, 0);
     k_view<true><<<c.S * c.R, VIEW_THREADS, h->view_smem, st>>>(d, nullptr, 0);
     k_stamp_agents<<<c.S * (c.R + c.P), 128, 0, st>>>(d, nullptr, 1);
-    cudaError_t e = cudaMemcpyAsync(host_out, buf, n, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaSuccess;
+    if (host_out) e = cudaMemcpyAsync(host_out, buf, n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && stats_out) e = cudaMemcpyAsync(stats_out, sbuf, (size_t)c.S * c.R * 16, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(buf);
+    if (buf) cudaFree(buf);
+    if (sbuf) cudaFree(sbuf);
     if (e != cudaSuccess) return fail(std::string("imgenv_debug_view_maps: ") + cudaGetErrorString(e));
     return 0;
 }

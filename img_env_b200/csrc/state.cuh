@@ -118,6 +118,8 @@ struct Dev {
     unsigned long long* step_no;  // [S]
     // solver state
     float* rvo_pos; float* rvo_vel;         // [S][NA][2]
+    float* rvo_nvel;                        // [S][NA][2] new velocities (scratch between solve and apply)
+    double* sfm_force;                      // [S][NA][12] SFM forces (scratch between solve and apply)
     float* rvo_verts;                       // [S][max_verts][8]: px,py,dx,dy,convex,next,prev,0
     int* rvo_nodes;                         // [S][max_verts][3]: obstacle, left, right
     int* rvo_counts;                        // [S][2]: n_verts, root(-1 none)
@@ -132,6 +134,7 @@ struct Dev {
     float* o_vec; uint16_t* o_sensor; int8_t* o_coll; uint8_t* o_arr; float* o_laser;
     float* o_pvs; float* o_pmap; float* o_stepd; float* o_mind;
     uint8_t* dbg_view;            // optional [S][R][vh][vw]
+    int* dbg_stats;               // optional [S][R][4]: active raster tiles, boundary cells, heavy cells, marching fallback
 };
 
 __host__ __device__ inline double& RBF(const Dev& d, int f, int idx) { return d.rb[(size_t)f * d.c.S * d.c.R + idx]; }

@@ -219,7 +219,7 @@ __device__ __forceinline__ int ray_touch(int ox, int oy, int ex, int ey, int pr,
 //   region B  boundary-cell list 24 KB        (phase C)       | later: horizontal resize buffer 144*48*4 = 27.6 KB (phase F)
 //   pix       144*144 u8 = 20.7 KB            (phases D-F)
 //   hitkey    range_total*4, ray end cells range_total*4, needed-line indices
-#define BL_CAP 2048          // boundary cells kept in shared memory; more -> per-ray marching fallback
+#define BL_CAP 3072          // boundary cells kept in shared memory; more -> per-ray marching fallback
 #define BL2_CAP 256          // cells touched by many rays (close to the origin): processed warp-cooperatively
 #define BL_HEAVY 24
 #define NOHIT 0xFFFFFFFFu
@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             }
             __syncthreads();
             const int nl = sh->red[0], nl2 = sh->red[1];
+            if (d.dbg_stats && tid == 0) { int* st = d.dbg_stats + 4 * (size_t)idx; st[0] = sh->red[2]; st[1] = nl; st[2] = nl2; st[3] = !(nl <= BL_CAP && nl2 <= BL2_CAP); }
             if (nl <= BL_CAP && nl2 <= BL2_CAP) {
                 for (int q = tid; q < nl; q += VIEW_THREADS) {
                     const int full = blist[q], pr = full / vw, pc = full - pr * vw;

@@ -35,7 +35,7 @@ class ImgenvOutputs(C.Structure):
 
 
 EXPORTS = ["imgenv_create", "imgenv_destroy", "imgenv_bind_outputs", "imgenv_reset", "imgenv_step", "imgenv_step_host",
-           "imgenv_end_episode", "imgenv_get_internal", "imgenv_set_internal", "imgenv_debug_view_maps",
+           "imgenv_end_episode", "imgenv_get_internal", "imgenv_set_internal", "imgenv_debug_view_maps", "imgenv_debug_view_maps2",
            "imgenv_solver_agents", "imgenv_view_dims", "imgenv_launches_per_step",
            "imgenv_algorithmic_bytes_per_robot_step", "imgenv_last_error", "imgenv_version"]
 
@@ -211,6 +211,11 @@ class BatchedSim:
         pd = np.ascontiguousarray(pd, dtype=np.float64) if (pd is not None and self.P) else None
         sv = np.ascontiguousarray(sv, dtype=np.float64) if (sv is not None and self.solver_agents) else None
         self._check(self.lib.imgenv_set_internal(self.h, _ptr(rb), _ptr(pd), _ptr(sv)))
+
+    def debug_stats(self):
+        out = np.zeros((self.S, self.R, 4), np.int32)
+        self._check(self.lib.imgenv_debug_view_maps2(self.h, None, _ptr(out, C.c_int32), self._stream()))
+        return out
 
     def debug_view_maps(self):
         vh, vw = C.c_int32(), C.c_int32()

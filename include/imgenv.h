@@ -112,6 +112,9 @@ int imgenv_get_internal(imgenv_t* h, double* robot, double* ped, double* solver)
 int imgenv_set_internal(imgenv_t* h, const double* robot, const double* ped, const double* solver);
 /* Debug raster: the 400x400 view_map_ of every robot as the node would send it (u8 [S][R][vh][vw]). */
 int imgenv_debug_view_maps(imgenv_t* h, uint8_t* host_out, void* stream);
+/* Same + per-robot kernel statistics int32 [S][R][4] (active raster tiles, boundary cells, heavy cells, marching
+ * fallback taken). Either output may be NULL. */
+int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* stats_out, void* stream);
 /* ped_min_dists persistence (NearbyPed, reset_helper.py:85-99) and dones are library state. */
 int imgenv_solver_agents(const imgenv_t* h);   /* P + R' */
 int imgenv_view_dims(const imgenv_t* h, int32_t* vh, int32_t* vw);
