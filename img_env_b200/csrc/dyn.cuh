@@ -10,6 +10,7 @@
 #include "state.cuh"
 #include "kin.cuh"
 #include "orca.cuh"
+#include "sfmtree.cuh"
 
 #define DYN_THREADS 64
 
@@ -31,8 +32,17 @@ __device__ __forceinline__ double dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.
 struct SfmForces { V3 desired, social, obstacle, lookahead; };
 
 // Tagent::computeForces for agent `self` (reads the pre-move state of all agents)
+__device__ __forceinline__ QTreeView qt_view(const Dev& d, int s, const double* pos) {
+    QTreeView t;
+    t.n_nodes = d.qt_nodes + s; t.box = d.qt_box + (size_t)s * QT_MAX_NODES * 4; t.child0 = d.qt_child0 + (size_t)s * QT_MAX_NODES;
+    t.count = d.qt_count + (size_t)s * QT_MAX_NODES; t.leaf = d.qt_leaf + (size_t)s * d.c.NA * QT_LEAVES; t.hash = d.qt_hash + (size_t)s * d.c.NA;
+    t.pos = pos; t.na = d.c.NA;
+    return t;
+}
+
 __device__ inline SfmForces sfm_forces(const Dev& d, int s, int self, double* rec_self, const double* recs, int n_agents) {
     const Cfg& c = d.c;
+    const QTreeView qt = qt_view(d, s, nullptr);
     SfmForces F;
     V3 p = v3(rec_self[0], rec_self[1], rec_self[2]);
     V3 vself = v3(rec_self[3], rec_self[4], rec_self[5]);
@@ -54,15 +64,15 @@ __device__ inline SfmForces sfm_forces(const Dev& d, int s, int self, double* re
     if (dest >= 0 && reached) { lastdest = dest; dest = -1; }
     rec_self[7] = dest; rec_self[8] = lastdest; rec_self[9] = front;
     F.desired = normalized(desiredDirection) * vmax;
-    // ---- neighbours: every agent currently held by the quadtree (SFM visibility) ----
+    // ---- neighbours: agents held by quadtree leaves that intersect the 20 m query box (sfmtree.cuh) ----
     // lookaheadForce
     const double pi = 3.14159265;
     int lookforwardcount = 0;
     V3 soc = v3(0, 0, 0);
     for (int o = 0; o < n_agents; o++) {
         const double* ro = recs + (size_t)o * SFM_REC;
-        if (ro[10] == 0.0) continue;      // not in the tree -> never returned by getNeighbors
         if (o == self) continue;
+        if (!qt_visible(qt, o, p.x, p.y, 20.0)) continue;      // scene->getNeighbors(p.x, p.y, 20) (ped_agent.cpp:499-500)
         V3 op = v3(ro[0], ro[1], ro[2]), ov = v3(ro[3], ro[4], ro[5]);
         {
             double distancex = op.x - p.x, distancey = op.y - p.y;
@@ -309,10 +319,8 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_apply(Dev d, const float* a
             SfmForces F;
             F.desired = v3(f[0], f[1], f[2]); F.social = v3(f[3], f[4], f[5]); F.obstacle = v3(f[6], f[7], f[8]); F.lookahead = v3(f[9], f[10], f[11]);
             sfm_move(d, s, rec, F, c.step_hz);
-            // Ttree::moveAgent with the never-split root leaf [0,10]x[10,20] (pedscene.h:19,
-            // ped_tree.cpp:124-130): an agent outside the box is re-inserted, then erased.
-            bool outside = (rec[0] < 0) || (rec[0] > 10) || (rec[1] < 10) || (rec[1] > 20);
-            if (outside) rec[10] = 0.0;
+            // scene->moveAgent(this) needs the post-move position (robots are overwritten below): k_sfm_tree
+            d.sfm_newpos[((size_t)s * c.NA + a) * 2] = rec[0]; d.sfm_newpos[((size_t)s * c.NA + a) * 2 + 1] = rec[1];
             if (a < c.P) {
                 int pi = s * c.P + a;
                 PDF(d, PD_LX, pi) = PDF(d, PD_X, pi); PDF(d, PD_LY, pi) = PDF(d, PD_Y, pi); PDF(d, PD_LYAW, pi) = PDF(d, PD_YAW, pi);
@@ -355,6 +363,15 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_apply(Dev d, const float* a
         }
     }
     if (blk == 0 && tid == 0) d.step_no[s] += 1;
+}
+
+// Tscene::moveAgent for every agent in index order (the order Tscene::moveAgents moves them): one thread per scene.
+__global__ void k_sfm_tree(Dev d) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= d.c.S) return;
+    const QTreeView t = qt_view(d, s, d.sfm_newpos + (size_t)s * d.c.NA * 2);
+    for (int a = 0; a < d.c.NA; a++) qt_move(t, a);
+    for (int a = 0; a < d.c.NA; a++) d.sfm[((size_t)s * d.c.NA + a) * SFM_REC + 10] = qt_in_tree(t, a) ? 1.0 : 0.0;
 }
 
 inline size_t dyn_smem_bytes(const Cfg& c) { return (size_t)c.NA * 2 * 8 + (size_t)c.R * 12 + 64; }

@@ -14,6 +14,7 @@
 #include "view.cuh"
 #include "dyn.cuh"
 #include "host_tables.h"
+#include <random>
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return -1; }
@@ -91,10 +92,9 @@ __global__ void k_init_state(Dev d) {
     if (d.c.scene_type == 1)
         for (size_t i = t0; i < na; i += stride) {
             double* rec = d.sfm + i * SFM_REC;
-            rec[6] = 1.2;      // Tagent(): vmax ~ N(1.2, 0.2) from a process-global engine (ped_agent.cpp:43-44); overridable via set_internal
+            rec[6] = d.sfm_vmax0[i % d.c.NA];   // Tagent(): vmax ~ N(1.2, 0.2) (ped_agent.cpp:43-44), setVmax for pedestrians (pedscene.h:66)
             rec[7] = -1; rec[8] = -1; rec[9] = 0;
             rec[10] = 1.0;     // every agent is inserted into the quadtree by addAgent (ped_scene.cpp:69-75)
-            if ((int)(i % d.c.NA) < d.c.P) rec[6] = d.ped_maxspeed[i % d.c.NA];   // setVmax (pedscene.h:66)
         }
 }
 
@@ -238,7 +238,44 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_nvel, S * c.NA * 2) AL(sfm_force, c.scene_type == 1 ? S * c.NA * 12 : 1) AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 3)
     AL(rvo_counts, S * 2) AL(sfm, S * c.NA * SFM_REC) AL(sfm_obs, S * c.max_obs * 4) AL(sfm_nobs, S)
     AL(sfm_wp, S * c.P * (1 + c.max_traj) * 3)
+    {
+        const bool sf = c.scene_type == 1;
+        AL(qt_nodes, sf ? S : 1) AL(qt_box, sf ? S * QT_MAX_NODES * 4 : 1) AL(qt_child0, sf ? S * QT_MAX_NODES : 1) AL(qt_count, sf ? S * QT_MAX_NODES : 1)
+        AL(qt_leaf, sf ? S * c.NA * QT_LEAVES : 1) AL(qt_hash, sf ? S * c.NA : 1) AL(sfm_newpos, sf ? S * c.NA * 2 : 1)
+    }
 #undef AL
+    {   // SFM start-up state of a fresh reference process (pedscene.h:58-83): per Tagent one N(1.2,0.2) draw from a
+        // default-seeded std::default_random_engine (ped_agent.cpp:19,43-44), pedestrians placed at
+        // rand()/2147483647*10 (glibc rand, seed 1) and inserted into the quadtree, robots inserted at (0,0).
+        std::vector<double> vmax0(std::max(c.NA, 1), 1.2);
+        if (c.scene_type == 1) {
+            std::default_random_engine generator;
+            std::vector<double> pos(2 * (size_t)c.NA, 0.0);
+            struct random_data rd; char statebuf[128]; memset(&rd, 0, sizeof rd);
+            initstate_r(1, statebuf, sizeof statebuf, &rd);
+            for (int a = 0; a < c.P + c.R; a++) {
+                std::normal_distribution<double> distribution(1.2, 0.2);
+                double v = distribution(generator);
+                if (a < c.NA) vmax0[a] = a < c.P ? pmax[a] : v;
+                if (a < c.P) { int32_t r1, r2; random_r(&rd, &r1); random_r(&rd, &r2); pos[2 * a] = r1 / 2147483647.0 * 10.0; pos[2 * a + 1] = r2 / 2147483647.0 * 10.0; }
+            }
+            std::vector<int> n_nodes(1), child0(QT_MAX_NODES, -1), count(QT_MAX_NODES, 0), leaf((size_t)c.NA * QT_LEAVES, -1), hash(c.NA, -1);
+            std::vector<double> box((size_t)QT_MAX_NODES * 4, 0.0);
+            QTreeView t; t.n_nodes = n_nodes.data(); t.box = box.data(); t.child0 = child0.data(); t.count = count.data();
+            t.leaf = leaf.data(); t.hash = hash.data(); t.pos = pos.data(); t.na = c.NA;
+            qt_init(t);
+            for (int a = 0; a < c.NA; a++) qt_add(t, a, 0);      // addPed ... addRobot order == agent index order
+            for (size_t sc = 0; sc < S; sc++) {
+                CK(cudaMemcpy(d.qt_nodes + sc, n_nodes.data(), 4, cudaMemcpyHostToDevice));
+                CK(cudaMemcpy(d.qt_box + sc * QT_MAX_NODES * 4, box.data(), box.size() * 8, cudaMemcpyHostToDevice));
+                CK(cudaMemcpy(d.qt_child0 + sc * QT_MAX_NODES, child0.data(), child0.size() * 4, cudaMemcpyHostToDevice));
+                CK(cudaMemcpy(d.qt_count + sc * QT_MAX_NODES, count.data(), count.size() * 4, cudaMemcpyHostToDevice));
+                CK(cudaMemcpy(d.qt_leaf + sc * c.NA * QT_LEAVES, leaf.data(), leaf.size() * 4, cudaMemcpyHostToDevice));
+                CK(cudaMemcpy(d.qt_hash + sc * c.NA, hash.data(), hash.size() * 4, cudaMemcpyHostToDevice));
+            }
+        }
+        if (dupload(h, &d.sfm_vmax0, vmax0)) return -1;
+    }
     if (dalloc(h, &h->act_d, S * c.R * 3)) return -1;
     if (dalloc(h, &h->alive_d, S * c.R)) return -1;
     {   // rvo root = -1 (no obstacle tree) until the first reset
@@ -455,7 +492,7 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     return 0;
 }
 
-extern "C" int imgenv_launches_per_step(const imgenv_t* h) { return (h && h->d.c.NA > 0) ? 5 : 4; }
+extern "C" int imgenv_launches_per_step(const imgenv_t* h) { return !h ? 4 : (h->d.c.scene_type == 1 ? 6 : (h->d.c.NA > 0 ? 5 : 4)); }
 
 extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d_alive, void* stream) {
     if (!h) return fail("imgenv_step: null handle");
@@ -470,6 +507,7 @@ extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d
         const int nmax = c.NA > c.R ? c.NA : c.R, nblk = (nmax + DYN_THREADS - 1) / DYN_THREADS;
         if (c.NA > 0) k_dyn_solve<<<c.S * nblk, DYN_THREADS, h->dyn_smem, st>>>(d, d_actions, d_alive);
         k_dyn_apply<<<c.S * nblk, DYN_THREADS, 0, st>>>(d, d_actions, d_alive, h->ped_yaw_mode);
+        if (c.scene_type == 1) k_sfm_tree<<<(c.S + 31) / 32, 32, 0, st>>>(d);
     }
     if (ev) cudaEventRecord(ev[1], st);
     return launch_observe(h, nullptr, c.S, 0, st, ev);
@@ -624,5 +662,38 @@ extern "C" int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* 
     if (buf) cudaFree(buf);
     if (sbuf) cudaFree(sbuf);
     if (e != cudaSuccess) return fail(std::string("imgenv_debug_view_maps: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+// libpedsim quadtree state of one scene (tests): nodes[n][5] = x,y,w,h,child0 ; leaf[NA][4] ; hash[NA]
+extern "C" int imgenv_sfm_tree_get(imgenv_t* h, int32_t scene, int32_t* n_nodes, double* nodes, int32_t* leaf, int32_t* hash) {
+    if (!h || h->d.c.scene_type != 1) return fail("imgenv_sfm_tree_get: not an SFM handle");
+    Dev& d = h->d; const Cfg& c = d.c;
+    CK(cudaDeviceSynchronize());
+    int n = 0;
+    CK(cudaMemcpy(&n, d.qt_nodes + scene, 4, cudaMemcpyDeviceToHost));
+    *n_nodes = n;
+    std::vector<double> box((size_t)QT_MAX_NODES * 4); std::vector<int> ch(QT_MAX_NODES);
+    CK(cudaMemcpy(box.data(), d.qt_box + (size_t)scene * QT_MAX_NODES * 4, box.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ch.data(), d.qt_child0 + (size_t)scene * QT_MAX_NODES, ch.size() * 4, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < n; k++) { for (int q = 0; q < 4; q++) nodes[5 * k + q] = box[4 * k + q]; nodes[5 * k + 4] = ch[k]; }
+    CK(cudaMemcpy(leaf, d.qt_leaf + (size_t)scene * c.NA * QT_LEAVES, (size_t)c.NA * QT_LEAVES * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hash, d.qt_hash + (size_t)scene * c.NA, (size_t)c.NA * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int imgenv_sfm_tree_set(imgenv_t* h, int32_t scene, int32_t n_nodes, const double* nodes, const int32_t* leaf, const int32_t* hash) {
+    if (!h || h->d.c.scene_type != 1) return fail("imgenv_sfm_tree_set: not an SFM handle");
+    if (n_nodes < 1 || n_nodes > QT_MAX_NODES) return fail("imgenv_sfm_tree_set: bad node count");
+    Dev& d = h->d; const Cfg& c = d.c;
+    CK(cudaDeviceSynchronize());
+    std::vector<double> box((size_t)QT_MAX_NODES * 4, 0.0); std::vector<int> ch(QT_MAX_NODES, -1), cnt(QT_MAX_NODES, 0);
+    for (int k = 0; k < n_nodes; k++) { for (int q = 0; q < 4; q++) box[4 * k + q] = nodes[5 * k + q]; ch[k] = (int)nodes[5 * k + 4]; }
+    for (int a = 0; a < c.NA; a++) for (int k = 0; k < QT_LEAVES; k++) { int n = leaf[a * QT_LEAVES + k]; if (n >= 0 && n < n_nodes) cnt[n]++; }
+    CK(cudaMemcpy(d.qt_nodes + scene, &n_nodes, 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.qt_box + (size_t)scene * QT_MAX_NODES * 4, box.data(), box.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.qt_child0 + (size_t)scene * QT_MAX_NODES, ch.data(), ch.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.qt_count + (size_t)scene * QT_MAX_NODES, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.qt_leaf + (size_t)scene * c.NA * QT_LEAVES, leaf, (size_t)c.NA * QT_LEAVES * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.qt_hash + (size_t)scene * c.NA, hash, (size_t)c.NA * 4, cudaMemcpyHostToDevice));
     return 0;
 }

@@ -128,8 +128,14 @@ struct Dev {
     double* sfm_obs;                        // [S][max_obs][4] segment ax,ay,bx,by
     int* sfm_nobs;                          // [S]
     double* sfm_wp;                         // [S][P][1+max_traj][3] waypoints x,y,r
-    int* sfm_tree;                          // [S][...] quadtree emulation (see sfm.cuh)
-    int sfm_tree_stride;
+    // libpedsim quadtree emulation (sfmtree.cuh), per scene
+    int* qt_nodes;                          // [S]
+    double* qt_box;                         // [S][QT_MAX_NODES][4]
+    int* qt_child0; int* qt_count;          // [S][QT_MAX_NODES]
+    int* qt_leaf;                           // [S][NA][4]
+    int* qt_hash;                           // [S][NA]
+    double* sfm_newpos;                     // [S][NA][2] post-move positions handed to the tree update
+    const double* sfm_vmax0;                // [NA] initial vmax (Tagent(): N(1.2,0.2), setVmax for pedestrians)
     // outputs
     float* o_vec; uint16_t* o_sensor; int8_t* o_coll; uint8_t* o_arr; float* o_laser;
     float* o_pvs; float* o_pmap; float* o_stepd; float* o_mind;

@@ -212,6 +212,17 @@ class BatchedSim:
         sv = np.ascontiguousarray(sv, dtype=np.float64) if (sv is not None and self.solver_agents) else None
         self._check(self.lib.imgenv_set_internal(self.h, _ptr(rb), _ptr(pd), _ptr(sv)))
 
+    def sfm_tree_get(self, scene=0):
+        na = self.solver_agents
+        nodes = np.zeros((1024, 5)); leaf = np.zeros((na, 4), np.int32); hash_ = np.zeros(na, np.int32); n = C.c_int32()
+        self._check(self.lib.imgenv_sfm_tree_get(self.h, int(scene), C.byref(n), _ptr(nodes), _ptr(leaf, C.c_int32), _ptr(hash_, C.c_int32)))
+        return nodes[: n.value].copy(), leaf, hash_
+
+    def sfm_tree_set(self, nodes, leaf, hash_, scene=0):
+        nodes = np.ascontiguousarray(nodes, dtype=np.float64); leaf = np.ascontiguousarray(leaf, dtype=np.int32)
+        hash_ = np.ascontiguousarray(hash_, dtype=np.int32)
+        self._check(self.lib.imgenv_sfm_tree_set(self.h, int(scene), nodes.shape[0], _ptr(nodes), _ptr(leaf, C.c_int32), _ptr(hash_, C.c_int32)))
+
     def debug_stats(self):
         out = np.zeros((self.S, self.R, 4), np.int32)
         self._check(self.lib.imgenv_debug_view_maps2(self.h, None, _ptr(out, C.c_int32), self._stream()))

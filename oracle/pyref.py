@@ -177,6 +177,12 @@ class RefEnv:
         a = _dbl(a)
         self.lib.sfm_set_pv(self.h, _p(a, C.c_double))
 
+    def sfm_tree(self):
+        na = self.lib.sfm_num_agents(self.h) if int(self.spec["scalars"][19]) == 1 else self.P
+        nodes = np.zeros((1024, 5)); leaf = np.zeros((na, 4), np.int32); hash_ = np.zeros(na, np.int32)
+        n = self.lib.sfm_tree2(self.h, _p(nodes, C.c_double), 1024, _p(leaf, C.c_int), _p(hash_, C.c_int))
+        return nodes[:n].copy(), leaf, hash_
+
     def get_map(self, which):
         m = np.zeros((self.H, self.W), np.uint8)
         self.lib.get_map(self.h, which, _p(m, C.c_uint8))

@@ -349,6 +349,33 @@ int ref_sfm_tree(void* h, double* nodes, int max_nodes, int* member, int max_mem
     return nn | ((int)(mb.size() / 2) << 16);
 }
 
+// Quadtree in the flat format of img_env_b200/csrc/sfmtree.cuh: nodes[n][5] = x,y,w,h,child0 (children tree1..tree4
+// get consecutive ids), leaf[NA][4] = leaves holding agent a (-1 empty), hash[NA] = treehash[a]. Returns n.
+int ref_sfm_tree2(void* h, double* nodes, int max_nodes, int* leaf, int* hash) {
+    Ref* r = static_cast<Ref*>(h); PedScene* s = sfm_of(r); if (!s) return 0;
+    int na = r->svc.ImgEnv_env.relation_ped_robo == 1 ? ref_sfm_num_agents(h) : (int)s->peds_sim_.size();
+    std::vector<Ped::Ttree*> order; std::map<Ped::Ttree*, int> id;
+    order.push_back(s->pedscene_->tree); id[s->pedscene_->tree] = 0;
+    for (size_t k = 0; k < order.size(); k++) {
+        Ped::Ttree* t = order[k];
+        if (!t->isleaf) { Ped::Ttree* c[4] = {t->tree1, t->tree2, t->tree3, t->tree4}; for (int q = 0; q < 4; q++) { id[c[q]] = (int)order.size(); order.push_back(c[q]); } }
+    }
+    if ((int)order.size() > max_nodes) return -1;
+    for (size_t k = 0; k < order.size(); k++) {
+        Ped::Ttree* t = order[k]; double* o = nodes + 5 * k;
+        o[0] = t->x; o[1] = t->y; o[2] = t->w; o[3] = t->h; o[4] = t->isleaf ? -1 : id[t->tree1];
+    }
+    for (int a = 0; a < na; a++) {
+        Ped::Tagent* ag = sfm_agent(s, a);
+        for (int q = 0; q < 4; q++) leaf[4 * a + q] = -1;
+        int n = 0;
+        for (size_t k = 0; k < order.size(); k++) if (order[k]->isleaf && order[k]->agents.count(ag) && n < 4) leaf[4 * a + n++] = (int)k;
+        auto it = s->pedscene_->treehash.find(ag);
+        hash[a] = it == s->pedscene_->treehash.end() ? -1 : id[it->second];
+    }
+    return (int)order.size();
+}
+
 // obs_map_ / peds_map_ of the node (for raster-level checks)
 void ref_get_map(void* h, int which, uint8_t* out) {
     Ref* r = static_cast<Ref*>(h);

@@ -51,13 +51,15 @@ def base_cfg(R=1, P=0, scene="rvoscene", n_obj=4, map_px=110, ped_shape="leg", r
     return cfg
 
 
-def make_reset(spec, rng, n_obj=None, lo=2.5, hi=8.5, robots_xy=None, peds_xy=None):
+def make_reset(spec, rng, n_obj=None, lo=2.5, hi=8.5, robots_xy=None, peds_xy=None, ylo=None, yhi=None):
     """Seeded ResetEnv request in the array layout of include/imgenv.h / oracle/ref_driver.cpp."""
     R, P = spec["R"], spec["P"]
     n_obj = spec["max_obstacles"] if n_obj is None else n_obj
+    ylo = lo if ylo is None else ylo
+    yhi = hi if yhi is None else yhi
     obs = np.zeros((n_obj, 11))
     for k in range(n_obj):
-        x, y, yaw = rng.uniform(lo, hi), rng.uniform(lo, hi), rng.uniform(-3.14, 3.14)
+        x, y, yaw = rng.uniform(lo, hi), rng.uniform(ylo, yhi), rng.uniform(-3.14, 3.14)
         if k % 2 == 0:
             obs[k, :5] = [0, 0, 0, 0.3, 0]
         else:
@@ -66,16 +68,16 @@ def make_reset(spec, rng, n_obj=None, lo=2.5, hi=8.5, robots_xy=None, peds_xy=No
         obs[k, 7:11] = rpy_to_q(yaw)
     robots = np.zeros((R, 8))
     for j in range(R):
-        x, y = (rng.uniform(lo, hi), rng.uniform(lo, hi)) if robots_xy is None else robots_xy[j]
+        x, y = (rng.uniform(lo, hi), rng.uniform(ylo, yhi)) if robots_xy is None else robots_xy[j]
         robots[j, :2] = [x, y]
         robots[j, 2:6] = rpy_to_q(rng.uniform(-3.14, 3.14))
-        robots[j, 6:8] = [rng.uniform(lo, hi), rng.uniform(lo, hi)]
+        robots[j, 6:8] = [rng.uniform(lo, hi), rng.uniform(ylo, yhi)]
     peds = np.zeros((P, 8)); traj_len = np.zeros(P, np.int32); traj = np.zeros((P, 2, 3))
     for j in range(P):
-        x, y = (rng.uniform(lo, hi), rng.uniform(lo, hi)) if peds_xy is None else peds_xy[j]
+        x, y = (rng.uniform(lo, hi), rng.uniform(ylo, yhi)) if peds_xy is None else peds_xy[j]
         peds[j, :2] = [x, y]
         peds[j, 2:6] = rpy_to_q(rng.uniform(-3.14, 3.14))
-        peds[j, 6:8] = [rng.uniform(lo, hi), rng.uniform(lo, hi)]
+        peds[j, 6:8] = [rng.uniform(lo, hi), rng.uniform(ylo, yhi)]
         traj_len[j] = 2                                    # go_back: yes (reset_helper.py:337-342)
         traj[j, 0] = [peds[j, 6], peds[j, 7], 0]
         traj[j, 1] = [x, y, 0]

@@ -15,7 +15,7 @@ def _to_np(out, s):
 
 
 def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False, n_obj=None, lo=2.5, hi=8.5,
-                 check_view=True):
+                 check_view=True, tree_sync="once", ylo=None, yhi=None):
     import torch
     from img_env_b200.lib import BatchedSim
     from oracle.pyref import RefEnv, PyPost, have_ref
@@ -27,7 +27,7 @@ def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False
     sim = BatchedSim(spec, num_scenes=S, ped_yaw_mode=1)
     refs = [RefEnv(spec) for _ in range(S)]
     posts = [PyPost(spec) for _ in range(S)]
-    resets = [make_reset(spec, rng, n_obj=n_obj, lo=lo, hi=hi) for _ in range(S)]
+    resets = [make_reset(spec, rng, n_obj=n_obj, lo=lo, hi=hi, ylo=ylo, yhi=yhi) for _ in range(S)]
     out = sim.reset(resets)
     torch.cuda.synchronize()
     errs = []
@@ -41,6 +41,10 @@ def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False
             if nb:
                 errs.append("reset scene %d: %d view_map pixels differ" % (s, nb))
     assert not errs, "\n".join(errs[:20])
+    sfm = spec["scene_type"] == "pedscene" and spec["P"] > 0
+    if sfm:   # the node's quadtree depends on the process-global rand() history: import it once, then only emulate
+        for s in range(S):
+            sim.sfm_tree_set(*refs[s].sfm_tree(), scene=s)
     dones = np.zeros((S, R), np.int64)
     for t in range(steps):
         acts = np.stack([random_actions(R, rng, beep=beep) for _ in range(S)])
@@ -64,6 +68,9 @@ def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False
                     a = refs[s].rvo_get() if spec["scene_type"] in ("rvoscene", "ervoscene") else refs[s].sfm_get()
                     svs.append(a.astype(np.float64))
             sim.set_internal(np.stack(rbs), np.stack(pds) if spec["P"] else None, np.stack(svs) if svs else None)
+            if sfm and tree_sync == "every":
+                for s in range(S):
+                    sim.sfm_tree_set(*refs[s].sfm_tree(), scene=s)
         out = sim.step(torch.from_numpy(acts).cuda(), torch.from_numpy(alive).cuda())
         torch.cuda.synchronize()
         vm = sim.debug_view_maps() if check_view else None
@@ -76,6 +83,10 @@ def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False
             rb, pd, sv = sim.get_internal()
             if not np.allclose(rb[s][:, :12], rb_ref[:, :12], rtol=1e-4, atol=1e-6):
                 errs.append("step %d scene %d: robot internal state differs" % (t, s))
+            if sfm:
+                vis_ref = refs[s].sfm_get()[: sim.solver_agents, 10]
+                if not np.array_equal(sv[s][:, 10], vis_ref):
+                    errs.append("step %d scene %d: quadtree membership differs: %s vs %s" % (t, s, sv[s][:, 10], vis_ref))
             if spec["P"] and not np.allclose(pd[s][:, [0, 1, 6, 7, 8, 10, 11, 12, 14, 15, 17]], pd_ref[:, [0, 1, 6, 7, 8, 10, 11, 12, 14, 15, 17]], rtol=1e-4, atol=1e-5):
                 errs.append("step %d scene %d: pedestrian state differs\n%s\n%s" % (t, s, pd[s][:, :8], pd_ref[:, :8]))
             if check_view:
@@ -122,9 +133,15 @@ def test_c5_sfm():
 
 
 def test_sfm_many_agents_in_tree_bounds():
-    # y in [10, 20] keeps agents inside the quadtree root box (pedscene.h:19): neighbours stay visible
+    # y in [10, 20] keeps agents inside the quadtree root box (pedscene.h:19): neighbours stay visible, leaves split
     cfg = base_cfg(R=4, P=12, scene="pedscene", n_obj=2, max_ped=12, map_px=220)
-    run_lockstep(cfg, seed=8, steps=6, lo=3.0, hi=17.0)
+    # (x must stay in [0,10]: the reference itself recurses forever when > 8 agents sit beyond the same side of the root box)
+    run_lockstep(cfg, seed=8, steps=10, lo=1.5, hi=8.5, ylo=8.0, yhi=19.0)
+
+
+def test_sfm_quadtree_splits_64_agents():
+    cfg = base_cfg(R=8, P=56, scene="pedscene", n_obj=0, max_ped=56, map_px=220)
+    run_lockstep(cfg, seed=10, steps=8, lo=1.0, hi=9.0, ylo=6.0, yhi=19.0, check_view=False)
 
 
 def test_omni_and_limiters():
