@@ -211,14 +211,18 @@ __device__ inline void ped_gait(const Dev& d, int pi, int p) {
 __device__ __forceinline__ bool robot_alive(const Dev& d, const uint8_t* alive, int idx) {
     return alive ? alive[idx] != 0 : RBF(d, RB_DONE, idx) == 0.0;
 }
-__device__ __forceinline__ int dyn_nblk(const Cfg& c) { int n = c.NA > c.R ? c.NA : c.R; return (n + DYN_THREADS - 1) / DYN_THREADS; }
+__host__ __device__ __forceinline__ int dyn_nblk(const Cfg& c) {
+    int n = c.NA > c.R ? c.NA : c.R;
+    if (c.scene_type == 4 && c.P > n) n = c.P;
+    return (n + DYN_THREADS - 1) / DYN_THREADS;
+}
 
 __global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* actions, const uint8_t* alive) {
     extern __shared__ __align__(16) unsigned char dsm[];
     const Cfg& c = d.c;
     const int nblk = dyn_nblk(c);
     const int s = blockIdx.x / nblk, blk = blockIdx.x % nblk, tid = threadIdx.x;
-    if (!(c.P > 0 && c.scene_type != 0)) return;
+    if (!(c.P > 0 && c.scene_type != 0 && c.scene_type != 4)) return;
     V2* pos = reinterpret_cast<V2*>(dsm);
     V2* vel = pos + c.NA;
     V2* beep_p = vel + c.NA;
@@ -332,6 +336,18 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_apply(Dev d, const float* a
             }
         }
     }
+    if (c.scene_type == 4 && a < c.P) {   // ImgEnv::_step_ped_dataset (img_env.cpp:361-386): replay trajectory[step_]
+        const int pi = s * c.P + a;
+        const int tl = d.traj_len[pi];
+        const unsigned long long st = d.step_no[s];
+        const int ti = st >= (unsigned long long)tl ? tl - 1 : (int)st;
+        const double* tp = d.traj + ((size_t)pi * c.max_traj + ti) * 3;
+        const double* tv = d.traj_v + ((size_t)pi * c.max_traj + ti) * 3;
+        PDF(d, PD_LX, pi) = PDF(d, PD_X, pi); PDF(d, PD_LY, pi) = PDF(d, PD_Y, pi); PDF(d, PD_LYAW, pi) = PDF(d, PD_YAW, pi);
+        PDF(d, PD_X, pi) = tp[0]; PDF(d, PD_Y, pi) = tp[1]; PDF(d, PD_YAW, pi) = atan2(tv[1], tv[0]);
+        PDF(d, PD_VX, pi) = tv[0]; PDF(d, PD_VY, pi) = tv[1];
+        ped_gait(d, pi, a);
+    }
     // ---- robots (img_env.cpp:388-419). Robot j is handled by the thread that (if the robots are solver
     // agents) also updated solver agent P + j, so the solver write above is ordered before the overwrite below.
     const bool robots_in_solver = c.relation == 1 && c.NA > 0;
@@ -362,7 +378,6 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_apply(Dev d, const float* a
             }
         }
     }
-    if (blk == 0 && tid == 0) d.step_no[s] += 1;
 }
 
 // Tscene::moveAgent for every agent in index order (the order Tscene::moveAgents moves them): one thread per scene.

@@ -116,7 +116,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     c.S = cfg->num_scenes; c.R = cfg->num_robots; c.P = cfg->num_peds;
     c.scene_type = c.P > 0 ? cfg->scene_type : 0;
     c.relation = cfg->relation_ped_robo;
-    c.NA = (c.scene_type != 0) ? c.P + (c.relation == 1 ? c.R : 0) : 0;
+    c.NA = (c.scene_type != 0 && c.scene_type != 4) ? c.P + (c.relation == 1 ? c.R : 0) : 0;
     c.H = H; c.W = W; c.Wb = (W + 31) / 32; c.Hc = (H + 31) / 32;
     c.res = f32(cfg->view_resolution);
     double vwid = f32(cfg->view_width), vhei = f32(cfg->view_height);
@@ -142,7 +142,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     if (c.state_dim < 3 || c.state_dim > 5) return fail("imgenv_create: state_dim must be 3, 4 or 5");
     if (c.R < 1 || c.R > 4096 || c.P < 0 || c.P > 4096 || c.S < 1) return fail("imgenv_create: bad S/R/P");
     if (c.range_total > 4000 || c.range_total < 1) return fail("imgenv_create: range_total out of range");
-    if (c.scene_type < 0 || c.scene_type > 3) return fail("imgenv_create: unknown scene type");
+    if (c.scene_type < 0 || c.scene_type > 4) return fail("imgenv_create: unknown scene type");
 
     // ---- static tables ----
     std::vector<short> need_idx, tap, coef;
@@ -234,7 +234,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
 #define AL(field, n) if (dalloc(h, &d.field, (size_t)(n))) return -1;
     AL(occ_all, S * H * c.Wb) AL(flags, S * pc) AL(rmin, S * pc) AL(coarse, S * c.Hc * c.Wb)
     AL(rb, (size_t)RB_FIELDS * S * c.R) AL(pd, (size_t)PD_FIELDS * S * c.P)
-    AL(traj, S * c.P * c.max_traj * 3) AL(traj_len, S * c.P) AL(obs, S * c.max_obs * 8) AL(n_obs, S) AL(step_no, S)
+    AL(traj, S * c.P * c.max_traj * 3) AL(traj_v, c.scene_type == 4 ? S * c.P * c.max_traj * 3 : 1) AL(traj_len, S * c.P) AL(obs, S * c.max_obs * 8) AL(n_obs, S) AL(step_no, S)
     AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_nvel, S * c.NA * 2) AL(sfm_force, c.scene_type == 1 ? S * c.NA * 12 : 1) AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 3)
     AL(rvo_counts, S * 2) AL(sfm, S * c.NA * SFM_REC) AL(sfm_obs, S * c.max_obs * 4) AL(sfm_nobs, S)
     AL(sfm_wp, S * c.P * (1 + c.max_traj) * 3)
@@ -284,7 +284,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         CK(cudaMemcpy(d.rvo_counts, rc.data(), rc.size() * 4, cudaMemcpyHostToDevice));
     }
     // reset staging: per scene doubles = obs 8*max_obs + robots 5*R + peds 5*P + traj 3*max_traj*P + sfm segs 4*max_obs
-    h->st_doubles = S * ((size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 3 * (size_t)c.max_traj * c.P + 4 * c.max_obs) + 8;
+    h->st_doubles = S * ((size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 6 * (size_t)c.max_traj * c.P + 4 * c.max_obs) + 8;
     h->st_ints = S * ((size_t)5 + c.P + 3 * (size_t)d.max_verts) + S + 8;
     h->st_floats = S * ((size_t)8 * d.max_verts) + 8;
     CK(cudaMallocHost((void**)&h->st_h, h->st_doubles * 8)); if (dalloc(h, &h->st_d, h->st_doubles)) return -1;
@@ -329,7 +329,7 @@ extern "C" int imgenv_bind_outputs(imgenv_t* h, const imgenv_outputs* o) {
 }
 
 // staged reset record layout (per listed scene), doubles:
-//   obs[max_obs][8] | robots[R][5] x,y,yaw,gx,gy | peds[P][5] x,y,yaw,gx,gy | traj[P][max_traj][3] | segs[max_obs][4]
+//   obs[max_obs][8] | robots[R][5] x,y,yaw,gx,gy | peds[P][5] x,y,yaw,gx,gy | traj[P][max_traj][3] | segs[max_obs][4] | traj_v[P][max_traj][3]
 // ints: scene_id, n_obs, n_segs, n_verts, root | traj_len[P] | nodes[max_verts][3]   floats: verts[max_verts][8]
 __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, const float* stf, size_t dper, size_t iper, size_t fper) {
     const Cfg& c = d.c;
@@ -339,6 +339,7 @@ __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, co
     int s = I[0];
     const double* obs = D; const double* rob = obs + 8 * (size_t)c.max_obs; const double* ped = rob + 5 * (size_t)c.R;
     const double* traj = ped + 5 * (size_t)c.P; const double* segs = traj + 3 * (size_t)c.max_traj * c.P;
+    const double* trajv = segs + 4 * (size_t)c.max_obs;
     const int* tl = I + 5; const int* nodes = tl + c.P;
     for (int k = threadIdx.x; k < 8 * c.max_obs; k += blockDim.x) d.obs[(size_t)s * c.max_obs * 8 + k] = obs[k];
     for (int k = threadIdx.x; k < 4 * c.max_obs; k += blockDim.x) d.sfm_obs[(size_t)s * c.max_obs * 4 + k] = segs[k];
@@ -374,6 +375,7 @@ __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, co
         PDF(d, PD_TIDX, pi) = 0;
         d.traj_len[pi] = tl[p];
         for (int k = 0; k < 3 * c.max_traj; k++) d.traj[(size_t)pi * c.max_traj * 3 + k] = traj[(size_t)p * c.max_traj * 3 + k];
+        if (c.scene_type == 4) for (int k = 0; k < 3 * c.max_traj; k++) d.traj_v[(size_t)pi * c.max_traj * 3 + k] = trajv[(size_t)p * c.max_traj * 3 + k];
         if (c.scene_type == 2 || c.scene_type == 3) {                       // setPedPos (velocity is NOT reset by the node)
             d.rvo_pos[((size_t)s * c.NA + p) * 2] = (float)q[0]; d.rvo_pos[((size_t)s * c.NA + p) * 2 + 1] = (float)q[1];
         } else if (c.scene_type == 1) {
@@ -395,7 +397,7 @@ static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int i
     if (ev) cudaEventRecord(ev[2], st);
     k_view<false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
     if (ev) cudaEventRecord(ev[3], st);
-    k_stamp_agents<<<n_scenes * (c.R + c.P), 128, 0, st>>>(d, d_scene_ids, 1);
+    k_stamp_agents<<<n_scenes * (c.R + c.P), 128, 0, st>>>(d, d_scene_ids, is_reset ? 1 : 2);    // 2: also step_++
     if (ev) cudaEventRecord(ev[4], st);
     CK(cudaGetLastError());
     return 0;
@@ -403,7 +405,7 @@ static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int i
 
 extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, const int32_t* n_obs, const double* obs,
                             const double* robots, const double* peds, const int32_t* traj_len, const double* traj,
-                            int32_t ignore_obstacle, void* stream) {
+                            const double* traj_v, int32_t ignore_obstacle, void* stream) {
     if (!h) return fail("imgenv_reset: null handle");
     if (!h->outputs_bound) return fail("imgenv_reset: outputs not bound (imgenv_bind_outputs)");
     Dev& d = h->d; const Cfg& c = d.c;
@@ -412,7 +414,8 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaStreamSynchronize(st));   // staging buffers are reused
     using ht::f32;
-    size_t dper = (size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 3 * (size_t)c.max_traj * c.P + 4 * c.max_obs;
+    if (c.scene_type == 4 && !traj_v) return fail("imgenv_reset: dataset replay needs traj_v");
+    size_t dper = (size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 6 * (size_t)c.max_traj * c.P + 4 * c.max_obs;
     size_t iper = (size_t)5 + c.P + 3 * (size_t)d.max_verts;
     size_t fper = (size_t)8 * d.max_verts;
     memset(h->st_h, 0, dper * n * 8); memset(h->sti_h, 0, iper * n * 4); memset(h->stf_h, 0, fper * n * 4);
@@ -422,6 +425,7 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
         double* D = h->st_h + dper * sl; int* I = h->sti_h + iper * sl; float* Fp = h->stf_h + fper * sl;
         double* o_obs = D; double* o_rob = o_obs + 8 * (size_t)c.max_obs; double* o_ped = o_rob + 5 * (size_t)c.R;
         double* o_traj = o_ped + 5 * (size_t)c.P; double* o_seg = o_traj + 3 * (size_t)c.max_traj * c.P;
+        double* o_trajv = o_seg + 4 * (size_t)c.max_obs;
         int no = n_obs ? n_obs[sl] : 0;
         if (no < 0 || no > c.max_obs) return fail("imgenv_reset: too many obstacles for max_obstacles");
         I[0] = s; I[1] = no;
@@ -473,6 +477,7 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
             if (tl < 1 || tl > c.max_traj) return fail("imgenv_reset: pedestrian trajectory length must be in [1, max_traj]");
             I[5 + p] = tl;
             for (int k = 0; k < 3 * tl; k++) o_traj[(size_t)p * c.max_traj * 3 + k] = traj[((size_t)sl * c.P + p) * c.max_traj * 3 + k];
+            if (c.scene_type == 4) for (int k = 0; k < 3 * tl; k++) o_trajv[(size_t)p * c.max_traj * 3 + k] = traj_v[((size_t)sl * c.P + p) * c.max_traj * 3 + k];
         }
     }
     CK(cudaMemcpyAsync(h->st_d, h->st_h, dper * n * 8, cudaMemcpyHostToDevice, st));
@@ -504,7 +509,7 @@ extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d
     if (h->prof_n < h->prof_max) { ev = h->evs.data() + 5 * (size_t)h->prof_n; h->prof_n++; }
     if (ev) cudaEventRecord(ev[0], st);
     {
-        const int nmax = c.NA > c.R ? c.NA : c.R, nblk = (nmax + DYN_THREADS - 1) / DYN_THREADS;
+        const int nblk = dyn_nblk(c);
         if (c.NA > 0) k_dyn_solve<<<c.S * nblk, DYN_THREADS, h->dyn_smem, st>>>(d, d_actions, d_alive);
         k_dyn_apply<<<c.S * nblk, DYN_THREADS, 0, st>>>(d, d_actions, d_alive, h->ped_yaw_mode);
         if (c.scene_type == 1) k_sfm_tree<<<(c.S + 31) / 32, 32, 0, st>>>(d);

@@ -112,6 +112,7 @@ struct Dev {
     double* rb;                   // [RB_FIELDS][S*R]
     double* pd;                   // [PD_FIELDS][S*P]
     double* traj;                 // [S][P][max_traj][3]
+    double* traj_v;               // [S][P][max_traj][3] (dataset replay)
     int* traj_len;                // [S][P]
     double* obs;                  // [S][max_obs][8]: shape, size[4], x, y, yaw
     int* n_obs;                   // [S]

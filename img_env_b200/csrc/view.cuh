@@ -106,6 +106,7 @@ __global__ void k_stamp_agents(Dev d, const int* scene_ids, int unstamp) {
     int sl = blockIdx.x / per, a = blockIdx.x % per;
     int s = scene_ids ? scene_ids[sl] : sl;
     int add = unstamp ? 8 : 0;
+    if (unstamp == 2 && a == 0 && threadIdx.x == 0) d.step_no[s] += 1;   // step_++ (img_env.cpp:518), after every reader of this step
     if (a < d.c.R) {
         int idx = s * d.c.R + a;
         Tf2 t = tf_from_pose(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx));

@@ -145,6 +145,7 @@ class BatchedSim:
         n_obs = np.zeros(n, np.int32)
         obs = np.zeros((n, mo, 11)); robots = np.zeros((n, self.R, 8)); peds = np.zeros((n, max(self.P, 1), 8))
         tl = np.zeros((n, max(self.P, 1)), np.int32); traj = np.zeros((n, max(self.P, 1), mt, 3))
+        trajv = np.zeros((n, max(self.P, 1), mt, 3)) if self.spec["scene_type"] == "dataset" else None
         ign = 0
         for i, rs in enumerate(resets):
             o = np.asarray(rs["obs"], dtype=np.float64).reshape(-1, 11)
@@ -156,9 +157,11 @@ class BatchedSim:
                 tl[i] = np.asarray(rs["traj_len"], dtype=np.int32)
                 for p in range(self.P):
                     traj[i, p, : tl[i, p]] = np.asarray(rs["traj"][p], dtype=np.float64).reshape(-1, 3)[: tl[i, p]]
+                    if trajv is not None:
+                        trajv[i, p, : tl[i, p]] = np.asarray(rs["traj_v"][p], dtype=np.float64).reshape(-1, 3)[: tl[i, p]]
             ign = int(rs.get("ignore_obstacle", 0))
         rc = self.lib.imgenv_reset(self.h, n, _ptr(ids, C.c_int32), _ptr(n_obs, C.c_int32), _ptr(obs), _ptr(robots), _ptr(peds),
-                                   _ptr(tl, C.c_int32), _ptr(traj), ign, self._stream())
+                                   _ptr(tl, C.c_int32), _ptr(traj), _ptr(trajv) if trajv is not None else None, ign, self._stream())
         self._check(rc)
         return self.out
 

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 SHAPES = {"circle": 0, "rectangle": 1, "leg": 2}
-SCENES = {"": 0, "pedscene": 1, "rvoscene": 2, "ervoscene": 3}
+SCENES = {"": 0, "pedscene": 1, "rvoscene": 2, "ervoscene": 3, "dataset": 4}
 KTYPES = {"diff": 0, "omni": 1}
 
 
@@ -101,5 +101,5 @@ def build_spec(cfg, map_dir=None, opt_in_beep=False):
                 image_size=tuple(cfg["image_size"]), ped_image_size=tuple(cfg["ped_image_size"]), max_ped=int(cfg["max_ped"]),
                 ped_vec_dim=int(cfg["ped_vec_dim"]), ped_image_r=float(cfg["ped_image_r"]), laser_max=float(cfg["laser_max"]),
                 laser_norm=bool(cfg.get("laser_norm", True)), robot_size_last=size_last,
-                max_obstacles=int(cfg.get("object", {}).get("total", 0)), max_traj=2,
+                max_obstacles=int(cfg.get("object", {}).get("total", 0)), max_traj=int(cfg["ped_sim"].get("max_traj", 2)),
                 ignore_obstacle=bool(cfg["ped_sim"].get("ignore_obstacle", False)))

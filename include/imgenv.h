@@ -28,7 +28,8 @@ extern "C" {
 
 typedef struct imgenv imgenv_t;
 
-enum { IMGENV_SCENE_EMPTY = 0, IMGENV_SCENE_PEDSCENE = 1, IMGENV_SCENE_RVO = 2, IMGENV_SCENE_ERVO = 3 };
+enum { IMGENV_SCENE_EMPTY = 0, IMGENV_SCENE_PEDSCENE = 1, IMGENV_SCENE_RVO = 2, IMGENV_SCENE_ERVO = 3,
+       IMGENV_SCENE_DATASET = 4 /* trajectory replay, ImgEnv::_step_ped_dataset img_env.cpp:361-386 */ };
 enum { IMGENV_SHAPE_CIRCLE = 0, IMGENV_SHAPE_RECTANGLE = 1, IMGENV_SHAPE_LEG = 2 };
 enum { IMGENV_KTYPE_DIFF = 0, IMGENV_KTYPE_OMNI = 1 };
 
@@ -89,11 +90,12 @@ int imgenv_bind_outputs(imgenv_t* h, const imgenv_outputs* out);
  *   scene_ids[n]; n_obs[n]; obs[n][max_obstacles][11] = shape,size[4],x,y,q[4]
  *   robots[n][R][8] = x,y,q[4],goal_x,goal_y ;  peds[n][P][8] likewise
  *   traj_len[n][P] ; traj[n][P][max_traj][3]   (Agent.msg trajectory, reset_helper.py:337-342)
+ *   traj_v[n][P][max_traj][3] or NULL          (Agent.msg trajectory_v; dataset replay only, reset_helper.py:417-434)
  * Runs the node's _reset (img_env.cpp:162-292) incl. view_agent + get_states, then the Python
  * _get_states; outputs of those scenes are written to the bound tensors. */
 int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, const int32_t* n_obs, const double* obs,
                  const double* robots, const double* peds, const int32_t* traj_len, const double* traj,
-                 int32_t ignore_obstacle, void* stream);
+                 const double* traj_v, int32_t ignore_obstacle, void* stream);
 
 /* StepEnv.srv for all S scenes. d_actions[S][R][3] = v, w, v_y(beep) float32 DEVICE pointer;
  * d_alive[S][R] uint8 DEVICE pointer, or NULL to use the library's own dones bookkeeping

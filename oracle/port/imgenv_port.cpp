@@ -106,7 +106,7 @@ struct Ped {     // PedAgent
     int shape = 0; double size[6] = {0, 0, 0, 0, 0, 0}; double max_speed = 0; Pts bbox, lbox, rbox;
     double x = 0, y = 0, yaw = 0, lx = 0, ly = 0, lyaw = 0, vx = 0, vy = 0;
     int state = 0, last_state = 0; double rem = 0, ll[3] = {0, 0, 0}, rl[3] = {0, 0, 0};
-    int tidx = 0; std::vector<double> traj;   // xyz triples
+    int tidx = 0; std::vector<double> traj, trajv;   // xyz triples
 };
 
 // ---------------- RVO2 (ervo_ros) ----------------
@@ -401,6 +401,7 @@ struct Port {
     T2 view_base, base_view;
     Rvo rvo; Sfm sfm;
     std::vector<double> obj_seg;
+    int step_ = 0;
     // last reply
     std::vector<std::vector<float>> st_state, st_laser, st_ped; std::vector<int> st_coll, st_arr;
 };
@@ -531,7 +532,7 @@ int port_init(void* h, const double* sc, double, const uint8_t* grid, int H, int
     P.beep_r = f32(sc[17]); P.ped_ca_p = f32(sc[18]); P.relation = (int)sc[19];
     P.ktype = std::string(ktype) == "omni" ? 1 : 0;
     std::string st = scene_type;
-    P.scene = Pn == 0 ? 0 : (st == "pedscene" ? 1 : st == "rvoscene" ? 2 : st == "ervoscene" ? 3 : 0);
+    P.scene = Pn == 0 ? 0 : (st == "pedscene" ? 1 : st == "rvoscene" ? 2 : st == "ervoscene" ? 3 : st == "dataset" ? 4 : 0);
     P.vw = (int)(P.vwid / P.res); P.vh = (int)(P.vhei / P.res);
     P.view_base = t2_pose(P.vhei / 2, P.vwid / 2, 3.14159); P.base_view = t2_inv(P.view_base);   // agent.cpp:79-90
     P.stat.h = H; P.stat.w = W; P.stat.res = P.res; P.stat.m.assign(grid, grid + (size_t)H * W); P.obsm = P.stat;
@@ -549,15 +550,16 @@ int port_init(void* h, const double* sc, double, const uint8_t* grid, int H, int
         if (p.shape == 0) shape_circle(p.size[0], p.size[1], p.size[2], p.bbox);
         else if (p.shape == 2) { shape_circle(0, 0, p.size[2], p.lbox); shape_circle(0, 0, p.size[5], p.rbox); }
     }
-    int NA = P.scene ? Pn + (P.relation == 1 ? R : 0) : 0;
+    int NA = (P.scene && P.scene != 4) ? Pn + (P.relation == 1 ? R : 0) : 0;
     if (P.scene == 2 || P.scene == 3) { P.rvo.ag.assign(NA, RvoAgent()); P.rvo.dt = (float)P.step_hz; for (int i = 0; i < NA; i++) P.rvo.ag[i].maxSpeed = i < Pn ? (float)P.peds[i].max_speed : 0.6f; }
     if (P.scene == 1) { P.sfm.ag.assign(NA, SfmAgent()); for (int i = 0; i < Pn; i++) P.sfm.ag[i].vmax = P.peds[i].max_speed; }
     return 0;
 }
 
 int port_reset(void* h, int n_obs, const double* obs, const double* robots, const double* peds, const int* traj_len, const double* traj,
-               const int*, const double*, int ignore_obstacle) {   // img_env.cpp:162-292
+               const int* trajv_len, const double* trajv, int ignore_obstacle) {   // img_env.cpp:162-292
     Port& P = *static_cast<Port*>(h);
+    P.step_ = 0;
     P.obsm = P.stat; P.rvo.ob.clear(); P.sfm.obs.clear();
     for (int i = 0; i < n_obs; i++) {
         const double* d = obs + 11 * i; int shape = (int)d[0]; double size[4]; for (int k = 0; k < 4; k++) size[k] = f32(d[1 + k]);
@@ -574,14 +576,16 @@ int port_reset(void* h, int n_obs, const double* obs, const double* robots, cons
     int Pn = (int)P.peds.size(), R = (int)P.robots.size(); size_t to = 0;
     for (int i = 0; i < Pn; i++) {
         const double* d = peds + 8 * i; Ped& p = P.peds[i];
-        p.x = d[0]; p.y = d[1]; p.yaw = quat_yaw(d[2], d[3], d[4], d[5]); p.tidx = 0; p.traj.assign(traj + 3 * to, traj + 3 * (to + traj_len[i])); to += traj_len[i];
+        p.x = d[0]; p.y = d[1]; p.yaw = quat_yaw(d[2], d[3], d[4], d[5]); p.tidx = 0; p.traj.assign(traj + 3 * to, traj + 3 * (to + traj_len[i]));
+        if (trajv_len && trajv) p.trajv.assign(trajv + 3 * to, trajv + 3 * (to + trajv_len[i]));
+        to += traj_len[i];
         if (P.scene == 2 || P.scene == 3) P.rvo.ag[i].pos = mk((float)d[0], (float)d[1]);
         if (P.scene == 1) { SfmAgent& a = P.sfm.ag[i]; a.p = d3(d[0], d[1], 0); a.wp.clear(); a.wp.push_back(d3(d[6], d[7], 1)); for (int k = 0; k < traj_len[i]; k++) a.wp.push_back(d3(p.traj[3 * k], p.traj[3 * k + 1], p.traj[3 * k + 2])); a.dest = 0; a.lastdest = -1; a.front = 0; }
     }
     for (int i = 0; i < R; i++) {
         const double* d = robots + 8 * i; Robot& r = P.robots[i];
         r.x = d[0]; r.y = d[1]; r.yaw = quat_yaw(d[2], d[3], d[4], d[5]); r.l0v = r.l0w = 0; r.gx = d[6]; r.gy = d[7]; r.gyaw = r.yaw; r.coll = 0; r.arrive = false;
-        if (P.relation == 1 && P.scene) {
+        if (P.relation == 1 && P.scene && P.scene != 4) {
             if (P.scene == 1) P.sfm.ag[Pn + i].p = d3(d[0], d[1], 1);
             else { P.rvo.ag[Pn + i].pos = mk((float)d[0], (float)d[1]); P.rvo.ag[Pn + i].vel = mk(0, 0); }
         }
@@ -594,7 +598,21 @@ int port_reset(void* h, int n_obs, const double* obs, const double* robots, cons
 int port_step(void* h, const float* act, const uint8_t* alive) {   // img_env.cpp:304-359, 388-419, 421-525
     Port& P = *static_cast<Port*>(h);
     int Pn = (int)P.peds.size(), R = (int)P.robots.size();
-    if (P.scene) {
+    if (P.scene == 4) {   // _step_ped_dataset, img_env.cpp:361-386
+        for (auto& p : P.peds) {
+            int tl = (int)p.traj.size() / 3, ti = P.step_ >= tl ? tl - 1 : P.step_;
+            double vx = p.trajv[3 * ti], vy = p.trajv[3 * ti + 1];
+            p.lx = p.x; p.ly = p.y; p.lyaw = p.yaw;
+            p.x = p.traj[3 * ti]; p.y = p.traj[3 * ti + 1]; p.yaw = atan2(vy, vx); p.vx = vx; p.vy = vy;
+            if (p.shape == 2) {
+                const double sl = 0.3; double md = sqrt((p.x - p.lx) * (p.x - p.lx) + (p.y - p.ly) * (p.y - p.ly));
+                p.last_state = p.state; p.state = (int)((md + p.rem) / sl + p.last_state); p.rem = md + p.rem - (p.state - p.last_state) * sl; p.state %= 7;
+                if (p.state == 0 || p.state == 4) { p.ll[0] = p.size[0]; p.ll[1] = p.size[1]; p.ll[2] = 0; p.rl[0] = p.size[3]; p.rl[1] = p.size[4]; p.rl[2] = 0; }
+                else if (p.state == 1 || p.state == 3) { p.ll[0] = -sl / 2; p.rl[0] = sl / 2; } else if (p.state == 2) { p.ll[0] = -sl; p.rl[0] = sl; }
+                else if (p.state == 5) { p.ll[0] = sl / 2; p.rl[0] = -sl / 2; } else if (p.state == 6) { p.ll[0] = sl; p.rl[0] = -sl; }
+            }
+        }
+    } else if (P.scene) {
         std::vector<F2> goals, ps; std::vector<float> rs;
         for (auto& p : P.peds) {
             int tl = (int)p.traj.size() / 3;
@@ -650,11 +668,12 @@ int port_step(void* h, const float* act, const uint8_t* alive) {   // img_env.cp
             if (sqrt((r.x - r.gx) * (r.x - r.gx) + (r.y - r.gy) * (r.y - r.gy)) <= 0.3) arr = true;
             r.arrive = arr;
         }
-        if (P.relation == 1 && P.scene) {
+        if (P.relation == 1 && P.scene && P.scene != 4) {
             if (P.scene == 1) P.sfm.ag[Pn + j].p = d3(r.x, r.y, 1);
             else { P.rvo.ag[Pn + j].pos = mk((float)r.x, (float)r.y); P.rvo.ag[Pn + j].vel = mk((float)r.vx, (float)r.vy); }
         }
     }
+    P.step_ += 1;
     observe(P);
     return 0;
 }

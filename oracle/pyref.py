@@ -111,8 +111,12 @@ class RefEnv:
         for i in range(self.P):
             flat.append(np.asarray(traj[i][: tl[i]], dtype=np.float64).reshape(-1, 3))
         flat = _dbl(np.concatenate(flat, 0)) if flat else np.zeros((0, 3))
+        flatv = None
+        if rs.get("traj_v") is not None:
+            flatv = _dbl(np.concatenate([np.asarray(rs["traj_v"][i][: tl[i]], dtype=np.float64).reshape(-1, 3) for i in range(self.P)], 0))
         rc = self.lib.reset(self.h, obs.shape[0], _p(obs, C.c_double), _p(robots, C.c_double), _p(peds, C.c_double),
-                                _p(tl, C.c_int), _p(flat, C.c_double), None, None, int(rs.get("ignore_obstacle", 0)))
+                                _p(tl, C.c_int), _p(flat, C.c_double), _p(tl, C.c_int) if flatv is not None else None,
+                                _p(flatv, C.c_double) if flatv is not None else None, int(rs.get("ignore_obstacle", 0)))
         if rc != 0:
             raise RuntimeError("ref_reset failed")
         return self.get_states()

@@ -140,3 +140,22 @@ def golden_reset_request(g):
 
 def golden_state(g, prefix):
     return {k: g["%s_%s" % (prefix, k)] for k in STATE_KEYS}
+
+
+def make_dataset_reset(spec, rng, T=6, lo=3.0, hi=8.0):
+    """ResetEnv request for trajectory-replay pedestrians (PedTrajectoryDatasetWrapper / EnvPos.init_ped_dataset,
+    reset_helper.py:417-434): per pedestrian T positions (x, y, yaw) and velocities (vx, vy, 0)."""
+    rs = make_reset(spec, rng, lo=lo, hi=hi)
+    P = spec["P"]
+    traj = np.zeros((P, T, 3)); trajv = np.zeros((P, T, 3))
+    for p in range(P):
+        pos = np.array([rng.uniform(lo, hi), rng.uniform(lo, hi)])
+        for t in range(T):
+            v = rng.uniform(-0.8, 0.8, 2)
+            traj[p, t] = [pos[0], pos[1], math.atan2(v[1], v[0])]
+            trajv[p, t] = [v[0], v[1], 0]
+            pos = pos + 0.4 * v
+        rs["peds"][p, :2] = traj[p, 0, :2]
+        rs["peds"][p, 2:6] = rpy_to_q(traj[p, 0, 2])
+    rs["traj"] = traj; rs["traj_v"] = trajv; rs["traj_len"] = np.full(P, T, np.int32)
+    return rs

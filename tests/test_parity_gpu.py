@@ -5,7 +5,7 @@ box) + the restated Python post-processing, single-step on identical pre-step st
 import numpy as np
 import pytest
 
-from helpers import base_cfg, build_spec, compare_state, make_reset, random_actions
+from helpers import base_cfg, build_spec, compare_state, make_dataset_reset, make_reset, random_actions
 
 pytestmark = pytest.mark.gpu
 
@@ -27,7 +27,10 @@ def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False
     sim = BatchedSim(spec, num_scenes=S, ped_yaw_mode=1)
     refs = [RefEnv(spec) for _ in range(S)]
     posts = [PyPost(spec) for _ in range(S)]
-    resets = [make_reset(spec, rng, n_obj=n_obj, lo=lo, hi=hi, ylo=ylo, yhi=yhi) for _ in range(S)]
+    if spec["scene_type"] == "dataset":
+        resets = [make_dataset_reset(spec, rng, T=spec["max_traj"], lo=lo, hi=hi) for _ in range(S)]
+    else:
+        resets = [make_reset(spec, rng, n_obj=n_obj, lo=lo, hi=hi, ylo=ylo, yhi=yhi) for _ in range(S)]
     out = sim.reset(resets)
     torch.cuda.synchronize()
     errs = []
@@ -64,7 +67,7 @@ def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False
                 td = posts[s].tmp_distances
                 rb[:, 15] = td if td is not None else np.nan
                 rbs.append(rb); pds.append(pd)
-                if sim.solver_agents:
+                if sim.solver_agents and spec["scene_type"] != "dataset":
                     a = refs[s].rvo_get() if spec["scene_type"] in ("rvoscene", "ervoscene") else refs[s].sfm_get()
                     svs.append(a.astype(np.float64))
             sim.set_internal(np.stack(rbs), np.stack(pds) if spec["P"] else None, np.stack(svs) if svs else None)
@@ -151,3 +154,9 @@ def test_omni_and_limiters():
     cfg["speed_limiter_w"] = dict(has_velocity_limits=True, has_acceleration_limits=True, has_jerk_limits=False, min_velocity=-0.8,
                                   max_velocity=0.8, min_acceleration=-0.6, max_acceleration=2, min_jerk=0, max_jerk=0)
     run_lockstep(cfg, seed=9, steps=8, beep=True)
+
+
+def test_dataset_replay_pedestrians():
+    cfg = base_cfg(R=2, P=5, scene="dataset", n_obj=2)
+    cfg["ped_sim"]["max_traj"] = 5
+    run_lockstep(cfg, seed=11, steps=8, lo=3.0, hi=8.0)     # runs past the end of the trajectories (index clamps)
