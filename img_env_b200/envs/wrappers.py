@@ -1,10 +1,67 @@
-"""Wrapper registry. The reference's wrapper stack (envs/wrapper/base.py) is a "next" row of the scope
-table; round 1 ships the pass-through registry so cfg `wrapper:` lists load, plus the
-two wrappers that only touch actions/time."""
+"""The reference's wrapper stack (envs/wrapper/base.py, filter_states.py), vectorised.
+
+Same class names, constructor signature `(env, cfg)`, registry `wrapper_dict` and per-robot semantics
+as the reference, but every wrapper works on whole arrays (torch CUDA tensors straight from the
+library, or numpy arrays) instead of per-robot Python loops, and understands an env that batches
+several scenes: arrays have N = S*R rows, scene-major, and `reset(scene_ids=[...])` re-initialises
+only the listed scenes (NeverStopWrapper auto-resets a scene once all of its robots are done).
+Wrappers that only exist for ROS bags / real robots / evaluation harnesses are out of scope
+ and resolve to a pass-through.
+"""
+import math
+import time
+
+import numpy as np
+
+from .action import ContinuousAction, DiscreteActions
 
 
-class _Wrapper:
-    def __init__(self, env, cfg):
+# --------------------------------------------------------------------------------------------
+# tiny array shim: the same code runs on numpy arrays and torch tensors
+# --------------------------------------------------------------------------------------------
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _where(c, a, b):
+    if _is_torch(c):
+        import torch
+        a = a if _is_torch(a) else torch.as_tensor(a, device=c.device)
+        b = b if _is_torch(b) else torch.as_tensor(b, device=c.device)
+        return torch.where(c, a, b)
+    return np.where(c, a, b)
+
+
+def _zeros_like(x):
+    if _is_torch(x):
+        import torch
+        return torch.zeros_like(x)
+    return np.zeros_like(x)
+
+
+def _cat(xs, axis):
+    if _is_torch(xs[0]):
+        import torch
+        return torch.cat(xs, dim=axis)
+    return np.concatenate(xs, axis=axis)
+
+
+def _f64(x):
+    return x.double() if _is_torch(x) else np.asarray(x, dtype=np.float64)
+
+
+def _i64(x):
+    return x.long() if _is_torch(x) else np.asarray(x).astype(np.int64)
+
+
+def _sqrt(x):
+    return x.sqrt() if _is_torch(x) else np.sqrt(x)
+
+
+class Wrapper:
+    """Minimal stand-in for gym.Wrapper (gym is not a dependency)."""
+
+    def __init__(self, env, cfg=None):
         self.env, self.cfg = env, cfg
 
     def __getattr__(self, name):
@@ -13,51 +70,327 @@ class _Wrapper:
     def __len__(self):
         return len(self.env)
 
-    def reset(self, **kw):
-        return self.env.reset(**kw)
+    def reset(self, **kwargs):
+        return self.env.reset(**kwargs)
 
     def step(self, action):
         return self.env.step(action)
 
+    # helpers for batched scenes
+    def _robots_per_scene(self):
+        return int(self.cfg["robot"]["total"])
 
-class VelActionWrapper(_Wrapper):
-    """envs/wrapper/base.py:37-59: discrete index -> (v, w[, beep]) table lookup, or pass continuous through."""
-
-    def __init__(self, env, cfg):
-        super().__init__(env, cfg)
-        import torch
-        self.discrete = bool(cfg.get("discrete_action", False))
-        if self.discrete:
-            tab = [list(a) + [0] * (3 - len(a)) for a in cfg["discrete_actions"]]
-            self.table = torch.tensor(tab, dtype=torch.float32, device=env.sim.device)
-
-    def step(self, action):
-        import torch
-        if self.discrete:
-            idx = torch.as_tensor(action, device=self.env.sim.device).long().reshape(-1)
-            return self.env.step(self.table[idx])
-        return self.env.step(action)
+    def _rows(self, n, scene_ids):
+        """row mask/indices of the robots that belong to `scene_ids` (None = all rows)."""
+        if scene_ids is None:
+            return slice(None)
+        r = self._robots_per_scene()
+        return np.concatenate([np.arange(s * r, (s + 1) * r) for s in scene_ids]) if len(scene_ids) else np.zeros(0, np.int64)
 
 
-class TimeLimitWrapper(_Wrapper):
-    """envs/wrapper/base.py:62-79: dones |= step >= time_max (reported in info['dones_info'] as 10)."""
-
-    def __init__(self, env, cfg):
-        super().__init__(env, cfg)
-        self.time_max = cfg.get("time_max", 100)
-        self.t = 0
-
-    def reset(self, **kw):
-        self.t = 0
-        return self.env.reset(**kw)
+class ObservationWrapper(Wrapper):
+    def reset(self, **kwargs):
+        return self.observation(self.env.reset(**kwargs))
 
     def step(self, action):
         state, reward, done, info = self.env.step(action)
-        self.t += 1
-        if self.t >= self.time_max:
-            info["dones_info"] = info["dones_info"] + (done == 0) * 10
-            done = done * 0 + 1
+        return self.observation(state), reward, done, info
+
+    def observation(self, state):
+        return state
+
+
+class StatePedVectorWrapper(ObservationWrapper):
+    """base.py:19-34: (x - avg) / std on the first ped_tmp[0] pedestrians' 7-vectors."""
+    avg = [0.0, 0.0, 0.0, 0.0, 0.25, 0.25, 0.0]
+    std = [6.0, 6.0, 0.6, 0.9, 0.50, 0.5, 6.0]
+
+    def observation(self, state):
+        p = state.ped_vector_states
+        n = p.shape[0]
+        k = (p.shape[1] - 1) // 7
+        body = p[:, 1:1 + 7 * k].reshape(n, k, 7)
+        if _is_torch(p):
+            import torch
+            avg = torch.tensor(self.avg, dtype=torch.float64, device=p.device); std = torch.tensor(self.std, dtype=torch.float64, device=p.device)
+            idx = torch.arange(k, device=p.device)[None, :] < p[:, :1]
+            norm = ((body.double() - avg) / std).to(p.dtype)
+            p[:, 1:1 + 7 * k] = torch.where(idx[..., None], norm, body).reshape(n, 7 * k)
+        else:
+            idx = np.arange(k)[None, :] < p[:, :1]
+            norm = ((body.astype(np.float64) - np.array(self.avg)) / np.array(self.std)).astype(p.dtype)
+            p[:, 1:1 + 7 * k] = np.where(idx[..., None], norm, body).reshape(n, 7 * k)
+        return state
+
+
+class VelActionWrapper(Wrapper):
+    """base.py:37-66. Discrete: index -> (v, w, beep) table; continuous: per-component clip to cfg ranges."""
+
+    def __init__(self, env, cfg):
+        super().__init__(env, cfg)
+        self.discrete = bool(cfg["discrete_action"])
+        if self.discrete:
+            self.actions = DiscreteActions(cfg["discrete_actions"])
+            self.table = np.array([a.reverse() for a in self.actions.actions], dtype=np.float32)
+        else:
+            self.clip_range = cfg["continuous_actions"]
+
+    def action(self, actions):
+        """-> float32 array [N, 3] of (v, w, beep)"""
+        if _is_torch(actions):
+            actions = actions.detach().cpu().numpy()
+        actions = np.asarray(actions)
+        if self.discrete:
+            if actions.ndim == 1:
+                return self.table[actions.astype(np.int64)]
+            out = np.zeros((actions.shape[0], 3), np.float32); out[:, : actions.shape[1]] = actions
+            return out
+        out = np.zeros((actions.shape[0], 3), np.float32)
+        for i in range(actions.shape[1]):
+            out[:, i] = np.clip(actions[:, i], self.clip_range[i][0], self.clip_range[i][1])
+        return out
+
+    def step(self, action):
+        a = self.action(action)
+        state, reward, done, info = self.env.step(a)
+        info["speeds"] = a[:, :2].astype(np.float64)
         return state, reward, done, info
 
+    def reverse_action(self, actions):
+        return actions
 
-wrapper_dict = {"VelActionWrapper": VelActionWrapper, "TimeLimitWrapper": TimeLimitWrapper}
+
+class MultiRobotCleanWrapper(Wrapper):
+    """base.py:69-95: a robot that finished keeps stepping but its reward / speeds are masked afterwards."""
+
+    def __init__(self, env, cfg):
+        super().__init__(env, cfg)
+        self.is_clean = None
+
+    def step(self, action):
+        state, reward, done, info = self.env.step(action)
+        if self.is_clean is None:
+            self.is_clean = _zeros_like(done) == 0
+        clean = self.is_clean.clone() if _is_torch(self.is_clean) else self.is_clean.copy()
+        info["is_clean"] = clean
+        reward = _where(clean, reward, _zeros_like(reward))
+        if "speeds" in info:
+            c = clean.cpu().numpy() if _is_torch(clean) else clean
+            info["speeds"] = np.where(c[:, None], info["speeds"], 0.0)
+        self.is_clean = _where(done > 0, _zeros_like(clean), clean)
+        return state, reward, done, info
+
+    def reset(self, **kwargs):
+        state = self.env.reset(**kwargs)
+        if self.is_clean is not None:
+            rows = self._rows(len(self.is_clean), kwargs.get("scene_ids"))
+            self.is_clean[rows] = True
+        return state
+
+
+class StateBatchWrapper(Wrapper):
+    """base.py:97-150: frame stacking of sensor_maps / vector_states / lasers (zeros until the queue is full)."""
+
+    def __init__(self, env, cfg):
+        super().__init__(env, cfg)
+        self.depth = {"sensor_maps": cfg["image_batch"] if cfg["image_batch"] > 0 else None,
+                      "vector_states": cfg["state_batch"] if cfg["state_batch"] > 0 else None,
+                      "lasers": max(cfg["laser_batch"], 1) if cfg["laser_batch"] >= 0 else None}
+        self.q = {}
+
+    def _concate(self, name, t, clear_rows):
+        k = self.depth[name]
+        if k is None:
+            return t
+        t1 = t[:, None]
+        if name not in self.q:
+            self.q[name] = _cat([_zeros_like(t1)] * k, 1)
+        q = self.q[name]
+        if clear_rows is not None:
+            q[clear_rows] = 0
+        q = _cat([q[:, 1:], t1], 1)
+        self.q[name] = q
+        return q.clone() if _is_torch(q) else q.copy()
+
+    def batch_state(self, state, clear_rows=None):
+        state.sensor_maps = self._concate("sensor_maps", state.sensor_maps, clear_rows)
+        tmp = self._concate("vector_states", state.vector_states, clear_rows)
+        if self.depth["vector_states"] is not None:
+            tmp = tmp.reshape(tmp.shape[0], tmp.shape[1] * tmp.shape[2])
+        state.vector_states = tmp
+        state.lasers = self._concate("lasers", state.lasers, clear_rows)
+        return state
+
+    def step(self, action):
+        state, reward, done, info = self.env.step(action)
+        return self.batch_state(state), reward, done, info
+
+    def reset(self, **kwargs):
+        state = self.env.reset(**kwargs)
+        n = state.sensor_maps.shape[0]
+        ids = kwargs.get("scene_ids")
+        if ids is None:
+            self.q = {}
+            return self.batch_state(state)
+        # partial reset: only the listed scenes restart their queues; the other rows must not be pushed twice
+        rows = self._rows(n, ids)
+        keep = {k: (v.clone() if _is_torch(v) else v.copy()) for k, v in self.q.items()}
+        out = self.batch_state(state, clear_rows=rows)
+        mask = np.ones(n, bool); mask[rows] = False
+        for k, v in keep.items():
+            self.q[k][mask] = v[mask]
+        # rows of untouched scenes keep showing their current stack
+        for name, attr in (("sensor_maps", "sensor_maps"), ("lasers", "lasers")):
+            if self.depth[name] is not None:
+                getattr(out, attr)[mask] = self.q[name][mask]
+        if self.depth["vector_states"] is not None:
+            q = self.q["vector_states"]
+            out.vector_states[mask] = q.reshape(q.shape[0], -1)[mask]
+        return out
+
+
+class SensorsPaperRewardWrapper(Wrapper):
+    """base.py:152-190 (Sensors-20 reward), one expression over all robots."""
+
+    def __init__(self, env, cfg):
+        super().__init__(env, cfg)
+        self.ped_safety_space = cfg["ped_safety_space"]
+
+    def reward(self, reward, states):
+        md = _f64(states.ped_min_dists)
+        vs = _f64(states.vector_states)
+        coll = _i64(states.is_collisions) > 0
+        arr = _i64(states.is_arrives) > 0
+        step_d = _f64(states.step_ds)
+        zero = _zeros_like(md)
+        collision_reward = _where(md <= self.ped_safety_space, -50 * (self.ped_safety_space - md), zero)
+        collision_reward = _where(coll, zero - 500.0, collision_reward)
+        d = _sqrt(vs[:, 0] ** 2 + vs[:, 1] ** 2)
+        reached = (d < 0.3) | arr
+        reach_reward = _where(~coll & reached, zero + 500.0, zero)
+        moving = ~coll & ~reached
+        distance_reward = _where(moving, step_d * 200, zero)
+        step_reward = _where(moving, zero - 5.0, zero)
+        return collision_reward + reach_reward + step_reward + distance_reward
+
+    def step(self, action):
+        states, reward, done, info = self.env.step(action)
+        return states, self.reward(reward, states), done, info
+
+
+class NeverStopWrapper(Wrapper):
+    """base.py:193-211: reset as soon as every robot (of a scene) is done; must be the outermost wrapper."""
+
+    def step(self, action):
+        states, reward, done, info = self.env.step(action)
+        ad = info["all_down"]
+        ad = ad.cpu().numpy() if _is_torch(ad) else np.asarray(ad)
+        r = self._robots_per_scene()
+        scenes = [s for s in range(len(ad) // r) if ad[s * r]]
+        if scenes:
+            if len(scenes) == len(ad) // r:
+                states = self.env.reset(**{k: v for k, v in info.items() if k == "dones_info"})
+            else:
+                states = self.env.reset(scene_ids=scenes)
+        return states, reward, done, info
+
+
+class TimeLimitWrapper(Wrapper):
+    """base.py:214-230: done / dones_info=10 once a robot's episode ran longer than cfg time_max."""
+
+    def __init__(self, env, cfg):
+        super().__init__(env, cfg)
+        self._max_episode_steps = cfg["time_max"]
+        self._elapsed_steps = None
+
+    def step(self, ac):
+        observation, reward, done, info = self.env.step(ac)
+        if self._elapsed_steps is None:
+            self._elapsed_steps = _i64(_zeros_like(done))
+        self._elapsed_steps = self._elapsed_steps + 1
+        over = self._elapsed_steps > self._max_episode_steps
+        done = _where(over, _zeros_like(done) + 1, done)
+        info["dones_info"] = _where(over, _zeros_like(info["dones_info"]) + 10, info["dones_info"])
+        return observation, reward, done, info
+
+    def reset(self, **kwargs):
+        if self._elapsed_steps is not None:
+            self._elapsed_steps[self._rows(len(self._elapsed_steps), kwargs.get("scene_ids"))] = 0
+        return self.env.reset(**kwargs)
+
+
+class InfoLogWrapper(Wrapper):
+    """base.py:233-254."""
+
+    def __init__(self, env, cfg):
+        super().__init__(env, cfg)
+        self.robot_total = cfg["robot"]["total"]
+        self.ped = cfg["ped_sim"]["total"] > 0 and cfg["env_type"] == "robot_nav"
+
+    def step(self, action):
+        states, reward, done, info = self.env.step(action)
+        coll, arr = _i64(states.is_collisions), _i64(states.is_arrives)
+        info["arrive"] = states.is_arrives
+        info["collision"] = states.is_collisions
+        di = _where(coll > 0, coll, _i64(info["dones_info"]))
+        info["dones_info"] = _where(arr == 1, _zeros_like(di) + 5, di)
+        r = self.robot_total
+        down = (done > 0).reshape(-1, r)
+        if _is_torch(down):
+            per_scene = down.sum(1) == r
+            info["all_down"] = per_scene[:, None].expand(-1, r).reshape(-1)
+        else:
+            per_scene = down.sum(1) == r
+            info["all_down"] = np.repeat(per_scene, r)
+        if self.ped:
+            info["bool_get_close_to_human"] = _where(states.ped_min_dists < 1, _zeros_like(coll) + 1, _zeros_like(coll))
+        return states, reward, done, info
+
+
+class ObsStateTmp(ObservationWrapper):
+    """filter_states.py:6-12"""
+
+    def observation(self, states):
+        return [states.sensor_maps, states.vector_states, states.ped_maps]
+
+
+class ObsLaserStateTmp(ObservationWrapper):
+    """filter_states.py:15-20"""
+
+    def observation(self, states):
+        return [states.lasers, states.vector_states, states.ped_maps]
+
+
+class TimeControlWrapper(Wrapper):
+    """base.py:301-312: wall-clock pacing to control_hz."""
+
+    def step(self, action):
+        start = time.time()
+        out = self.env.step(action)
+        while time.time() - start < self.cfg["control_hz"]:
+            time.sleep(0.02)
+        return out
+
+
+class _PassThrough(Wrapper):
+    """ROS-bag recording, real-robot and evaluation harness wrappers: out of scope, kept loadable."""
+
+
+wrapper_dict = {
+    "StatePedVectorWrapper": StatePedVectorWrapper,
+    "VelActionWrapper": VelActionWrapper,
+    "StateBatchWrapper": StateBatchWrapper,
+    "SensorsPaperRewardWrapper": SensorsPaperRewardWrapper,
+    "NeverStopWrapper": NeverStopWrapper,
+    "ObsStateTmp": ObsStateTmp,
+    "TimeLimitWrapper": TimeLimitWrapper,
+    "MultiRobotCleanWrapper": MultiRobotCleanWrapper,
+    "InfoLogWrapper": InfoLogWrapper,
+    "ObsLaserStateTmp": ObsLaserStateTmp,
+    "TimeControlWrapper": TimeControlWrapper,
+    "BagRecordWrapper": _PassThrough,
+    "TestEpisodeWrapper": _PassThrough,
+    "BarnDataSetWrapper": _PassThrough,
+    "RealTestRecoderWrapper": _PassThrough,
+    "PedTrajectoryDatasetWrapper": _PassThrough,
+}

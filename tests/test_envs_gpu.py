@@ -18,7 +18,7 @@ def _cfg():
     cfg.update(sampler)
     cfg["discrete_action"] = True
     cfg["discrete_actions"] = [[0.0, -0.9], [0.2, 0.0], [0.6, 0.3], [0.4, 0.9]]
-    cfg["wrapper"] = ["VelActionWrapper", "TimeLimitWrapper", "SensorsPaperRewardWrapper"]   # unknown names are skipped (next rows)
+    cfg["wrapper"] = ["VelActionWrapper", "TimeLimitWrapper", "SensorsPaperRewardWrapper"]
     return cfg
 
 
@@ -52,4 +52,27 @@ def test_numpy_state_has_reference_dtypes():
     assert s.is_arrives.dtype == bool and s.lasers.dtype == np.float64 and s.ped_maps.dtype == np.float32
     s, r, d, info = env.step([ContinuousAction(0.3, 0.1)])
     assert r.shape == (1,) and d.dtype == np.int64
+    env.close()
+
+
+def test_full_reference_wrapper_stack_with_auto_reset():
+    """envs/cfg/test.yaml's wrapper list on 4 batched scenes: the RL loop never leaves the GPU except for actions."""
+    import torch
+    from img_env_b200.envs import make_env
+    random.seed(5)
+    cfg = _cfg()
+    cfg.update(agent_num_per_env=1, image_batch=1, state_batch=3, laser_batch=0, time_max=6, continuous_actions=[[0, 0.6], [-0.9, 0.9]])
+    cfg["wrapper"] = ["VelActionWrapper", "TimeLimitWrapper", "SensorsPaperRewardWrapper", "InfoLogWrapper", "MultiRobotCleanWrapper",
+                      "TestEpisodeWrapper", "StateBatchWrapper", "ObsLaserStateTmp", "NeverStopWrapper"]
+    env = make_env(cfg, num_scenes=4)
+    obs = env.reset()
+    lasers, vec, pm = obs
+    assert tuple(lasers.shape) == (4, 1, 1000) and tuple(vec.shape) == (4, 9) and tuple(pm.shape) == (4, 3, 48, 48)
+    resets = 0
+    for t in range(20):
+        obs, r, done, info = env.step(torch.tensor([2, 2, 1, 3]))
+        assert r.shape == (4,) and r.dtype == torch.float64
+        resets += int(info["all_down"].any())
+        assert torch.isfinite(obs[0]).all()
+    assert resets >= 2          # time_max=6 forces episodes to end and scenes to restart
     env.close()
