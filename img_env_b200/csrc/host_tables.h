@@ -62,7 +62,7 @@ struct TypeTables {
     std::vector<short> ray_end;
     std::vector<short> spans;
     std::vector<unsigned short> khi, klo;
-    std::vector<uint32_t> own_mask, tile_fov;
+    std::vector<uint32_t> own_mask, tile_fov, edge_px;
 };
 
 // desc: shape, size[4], sensor_cfg[2] (already float32-widened)
@@ -121,6 +121,31 @@ inline std::string build_type(const Cfg& c, const double* desc, double view_angl
                 for (int wj = c0 >> 5; wj <= (c1 - 1) >> 5; wj++) { int t = (i >> 5) * tw + wj; T.tile_fov[t >> 5] |= 1u << (t & 31); }
             }
     }
+    {   // FOV bounding box and FOV-edge pixels (in FOV with an 8-neighbour inside the raster that is not in FOV)
+        auto in_fov = [&](int i, int j) {
+            if (i < 0 || i >= c.vh || j < 0 || j >= c.vw) return false;
+            for (int sp = 0; sp < MAX_SPANS; sp++) {
+                int c0 = T.spans[(i * MAX_SPANS + sp) * 2], c1 = T.spans[(i * MAX_SPANS + sp) * 2 + 1];
+                if (c0 >= 0 && j >= c0 && j < c1) return true;
+            }
+            return false;
+        };
+        T.t.fov_r0 = c.vh; T.t.fov_r1 = -1; T.t.fov_c0 = c.vw; T.t.fov_c1 = -1;
+        for (int i = 0; i < c.vh; i++)
+            for (int j = 0; j < c.vw; j++) {
+                if (!in_fov(i, j)) continue;
+                T.t.fov_r0 = std::min(T.t.fov_r0, i); T.t.fov_r1 = std::max(T.t.fov_r1, i);
+                T.t.fov_c0 = std::min(T.t.fov_c0, j); T.t.fov_c1 = std::max(T.t.fov_c1, j);
+                bool edge = false;
+                for (int di = -1; di <= 1 && !edge; di++)
+                    for (int dj = -1; dj <= 1; dj++) {
+                        int ii = i + di, jj = j + dj;
+                        if (ii < 0 || ii >= c.vh || jj < 0 || jj >= c.vw) continue;
+                        if (!in_fov(ii, jj)) { edge = true; break; }
+                    }
+                if (edge) T.edge_px.push_back(((uint32_t)i << 16) | (uint32_t)j);
+            }
+    }
     // own footprint cells in the view raster: draw(view_map_, 100, "view_map", bbox_) agent.cpp:503
     size_t npx = (size_t)c.vh * c.vw;
     T.own_mask.assign((npx + 31) / 32, 0u);
@@ -137,6 +162,11 @@ inline std::string build_type(const Cfg& c, const double* desc, double view_angl
     }
     // conservative box where a set occupancy bit may be the robot's own stamp (superset is always safe)
     T.t.zone_r0 = r0 - 4; T.t.zone_r1 = r1 + 4; T.t.zone_c0 = c0 - 4; T.t.zone_c1 = c1 + 4;
+    {   // the same thing in world cells: radius of the footprint around the robot position + margin
+        double rmax = 0;
+        for (int k = 0; k < T.t.n_pts; k++) rmax = std::max(rmax, sqrt(T.lattice[2 * k] * T.lattice[2 * k] + T.lattice[2 * k + 1] * T.lattice[2 * k + 1]));
+        T.t.zone_rad = (int)ceil(rmax / c.res) + 5;
+    }
     // per-pixel highest / lowest touching ray: walk every ray over its full static cell sequence
     T.khi.assign(npx, 0xFFFF); T.klo.assign(npx, 0xFFFF);
     for (int k = 0; k < c.range_total; k++) {

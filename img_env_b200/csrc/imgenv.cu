@@ -183,7 +183,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         }
     }
     c.n_types = (int)types.size();
-    std::vector<double> lattice; std::vector<short> ray_end, spans; std::vector<unsigned short> khi, klo; std::vector<uint32_t> own_mask, tile_fov;
+    std::vector<double> lattice; std::vector<short> ray_end, spans; std::vector<unsigned short> khi, klo; std::vector<uint32_t> own_mask, tile_fov, edge_px;
     std::vector<RobotType> rts;
     for (auto& T : types) {
         T.t.pts_off = (int)lattice.size() / 2; lattice.insert(lattice.end(), T.lattice.begin(), T.lattice.end());
@@ -192,6 +192,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         T.t.khi_off = (int)khi.size(); khi.insert(khi.end(), T.khi.begin(), T.khi.end()); klo.insert(klo.end(), T.klo.begin(), T.klo.end());
         T.t.own_mask_off = (int)own_mask.size(); own_mask.insert(own_mask.end(), T.own_mask.begin(), T.own_mask.end());
         T.t.tile_off = (int)tile_fov.size(); tile_fov.insert(tile_fov.end(), T.tile_fov.begin(), T.tile_fov.end());
+        T.t.edge_off = (int)edge_px.size(); T.t.n_edge = (int)T.edge_px.size(); edge_px.insert(edge_px.end(), T.edge_px.begin(), T.edge_px.end());
         T.t.n_own = 0; T.t.own_off = 0;
         rts.push_back(T.t);
     }
@@ -226,7 +227,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     UP(kpack, kpack) UP(grid, g) UP(static_occ, socc) UP(types, rts) UP(type_of, type_of) UP(lattice_xy, lattice) UP(ray_end, ray_end)
     UP(fov_spans, spans) UP(khi, khi) UP(klo, klo) UP(own_mask, own_mask) UP(need_idx, need_idx) UP(cubic_tap, tap)
     UP(cubic_coef, coef) UP(f16_lut, lut) UP(lim_v, lv) UP(lim_w, lw) UP(ped_shape, pshape) UP(ped_size, psize)
-    UP(tile_fov, tile_fov) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(own_cells, own_dummy)
+    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(own_cells, own_dummy)
 #undef UP
     size_t S = c.S;
     size_t pc = ((size_t)H * W + 3) & ~(size_t)3;

@@ -173,6 +173,11 @@ struct ViewShared {
     int frozen;
     int red[VIEW_THREADS / 32];
     int coll_key;
+    // inverse (world cell -> view pixel) search: pixel = inv * (cell - org), in double; world block range of the FOV
+    double inv[4], org[2];
+    int blk[4];              // first block row / col, number of block rows / cols covering the FOV's world bounding box
+    int wbb[4];              // world bounding box of the FOV in cells (x0, x1, y0, y1), clamped to the map
+    int zc[2];               // robot position in world cells
 };
 
 // python float floor division (Objects/floatobject.c float_floor_div) used by yaml_env.py:414-415
@@ -226,7 +231,8 @@ __device__ __forceinline__ int ray_touch(int ox, int oy, int ex, int ey, int pr,
 #define NOHIT 0xFFFFFFFFu
 
 #define HB_COLS 16           // output columns per vertical-pass block (bounds the horizontal buffer)
-struct ViewLayout { size_t sh, regA, regB, pix, hitkey, rays, need, spans, total; };
+#define INV_MAX_BLOCKS 512   // 32x32-cell world blocks under the FOV; more -> forward (tile) rasterisation
+struct ViewLayout { size_t sh, regA, regB, pix, hitkey, rays, need, spans, blocks, total; };
 __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     ViewLayout L;
     size_t off = 0;
@@ -241,6 +247,7 @@ __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     L.rays = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
     L.need = off; off += ((size_t)c.ns * 2 + 15) & ~(size_t)15;
     L.spans = off; off += ((size_t)c.vh * 8 + 15) & ~(size_t)15;
+    L.blocks = off; off += (size_t)INV_MAX_BLOCKS * 4;
     L.total = off + 16;
     return L;
 }
@@ -269,6 +276,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
     uint32_t* pix = reinterpret_cast<uint32_t*>(smem_raw + L.pix);     // 2-bit codes: 0 -> 0, 1 -> 100, 2 -> 200, 3 -> 255
     const int pixw = (c.ns + 15) / 16;
     short* spans = reinterpret_cast<short*>(smem_raw + L.spans);
+    uint32_t* blocks = reinterpret_cast<uint32_t*>(smem_raw + L.blocks);
     unsigned* hitkey = reinterpret_cast<unsigned*>(smem_raw + L.hitkey);
     short* rend = reinterpret_cast<short*>(smem_raw + L.rays);
     short* need = reinterpret_cast<short*>(smem_raw + L.need);
@@ -291,7 +299,25 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         // Agent::view early-out (agent.cpp:358-360): stale view_map_/hits_/is_collision_ are re-sent
         sh->frozen = (RBF(d, RB_COLL, idx) != 0.0) || (RBF(d, RB_ARR, idx) != 0.0);
         sh->coll_key = 0;      // reused as boundary-list counters below
-        sh->red[0] = 0; sh->red[1] = 0; sh->red[2] = 0;
+        sh->red[0] = 0; sh->red[1] = 0; sh->red[2] = 0; sh->red[3] = 0;
+        {   // inverse map and the FOV's world bounding box (for the world->view rasterisation)
+            const double det = A.m00 * A.m11 - A.m01 * A.m10;
+            sh->inv[0] = A.m11 / det; sh->inv[1] = -A.m01 / det; sh->inv[2] = -A.m10 / det; sh->inv[3] = A.m00 / det;
+            sh->org[0] = A.ox / c.res; sh->org[1] = A.oy / c.res;
+            int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
+            for (int k = 0; k < 4; k++) {
+                const int ii = (k & 1) ? ty.fov_r1 : ty.fov_r0, jj = (k & 2) ? ty.fov_c1 : ty.fov_c0;
+                const int cx = (int)((sh->cx + (long long)ii * sh->ax + (long long)jj * sh->bx) >> 32);
+                const int cy = (int)((sh->cy + (long long)ii * sh->ay + (long long)jj * sh->by) >> 32);
+                xmin = min(xmin, cx); xmax = max(xmax, cx); ymin = min(ymin, cy); ymax = max(ymax, cy);
+            }
+            xmin = max(xmin - 1, 0); ymin = max(ymin - 1, 0); xmax = min(xmax + 1, c.H - 1); ymax = min(ymax + 1, c.W - 1);
+            sh->wbb[0] = xmin; sh->wbb[1] = xmax; sh->wbb[2] = ymin; sh->wbb[3] = ymax;
+            const bool empty = xmin > xmax || ymin > ymax || ty.fov_r1 < ty.fov_r0;
+            sh->blk[0] = xmin >> 5; sh->blk[1] = ymin >> 5;
+            sh->blk[2] = empty ? 0 : (xmax >> 5) - (xmin >> 5) + 1; sh->blk[3] = empty ? 0 : (ymax >> 5) - (ymin >> 5) + 1;
+            sh->zc[0] = world2cell(x, c.res); sh->zc[1] = world2cell(y, c.res);
+        }
     }
     {   // static tables into shared memory
         const short* g_rend = d.ray_end + 2 * (size_t)ty.ray_off;
@@ -332,9 +358,122 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         const uint32_t* coarse = d.coarse + (size_t)s * c.Hc * c.Wb;
         const unsigned H = c.H, W = c.W, Wb = c.Wb;
         const int n_trow = (vh + 31) >> 5, n_tiles = n_trow * vwb;
+        // (1) World -> view ("inverse") rasterisation, used when lasers are on: only raster cells that can be the
+        //     first hit of a ray matter, and every such cell has a free 8-neighbour in the view, hence its world
+        //     cell has a free cell within its 5x5 neighbourhood (a view step moves at most 2 world cells), is
+        //     within 2 cells of the map border, lies next to the robot's own stamp, or the view cell sits on the
+        //     FOV edge.  So: walk the occupied world words under the FOV (32x32 blocks with a non-zero count),
+        //     drop 5x5-interior cells with word-parallel bit operations, map each remaining cell back to its
+        //     <= 4 candidate view pixels and keep those whose EXACT forward map returns that cell; FOV-edge
+        //     pixels (static list) are evaluated forward.  Every bit set is a truly occupied view cell and the
+        //     first hit of every ray is among them.
+        // (2) Otherwise (lasers off, or a huge FOV): forward rasterisation in 32x32-pixel tiles, skipping tiles
+        //     whose world footprint only touches blocks with a zero count.
+        const bool use_inverse = c.use_laser && sh->blk[2] * sh->blk[3] <= INV_MAX_BLOCKS;
+        for (int q = tid; q < vh * vwb; q += VIEW_THREADS) { occ[q] = 0u; if (!c.use_laser) known[q] = 0u; }
+        if (use_inverse) {
+            const int nbj = sh->blk[3], nb = sh->blk[2] * nbj;
+            for (int t = tid; t < nb; t += VIEW_THREADS) {
+                const int bi = sh->blk[0] + t / nbj, bj = sh->blk[1] + t % nbj;
+                if (__ldg(coarse + (unsigned)bi * Wb + bj)) blocks[atomicAdd(&sh->red[3], 1)] = ((unsigned)bi << 16) | (unsigned)bj;
+            }
+            if (!DEBUG_FULL && lane == 0) atomicMax(&sh->coll_key, best);
+            __syncthreads();
+            // FOV-edge pixels: forward
+            const uint32_t* edge = d.edge_px + ty.edge_off;
+            for (int e = tid; e < ty.n_edge; e += VIEW_THREADS) {
+                const unsigned ep = __ldg(edge + e);
+                const int i = ep >> 16, j = ep & 0xFFFF;
+                const long long tx = sh->cx + (long long)i * sh->ax + (long long)j * sh->bx;
+                const long long tyy = sh->cy + (long long)i * sh->ay + (long long)j * sh->by;
+                int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
+                if ((unsigned)tx + FX_GUARD < 2 * FX_GUARD || (unsigned)tyy + FX_GUARD < 2 * FX_GUARD) {
+                    double wx, wy;
+                    tf_apply(sh->view_world, i * c.res, j * c.res, wx, wy);
+                    cx = world2cell(wx, c.res); cy = world2cell(wy, c.res);
+                }
+                if ((unsigned)cx < H && (unsigned)cy < W) {
+                    bool o = (__ldg(occ_all + (unsigned)cx * Wb + ((unsigned)cy >> 5)) >> (cy & 31)) & 1u;
+                    if (o && i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1) o = global_value(d, s, r, cx, cy) < 250;
+                    if (o) atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31));
+                }
+            }
+            // occupied world words -> candidate cells -> view pixels
+            const int n_items = sh->red[3] * 32;
+            const int X0 = sh->wbb[0], X1 = sh->wbb[1], Y0 = sh->wbb[2], Y1 = sh->wbb[3];
+            const int zx = sh->zc[0], zy = sh->zc[1], zr = ty.zone_rad;
+            const float i00 = (float)sh->inv[0], i01 = (float)sh->inv[1], i10 = (float)sh->inv[2], i11 = (float)sh->inv[3];
+            // each warp takes 32 words (one per lane), then expands their candidate bits over all lanes
+            for (int base = warp * 32; base < n_items; base += VIEW_THREADS) {
+                const int item = base + lane;
+                unsigned cand = 0; int X = 0, bj = 0;
+                if (item < n_items) {
+                    const unsigned bb = blocks[item >> 5];
+                    X = (int)(bb >> 16) * 32 + (item & 31); bj = (int)(bb & 0xFFFF);
+                    unsigned w = 0;
+                    if (X >= X0 && X <= X1) w = __ldg(occ_all + (unsigned)X * Wb + bj);
+                    if (w) {
+                        unsigned interior = 0xffffffffu;
+                        for (int dxr = -2; dxr <= 2 && interior; dxr++) {
+                            const int Xr = X + dxr;
+                            if (Xr < 0 || Xr >= (int)H) { interior = 0; break; }
+                            const uint32_t* rp = occ_all + (unsigned)Xr * Wb + bj;
+                            const unsigned wc = __ldg(rp), wl = bj > 0 ? __ldg(rp - 1) : 0u, wr = bj + 1 < (int)Wb ? __ldg(rp + 1) : 0u;
+                            interior &= wc & ((wc << 1) | (wl >> 31)) & ((wc << 2) | (wl >> 30)) & ((wc >> 1) | (wr << 31)) & ((wc >> 2) | (wr << 30));
+                        }
+                        cand = w & ~interior;
+                        if (abs(X - zx) <= zr) {      // next to the robot's own stamp: no interior filter
+                            const int lo = max(zy - zr - bj * 32, 0), hi = min(zy + zr - bj * 32, 31);
+                            if (lo <= hi) cand |= w & ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo));
+                        }
+                        const int lo = max(Y0 - bj * 32, 0), hi = min(Y1 - bj * 32, 31);    // only columns under the FOV's bounding box
+                        cand = lo <= hi ? cand & ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo)) : 0u;
+                    }
+                }
+                const int cnt = __popc(cand);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                const int total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - cnt;
+                for (int k0 = 0; k0 < total; k0 += 32) {
+                    const int k = k0 + lane;
+                    int src = 0;
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        const int e = __shfl_sync(0xffffffffu, excl, (src + step) & 31);
+                        if (src + step < 32 && e <= k) src += step;
+                    }
+                    const int n = k - __shfl_sync(0xffffffffu, excl, src);
+                    const unsigned m = __shfl_sync(0xffffffffu, cand, src);
+                    const int cX = __shfl_sync(0xffffffffu, X, src), cbj = __shfl_sync(0xffffffffu, bj, src);
+                    if (k >= total) continue;
+                    const int cY = cbj * 32 + (int)__fns(m, 0, n + 1);
+                    const float u = (float)((double)cX - sh->org[0]), v = (float)((double)cY - sh->org[1]);
+                    const float qi = i00 * u + i01 * v, qj = i10 * u + i11 * v;
+                    const int ia = max((int)ceilf(qi - 0.72f), 0), ib = min((int)floorf(qi + 0.72f), vh - 1);
+                    const int ja = max((int)ceilf(qj - 0.72f), 0), jb = min((int)floorf(qj + 0.72f), vw - 1);
+                    for (int i = ia; i <= ib; i++) {
+                        const int a0 = spans[i * 4 + 0], a1 = spans[i * 4 + 1], b0 = spans[i * 4 + 2], b1 = spans[i * 4 + 3];
+                        for (int j = ja; j <= jb; j++) {
+                            if (!((j >= a0 && j < a1) || (j >= b0 && j < b1))) continue;
+                            const long long tx = sh->cx + (long long)i * sh->ax + (long long)j * sh->bx;
+                            const long long tyy = sh->cy + (long long)i * sh->ay + (long long)j * sh->by;
+                            int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
+                            if ((unsigned)tx + FX_GUARD < 2 * FX_GUARD || (unsigned)tyy + FX_GUARD < 2 * FX_GUARD) {
+                                double wx, wy;
+                                tf_apply(sh->view_world, i * c.res, j * c.res, wx, wy);
+                                cx = world2cell(wx, c.res); cy = world2cell(wy, c.res);
+                            }
+                            if (cx != cX || cy != cY) continue;
+                            if (i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1 && !(global_value(d, s, r, cX, cY) < 250)) continue;
+                            atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31));
+                        }
+                    }
+                }
+            }
+        } else {
         int* n_active = &sh->red[2];
         unsigned short* tile_list = reinterpret_cast<unsigned short*>(blist);     // region B is free until phase C
-        for (int q = tid; q < vh * vwb; q += VIEW_THREADS) { occ[q] = 0u; if (!c.use_laser) known[q] = 0u; }
         for (int t = tid; t < n_tiles; t += VIEW_THREADS) {
             if (!((d.tile_fov[ty.tile_off + (t >> 5)] >> (t & 31)) & 1u)) continue;
             bool active = !c.use_laser;          // the "known" plane needs every FOV pixel
@@ -394,6 +533,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 if (lane == 0) occ[i * vwb + wj] = wo;
             }
         }
+        }   // forward tile path
         __syncthreads();
         if (!DEBUG_FULL && tid == 0) {
             int code = sh->coll_key & 3;
@@ -445,7 +585,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             }
             __syncthreads();
             const int nl = sh->red[0], nl2 = sh->red[1];
-            if (d.dbg_stats && tid == 0) { int* st = d.dbg_stats + 4 * (size_t)idx; st[0] = sh->red[2]; st[1] = nl; st[2] = nl2; st[3] = !(nl <= BL_CAP && nl2 <= BL2_CAP); }
+            if (d.dbg_stats && tid == 0) { int* st = d.dbg_stats + 4 * (size_t)idx; st[0] = sh->red[2] + sh->red[3]; st[1] = nl; st[2] = nl2; st[3] = !(nl <= BL_CAP && nl2 <= BL2_CAP); }
             if (nl <= BL_CAP && nl2 <= BL2_CAP) {
                 for (int q = tid; q < nl; q += VIEW_THREADS) {
                     const int full = blist[q], pr = full / vw, pc = full - pr * vw;
