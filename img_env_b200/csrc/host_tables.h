@@ -62,7 +62,7 @@ struct TypeTables {
     std::vector<short> ray_end;
     std::vector<short> spans;
     std::vector<unsigned short> khi, klo;
-    std::vector<uint32_t> own_mask, tile_fov, edge_px;
+    std::vector<uint32_t> own_mask, tile_fov, edge_px, dtab;
 };
 
 // desc: shape, size[4], sensor_cfg[2] (already float32-widened)
@@ -143,7 +143,7 @@ inline std::string build_type(const Cfg& c, const double* desc, double view_angl
                         if (ii < 0 || ii >= c.vh || jj < 0 || jj >= c.vw) continue;
                         if (!in_fov(ii, jj)) { edge = true; break; }
                     }
-                if (edge) T.edge_px.push_back(((uint32_t)i << 16) | (uint32_t)j);
+                if (edge || (i == T.t.org_x && j == T.t.org_y)) T.edge_px.push_back(((uint32_t)i << 16) | (uint32_t)j);   // + the laser origin (no predecessor)
             }
     }
     // own footprint cells in the view raster: draw(view_map_, 100, "view_map", bbox_) agent.cpp:503

@@ -141,7 +141,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     if (c.ped_vec_dim != 7) return fail("imgenv_create: ped_vec_dim must be 7 (yaml_env.py:399-408)");
     if (c.state_dim < 3 || c.state_dim > 5) return fail("imgenv_create: state_dim must be 3, 4 or 5");
     if (c.R < 1 || c.R > 4096 || c.P < 0 || c.P > 4096 || c.S < 1) return fail("imgenv_create: bad S/R/P");
-    if (c.range_total > 4000 || c.range_total < 1) return fail("imgenv_create: range_total out of range");
+    if (c.range_total > 4000 || c.range_total < 1) return fail("imgenv_create: range_total out of range");   // 12-bit ray ids, 0xFFF = none
     if (c.scene_type < 0 || c.scene_type > 4) return fail("imgenv_create: unknown scene type");
 
     // ---- static tables ----
@@ -183,7 +183,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         }
     }
     c.n_types = (int)types.size();
-    std::vector<double> lattice; std::vector<short> ray_end, spans; std::vector<unsigned short> khi, klo; std::vector<uint32_t> own_mask, tile_fov, edge_px;
+    std::vector<double> lattice; std::vector<short> ray_end, spans; std::vector<unsigned short> khi, klo; std::vector<uint32_t> own_mask, tile_fov, edge_px, dtab;
     std::vector<RobotType> rts;
     for (auto& T : types) {
         T.t.pts_off = (int)lattice.size() / 2; lattice.insert(lattice.end(), T.lattice.begin(), T.lattice.end());
@@ -193,6 +193,25 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         T.t.own_mask_off = (int)own_mask.size(); own_mask.insert(own_mask.end(), T.own_mask.begin(), T.own_mask.end());
         T.t.tile_off = (int)tile_fov.size(); tile_fov.insert(tile_fov.end(), T.tile_fov.begin(), T.tile_fov.end());
         T.t.edge_off = (int)edge_px.size(); T.t.n_edge = (int)T.edge_px.size(); edge_px.insert(edge_px.end(), T.edge_px.begin(), T.edge_px.end());
+        {   // compact per-needed-pixel table for the laser_map reconstruction (view.cuh phase D)
+            T.dtab.assign((size_t)c.ns * c.ns, 0u);
+            for (int rr = 0; rr < c.ns; rr++)
+                for (int cc = 0; cc < c.ns; cc++) {
+                    const int pr = need_idx[rr], pc = need_idx[cc];
+                    const size_t full = (size_t)pr * c.vw + pc;
+                    uint32_t kh = T.khi[full], e;
+                    if (kh == 0xFFFF) e = 0xFFFu;
+                    else {
+                        const int w0 = abs((int)T.ray_end[2 * kh] - T.t.org_x), h0 = abs((int)T.ray_end[2 * kh + 1] - T.t.org_y);
+                        const uint32_t itop = (uint32_t)(w0 > h0 ? abs(pr - T.t.org_x) : abs(pc - T.t.org_y));
+                        const uint32_t below = std::min<uint32_t>(kh - T.klo[full], 511u);
+                        e = kh | (itop << 12) | (below << 22);
+                    }
+                    if ((T.own_mask[full >> 5] >> (full & 31)) & 1u) e |= 1u << 31;
+                    T.dtab[(size_t)rr * c.ns + cc] = e;
+                }
+        }
+        T.t.dtab_off = (int)dtab.size(); dtab.insert(dtab.end(), T.dtab.begin(), T.dtab.end());
         T.t.n_own = 0; T.t.own_off = 0;
         rts.push_back(T.t);
     }
@@ -227,7 +246,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     UP(kpack, kpack) UP(grid, g) UP(static_occ, socc) UP(types, rts) UP(type_of, type_of) UP(lattice_xy, lattice) UP(ray_end, ray_end)
     UP(fov_spans, spans) UP(khi, khi) UP(klo, klo) UP(own_mask, own_mask) UP(need_idx, need_idx) UP(cubic_tap, tap)
     UP(cubic_coef, coef) UP(f16_lut, lut) UP(lim_v, lv) UP(lim_w, lw) UP(ped_shape, pshape) UP(ped_size, psize)
-    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(own_cells, own_dummy)
+    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(dtab, dtab) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(own_cells, own_dummy)
 #undef UP
     size_t S = c.S;
     size_t pc = ((size_t)H * W + 3) & ~(size_t)3;

@@ -51,6 +51,7 @@ struct RobotType {
     int tile_off;         // offset into tile_fov (u32 words): bit per 32x32 view tile that contains FOV pixels
     int edge_off, n_edge; // FOV pixels with an 8-neighbour outside the FOV (u32 row<<16|col), always evaluated forward
     int fov_r0, fov_r1, fov_c0, fov_c1;   // bounding box (inclusive) of the FOV pixels in the view raster
+    int dtab_off;         // offset into dtab (ns*ns u32)
     int zone_rad;         // world cells around the robot's position inside which a set occ_all bit may be its own stamp
     double size_last;     // python: robots[i].size[-1]
     double sensor_x, sensor_y;
@@ -94,6 +95,7 @@ struct Dev {
     const uint32_t* own_mask;     // per type: bit per view pixel = own footprint cell
     const uint32_t* tile_fov;     // per type: bit per 32x32 view tile (row-major, vwb per row) with any FOV pixel
     const uint32_t* edge_px;      // per type: FOV-edge pixels
+    const uint32_t* dtab;         // per type, per pixel the resize reads: top ray (12b) | its step index there (10b) | #rays below, capped (9b) | own footprint (1b)
     const short* need_idx;        // [ns] source row/col index of the k-th needed row/col
     const short* cubic_tap;       // [img][4] index into need_idx space (0..ns-1) of the 4 taps
     const short* cubic_coef;      // [img][4] fixed-point weights (x2048)

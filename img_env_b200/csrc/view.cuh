@@ -225,7 +225,7 @@ __device__ __forceinline__ int ray_touch(int ox, int oy, int ex, int ey, int pr,
 //   region B  boundary-cell list 24 KB        (phase C)       | later: horizontal resize buffer 144*48*4 = 27.6 KB (phase F)
 //   pix       144*144 u8 = 20.7 KB            (phases D-F)
 //   hitkey    range_total*4, ray end cells range_total*4, needed-line indices
-#define BL_CAP 3072          // boundary cells kept in shared memory; more -> per-ray marching fallback
+#define BL_CAP 3072          // candidate cells kept in shared memory; further cells are resolved inline by their finder
 #define BL2_CAP 256          // cells touched by many rays (close to the origin): processed warp-cooperatively
 #define BL_HEAVY 24
 #define NOHIT 0xFFFFFFFFu
@@ -357,6 +357,29 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         const uint32_t* occ_all = d.occ_all + (size_t)s * c.H * c.Wb;
         const uint32_t* coarse = d.coarse + (size_t)s * c.Hc * c.Wb;
         const unsigned H = c.H, W = c.W, Wb = c.Wb;
+        const int ox = ty.org_x, oy = ty.org_y;
+        const uint32_t* kpack = d.kpack + (size_t)ty.khi_off;
+        int* n_list = &sh->red[0]; int* n_list2 = &sh->red[1];
+        // a newly set raster cell goes straight to the ray-hit candidate lists (phase C)
+        // every ray of [k0, k0+kstep, ...] within the cell's static ray interval that really passes through it
+        // keeps the minimum step: hitkey[k] = min(step << 22 | cell)
+        auto cell_rays = [&](int full, unsigned kp, int k0, int kstep) {
+            const int pr = full / vw, pc = full - pr * vw;
+            const int kh = kp & 0xFFFF, kl = kp >> 16;
+            for (int k = kl + k0; k <= kh; k += kstep) {
+                const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
+                if (i >= 0) atomicMin(&hitkey[k], hit_key(i, pr, pc));
+            }
+        };
+        auto push_cell = [&](int full) {
+            const unsigned kp = __ldg(kpack + full);
+            const int kh = kp & 0xFFFF;
+            if (kh == 0xFFFF) return;                                      // no ray passes through this cell
+            const bool heavy = kh - (int)(kp >> 16) + 1 > BL_HEAVY;
+            const int p = atomicAdd(heavy ? n_list2 : n_list, 1);
+            if (p < (heavy ? BL2_CAP : BL_CAP)) (heavy ? blist2 : blist)[p] = (unsigned)full;
+            else cell_rays(full, kp, 0, 1);                                // list full: resolve this cell right here
+        };
         const int n_trow = (vh + 31) >> 5, n_tiles = n_trow * vwb;
         // (1) World -> view ("inverse") rasterisation, used when lasers are on: only raster cells that can be the
         //     first hit of a ray matter, and every such cell has a free 8-neighbour in the view, hence its world
@@ -395,11 +418,11 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 if ((unsigned)cx < H && (unsigned)cy < W) {
                     bool o = (__ldg(occ_all + (unsigned)cx * Wb + ((unsigned)cy >> 5)) >> (cy & 31)) & 1u;
                     if (o && i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1) o = global_value(d, s, r, cx, cy) < 250;
-                    if (o) atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31));
+                    if (o && !(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31)))) push_cell(i * vw + j);
                 }
             }
             // occupied world words -> candidate cells -> view pixels
-            const int n_items = sh->red[3] * 32;
+            const int n_blocks = sh->red[3], n_items = n_blocks * 32;
             const int X0 = sh->wbb[0], X1 = sh->wbb[1], Y0 = sh->wbb[2], Y1 = sh->wbb[3];
             const int zx = sh->zc[0], zy = sh->zc[1], zr = ty.zone_rad;
             const float i00 = (float)sh->inv[0], i01 = (float)sh->inv[1], i10 = (float)sh->inv[2], i11 = (float)sh->inv[3];
@@ -466,7 +489,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                             }
                             if (cx != cX || cy != cY) continue;
                             if (i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1 && !(global_value(d, s, r, cX, cY) < 250)) continue;
-                            atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31));
+                            if (!(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31)))) push_cell(i * vw + j);
                         }
                     }
                 }
@@ -544,11 +567,9 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         // A ray's hit cell always has a free 8-neighbour (its predecessor on the ray), so only the boundary
         // cells of the raster can be hits.  For each boundary cell the (static) interval of ray indices whose
         // integer line walk passes through it is scanned with the closed-form touch test and the ray keeps
-        // the minimum step (atomicMin on step<<22|cell).  Dense rasters overflow the list -> marching fallback.
-        const int ox = ty.org_x, oy = ty.org_y;
-        const uint32_t* kpack = d.kpack + (size_t)ty.khi_off;
+        // the minimum step (atomicMin on step<<22|cell).  Cells that do not fit the lists are resolved inline.
         if (c.use_laser) {
-            int* n_list = &sh->red[0]; int* n_list2 = &sh->red[1];
+            if (!use_inverse)
             for (int q = tid; q < vh * 16 * ((vwb + 15) / 16); q += VIEW_THREADS) {
                 const int wpr = 16 * ((vwb + 15) / 16);                  // words per row rounded up to 16: shift/mask indexing
                 const int i = (wpr == 16) ? (q >> 4) : q / wpr, wj = (wpr == 16) ? (q & 15) : q - i * wpr;
@@ -575,63 +596,14 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     const int col = wj * 32 + b;
                     if (col >= vw) break;
                     const int full = i * vw + col;
-                    const unsigned kp = __ldg(kpack + full);
-                    const int kh = kp & 0xFFFF;
-                    if (kh == 0xFFFF) continue;                                  // no ray passes through this cell
-                    const int nr = kh - (int)(kp >> 16) + 1;
-                    if (nr > BL_HEAVY) { int p = atomicAdd(n_list2, 1); if (p < BL2_CAP) blist2[p] = (unsigned)full; }
-                    else { int p = atomicAdd(n_list, 1); if (p < BL_CAP) blist[p] = (unsigned)full; }
+                    push_cell(full);
                 }
             }
             __syncthreads();
-            const int nl = sh->red[0], nl2 = sh->red[1];
-            if (d.dbg_stats && tid == 0) { int* st = d.dbg_stats + 4 * (size_t)idx; st[0] = sh->red[2] + sh->red[3]; st[1] = nl; st[2] = nl2; st[3] = !(nl <= BL_CAP && nl2 <= BL2_CAP); }
-            if (nl <= BL_CAP && nl2 <= BL2_CAP) {
-                for (int q = tid; q < nl; q += VIEW_THREADS) {
-                    const int full = blist[q], pr = full / vw, pc = full - pr * vw;
-                    const unsigned kp = __ldg(kpack + full);
-                    const int kh = kp & 0xFFFF, kl = kp >> 16;
-                    for (int k = kl; k <= kh; k++) {
-                        const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
-                        if (i >= 0) atomicMin(&hitkey[k], hit_key(i, pr, pc));
-                    }
-                }
-                for (int q = warp; q < nl2; q += VIEW_THREADS / 32) {
-                    const int full = blist2[q], pr = full / vw, pc = full - pr * vw;
-                    const unsigned kp = __ldg(kpack + full);
-                    const int kh = kp & 0xFFFF, kl = kp >> 16;
-                    for (int k = kl + lane; k <= kh; k += 32) {
-                        const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
-                        if (i >= 0) atomicMin(&hitkey[k], hit_key(i, pr, pc));
-                    }
-                }
-            } else {
-                // fallback: one thread per ray marches the bit raster with the reference's integer line walk
-                for (int k = tid; k < c.range_total; k += VIEW_THREADS) {
-                    int x1 = ox, y1 = oy, x2 = rend[2 * k], y2 = rend[2 * k + 1];
-                    int w = x2 - x1, h = y2 - y1;
-                    const int dx = w > 0 ? 1 : -1, dy = h > 0 ? 1 : -1;
-                    w = abs(w); h = abs(h);
-                    int x = x1, y = y1, f;
-                    unsigned key = NOHIT;
-                    if (w > h) {
-                        f = 2 * h - w;
-                        for (int i = 0; x != x2; x += dx, i++) {
-                            if ((unsigned)x >= (unsigned)vh || (unsigned)y >= (unsigned)vw) break;
-                            if ((occ[x * vwb + (y >> 5)] >> (y & 31)) & 1u) { key = hit_key(i, x, y); break; }
-                            if (f < 0) f += 2 * h; else { y += dy; f += 2 * (h - w); }
-                        }
-                    } else {
-                        f = 2 * w - h;
-                        for (int i = 0; y != y2; y += dy, i++) {
-                            if ((unsigned)x >= (unsigned)vh || (unsigned)y >= (unsigned)vw) break;
-                            if ((occ[x * vwb + (y >> 5)] >> (y & 31)) & 1u) { key = hit_key(i, x, y); break; }
-                            if (f < 0) f += 2 * w; else { x += dx; f += 2 * (w - h); }
-                        }
-                    }
-                    hitkey[k] = key;
-                }
-            }
+            const int nl = min(sh->red[0], BL_CAP), nl2 = min(sh->red[1], BL2_CAP);
+            if (d.dbg_stats && tid == 0) { int* st = d.dbg_stats + 4 * (size_t)idx; st[0] = sh->red[2] + sh->red[3]; st[1] = sh->red[0]; st[2] = sh->red[1]; st[3] = sh->red[0] > BL_CAP || sh->red[1] > BL2_CAP; }
+            for (int q = tid; q < nl; q += VIEW_THREADS) { const int full = blist[q]; cell_rays(full, __ldg(kpack + full), 0, 1); }
+            for (int q = warp; q < nl2; q += VIEW_THREADS / 32) { const int full = blist2[q]; cell_rays(full, __ldg(kpack + full), lane, 32); }
             __syncthreads();
             if (!DEBUG_FULL) {
                 for (int k = tid; k < c.range_total; k += VIEW_THREADS) {
@@ -654,6 +626,50 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         // kpack = highest | lowest<<16 touching ray; the highest one touches by construction, so only its
         // step index is needed; the full touch test runs only on the (rare) fall-through candidates.
         const uint32_t* own_mask = d.own_mask + (size_t)ty.own_mask_off;
+        if (!DEBUG_FULL && c.use_laser) {
+            // fast path over the ns x ns pixels the resize reads: one coalesced table word per pixel
+            const uint32_t* dtab = d.dtab + (size_t)ty.dtab_off;
+            for (int rr = warp; rr < c.ns; rr += VIEW_THREADS / 32) {
+              for (int cc0 = 0; cc0 < c.ns; cc0 += 128) {
+                unsigned ev[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const int cc = cc0 + u * 32 + lane; ev[u] = cc < c.ns ? __ldg(dtab + rr * c.ns + cc) : 0u; }   // 4 loads in flight
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int cc = cc0 + u * 32 + lane;
+                    if (cc >= c.ns) continue;
+                    const unsigned e = ev[u];
+                    const int kh = e & 0xFFF;
+                    unsigned code = 2u;                                        // 200: untouched
+                    if (kh != 0xFFF) {
+                        const unsigned key = hitkey[kh];
+                        const int hp = (int)(key >> 22), i0 = (e >> 12) & 0x3FF;
+                        if (i0 < hp) code = 3u;
+                        else if (i0 == hp) code = 0u;
+                        else {
+                            const int pr = need[rr], pc = need[cc];
+                            if (pr != (int)((key >> 11) & 2047) && pc != (int)(key & 2047)) code = 2u;       // shadow write
+                            else {                                                                           // fall through to lower rays
+                                const unsigned kp = __ldg(kpack + pr * vw + pc);
+                                const int kl = kp >> 16;
+                                for (int k = kh - 1; k >= kl; k--) {
+                                    const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
+                                    if (i < 0) continue;
+                                    const unsigned key2 = hitkey[k];
+                                    const int hp2 = (int)(key2 >> 22);
+                                    if (i < hp2) { code = 3u; break; }
+                                    if (i == hp2) { code = 0u; break; }
+                                    if (pr != (int)((key2 >> 11) & 2047) && pc != (int)(key2 & 2047)) { code = 2u; break; }
+                                }
+                            }
+                        }
+                    }
+                    if (code != 0u && (e >> 31)) code = 1u;                    // own footprint (100) unless the cell is 0
+                    if (code) atomicOr(&pix[rr * pixw + (cc >> 4)], code << (2 * (cc & 15)));
+                }
+              }
+            }
+        } else {
         const int nrows = DEBUG_FULL ? vh : c.ns, ncols = DEBUG_FULL ? vw : c.ns;
         for (int rr = warp; rr < nrows; rr += VIEW_THREADS / 32) {
             const int pr = DEBUG_FULL ? rr : need[rr];
@@ -691,6 +707,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     if (code) atomicOr(&pix[rr * pixw + (cc >> 4)], code << (2 * (cc & 15)));
                 }
             }
+        }
         }
         __syncthreads();
 
