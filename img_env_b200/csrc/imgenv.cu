@@ -118,7 +118,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     c.relation = cfg->relation_ped_robo;
     c.NA = (c.scene_type != 0 && c.scene_type != 4) ? c.P + (c.relation == 1 ? c.R : 0) : 0;
     c.H = H; c.W = W; c.Wb = (W + 31) / 32; c.Hc = (H + 31) / 32;
-    c.res = f32(cfg->view_resolution);
+    c.res = f32(cfg->view_resolution); c.inv_res = 1.0 / c.res;
     double vwid = f32(cfg->view_width), vhei = f32(cfg->view_height);
     c.vw = (int)(vwid / c.res); c.vh = (int)(vhei / c.res);       // agent.cpp:82-83
     c.vwb = (c.vw + 31) / 32;
@@ -129,6 +129,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     c.view_max_dist = f32(cfg->view_max_dist);
     c.view_base = tf_from_pose(vhei / 2, vwid / 2, 3.14159);      // agent.cpp:84-87
     c.base_view = tf_inv(c.view_base);
+    c.cull_reach = hypot(vhei / 2, vwid / 2) + 4 * c.res;          // view pixels lie within [-h/2, h/2] x [-w/2, w/2] of the base frame
     c.img = cfg->image_size; c.max_ped = cfg->max_ped; c.ped_vec_dim = cfg->ped_vec_dim;
     c.pvs_len = 1 + c.max_ped * c.ped_vec_dim;
     c.ped_image_r = cfg->ped_image_r; c.ped_res = 6.0 / cfg->ped_image_size; c.laser_max = cfg->laser_max;
@@ -219,6 +220,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     std::vector<int> pshape(c.P), poff(2 * (size_t)c.P, 0), pn(2 * (size_t)c.P, 0);
     std::vector<double> psize(6 * (size_t)c.P), pmax(c.P), prr(c.P);
     std::vector<float> prw(c.P);
+    std::vector<double> pext(std::max(c.P, 1), 0.0);
     for (int p = 0; p < c.P; p++) {
         const double* q = ped_desc + 8 * (size_t)p;
         pshape[p] = (int)q[0];
@@ -229,6 +231,12 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         std::vector<double> a, b;
         if (pshape[p] == 0) ht::lattice_circle(psize[6 * p], psize[6 * p + 1], psize[6 * p + 2], a);
         else if (pshape[p] == 2) { ht::lattice_circle(0, 0, psize[6 * p + 2], a); ht::lattice_circle(0, 0, psize[6 * p + 5], b); }
+        {   // stamp extent: body offset + radius, or leg offset (configured or gait +-0.3, agent.cpp:696-735) + leg radius
+            const double* z = psize.data() + 6 * p;
+            pext[p] = pshape[p] == 0 ? hypot(z[0], z[1]) + z[2]
+                                     : hypot(std::max(std::max(fabs(z[0]), fabs(z[3])), 0.3), std::max(fabs(z[1]), fabs(z[4]))) + std::max(z[2], z[5]);
+            pext[p] += 3 * c.res;
+        }
         poff[2 * p] = (int)lattice.size() / 2; pn[2 * p] = (int)a.size() / 2; lattice.insert(lattice.end(), a.begin(), a.end());
         poff[2 * p + 1] = (int)lattice.size() / 2; pn[2 * p + 1] = (int)b.size() / 2; lattice.insert(lattice.end(), b.begin(), b.end());
     }
@@ -246,7 +254,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     UP(kpack, kpack) UP(grid, g) UP(static_occ, socc) UP(types, rts) UP(type_of, type_of) UP(lattice_xy, lattice) UP(ray_end, ray_end)
     UP(fov_spans, spans) UP(khi, khi) UP(klo, klo) UP(own_mask, own_mask) UP(need_idx, need_idx) UP(cubic_tap, tap)
     UP(cubic_coef, coef) UP(f16_lut, lut) UP(lim_v, lv) UP(lim_w, lw) UP(ped_shape, pshape) UP(ped_size, psize)
-    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(dtab, dtab) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(own_cells, own_dummy)
+    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(dtab, dtab) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(ped_ext, pext) UP(own_cells, own_dummy)
 #undef UP
     size_t S = c.S;
     size_t pc = ((size_t)H * W + 3) & ~(size_t)3;
@@ -413,11 +421,11 @@ __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, co
 
 static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int is_reset, cudaStream_t st, cudaEvent_t* ev = nullptr) {
     Dev& d = h->d; const Cfg& c = d.c;
-    k_stamp_agents<<<n_scenes * (c.R + c.P), 128, 0, st>>>(d, d_scene_ids, 0);
+    k_stamp_agents<<<n_scenes * (c.R + c.P), STAMP_THREADS, 0, st>>>(d, d_scene_ids, 0);
     if (ev) cudaEventRecord(ev[2], st);
     k_view<false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
     if (ev) cudaEventRecord(ev[3], st);
-    k_stamp_agents<<<n_scenes * (c.R + c.P), 128, 0, st>>>(d, d_scene_ids, is_reset ? 1 : 2);    // 2: also step_++
+    k_stamp_agents<<<n_scenes * (c.R + c.P), STAMP_THREADS, 0, st>>>(d, d_scene_ids, is_reset ? 1 : 2);    // 2: also step_++
     if (ev) cudaEventRecord(ev[4], st);
     CK(cudaGetLastError());
     return 0;
@@ -677,9 +685,9 @@ extern "C" int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* 
     if (host_out) CK(cudaMalloc((void**)&buf, n));
     if (stats_out) { CK(cudaMalloc((void**)&sbuf, (size_t)c.S * c.R * 16)); CK(cudaMemsetAsync(sbuf, 0, (size_t)c.S * c.R * 16, st)); }
     d.dbg_view = buf; d.dbg_stats = sbuf;
-    k_stamp_agents<<<c.S * (c.R + c.P), 128, 0, st>>>(d, nullptr, 0);
+    k_stamp_agents<<<c.S * (c.R + c.P), STAMP_THREADS, 0, st>>>(d, nullptr, 0);
     k_view<true><<<c.S * c.R, VIEW_THREADS, h->view_smem, st>>>(d, nullptr, 0);
-    k_stamp_agents<<<c.S * (c.R + c.P), 128, 0, st>>>(d, nullptr, 1);
+    k_stamp_agents<<<c.S * (c.R + c.P), STAMP_THREADS, 0, st>>>(d, nullptr, 1);
     cudaError_t e = cudaSuccess;
     if (host_out) e = cudaMemcpyAsync(host_out, buf, n, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && stats_out) e = cudaMemcpyAsync(stats_out, sbuf, (size_t)c.S * c.R * 16, cudaMemcpyDeviceToHost, st);

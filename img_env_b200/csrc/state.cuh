@@ -62,7 +62,8 @@ struct Cfg {
     int S, R, P, NA;         // NA = solver agents = P + (relation ? R : 0)
     int H, W, Wb, Hc;        // grid rows, cols, u32 words per bit-plane row, 32-row blocks
     int vh, vw, vwb;         // view raster rows/cols, words per row
-    double res;              // view resolution == grid resolution (float32 widened)
+    double res, inv_res;     // view resolution == grid resolution (float32 widened), 1/res
+    double cull_reach;       // farthest world distance from a robot's position to anything its observation can read
     double step_hz, control_hz;   // period (float32 widened), 0.05
     int state_dim, use_laser, range_total, ktype, scene_type, relation;
     double beep_r, ped_ca_p;
@@ -109,6 +110,7 @@ struct Dev {
     const float* ped_r_wire;      // [P] float32 r_ = sizes_[2]
     const int* ped_pts_off;       // [P][2] lattice offsets (body or left leg, right leg)
     const int* ped_pts_n;         // [P][2]
+    const double* ped_ext;        // [P] bound on the distance from the pedestrian position to any cell it stamps
     // per scene planes
     uint32_t* occ_all;            // [S][H][Wb]
     uint8_t* flags;               // [S][H][W]

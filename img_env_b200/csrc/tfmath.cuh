@@ -98,3 +98,13 @@ HD double tf_yaw_of(const Tf2& t) {
 }
 // GridMap::world2map (grid_map.cpp:40-44): int(round(x / res)), round half away from zero
 HD int world2cell(double x, double res) { return (int)round(x / res); }
+
+// Same result as world2cell() without the fp64 division in the common case: t = x * (1/res) differs from x/res
+// by a few ulp (< 1e-11 cells for |t| < 1e4), so whenever t is farther than 1e-9 from a rounding boundary
+// rint(t) == round(x/res); otherwise fall back to the exact expression.
+HD int world2cell_fast(double x, double res, double inv_res) {
+    const double t = x * inv_res;
+    const double r = rint(t);
+    if (fabs(t - r) > 0.499999999) return (int)round(x / res);
+    return (int)r;
+}

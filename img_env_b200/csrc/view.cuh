@@ -96,27 +96,42 @@ __device__ __forceinline__ void stamp_points(const Dev& d, int s, const Tf2& t, 
         }
         double wx, wy;
         tf_apply(t, bx, by, wx, wy);
-        stamp_cell(d, s, world2cell(wx, d.c.res), world2cell(wy, d.c.res), mode, id);
+        stamp_cell(d, s, world2cell_fast(wx, d.c.res, d.c.inv_res), world2cell_fast(wy, d.c.res, d.c.inv_res), mode, id);
     }
 }
 
 // grid = n_scenes * (R + P) CTAs; `unstamp` selects the inverse operation.
-__global__ void k_stamp_agents(Dev d, const int* scene_ids, int unstamp) {
-    int per = d.c.R + d.c.P;
-    int sl = blockIdx.x / per, a = blockIdx.x % per;
-    int s = scene_ids ? scene_ids[sl] : sl;
-    int add = unstamp ? 8 : 0;
+#define STAMP_THREADS 64
+__global__ void __launch_bounds__(STAMP_THREADS) k_stamp_agents(Dev d, const int* scene_ids, int unstamp) {
+    const int per = d.c.R + d.c.P;
+    const int sl = blockIdx.x / per, a = blockIdx.x % per;
+    const int s = scene_ids ? scene_ids[sl] : sl;
+    const int add = unstamp ? 8 : 0;
     if (unstamp == 2 && a == 0 && threadIdx.x == 0) d.step_no[s] += 1;   // step_++ (img_env.cpp:518), after every reader of this step
-    if (a < d.c.R) {
-        int idx = s * d.c.R + a;
-        Tf2 t = tf_from_pose(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx));
+    const bool is_robot = a < d.c.R;
+    const int p = a - d.c.R;
+    // An agent's stamp can only be read by a robot whose collision lattice or view raster reaches it: skip agents
+    // farther than (view half-diagonal + own extent) from every (other) robot. The decision only depends on poses,
+    // so stamp and unstamp agree.
+    double x, y, yaw, ext;
+    if (is_robot) { const int idx = s * d.c.R + a; x = RBF(d, RB_X, idx); y = RBF(d, RB_Y, idx); yaw = RBF(d, RB_YAW, idx); ext = d.types[d.type_of[a]].zone_rad * d.c.res; }
+    else { const int idx = s * d.c.P + p; x = PDF(d, PD_X, idx); y = PDF(d, PD_Y, idx); yaw = PDF(d, PD_YAW, idx); ext = d.ped_ext[p]; }
+    const double reach = d.c.cull_reach + ext;
+    int rel = 0;
+    for (int j = threadIdx.x; j < d.c.R; j += STAMP_THREADS) {
+        if (is_robot && j == a) continue;
+        const int idx = s * d.c.R + j;
+        const double dx = RBF(d, RB_X, idx) - x, dy = RBF(d, RB_Y, idx) - y;
+        rel |= dx * dx + dy * dy <= reach * reach;
+    }
+    if (!__syncthreads_or(rel)) return;
+    const Tf2 t = tf_from_pose(x, y, yaw);
+    if (is_robot) {
         const RobotType& ty = d.types[d.type_of[a]];
         stamp_points(d, s, t, d.lattice_xy + 2 * (size_t)ty.pts_off, ty.n_pts, 0 + add, a, 0, 0);
     } else {
-        int p = a - d.c.R;
-        int idx = s * d.c.P + p;
-        Tf2 t = tf_from_pose(PDF(d, PD_X, idx), PDF(d, PD_Y, idx), PDF(d, PD_YAW, idx));
-        int shape = d.ped_shape[p];
+        const int idx = s * d.c.P + p;
+        const int shape = d.ped_shape[p];
         if (shape == 0) {
             stamp_points(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p], d.ped_pts_n[2 * p], 1 + add, p, 0, 0);
         } else if (shape == 2) {
@@ -339,7 +354,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             for (int k = tid; k < ty.n_pts; k += VIEW_THREADS) {
                 double wx, wy;
                 tf_apply(sh->base_world, pts[2 * k], pts[2 * k + 1], wx, wy);
-                int cx = world2cell(wx, c.res), cy = world2cell(wy, c.res);
+                int cx = world2cell_fast(wx, c.res, c.inv_res), cy = world2cell_fast(wy, c.res, c.inv_res);
                 if ((unsigned)cx < (unsigned)c.H && (unsigned)cy < (unsigned)c.W) {
                     int v = global_value(d, s, r, cx, cy);
                     if (v <= 2) best = max(best, ((k + 1) << 2) | (v + 1));

@@ -37,7 +37,7 @@ def test_cuda_matches_reference_golden(name):
             want["ped_min_dists"] = got["ped_min_dists"].astype(np.float64)   # persists (inf) without pedestrians
         errs += compare_state(got, want, spec, where="step %d: " % t)
         vm = sim.debug_view_maps()[0]
-        frozen = (pre[:, 12] != 0) | (pre[:, 13] != 0)
+        frozen = (pre[:, 12] != 0) | (pre[:, 13] != 0) | (g["s%d_post_robot" % t][:, 13] != 0)   # arriving robots skip their view too
         for j in range(spec["R"]):
             if not frozen[j]:
                 nb = int((vm[j] != g["s%d_view_map" % t][j]).sum())

@@ -96,7 +96,7 @@ def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False
                 # frozen robots keep a stale view in the node; the debug raster is recomputed -> skip them
                 now_frozen = (rb_ref[:, 12] != 0) | (rb_ref[:, 13] != 0)
                 for j in range(R):
-                    if frozen_before[j]:
+                    if frozen_before[j] or rb_ref[j, 13] != 0:   # a robot that ARRIVES in this step skips its view too (cmd runs before view)
                         continue
                     nb = int((vm[s, j] != st["view_map"][j]).sum())
                     if nb:
@@ -160,3 +160,59 @@ def test_dataset_replay_pedestrians():
     cfg = base_cfg(R=2, P=5, scene="dataset", n_obj=2)
     cfg["ped_sim"]["max_traj"] = 5
     run_lockstep(cfg, seed=11, steps=8, lo=3.0, hi=8.0)     # runs past the end of the trajectories (index clamps)
+
+
+# ---- configuration sweep: every branch of the view / laser code against the reference node -------------------------
+def _variant(**kw):
+    over = {k: kw.pop(k) for k in list(kw) if k in ("view_angle_begin", "view_angle_end", "view_min_dist", "view_max_dist", "use_laser",
+                                                    "laser_norm", "laser_max", "sensor", "view", "grey_map")}
+    cfg = base_cfg(**kw)
+    for k in ("view_angle_begin", "view_angle_end", "view_min_dist", "view_max_dist", "use_laser", "laser_norm", "laser_max"):
+        if k in over:
+            cfg[k] = over[k]
+    if "sensor" in over:
+        cfg["robot"]["sensor_cfgs"] = [list(over["sensor"])] * cfg["robot"]["total"]
+    if "view" in over:
+        cfg["view_map"] = dict(resolution=over["view"][0], width=over["view"][1], height=over["view"][1])
+    if over.get("grey_map"):
+        # interpolated / hand-painted greys: 1 and 2 read as pedestrian / robot collisions, < 250 is occupied for the view
+        rng = np.random.default_rng(99)
+        img = cfg["global_map"]["image"].copy()
+        for v in (1, 2, 3, 100, 249, 250, 251):
+            r, c = rng.integers(20, 85, 2)
+            img[r:r + 6, c:c + 6] = v
+        cfg["global_map"]["image"] = img
+    return cfg
+
+
+def test_narrow_fov_with_sensor_offset_and_fewer_rays():
+    run_lockstep(_variant(R=3, P=4, scene="rvoscene", n_obj=3, range_total=360, view_angle_begin=-1.0, view_angle_end=1.2, sensor=(0.14, 0.0)),
+                 seed=21, steps=5, lo=3.5, hi=7.5)
+
+
+def test_min_and_max_view_distance():
+    run_lockstep(_variant(R=2, P=3, scene="rvoscene", n_obj=3, view_min_dist=0.3, view_max_dist=2.5, range_total=512), seed=22, steps=5, lo=3.5, hi=7.5)
+
+
+def test_without_lasers_view_map_is_the_raster():
+    run_lockstep(_variant(R=3, P=4, scene="rvoscene", n_obj=3, use_laser=False), seed=23, steps=5, lo=3.5, hi=7.5)
+
+
+def test_unnormalised_lasers_state_dim4():
+    run_lockstep(_variant(R=2, P=0, n_obj=4, laser_norm=False, state_dim=4), seed=24, steps=5)
+
+
+def test_grey_map_values_collide_like_agents():
+    run_lockstep(_variant(R=6, P=3, scene="rvoscene", n_obj=2, grey_map=True), seed=25, steps=8, lo=2.0, hi=8.5)
+
+
+def test_coarser_view_resolution():
+    run_lockstep(_variant(R=2, P=3, scene="rvoscene", n_obj=3, view=(0.02, 6)), seed=26, steps=5, lo=3.5, hi=7.5)
+
+
+def test_wide_fov_two_spans_per_row():
+    run_lockstep(_variant(R=2, P=3, scene="rvoscene", n_obj=3, view_angle_begin=-2.6, view_angle_end=2.6, range_total=720), seed=27, steps=5, lo=3.5, hi=7.5)
+
+
+def test_robot_near_map_border_and_outside_view():
+    run_lockstep(_variant(R=4, P=2, scene="rvoscene", n_obj=1), seed=28, steps=6, lo=0.3, hi=2.0)
