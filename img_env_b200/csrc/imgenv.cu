@@ -730,3 +730,49 @@ extern "C" int imgenv_sfm_tree_set(imgenv_t* h, int32_t scene, int32_t n_nodes, 
     CK(cudaMemcpy(d.qt_hash + (size_t)scene * c.NA, hash, (size_t)c.NA * 4, cudaMemcpyHostToDevice));
     return 0;
 }
+
+// The byte map robot `self` would see as its global_map_ (static + reset objects + pedestrians + other robots;
+// self < 0: peds_map_, i.e. no robots; self == -2: obs_map_, i.e. no pedestrians either) for one scene,
+// u8 [H][W] to host. Test / debugging aid: the node never materialises this on the GPU path.
+__global__ void k_debug_global_map(Dev d, int s, int self, uint8_t* out) {
+    const size_t n = (size_t)d.c.H * d.c.W;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const int cx = (int)(q / d.c.W), cy = (int)(q % d.c.W);
+        int v;
+        if (self >= 0) v = global_value(d, s, self, cx, cy);
+        else {
+            const size_t po = (size_t)s * plane_cells(d.c);
+            int sv = d.grid[q];
+            const unsigned f = d.flags[po + q];
+            if ((f & F_OBJ) && sv > 2) sv = 0;
+            if (self == -2) v = sv;
+            else if (f & F_RIGHT) v = 1;
+            else if (f & F_LEFT) v = (sv == 0) ? 0 : 1;
+            else if (f & F_CIRC) v = (sv <= 2) ? sv : 1;
+            else v = sv;
+        }
+        out[q] = (uint8_t)v;
+    }
+}
+extern "C" int imgenv_debug_global_map(imgenv_t* h, int32_t scene, int32_t self, uint8_t* host_out, void* stream) {
+    if (!h || !host_out) return fail("imgenv_debug_global_map: null argument");
+    Dev d = h->d; const Cfg& c = d.c;
+    if (scene < 0 || scene >= c.S || self >= c.R) return fail("imgenv_debug_global_map: bad scene / robot");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)c.H * c.W;
+    uint8_t* buf = nullptr;
+    CK(cudaMalloc((void**)&buf, n));
+    // stamp EVERY agent of the scene (no culling is involved in a whole-map dump: stamp with an infinite reach)
+    Dev dd = d; dd.c.cull_reach = 1e30;
+    int* ids = nullptr;
+    CK(cudaMalloc((void**)&ids, 4));
+    CK(cudaMemcpyAsync(ids, &scene, 4, cudaMemcpyHostToDevice, st));
+    k_stamp_agents<<<(c.R + c.P), STAMP_THREADS, 0, st>>>(dd, ids, 0);
+    k_debug_global_map<<<592, 256, 0, st>>>(dd, scene, self, buf);
+    k_stamp_agents<<<(c.R + c.P), STAMP_THREADS, 0, st>>>(dd, ids, 1);
+    cudaError_t e = cudaMemcpyAsync(host_out, buf, n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(buf); cudaFree(ids);
+    if (e != cudaSuccess) return fail(std::string("imgenv_debug_global_map: ") + cudaGetErrorString(e));
+    return 0;
+}

@@ -35,7 +35,7 @@ class ImgenvOutputs(C.Structure):
 
 
 EXPORTS = ["imgenv_create", "imgenv_destroy", "imgenv_bind_outputs", "imgenv_reset", "imgenv_step", "imgenv_step_host",
-           "imgenv_end_episode", "imgenv_get_internal", "imgenv_set_internal", "imgenv_debug_view_maps", "imgenv_debug_view_maps2",
+           "imgenv_end_episode", "imgenv_get_internal", "imgenv_set_internal", "imgenv_debug_view_maps", "imgenv_debug_view_maps2", "imgenv_debug_global_map",
            "imgenv_solver_agents", "imgenv_view_dims", "imgenv_launches_per_step",
            "imgenv_algorithmic_bytes_per_robot_step", "imgenv_last_error", "imgenv_version"]
 
@@ -225,6 +225,13 @@ class BatchedSim:
         nodes = np.ascontiguousarray(nodes, dtype=np.float64); leaf = np.ascontiguousarray(leaf, dtype=np.int32)
         hash_ = np.ascontiguousarray(hash_, dtype=np.int32)
         self._check(self.lib.imgenv_sfm_tree_set(self.h, int(scene), nodes.shape[0], _ptr(nodes), _ptr(leaf, C.c_int32), _ptr(hash_, C.c_int32)))
+
+    def debug_global_map(self, scene=0, robot=-1):
+        """robot >= 0: that robot's global_map_; -1: peds_map_; -2: obs_map_ (u8 [H, W])."""
+        H, W = self.spec["grid"].shape
+        out = np.zeros((H, W), np.uint8)
+        self._check(self.lib.imgenv_debug_global_map(self.h, int(scene), int(robot), _ptr(out, C.c_uint8), self._stream()))
+        return out
 
     def debug_stats(self):
         out = np.zeros((self.S, self.R, 4), np.int32)

@@ -117,6 +117,9 @@ int imgenv_debug_view_maps(imgenv_t* h, uint8_t* host_out, void* stream);
 /* Same + per-robot kernel statistics int32 [S][R][4] (active raster tiles, boundary cells, heavy cells, marching
  * fallback taken). Either output may be NULL. */
 int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* stats_out, void* stream);
+/* Debug raster: the composited byte map of one scene, u8 [H][W] to host. self >= 0: robot self's
+ * global_map_ (img_env.cpp:623-628); self == -1: peds_map_ (img_env.cpp:594-618); self == -2: obs_map_ (img_env.cpp:167-187). */
+int imgenv_debug_global_map(imgenv_t* h, int32_t scene, int32_t self, uint8_t* host_out, void* stream);
 /* ped_min_dists persistence (NearbyPed, reset_helper.py:85-99) and dones are library state. */
 int imgenv_solver_agents(const imgenv_t* h);   /* P + R' */
 int imgenv_view_dims(const imgenv_t* h, int32_t* vh, int32_t* vw);

@@ -216,3 +216,29 @@ def test_wide_fov_two_spans_per_row():
 
 def test_robot_near_map_border_and_outside_view():
     run_lockstep(_variant(R=4, P=2, scene="rvoscene", n_obj=1), seed=28, steps=6, lo=0.3, hi=2.0)
+
+
+def test_composited_maps_match_node_rasters():
+    """obs_map_ / peds_map_ of the node (img_env.cpp:167-187, 594-618) against the planes the CUDA path keeps instead:
+    objects, circle and leg pedestrians incl. the right-leg overwrite quirk, on a map with grey values."""
+    import torch
+    from img_env_b200.lib import BatchedSim
+    from oracle.pyref import RefEnv, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    for ped_shape in ("leg", "circle"):
+        cfg = _variant(R=3, P=12, scene="rvoscene", n_obj=6, grey_map=True, ped_shape=ped_shape, max_ped=12)
+        spec = build_spec(cfg)
+        rng = np.random.default_rng(31)
+        sim = BatchedSim(spec, 1, ped_yaw_mode=1); ref = RefEnv(spec)
+        rs = make_reset(spec, rng, lo=3.0, hi=6.0)            # crowded: overlapping stamps
+        sim.reset([rs]); ref.reset(rs)
+        for t in range(3):
+            assert np.array_equal(sim.debug_global_map(0, -2), ref.get_map(1)), "obs_map_ differs"
+            assert np.array_equal(sim.debug_global_map(0, -1), ref.get_map(2)), "peds_map_ differs (%s, step %d)" % (ped_shape, t)
+            acts = random_actions(3, rng)
+            rb, pd = ref.get_internal(); rb = rb.copy(); rb[:, 15] = np.nan
+            sim.set_internal(rb[None], pd[None], ref.rvo_get().astype(np.float64)[None])
+            sim.step(torch.from_numpy(acts[None]).cuda(), torch.ones(1, 3, dtype=torch.uint8, device="cuda"))
+            ref.step(acts, np.ones(3))
+        sim.close()
