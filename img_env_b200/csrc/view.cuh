@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         // Agent::view early-out (agent.cpp:358-360): stale view_map_/hits_/is_collision_ are re-sent
         sh->frozen = (RBF(d, RB_COLL, idx) != 0.0) || (RBF(d, RB_ARR, idx) != 0.0);
         sh->coll_key = 0;      // reused as boundary-list counters below
-        sh->red[0] = 0; sh->red[1] = 0; sh->red[2] = 0; sh->red[3] = 0;
+        sh->red[0] = 0; sh->red[1] = 0; sh->red[2] = 0; sh->red[3] = 0; sh->red[4] = 0;
         {   // inverse map and the FOV's world bounding box (for the world->view rasterisation)
             const double det = A.m00 * A.m11 - A.m01 * A.m10;
             sh->inv[0] = A.m11 / det; sh->inv[1] = -A.m01 / det; sh->inv[2] = -A.m10 / det; sh->inv[3] = A.m00 / det;
@@ -442,7 +442,12 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             const int zx = sh->zc[0], zy = sh->zc[1], zr = ty.zone_rad;
             const float i00 = (float)sh->inv[0], i01 = (float)sh->inv[1], i10 = (float)sh->inv[2], i11 = (float)sh->inv[3];
             // each warp takes 32 words (one per lane), then expands their candidate bits over all lanes
-            for (int base = warp * 32; base < n_items; base += VIEW_THREADS) {
+            // batches of 32 words are handed out dynamically: dense world blocks make the work per batch very uneven
+            for (;;) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&sh->red[4], 32);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n_items) break;
                 const int item = base + lane;
                 unsigned cand = 0; int X = 0, bj = 0;
                 if (item < n_items) {
