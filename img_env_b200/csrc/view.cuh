@@ -238,7 +238,7 @@ __device__ __forceinline__ int ray_touch(int ox, int oy, int ex, int ey, int pr,
 // Shared-memory plan (bytes for the canonical 400x400 view / 1000 rays / 48x48 outputs):
 //   region A  occ raster 400*13*4 = 20.8 KB   (phases B-C)   | later: ped map winners + pedestrian scratch (phase G)
 //   region B  boundary-cell list 24 KB        (phase C)       | later: horizontal resize buffer 144*48*4 = 27.6 KB (phase F)
-//   pix       144*144 u8 = 20.7 KB            (phases D-F)
+//   (no pixel buffer: the laser_map values are evaluated inside the horizontal resize pass)
 //   hitkey    range_total*4, ray end cells range_total*4, needed-line indices
 #define BL_CAP 3072          // candidate cells kept in shared memory; further cells are resolved inline by their finder
 #define BL2_CAP 256          // cells touched by many rays (close to the origin): processed warp-cooperatively
@@ -247,7 +247,7 @@ __device__ __forceinline__ int ray_touch(int ox, int oy, int ex, int ey, int pr,
 
 #define HB_COLS 16           // output columns per vertical-pass block (bounds the horizontal buffer)
 #define INV_MAX_BLOCKS 512   // 32x32-cell world blocks under the FOV; more -> forward (tile) rasterisation
-struct ViewLayout { size_t sh, regA, regB, pix, hitkey, rays, need, spans, blocks, total; };
+struct ViewLayout { size_t sh, regA, regB, hitkey, rays, need, spans, blocks, total; };
 __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     ViewLayout L;
     size_t off = 0;
@@ -257,7 +257,6 @@ __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     L.regA = off; off += ((occ > pedb ? occ : pedb) + 15) & ~(size_t)15;
     size_t bl = (size_t)(BL_CAP + BL2_CAP) * 4, hb = (size_t)c.ns * HB_COLS * 4;
     L.regB = off; off += ((bl > hb ? bl : hb) + 15) & ~(size_t)15;
-    L.pix = off; off += ((size_t)c.ns * ((c.ns + 15) / 16) * 4 + 15) & ~(size_t)15;      // 2 bits per needed pixel, rows padded to words
     L.hitkey = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
     L.rays = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
     L.need = off; off += ((size_t)c.ns * 2 + 15) & ~(size_t)15;
@@ -288,8 +287,6 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
     uint32_t* blist = reinterpret_cast<uint32_t*>(smem_raw + L.regB);
     uint32_t* blist2 = blist + BL_CAP;
     int* hbuf = reinterpret_cast<int*>(smem_raw + L.regB);
-    uint32_t* pix = reinterpret_cast<uint32_t*>(smem_raw + L.pix);     // 2-bit codes: 0 -> 0, 1 -> 100, 2 -> 200, 3 -> 255
-    const int pixw = (c.ns + 15) / 16;
     short* spans = reinterpret_cast<short*>(smem_raw + L.spans);
     uint32_t* blocks = reinterpret_cast<uint32_t*>(smem_raw + L.blocks);
     unsigned* hitkey = reinterpret_cast<unsigned*>(smem_raw + L.hitkey);
@@ -340,7 +337,6 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         for (int k = tid; k < c.ns; k += VIEW_THREADS) need[k] = d.need_idx[k];
         const short* g_spans = d.fov_spans + (size_t)ty.span_off;
         for (int k = tid; k < 4 * vh; k += VIEW_THREADS) spans[k] = g_spans[k];
-        for (int k = tid; k < c.ns * pixw; k += VIEW_THREADS) pix[k] = 0u;
         for (int k = tid; k < c.range_total; k += VIEW_THREADS) hitkey[k] = NOHIT;
     }
     __syncthreads();
@@ -640,102 +636,88 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             }
         }
 
-        // ---- Phase D/E: final view_map_ value of every pixel the cubic resize reads (or of the whole
-        // raster in debug mode): last-writer-wins over rays in index order, evaluated per pixel from the
-        // highest touching ray downwards, then the robot's own footprint (value 100, agent.cpp:503).
-        // kpack = highest | lowest<<16 touching ray; the highest one touches by construction, so only its
-        // step index is needed; the full touch test runs only on the (rare) fall-through candidates.
+        // ---- Phase D/E/F: laser_map reconstruction fused into the cubic resize.
+        // D/E: the final view_map_ value of a pixel = last-writer-wins over the rays in index order, evaluated from
+        //      the highest touching ray downwards (static tables), then the robot's own footprint (100, agent.cpp:503).
+        //      dtab packs, per pixel the resize reads, the top ray, its step index there and the own-footprint bit:
+        //      the top ray touches by construction, so the closed-form touch test only runs on fall-through.
+        // F:   cv2.resize(INTER_CUBIC) 400->48 (yaml_env.py:433-434), OpenCV's own path: horizontal pass in int32 with
+        //      11-bit weights, vertical pass as an fp32 FMA chain with weights * 2^-22, round-half-even, saturate; then
+        //      float16(x)/255 via a host-built table.  Every source pixel with a non-zero weight belongs to exactly one
+        //      output column, so the horizontal pass evaluates its (<= 4) pixels on the fly: no pixel buffer.
         const uint32_t* own_mask = d.own_mask + (size_t)ty.own_mask_off;
-        if (!DEBUG_FULL && c.use_laser) {
-            // fast path over the ns x ns pixels the resize reads: one coalesced table word per pixel
-            const uint32_t* dtab = d.dtab + (size_t)ty.dtab_off;
-            for (int rr = warp; rr < c.ns; rr += VIEW_THREADS / 32) {
-              for (int cc0 = 0; cc0 < c.ns; cc0 += 128) {
-                unsigned ev[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) { const int cc = cc0 + u * 32 + lane; ev[u] = cc < c.ns ? __ldg(dtab + rr * c.ns + cc) : 0u; }   // 4 loads in flight
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int cc = cc0 + u * 32 + lane;
-                    if (cc >= c.ns) continue;
-                    const unsigned e = ev[u];
-                    const int kh = e & 0xFFF;
-                    unsigned code = 2u;                                        // 200: untouched
-                    if (kh != 0xFFF) {
-                        const unsigned key = hitkey[kh];
-                        const int hp = (int)(key >> 22), i0 = (e >> 12) & 0x3FF;
-                        if (i0 < hp) code = 3u;
-                        else if (i0 == hp) code = 0u;
-                        else {
-                            const int pr = need[rr], pc = need[cc];
-                            if (pr != (int)((key >> 11) & 2047) && pc != (int)(key & 2047)) code = 2u;       // shadow write
-                            else {                                                                           // fall through to lower rays
-                                const unsigned kp = __ldg(kpack + pr * vw + pc);
-                                const int kl = kp >> 16;
-                                for (int k = kh - 1; k >= kl; k--) {
-                                    const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
-                                    if (i < 0) continue;
-                                    const unsigned key2 = hitkey[k];
-                                    const int hp2 = (int)(key2 >> 22);
-                                    if (i < hp2) { code = 3u; break; }
-                                    if (i == hp2) { code = 0u; break; }
-                                    if (pr != (int)((key2 >> 11) & 2047) && pc != (int)(key2 & 2047)) { code = 2u; break; }
-                                }
+        const uint32_t* dtab = d.dtab + (size_t)ty.dtab_off;
+        // value code of the needed pixel (rr, nc): 0 -> 0, 1 -> 100, 2 -> 200, 3 -> 255
+        auto pixel_code = [&](int rr, int nc) -> unsigned {
+            unsigned code = 2u; bool own;
+            if (c.use_laser) {
+                const unsigned e = __ldg(dtab + rr * c.ns + nc);
+                own = e >> 31;
+                const int kh = e & 0xFFF;
+                if (kh != 0xFFF) {
+                    const unsigned key = hitkey[kh];
+                    const int hp = (int)(key >> 22), i0 = (e >> 12) & 0x3FF;
+                    if (i0 < hp) code = 3u;
+                    else if (i0 == hp) code = 0u;
+                    else {
+                        const int pr = need[rr], pc = need[nc];
+                        if (!(pr != (int)((key >> 11) & 2047) && pc != (int)(key & 2047))) {     // no shadow write: fall through to lower rays
+                            const unsigned kp = __ldg(kpack + pr * vw + pc);
+                            const int kl = kp >> 16;
+                            for (int k = kh - 1; k >= kl; k--) {
+                                const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
+                                if (i < 0) continue;
+                                const unsigned key2 = hitkey[k];
+                                const int hp2 = (int)(key2 >> 22);
+                                if (i < hp2) { code = 3u; break; }
+                                if (i == hp2) { code = 0u; break; }
+                                if (pr != (int)((key2 >> 11) & 2047) && pc != (int)(key2 & 2047)) { code = 2u; break; }
                             }
                         }
                     }
-                    if (code != 0u && (e >> 31)) code = 1u;                    // own footprint (100) unless the cell is 0
-                    if (code) atomicOr(&pix[rr * pixw + (cc >> 4)], code << (2 * (cc & 15)));
                 }
-              }
+            } else {
+                const int pr = need[rr], pc = need[nc], full = pr * vw + pc;
+                const bool o = (occ[pr * vwb + (pc >> 5)] >> (pc & 31)) & 1u;
+                const bool kn = (known[pr * vwb + (pc >> 5)] >> (pc & 31)) & 1u;
+                code = o ? 0u : (kn ? 3u : 2u);
+                own = (own_mask[full >> 5] >> (full & 31)) & 1u;
+            }
+            if (code != 0u && own) code = 1u;
+            return code;
+        };
+        if (DEBUG_FULL) {
+            // whole 400x400 raster for the tests (generic per-pixel path)
+            for (int rr = warp; rr < vh; rr += VIEW_THREADS / 32) {
+                for (int cc = lane; cc < vw; cc += 32) {
+                    const int pr = rr, pc = cc, full = pr * vw + pc;
+                    int val = 200;
+                    if (c.use_laser) {
+                        const unsigned kp = __ldg(kpack + full);
+                        const int kh = kp & 0xFFFF;
+                        if (kh != 0xFFFF) {
+                            const int kl = kp >> 16;
+                            for (int k = kh; k >= kl; k--) {
+                                const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
+                                if (i < 0) continue;
+                                const unsigned key = hitkey[k];
+                                const int hp = (int)(key >> 22);
+                                if (i < hp) { val = 255; break; }
+                                if (i == hp) { val = 0; break; }
+                                if (pr != (int)((key >> 11) & 2047) && pc != (int)(key & 2047)) { val = 200; break; }   // shadow write (agent.cpp:557-558)
+                            }
+                        }
+                    } else {
+                        const bool o = (occ[pr * vwb + (pc >> 5)] >> (pc & 31)) & 1u;
+                        const bool kn = (known[pr * vwb + (pc >> 5)] >> (pc & 31)) & 1u;
+                        val = o ? 0 : (kn ? 255 : 200);
+                    }
+                    if (val != 0 && pr >= ty.zone_r0 && pr <= ty.zone_r1 && pc >= ty.zone_c0 && pc <= ty.zone_c1 &&
+                        ((own_mask[full >> 5] >> (full & 31)) & 1u)) val = 100;
+                    if (d.dbg_view) d.dbg_view[(size_t)idx * vh * vw + full] = (uint8_t)val;
+                }
             }
         } else {
-        const int nrows = DEBUG_FULL ? vh : c.ns, ncols = DEBUG_FULL ? vw : c.ns;
-        for (int rr = warp; rr < nrows; rr += VIEW_THREADS / 32) {
-            const int pr = DEBUG_FULL ? rr : need[rr];
-            for (int cc = lane; cc < ncols; cc += 32) {
-                const int pc = DEBUG_FULL ? cc : need[cc];
-                const int full = pr * vw + pc;
-                int val = 200;
-                if (c.use_laser) {
-                    const unsigned kp = __ldg(kpack + full);
-                    const int kh = kp & 0xFFFF;
-                    if (kh != 0xFFFF) {
-                        const int kl = kp >> 16;
-                        const int w0 = abs((int)rend[2 * kh] - ox), h0 = abs((int)rend[2 * kh + 1] - oy);
-                        int i = w0 > h0 ? abs(pr - ox) : abs(pc - oy);
-                        for (int k = kh;;) {
-                            const unsigned key = hitkey[k];
-                            const int hp = (int)(key >> 22);
-                            if (i < hp) { val = 255; break; }
-                            if (i == hp) { val = 0; break; }
-                            if (pr != (int)((key >> 11) & 2047) && pc != (int)(key & 2047)) { val = 200; break; }   // shadow write (agent.cpp:557-558)
-                            do { k--; i = k >= kl ? ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc) : 0; } while (k >= kl && i < 0);
-                            if (k < kl) break;
-                        }
-                    }
-                } else {
-                    const bool o = (occ[pr * vwb + (pc >> 5)] >> (pc & 31)) & 1u;
-                    const bool kn = (known[pr * vwb + (pc >> 5)] >> (pc & 31)) & 1u;
-                    val = o ? 0 : (kn ? 255 : 200);
-                }
-                if (val != 0 && pr >= ty.zone_r0 && pr <= ty.zone_r1 && pc >= ty.zone_c0 && pc <= ty.zone_c1 &&
-                    ((own_mask[full >> 5] >> (full & 31)) & 1u)) val = 100;
-                if (DEBUG_FULL) { if (d.dbg_view) d.dbg_view[(size_t)idx * vh * vw + full] = (uint8_t)val; }
-                else {
-                    const unsigned code = val == 0 ? 0u : val == 100 ? 1u : val == 200 ? 2u : 3u;
-                    if (code) atomicOr(&pix[rr * pixw + (cc >> 4)], code << (2 * (cc & 15)));
-                }
-            }
-        }
-        }
-        __syncthreads();
-
-        if (!DEBUG_FULL) {
-            // ---- Phase F: cv2.resize(INTER_CUBIC) 400->48 (yaml_env.py:433-434), OpenCV's own path:
-            // horizontal pass in int32 with 11-bit weights, vertical pass as an fp32 FMA chain with
-            // weights * 2^-22, round-half-even, saturate; then float16(x)/255 via a host-built table.
-            // Done in blocks of HB_COLS output columns to bound the int32 buffer.
             const float scale = 1.f / (2048.f * 2048.f);
             for (int cb = 0; cb < c.img; cb += HB_COLS) {
                 const int nc = min(HB_COLS, c.img - cb);
@@ -743,13 +725,13 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     const int rr = q / HB_COLS, ocl = q % HB_COLS;
                     if (ocl >= nc) continue;
                     const short* tp = d.cubic_tap + 4 * (cb + ocl); const short* cf = d.cubic_coef + 4 * (cb + ocl);
-                    const uint32_t* row = pix + rr * pixw;
                     int acc = 0;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const int n = tp[k];
-                        const unsigned code = (row[n >> 4] >> (2 * (n & 15))) & 3u;
-                        acc += (int)((0xFFC86400u >> (8 * code)) & 0xFFu) * cf[k];
+                        const int w = cf[k];
+                        if (w == 0) continue;
+                        const unsigned code = pixel_code(rr, tp[k]);
+                        acc += (int)((0xFFC86400u >> (8 * code)) & 0xFFu) * w;
                     }
                     hbuf[rr * HB_COLS + ocl] = acc;
                 }
