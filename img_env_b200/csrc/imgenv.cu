@@ -14,6 +14,7 @@
 #include "view.cuh"
 #include "dyn.cuh"
 #include "host_tables.h"
+#include "sampler.h"
 #include <random>
 
 static thread_local std::string g_err;
@@ -29,7 +30,10 @@ struct imgenv {
     bool outputs_bound = false;
     int ped_yaw_mode = 0;
     // reset staging (pinned host + device)
-    double* st_h = nullptr; double* st_d = nullptr; size_t st_doubles = 0;
+    // two sets used alternately: a reset only waits (on the set's event) for the reset before the previous one
+    struct Stage { double* h = nullptr; double* d = nullptr; int* ih = nullptr; int* id = nullptr; float* fh = nullptr; float* fd = nullptr; cudaEvent_t ev = nullptr; };
+    Stage stage[2]; int stage_i = 0;
+    double* st_h = nullptr; double* st_d = nullptr; size_t st_doubles = 0;   // aliases of the set in use
     int* sti_h = nullptr; int* sti_d = nullptr; size_t st_ints = 0;
     float* stf_h = nullptr; float* stf_d = nullptr; size_t st_floats = 0;
     float* act_d = nullptr; uint8_t* alive_d = nullptr;
@@ -102,9 +106,12 @@ extern "C" int imgenv_destroy(imgenv_t* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     for (void* p : h->allocs) cudaFree(p);
-    if (h->st_h) cudaFreeHost(h->st_h);
-    if (h->sti_h) cudaFreeHost(h->sti_h);
-    if (h->stf_h) cudaFreeHost(h->stf_h);
+    for (auto& g : h->stage) {
+        if (g.h) cudaFreeHost(g.h);
+        if (g.ih) cudaFreeHost(g.ih);
+        if (g.fh) cudaFreeHost(g.fh);
+        if (g.ev) cudaEventDestroy(g.ev);
+    }
     delete h;
     return 0;
 }
@@ -315,9 +322,12 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     h->st_doubles = S * ((size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 6 * (size_t)c.max_traj * c.P + 4 * c.max_obs) + 8;
     h->st_ints = S * ((size_t)5 + c.P + 3 * (size_t)d.max_verts) + S + 8;
     h->st_floats = S * ((size_t)8 * d.max_verts) + 8;
-    CK(cudaMallocHost((void**)&h->st_h, h->st_doubles * 8)); if (dalloc(h, &h->st_d, h->st_doubles)) return -1;
-    CK(cudaMallocHost((void**)&h->sti_h, h->st_ints * 4)); if (dalloc(h, &h->sti_d, h->st_ints)) return -1;
-    CK(cudaMallocHost((void**)&h->stf_h, h->st_floats * 4)); if (dalloc(h, &h->stf_d, h->st_floats)) return -1;
+    for (auto& g : h->stage) {
+        CK(cudaMallocHost((void**)&g.h, h->st_doubles * 8)); if (dalloc(h, &g.d, h->st_doubles)) return -1;
+        CK(cudaMallocHost((void**)&g.ih, h->st_ints * 4)); if (dalloc(h, &g.id, h->st_ints)) return -1;
+        CK(cudaMallocHost((void**)&g.fh, h->st_floats * 4)); if (dalloc(h, &g.fd, h->st_floats)) return -1;
+        CK(cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming));
+    }
 
     h->view_smem = view_smem_bytes(c);
     h->dyn_smem = dyn_smem_bytes(c);
@@ -440,7 +450,11 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     if (n < 1 || n > c.S) return fail("imgenv_reset: bad scene count");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaStreamSynchronize(st));   // staging buffers are reused
+    {   // staging is double-buffered: wait only until the reset that last used this set has consumed it
+        imgenv::Stage& g = h->stage[h->stage_i ^= 1];
+        CK(cudaEventSynchronize(g.ev));
+        h->st_h = g.h; h->st_d = g.d; h->sti_h = g.ih; h->sti_d = g.id; h->stf_h = g.fh; h->stf_d = g.fd;
+    }
     using ht::f32;
     if (c.scene_type == 4 && !traj_v) return fail("imgenv_reset: dataset replay needs traj_v");
     size_t dper = (size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 6 * (size_t)c.max_traj * c.P + 4 * c.max_obs;
@@ -521,7 +535,7 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     k_apply_reset<<<n, 128, 0, st>>>(d, n, h->st_d, h->sti_d, h->stf_d, dper, iper, fper);
     k_stamp_objects<<<n * c.max_obs, 128, 0, st>>>(d, ids_d, 0);     // obs.draw(obs_map_, 0, ...) img_env.cpp:187
     if (launch_observe(h, ids_d, n, 1, st)) return -1;                 // view_agent(); get_states() img_env.cpp:285-286
-    CK(cudaStreamSynchronize(st));
+    CK(cudaEventRecord(h->stage[h->stage_i].ev, st));                   // stream-ordered like imgenv_step: no host sync
     return 0;
 }
 
@@ -592,6 +606,95 @@ extern "C" int imgenv_step_host(imgenv_t* h, const float* h_actions, const uint8
     CK(cudaMemcpyAsync(h->act_d, h_actions, (size_t)c.S * c.R * 3 * 4, cudaMemcpyHostToDevice, st));
     if (h_alive) CK(cudaMemcpyAsync(h->alive_d, h_alive, (size_t)c.S * c.R, cudaMemcpyHostToDevice, st));
     return imgenv_step(h, h->act_d, h_alive ? h->alive_d : nullptr, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Native episode sampler (EnvPos.reset, reset_helper.py:115-345) and the fused sample+reset entry point.
+struct imgenv_sampler {
+    sampler::Sampler s;
+    std::vector<int32_t> n_obs, traj_len; std::vector<double> obs, robots, peds, traj;   // scratch of imgenv_reset_sampled
+};
+#define SAMPLER_HDR 8
+#define SAMPLER_POSE_REC (3 + SAMPLER_MAX_MULTI * 6)
+#define SAMPLER_AGENT_REC (1 + 2 * SAMPLER_POSE_REC)
+#define SAMPLER_OBJ_REC 14
+extern "C" int imgenv_sampler_create(const double* desc, int64_t n_desc, int32_t n_scenes, uint64_t seed, imgenv_sampler_t** out) {
+    if (!desc || !out || n_desc < SAMPLER_HDR || n_scenes < 1) return fail("imgenv_sampler_create: bad arguments");
+    imgenv_sampler* w = new imgenv_sampler();
+    sampler::Sampler& S = w->s;
+    S.R = (int)desc[0]; S.P = (int)desc[1]; const int nobj = (int)desc[2];
+    S.circle_lo = desc[3]; S.circle_hi = desc[4]; S.target_min_dist = desc[5]; S.go_back = (int)desc[6];
+    if (S.R < 0 || S.P < 0 || nobj < 0 || S.go_back < 0 || S.go_back > 2 ||
+        n_desc != SAMPLER_HDR + (int64_t)(S.R + S.P) * SAMPLER_AGENT_REC + (int64_t)nobj * SAMPLER_OBJ_REC) { delete w; return fail("imgenv_sampler_create: descriptor size does not match its header"); }
+    const double* q = desc + SAMPLER_HDR;
+    auto pose = [&](sampler::PoseSpec& ps) {
+        ps.type = (int)q[0]; ps.n_multi = (int)q[1]; ps.len = (int)q[2];
+        for (int m = 0; m < SAMPLER_MAX_MULTI; m++) for (int k = 0; k < 6; k++) ps.v[m][k] = q[3 + 6 * m + k];
+        q += SAMPLER_POSE_REC;
+        return ps.n_multi >= 0 && ps.n_multi <= SAMPLER_MAX_MULTI && (!(ps.type & sampler::T_MULTI) || ps.n_multi >= 1);
+    };
+    for (int i = 0; i < S.R + S.P; i++) {
+        sampler::AgentSpec a; a.msize = *q++;
+        if (!pose(a.begin) || !pose(a.target)) { delete w; return fail("imgenv_sampler_create: bad range_multi count"); }
+        // configurations on which the reference's loop never terminates (reset_helper.py:222-305): a begin pose that is
+        // not sampled ('range') next to a sampled target leaves reset_init True forever; 'view_plus' keeps a stale pose.
+        const bool fixed_b = a.begin.type & (sampler::T_EQ_FIX | sampler::T_EQ_RAND_ANGLE), fixed_t = a.target.type & (sampler::T_EQ_FIX | sampler::T_EQ_RAND_ANGLE);
+        if (!(fixed_b && fixed_t) && !(a.begin.type & sampler::T_RANGE)) { delete w; return fail("imgenv_sampler_create: begin_poses_type must be a 'range' type unless begin and target are both fixed (the reference loops forever)"); }
+        if (!fixed_t && !(a.target.type & (sampler::T_RANGE | sampler::T_CIRCLE_FIX))) { delete w; return fail("imgenv_sampler_create: unknown target_poses_type"); }
+        if (a.target.type & sampler::T_PLUS) { delete w; return fail("imgenv_sampler_create: 'view_plus' targets are not implemented by the reference"); }
+        S.agents.push_back(a);
+    }
+    for (int i = 0; i < nobj; i++) {
+        sampler::ObjectSpec o; o.shape = (int)q[0]; o.fixed = (int)q[1]; o.pose_len = (int)q[2];
+        for (int k = 0; k < 6; k++) o.pose[k] = q[3 + k];
+        for (int k = 0; k < 4; k++) o.size_range[k] = q[9 + k];
+        q += SAMPLER_OBJ_REC;
+        S.objects.push_back(o);
+    }
+    S.rng.resize(n_scenes);
+    for (int i = 0; i < n_scenes; i++) S.rng[i].seed(seed + (uint64_t)i);
+    *out = w;
+    return 0;
+}
+extern "C" int imgenv_sampler_destroy(imgenv_sampler_t* w) { delete w; return 0; }
+extern "C" int imgenv_sampler_seed(imgenv_sampler_t* w, int32_t scene, uint64_t seed) {
+    if (!w || scene < 0 || scene >= (int)w->s.rng.size()) return fail("imgenv_sampler_seed: bad arguments");
+    w->s.rng[scene].seed(seed);
+    return 0;
+}
+extern "C" int imgenv_sampler_sample(imgenv_sampler_t* w, int32_t n, const int32_t* scene_ids, int32_t max_obs, int32_t max_traj,
+                                     int32_t* n_obs, double* obs, double* robots, double* peds, int32_t* traj_len, double* traj) {
+    if (!w || n < 1) return fail("imgenv_sampler_sample: bad arguments");
+    const sampler::Sampler& S = w->s;
+    if ((int)S.objects.size() > max_obs) return fail("imgenv_sampler_sample: more objects than max_obs");
+    if (S.P > 0 && max_traj < 2) return fail("imgenv_sampler_sample: max_traj must be >= 2");
+    for (int i = 0; i < n; i++) {
+        const int sc = scene_ids ? scene_ids[i] : i;
+        if (sc < 0 || sc >= (int)S.rng.size()) return fail("imgenv_sampler_sample: scene id out of range");
+        n_obs[i] = (int)S.objects.size();
+        sampler::sample_scene(S, w->s.rng[sc], obs + (size_t)i * max_obs * 11, robots + (size_t)i * S.R * 8, peds + (size_t)i * S.P * 8,
+                              traj_len + (size_t)i * S.P, traj + (size_t)i * S.P * max_traj * 3, max_traj);
+    }
+    return 0;
+}
+// Debug: the raw double stream of one scene's generator (tests pin it against CPython's random module).
+extern "C" int imgenv_sampler_draw(imgenv_sampler_t* w, int32_t scene, int32_t kind, double a, double b, double* out) {
+    if (!w || scene < 0 || scene >= (int)w->s.rng.size()) return fail("imgenv_sampler_draw: bad arguments");
+    sampler::PyRandom& r = w->s.rng[scene];
+    *out = kind == 0 ? r.random() : kind == 1 ? r.uniform(a, b) : kind == 2 ? r.gauss(a, b) : (double)r.randint((int)a, (int)b);
+    return 0;
+}
+extern "C" int imgenv_reset_sampled(imgenv_t* h, imgenv_sampler_t* w, int32_t n, const int32_t* scene_ids, int32_t ignore_obstacle, void* stream) {
+    if (!h || !w) return fail("imgenv_reset_sampled: null handle");
+    const Cfg& c = h->d.c;
+    if (w->s.R != c.R || w->s.P != c.P) return fail("imgenv_reset_sampled: sampler and simulator disagree on the number of robots / pedestrians");
+    if (c.scene_type == 4) return fail("imgenv_reset_sampled: dataset replay takes recorded trajectories (imgenv_reset)");
+    if (n < 1 || n > c.S) return fail("imgenv_reset_sampled: bad scene count");
+    const size_t mo = std::max(c.max_obs, 1), mt = std::max(c.max_traj, 1), P1 = std::max(c.P, 1);
+    w->n_obs.resize(n); w->obs.assign((size_t)n * mo * 11, 0.0); w->robots.resize((size_t)n * c.R * 8); w->peds.resize((size_t)n * P1 * 8);
+    w->traj_len.resize((size_t)n * P1); w->traj.assign((size_t)n * P1 * mt * 3, 0.0);
+    if (imgenv_sampler_sample(w, n, scene_ids, c.max_obs, c.max_traj, w->n_obs.data(), w->obs.data(), w->robots.data(), w->peds.data(), w->traj_len.data(), w->traj.data())) return -1;
+    return imgenv_reset(h, n, scene_ids, w->n_obs.data(), w->obs.data(), w->robots.data(), w->peds.data(), w->traj_len.data(), w->traj.data(), nullptr, ignore_obstacle, stream);
 }
 
 extern "C" int imgenv_end_episode(imgenv_t* h, int32_t) { return h ? 0 : fail("imgenv_end_episode: null handle"); }

@@ -4,10 +4,12 @@ and attributes; `env_num` scenes of the cfg are simulated by ONE env object on o
 needs one ROS node + one ImageEnv per scene), so State arrays carry S*R robots, scene-major."""
 import numpy as np
 
-from ..lib import BatchedSim
+import random
+
+from ..lib import BatchedSim, NativeSampler
 from ..spec import build_spec
 from .action import ContinuousAction
-from .reset_helper import EnvPos, NearbyPed
+from .reset_helper import EnvPos, NearbyPed, sampler_desc
 from .state import ImageState
 
 
@@ -24,6 +26,14 @@ class ImageEnv:
         self.spec = build_spec(cfg, map_dir=map_dir, opt_in_beep=bool(cfg.get("opt_in_beep", False)))
         self.sim = BatchedSim(self.spec, num_scenes=self.num_scenes, device=device, seed=int(cfg.get("seed", 0)),
                               ped_yaw_mode=int(cfg.get("ped_yaw_mode", 1)))
+        # Episode sampling: the native EnvPos port (one CPython-compatible generator per scene, seeded from cfg['seed'] or
+        # from python's `random`, so random.seed() in the training script still fixes the episodes); cfg['native_sampler']
+        # = False keeps the per-scene python EnvPos objects drawing from the global `random`, exactly like the reference.
+        self.sampler = None
+        if cfg.get("native_sampler", True) and self.spec["scene_type"] != "dataset":
+            self.sampler = NativeSampler(sampler_desc(cfg), num_scenes=self.num_scenes, seed=int(cfg.get("sampler_seed", random.getrandbits(62))),
+                                         max_obs=self.spec["max_obstacles"], max_traj=self.spec["max_traj"])
+        self._ignore_obstacle = int(bool(cfg["ped_sim"].get("ignore_obstacle", False)))
         self.dones = None
         self._act = torch.zeros(self.num_scenes, self.robot_total, 3, dtype=torch.float32, device=self.sim.device)
 
@@ -56,7 +66,10 @@ class ImageEnv:
 
     def reset(self, scene_ids=None, **kwargs):
         ids = list(range(self.num_scenes)) if scene_ids is None else list(scene_ids)
-        self.sim.reset([self.env_pose[s].reset() for s in ids], scene_ids=ids)
+        if self.sampler is not None:
+            self.sim.reset_sampled(self.sampler, ids, self._ignore_obstacle)
+        else:
+            self.sim.reset([self.env_pose[s].reset() for s in ids], scene_ids=ids)
         state = self._state()
         if scene_ids is None or self.dones is None:
             self.dones = self.torch.zeros(len(self), dtype=self.torch.int64, device=self.sim.device)

@@ -205,3 +205,42 @@ class EnvPos:
                 traj[k, 1] = [init[i][0], init[i][1], 0]; tl[k] = 2
         self.init_poses, self.target_poses, self.circle_range = init, target, circle_range
         return dict(robots=robots, peds=peds, traj_len=tl, traj=traj)
+
+
+_MAX_MULTI = 8
+
+
+def _pose_spec(ptype, pose):
+    bits = (1 * (ptype == "fix") | 2 * (ptype == "rand_angle") | 4 * ("range" in ptype) | 8 * ("circle" in ptype) | 16 * ("fix" in ptype)
+            | 32 * ("multi" in ptype) | 64 * ("view" in ptype) | 128 * ("plus" in ptype) | 256 * ("circle_fix" in ptype))
+    rec = np.zeros(3 + _MAX_MULTI * 6)
+    rows = [list(r) for r in pose] if "multi" in ptype else [list(pose)]
+    if len(rows) > _MAX_MULTI or any(len(r) > 6 for r in rows) or len({len(r) for r in rows}) != 1:
+        raise ValueError("pose spec does not fit the native sampler descriptor: %r" % (pose,))
+    rec[0], rec[1], rec[2] = bits, len(rows) if "multi" in ptype else 0, len(rows[0])
+    for m, r in enumerate(rows):
+        rec[3 + 6 * m: 3 + 6 * m + len(r)] = r
+    return rec
+
+
+def sampler_desc(cfg):
+    """Flat float64 descriptor of this cfg's EnvPos for imgenv_sampler_create (include/imgenv.h)."""
+    rb, pd = cfg["robot"], cfg["ped_sim"]
+    nr, np_ = rb["total"], pd["total"]
+    ob = cfg.get("object", {"total": 0})
+    go_back = {"yes": 0, "no": 1, "random": 2}[pd.get("go_back", "yes")] if np_ else 0
+    cr = cfg.get("circle_ranges", [0.0, 0.0])
+    out = [np.array([nr, np_, ob["total"], cr[0], cr[1], cfg.get("target_min_dist", 0.0), go_back, 0.0])]
+    for src, n in ((rb, nr), (pd, np_)):
+        for i in range(n):
+            out.append(np.array([_module_size(src["size"][i], src["shape"][i])]))
+            out.append(_pose_spec(src["begin_poses_type"][i], src["begin_poses"][i]))
+            out.append(_pose_spec(src["target_poses_type"][i], src["target_poses"][i]))
+    for i in range(ob["total"]):
+        rec = np.zeros(14)
+        pose, size = list(ob["poses"][i]), list(ob["size_range"][i])
+        rec[0] = 0 if ob["shape"][i] == "circle" else 1
+        rec[1] = 1 if ob["poses_type"][i] == "fix" else 0
+        rec[2] = len(pose); rec[3:3 + len(pose)] = pose; rec[9:9 + min(len(size), 4)] = size[:4]
+        out.append(rec)
+    return np.concatenate(out)

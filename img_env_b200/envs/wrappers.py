@@ -80,12 +80,22 @@ class Wrapper:
     def _robots_per_scene(self):
         return int(self.cfg["robot"]["total"])
 
-    def _rows(self, n, scene_ids):
-        """row mask/indices of the robots that belong to `scene_ids` (None = all rows)."""
-        if scene_ids is None:
-            return slice(None)
-        r = self._robots_per_scene()
-        return np.concatenate([np.arange(s * r, (s + 1) * r) for s in scene_ids]) if len(scene_ids) else np.zeros(0, np.int64)
+    def _row_mask(self, like, kwargs):
+        """bool mask (same array family as `like`) of the robots whose scene is being reset; None = every row.
+        NeverStopWrapper hands its device-side mask down as `row_mask` so that a partial reset costs no host sync."""
+        m = kwargs.get("row_mask")
+        if m is None:
+            ids = kwargs.get("scene_ids")
+            if ids is None:
+                return None
+            m = np.zeros(like.shape[0], bool)
+            m.reshape(-1, self._robots_per_scene())[list(ids)] = True
+        if _is_torch(like) and not _is_torch(m):
+            import torch
+            m = torch.as_tensor(m, device=like.device)
+        elif not _is_torch(like) and _is_torch(m):
+            m = m.cpu().numpy()
+        return m
 
 
 class ObservationWrapper(Wrapper):
@@ -183,8 +193,8 @@ class MultiRobotCleanWrapper(Wrapper):
     def reset(self, **kwargs):
         state = self.env.reset(**kwargs)
         if self.is_clean is not None:
-            rows = self._rows(len(self.is_clean), kwargs.get("scene_ids"))
-            self.is_clean[rows] = True
+            m = self._row_mask(self.is_clean, kwargs)
+            self.is_clean = (self.is_clean | m) if m is not None else (_zeros_like(self.is_clean) == 0)
         return state
 
 
@@ -198,7 +208,8 @@ class StateBatchWrapper(Wrapper):
                       "lasers": max(cfg["laser_batch"], 1) if cfg["laser_batch"] >= 0 else None}
         self.q = {}
 
-    def _concate(self, name, t, clear_rows):
+    def _concate(self, name, t, reset_mask=None):
+        """push `t`; with a reset_mask only the masked rows restart (cleared, then pushed) and the others keep their queue."""
         k = self.depth[name]
         if k is None:
             return t
@@ -206,19 +217,21 @@ class StateBatchWrapper(Wrapper):
         if name not in self.q:
             self.q[name] = _cat([_zeros_like(t1)] * k, 1)
         q = self.q[name]
-        if clear_rows is not None:
-            q[clear_rows] = 0
-        q = _cat([q[:, 1:], t1], 1)
+        if reset_mask is None:
+            q = _cat([q[:, 1:], t1], 1)
+        else:
+            m = reset_mask.reshape((-1,) + (1,) * (q.ndim - 1))
+            q = _where(m, _cat([_zeros_like(q[:, 1:]), t1], 1), q)
         self.q[name] = q
         return q.clone() if _is_torch(q) else q.copy()
 
-    def batch_state(self, state, clear_rows=None):
-        state.sensor_maps = self._concate("sensor_maps", state.sensor_maps, clear_rows)
-        tmp = self._concate("vector_states", state.vector_states, clear_rows)
+    def batch_state(self, state, reset_mask=None):
+        state.sensor_maps = self._concate("sensor_maps", state.sensor_maps, reset_mask)
+        tmp = self._concate("vector_states", state.vector_states, reset_mask)
         if self.depth["vector_states"] is not None:
             tmp = tmp.reshape(tmp.shape[0], tmp.shape[1] * tmp.shape[2])
         state.vector_states = tmp
-        state.lasers = self._concate("lasers", state.lasers, clear_rows)
+        state.lasers = self._concate("lasers", state.lasers, reset_mask)
         return state
 
     def step(self, action):
@@ -227,26 +240,11 @@ class StateBatchWrapper(Wrapper):
 
     def reset(self, **kwargs):
         state = self.env.reset(**kwargs)
-        n = state.sensor_maps.shape[0]
-        ids = kwargs.get("scene_ids")
-        if ids is None:
+        m = self._row_mask(state.sensor_maps, kwargs)
+        if m is None:
             self.q = {}
-            return self.batch_state(state)
-        # partial reset: only the listed scenes restart their queues; the other rows must not be pushed twice
-        rows = self._rows(n, ids)
-        keep = {k: (v.clone() if _is_torch(v) else v.copy()) for k, v in self.q.items()}
-        out = self.batch_state(state, clear_rows=rows)
-        mask = np.ones(n, bool); mask[rows] = False
-        for k, v in keep.items():
-            self.q[k][mask] = v[mask]
-        # rows of untouched scenes keep showing their current stack
-        for name, attr in (("sensor_maps", "sensor_maps"), ("lasers", "lasers")):
-            if self.depth[name] is not None:
-                getattr(out, attr)[mask] = self.q[name][mask]
-        if self.depth["vector_states"] is not None:
-            q = self.q["vector_states"]
-            out.vector_states[mask] = q.reshape(q.shape[0], -1)[mask]
-        return out
+        # partial reset: only the listed scenes restart their queues; the other rows keep showing their current stack
+        return self.batch_state(state, reset_mask=m)
 
 
 class SensorsPaperRewardWrapper(Wrapper):
@@ -291,7 +289,7 @@ class NeverStopWrapper(Wrapper):
             if len(scenes) == len(ad) // r:
                 states = self.env.reset(**{k: v for k, v in info.items() if k == "dones_info"})
             else:
-                states = self.env.reset(scene_ids=scenes)
+                states = self.env.reset(scene_ids=scenes, row_mask=info["all_down"])
         return states, reward, done, info
 
 
@@ -315,7 +313,8 @@ class TimeLimitWrapper(Wrapper):
 
     def reset(self, **kwargs):
         if self._elapsed_steps is not None:
-            self._elapsed_steps[self._rows(len(self._elapsed_steps), kwargs.get("scene_ids"))] = 0
+            m = self._row_mask(self._elapsed_steps, kwargs)
+            self._elapsed_steps = _zeros_like(self._elapsed_steps) if m is None else _where(m, _zeros_like(self._elapsed_steps), self._elapsed_steps)
         return self.env.reset(**kwargs)
 
 

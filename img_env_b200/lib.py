@@ -37,7 +37,9 @@ class ImgenvOutputs(C.Structure):
 EXPORTS = ["imgenv_create", "imgenv_destroy", "imgenv_bind_outputs", "imgenv_reset", "imgenv_step", "imgenv_step_host",
            "imgenv_end_episode", "imgenv_get_internal", "imgenv_set_internal", "imgenv_debug_view_maps", "imgenv_debug_view_maps2", "imgenv_debug_global_map",
            "imgenv_solver_agents", "imgenv_view_dims", "imgenv_launches_per_step",
-           "imgenv_algorithmic_bytes_per_robot_step", "imgenv_last_error", "imgenv_version"]
+           "imgenv_algorithmic_bytes_per_robot_step", "imgenv_last_error", "imgenv_version",
+           "imgenv_sampler_create", "imgenv_sampler_destroy", "imgenv_sampler_seed", "imgenv_sampler_sample", "imgenv_sampler_draw",
+           "imgenv_reset_sampled"]
 
 
 def load_library(path=None):
@@ -63,6 +65,58 @@ def load_library(path=None):
 
 def _ptr(a, t=C.c_double):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+class NativeSampler:
+    """EnvPos.reset (reset_helper.py:115-345) in native code; host-only (usable without a GPU).
+    desc comes from img_env_b200.envs.reset_helper.sampler_desc(cfg)."""
+
+    def __init__(self, desc, num_scenes=1, seed=0, max_obs=None, max_traj=2):
+        self.lib = load_library()
+        d = np.ascontiguousarray(desc, dtype=np.float64)
+        self.R, self.P, self.n_obj = int(d[0]), int(d[1]), int(d[2])
+        self.max_obs = int(max_obs if max_obs is not None else self.n_obj); self.max_traj = int(max_traj)
+        self.num_scenes = int(num_scenes)
+        h = C.c_void_p()
+        rc = self.lib.imgenv_sampler_create(_ptr(d), C.c_int64(d.size), self.num_scenes, C.c_uint64(int(seed)), C.byref(h))
+        if rc != 0:
+            raise ValueError(self.lib.imgenv_last_error().decode())
+        self.h = h
+
+    def seed(self, scene, seed):
+        if self.lib.imgenv_sampler_seed(self.h, int(scene), C.c_uint64(int(seed))) != 0:
+            raise ValueError(self.lib.imgenv_last_error().decode())
+
+    def draw(self, scene, kind, a=0.0, b=0.0):
+        out = C.c_double()
+        if self.lib.imgenv_sampler_draw(self.h, int(scene), {"random": 0, "uniform": 1, "gauss": 2, "randint": 3}[kind],
+                                        C.c_double(a), C.c_double(b), C.byref(out)) != 0:
+            raise ValueError(self.lib.imgenv_last_error().decode())
+        return out.value
+
+    def sample(self, scene_ids=None):
+        """-> dict of arrays shaped like BatchedSim.reset's packed arguments (n_obs, obs, robots, peds, traj_len, traj)."""
+        ids = np.ascontiguousarray(scene_ids if scene_ids is not None else np.arange(self.num_scenes), dtype=np.int32)
+        n = ids.size
+        mo = max(self.max_obs, 1)
+        out = dict(n_obs=np.zeros(n, np.int32), obs=np.zeros((n, mo, 11)), robots=np.zeros((n, self.R, 8)), peds=np.zeros((n, self.P, 8)),
+                   traj_len=np.zeros((n, self.P), np.int32), traj=np.zeros((n, self.P, self.max_traj, 3)))
+        rc = self.lib.imgenv_sampler_sample(self.h, n, _ptr(ids, C.c_int32), self.max_obs, self.max_traj, _ptr(out["n_obs"], C.c_int32),
+                                            _ptr(out["obs"]), _ptr(out["robots"]), _ptr(out["peds"]), _ptr(out["traj_len"], C.c_int32), _ptr(out["traj"]))
+        if rc != 0:
+            raise ValueError(self.lib.imgenv_last_error().decode())
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.imgenv_sampler_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class BatchedSim:
@@ -163,6 +217,12 @@ class BatchedSim:
         rc = self.lib.imgenv_reset(self.h, n, _ptr(ids, C.c_int32), _ptr(n_obs, C.c_int32), _ptr(obs), _ptr(robots), _ptr(peds),
                                    _ptr(tl, C.c_int32), _ptr(traj), _ptr(trajv) if trajv is not None else None, ign, self._stream())
         self._check(rc)
+        return self.out
+
+    def reset_sampled(self, sampler, scene_ids=None, ignore_obstacle=0):
+        """EnvPos.reset + reset service for the listed scenes without leaving native code."""
+        ids = np.ascontiguousarray(scene_ids if scene_ids is not None else np.arange(self.S), dtype=np.int32)
+        self._check(self.lib.imgenv_reset_sampled(self.h, sampler.h, ids.size, _ptr(ids, C.c_int32), int(ignore_obstacle), self._stream()))
         return self.out
 
     def step(self, actions, alive=None):

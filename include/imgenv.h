@@ -15,7 +15,8 @@
  * One handle = one GPU = S independent scenes sharing one configuration (the reference runs
  * one ROS node per scene, create_launch.py:25-34).  Plain pointers and sizes only; no torch
  * types.  All device work is enqueued on the caller's cudaStream_t (passed as void*; NULL =
- * legacy default stream) and is stream-ordered: no host synchronisation inside step.
+ * legacy default stream) and is stream-ordered: no host synchronisation inside step or reset
+ * (reset waits at most for the reset before the previous one to have consumed its pinned staging).
  * The handle is not thread-safe.  Every entry point returns 0 on success, <0 on error;
  * imgenv_last_error() returns the message of the last failure on the calling thread.
  */
@@ -96,6 +97,27 @@ int imgenv_bind_outputs(imgenv_t* h, const imgenv_outputs* out);
 int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, const int32_t* n_obs, const double* obs,
                  const double* robots, const double* peds, const int32_t* traj_len, const double* traj,
                  const double* traj_v, int32_t ignore_obstacle, void* stream);
+
+/* Episode sampler: EnvPos.reset (envs/utils/reset_helper.py:115-345) in native code, drawing from a bit-exact
+ * CPython `random` (MT19937) so that the same seed gives the poses the reference's Python sampler gives.
+ * One generator per scene (seed + scene index).  desc (float64):
+ *   [0] R  [1] P  [2] n_objects  [3..4] circle_ranges  [5] target_min_dist  [6] go_back 0 yes / 1 no / 2 random  [7] 0
+ *   (R+P) agent records of 103: module size, then begin and target pose specs of 51 each:
+ *       type bits (1 =='fix', 2 =='rand_angle', 4 'range', 8 'circle', 16 'fix' substring, 32 'multi', 64 'view',
+ *       128 'plus', 256 'circle_fix'), n_multi, len of one range, 8 x 6 values (row 0 = the pose / range)
+ *   n_objects records of 14: shape (0 circle / 1 rectangle), fixed, len(pose), pose[6], size_range[4], 0
+ * Host-only: no CUDA call is made by the sampler itself. */
+typedef struct imgenv_sampler imgenv_sampler_t;
+int imgenv_sampler_create(const double* desc, int64_t n_desc, int32_t n_scenes, uint64_t seed, imgenv_sampler_t** out);
+int imgenv_sampler_destroy(imgenv_sampler_t* s);
+int imgenv_sampler_seed(imgenv_sampler_t* s, int32_t scene, uint64_t seed);
+/* Samples n scenes into arrays laid out like imgenv_reset's arguments. */
+int imgenv_sampler_sample(imgenv_sampler_t* s, int32_t n, const int32_t* scene_ids, int32_t max_obs, int32_t max_traj,
+                          int32_t* n_obs, double* obs, double* robots, double* peds, int32_t* traj_len, double* traj);
+/* One draw from a scene's generator: kind 0 random(), 1 uniform(a,b), 2 gauss(a,b), 3 randint(a,b). */
+int imgenv_sampler_draw(imgenv_sampler_t* s, int32_t scene, int32_t kind, double a, double b, double* out);
+/* EnvPos.reset + ResetEnv.srv for the listed scenes in one call (yaml_env.py:232-262 without the Python loop). */
+int imgenv_reset_sampled(imgenv_t* h, imgenv_sampler_t* s, int32_t n, const int32_t* scene_ids, int32_t ignore_obstacle, void* stream);
 
 /* StepEnv.srv for all S scenes. d_actions[S][R][3] = v, w, v_y(beep) float32 DEVICE pointer;
  * d_alive[S][R] uint8 DEVICE pointer, or NULL to use the library's own dones bookkeeping
