@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libimgenv_b200.so")
 SOURCES = ["imgenv.cu"]
-HEADERS = ["state.cuh", "tfmath.cuh", "kin.cuh", "view.cuh", "dyn.cuh", "orca.cuh", "host_tables.h"]
+HEADERS = ["state.cuh", "tfmath.cuh", "kin.cuh", "view.cuh", "dyn.cuh", "orca.cuh", "sfmtree.cuh", "host_tables.h", "sampler.h"]
 
 
 def nvcc_path():
@@ -38,6 +38,8 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
     return LIB
 
 

@@ -37,7 +37,7 @@ struct imgenv {
     int* sti_h = nullptr; int* sti_d = nullptr; size_t st_ints = 0;
     float* stf_h = nullptr; float* stf_d = nullptr; size_t st_floats = 0;
     float* act_d = nullptr; uint8_t* alive_d = nullptr;
-    size_t view_smem = 0, dyn_smem = 0;
+    size_t view_smem = 0, dyn_smem = 0, stamp_smem = 0;
     // optional per-kernel CUDA-event timing (bench.py roofline): 5 events per profiled step
     std::vector<cudaEvent_t> evs; int prof_max = 0, prof_n = 0;
 };
@@ -77,7 +77,7 @@ __global__ void k_init_state(Dev d) {
     size_t wpp = (size_t)d.c.H * d.c.Wb;
     size_t n = wpp * d.c.S;
     size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = t0; i < n; i += stride) d.occ_all[i] = d.static_occ[i % wpp];
+    for (size_t i = t0; i < n; i += stride) { d.occ_all[i] = d.static_occ[i % wpp]; d.base_occ[i] = d.static_occ[i % wpp]; }
     size_t pc = (((size_t)d.c.H * d.c.W + 3) & ~(size_t)3) * d.c.S;
     for (size_t i = t0; i < pc; i += stride) { d.rmin[i] = RMIN_EMPTY; d.flags[i] = 0; }
     size_t nb = (size_t)d.c.Hc * d.c.Wb;
@@ -201,23 +201,24 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         T.t.own_mask_off = (int)own_mask.size(); own_mask.insert(own_mask.end(), T.own_mask.begin(), T.own_mask.end());
         T.t.tile_off = (int)tile_fov.size(); tile_fov.insert(tile_fov.end(), T.tile_fov.begin(), T.tile_fov.end());
         T.t.edge_off = (int)edge_px.size(); T.t.n_edge = (int)T.edge_px.size(); edge_px.insert(edge_px.end(), T.edge_px.begin(), T.edge_px.end());
-        {   // compact per-needed-pixel table for the laser_map reconstruction (view.cuh phase D)
-            T.dtab.assign((size_t)c.ns * c.ns, 0u);
+        {   // per (needed row, output column, tap) table for the laser_map reconstruction fused into the horizontal
+            // cubic pass (view.cuh phase D/F): one 16-byte load gives a thread the four source pixels of its output.
+            T.dtab.assign((size_t)c.ns * c.img * 4, 0u);
             for (int rr = 0; rr < c.ns; rr++)
-                for (int cc = 0; cc < c.ns; cc++) {
-                    const int pr = need_idx[rr], pc = need_idx[cc];
-                    const size_t full = (size_t)pr * c.vw + pc;
-                    uint32_t kh = T.khi[full], e;
-                    if (kh == 0xFFFF) e = 0xFFFu;
-                    else {
-                        const int w0 = abs((int)T.ray_end[2 * kh] - T.t.org_x), h0 = abs((int)T.ray_end[2 * kh + 1] - T.t.org_y);
-                        const uint32_t itop = (uint32_t)(w0 > h0 ? abs(pr - T.t.org_x) : abs(pc - T.t.org_y));
-                        const uint32_t below = std::min<uint32_t>(kh - T.klo[full], 511u);
-                        e = kh | (itop << 12) | (below << 22);
+                for (int oc = 0; oc < c.img; oc++)
+                    for (int k = 0; k < 4; k++) {
+                        const int pr = need_idx[rr], pc = need_idx[tap[4 * oc + k]];
+                        const size_t full = (size_t)pr * c.vw + pc;
+                        uint32_t kh = T.khi[full], e;
+                        if (kh == 0xFFFF) e = 0xFFFu;
+                        else {
+                            const int w0 = abs((int)T.ray_end[2 * kh] - T.t.org_x), h0 = abs((int)T.ray_end[2 * kh + 1] - T.t.org_y);
+                            const uint32_t itop = (uint32_t)(w0 > h0 ? abs(pr - T.t.org_x) : abs(pc - T.t.org_y));
+                            e = kh | (itop << 12);
+                        }
+                        if ((T.own_mask[full >> 5] >> (full & 31)) & 1u) e |= 1u << 31;
+                        T.dtab[((size_t)rr * c.img + oc) * 4 + k] = e;
                     }
-                    if ((T.own_mask[full >> 5] >> (full & 31)) & 1u) e |= 1u << 31;
-                    T.dtab[(size_t)rr * c.ns + cc] = e;
-                }
         }
         T.t.dtab_off = (int)dtab.size(); dtab.insert(dtab.end(), T.dtab.begin(), T.dtab.end());
         T.t.n_own = 0; T.t.own_off = 0;
@@ -267,7 +268,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     size_t pc = ((size_t)H * W + 3) & ~(size_t)3;
     d.max_verts = 16 * c.max_obs + 16;
 #define AL(field, n) if (dalloc(h, &d.field, (size_t)(n))) return -1;
-    AL(occ_all, S * H * c.Wb) AL(flags, S * pc) AL(rmin, S * pc) AL(coarse, S * c.Hc * c.Wb)
+    AL(occ_all, S * H * c.Wb) AL(base_occ, S * H * c.Wb) AL(flags, S * pc) AL(rmin, S * pc) AL(coarse, S * c.Hc * c.Wb)
     AL(rb, (size_t)RB_FIELDS * S * c.R) AL(pd, (size_t)PD_FIELDS * S * c.P)
     AL(traj, S * c.P * c.max_traj * 3) AL(traj_v, c.scene_type == 4 ? S * c.P * c.max_traj * 3 : 1) AL(traj_len, S * c.P) AL(obs, S * c.max_obs * 8) AL(n_obs, S) AL(step_no, S)
     AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_nvel, S * c.NA * 2) AL(sfm_force, c.scene_type == 1 ? S * c.NA * 12 : 1) AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 3)
@@ -329,6 +330,14 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         CK(cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming));
     }
 
+    {   // shared-memory cell bitmap of k_stamp_agents: sized for the largest footprint box
+        int words = 1;
+        for (const auto& t : rts) words = std::max(words, stamp_bitmap_words(stamp_rad_cells(t.zone_rad * c.res, c.res)));
+        for (int p = 0; p < c.P; p++) words = std::max(words, stamp_bitmap_words(stamp_rad_cells(pext[p], c.res)));
+        h->stamp_smem = (size_t)words * 4;
+        if (h->stamp_smem > 200 * 1024) return fail("imgenv_create: an agent footprint is too large for the stamping kernel");
+        CK(cudaFuncSetAttribute(k_stamp_agents, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stamp_smem));
+    }
     h->view_smem = view_smem_bytes(c);
     h->dyn_smem = dyn_smem_bytes(c);
     if (h->view_smem > 227 * 1024) return fail("imgenv_create: view kernel needs too much shared memory for this configuration");
@@ -431,11 +440,11 @@ __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, co
 
 static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int is_reset, cudaStream_t st, cudaEvent_t* ev = nullptr) {
     Dev& d = h->d; const Cfg& c = d.c;
-    k_stamp_agents<<<n_scenes * (c.R + c.P), STAMP_THREADS, 0, st>>>(d, d_scene_ids, 0);
+    k_stamp_agents<<<n_scenes * (c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(d, d_scene_ids, 0);
     if (ev) cudaEventRecord(ev[2], st);
     k_view<false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
     if (ev) cudaEventRecord(ev[3], st);
-    k_stamp_agents<<<n_scenes * (c.R + c.P), STAMP_THREADS, 0, st>>>(d, d_scene_ids, is_reset ? 1 : 2);    // 2: also step_++
+    k_stamp_agents<<<n_scenes * (c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(d, d_scene_ids, is_reset ? 1 : 2);    // 2: also step_++
     if (ev) cudaEventRecord(ev[4], st);
     CK(cudaGetLastError());
     return 0;
@@ -788,9 +797,9 @@ extern "C" int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* 
     if (host_out) CK(cudaMalloc((void**)&buf, n));
     if (stats_out) { CK(cudaMalloc((void**)&sbuf, (size_t)c.S * c.R * 16)); CK(cudaMemsetAsync(sbuf, 0, (size_t)c.S * c.R * 16, st)); }
     d.dbg_view = buf; d.dbg_stats = sbuf;
-    k_stamp_agents<<<c.S * (c.R + c.P), STAMP_THREADS, 0, st>>>(d, nullptr, 0);
+    k_stamp_agents<<<c.S * (c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(d, nullptr, 0);
     k_view<true><<<c.S * c.R, VIEW_THREADS, h->view_smem, st>>>(d, nullptr, 0);
-    k_stamp_agents<<<c.S * (c.R + c.P), STAMP_THREADS, 0, st>>>(d, nullptr, 1);
+    k_stamp_agents<<<c.S * (c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(d, nullptr, 1);
     cudaError_t e = cudaSuccess;
     if (host_out) e = cudaMemcpyAsync(host_out, buf, n, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && stats_out) e = cudaMemcpyAsync(stats_out, sbuf, (size_t)c.S * c.R * 16, cudaMemcpyDeviceToHost, st);
@@ -870,9 +879,9 @@ extern "C" int imgenv_debug_global_map(imgenv_t* h, int32_t scene, int32_t self,
     int* ids = nullptr;
     CK(cudaMalloc((void**)&ids, 4));
     CK(cudaMemcpyAsync(ids, &scene, 4, cudaMemcpyHostToDevice, st));
-    k_stamp_agents<<<(c.R + c.P), STAMP_THREADS, 0, st>>>(dd, ids, 0);
+    k_stamp_agents<<<(c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(dd, ids, 0);
     k_debug_global_map<<<592, 256, 0, st>>>(dd, scene, self, buf);
-    k_stamp_agents<<<(c.R + c.P), STAMP_THREADS, 0, st>>>(dd, ids, 1);
+    k_stamp_agents<<<(c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(dd, ids, 1);
     cudaError_t e = cudaMemcpyAsync(host_out, buf, n, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(buf); cudaFree(ids);

@@ -51,7 +51,7 @@ struct RobotType {
     int tile_off;         // offset into tile_fov (u32 words): bit per 32x32 view tile that contains FOV pixels
     int edge_off, n_edge; // FOV pixels with an 8-neighbour outside the FOV (u32 row<<16|col), always evaluated forward
     int fov_r0, fov_r1, fov_c0, fov_c1;   // bounding box (inclusive) of the FOV pixels in the view raster
-    int dtab_off;         // offset into dtab (ns*ns u32)
+    int dtab_off;         // offset into dtab (ns*img*4 u32)
     int zone_rad;         // world cells around the robot's position inside which a set occ_all bit may be its own stamp
     double size_last;     // python: robots[i].size[-1]
     double sensor_x, sensor_y;
@@ -96,7 +96,7 @@ struct Dev {
     const uint32_t* own_mask;     // per type: bit per view pixel = own footprint cell
     const uint32_t* tile_fov;     // per type: bit per 32x32 view tile (row-major, vwb per row) with any FOV pixel
     const uint32_t* edge_px;      // per type: FOV-edge pixels
-    const uint32_t* dtab;         // per type, per pixel the resize reads: top ray (12b) | its step index there (10b) | #rays below, capped (9b) | own footprint (1b)
+    const uint32_t* dtab;         // per type [ns][img][4]: for tap k of output column oc on needed row rr: top ray (12b) | its step index there (10b) << 12 | own footprint << 31
     const short* need_idx;        // [ns] source row/col index of the k-th needed row/col
     const short* cubic_tap;       // [img][4] index into need_idx space (0..ns-1) of the 4 taps
     const short* cubic_coef;      // [img][4] fixed-point weights (x2048)
@@ -112,10 +112,12 @@ struct Dev {
     const int* ped_pts_n;         // [P][2]
     const double* ped_ext;        // [P] bound on the distance from the pedestrian position to any cell it stamps
     // per scene planes
-    uint32_t* occ_all;            // [S][H][Wb]
+    uint32_t* occ_all;            // [S][H][Wb] static | reset objects | this step's agent stamps
+    uint32_t* base_occ;           // [S][H][Wb] static | reset objects: what occ_all returns to when the agents are unstamped
     uint8_t* flags;               // [S][H][W]
-    unsigned short* rmin;         // [S][H][W]
-    uint32_t* coarse;             // [S][Hc][Wb] number of set occ_all bits per 32x32-cell block (0 = block is free)
+    unsigned short* rmin;         // [S][H][W] id of the robot stamped on the cell; only meaningful while F_ROBOT is set without F_MULTI
+    uint32_t* coarse;             // [S][Hc][Wb] per 32x32-cell block: bits 0..30 = number of set base_occ bits, bit 31 = an agent is stamped
+                                  //              somewhere in the block this step (0 = block is free)
     // dynamic state
     double* rb;                   // [RB_FIELDS][S*R]
     double* pd;                   // [PD_FIELDS][S*P]

@@ -26,16 +26,6 @@ __device__ __forceinline__ void flag_clear(uint8_t* flags, size_t ci, unsigned b
     unsigned* w = reinterpret_cast<unsigned*>(flags + (ci & ~(size_t)3));
     atomicAnd(w, ~(bits << (8 * (ci & 3))));
 }
-__device__ __forceinline__ unsigned short rmin_min(unsigned short* p, unsigned short id) {
-    unsigned short old = *p;
-    while (old > id) {
-        unsigned short assumed = old;
-        old = atomicCAS(p, assumed, id);
-        if (old == assumed) break;
-    }
-    return old;
-}
-
 // The value Agent::draw / Agent::view would read from robot `self`'s global_map_ at a cell:
 // obs_map_ (static + reset objects) -> peds_map_ (pedestrians, value 1) -> other robots (value 2);
 // a writer never overwrites 0/1/2 except the right-leg quirk (agent.cpp:767-770).
@@ -56,53 +46,124 @@ __device__ __forceinline__ int global_value(const Dev& d, int s, int self, int c
     return v;
 }
 
-// mode: 0 stamp robot(id), 1 stamp ped body (circle), 2 left leg, 3 right leg, 4 object,
-//       8+ = unstamp of (mode-8)
-__device__ __forceinline__ void stamp_cell(const Dev& d, int s, int cx, int cy, int mode, int id) {
+// Reset objects (mode 4 stamp, 12 unstamp) are written point by point: they only change at reset. They live in
+// base_occ as well as occ_all, and the block counts in coarse's low bits count them (no agent is stamped then).
+__device__ __forceinline__ void stamp_object_cell(const Dev& d, int s, int cx, int cy, int mode) {
     if ((unsigned)cx >= (unsigned)d.c.H || (unsigned)cy >= (unsigned)d.c.W) return;
-    size_t ci = (size_t)cx * d.c.W + cy;
-    size_t po = (size_t)s * plane_cells(d.c);
-    uint32_t* occ = d.occ_all + (size_t)s * d.c.H * d.c.Wb + (size_t)cx * d.c.Wb + (cy >> 5);
+    const size_t ci = (size_t)cx * d.c.W + cy;
+    const size_t po = (size_t)s * plane_cells(d.c);
+    const size_t wi = (size_t)s * d.c.H * d.c.Wb + (size_t)cx * d.c.Wb + (cy >> 5);
     uint32_t* cz = d.coarse + (size_t)s * d.c.Hc * d.c.Wb + (size_t)(cx >> 5) * d.c.Wb + (cy >> 5);
-    uint32_t bit = 1u << (cy & 31);
-    if (mode < 8) {
-        if (mode == 0) {
-            unsigned short old = rmin_min(d.rmin + po + ci, (unsigned short)id);
-            unsigned bits = F_ROBOT;
-            if (old != RMIN_EMPTY && old != (unsigned short)id) bits |= F_MULTI;
-            flag_or(d.flags + po, ci, bits);
-        } else {
-            flag_or(d.flags + po, ci, mode == 1 ? F_CIRC : mode == 2 ? F_LEFT : mode == 3 ? F_RIGHT : F_OBJ);
-        }
-        if (!(atomicOr(occ, bit) & bit)) atomicAdd(cz, 1u);     // first setter of the bit maintains the block count
+    const uint32_t bit = 1u << (cy & 31);
+    if (mode == 4) {
+        flag_or(d.flags + po, ci, F_OBJ);
+        atomicOr(d.occ_all + wi, bit);
+        if (!(atomicOr(d.base_occ + wi, bit) & bit)) atomicAdd(cz, 1u);     // first setter of the bit maintains the block count
     } else {
-        int m = mode - 8;
-        if (m == 0) { d.rmin[po + ci] = RMIN_EMPTY; flag_clear(d.flags + po, ci, F_ROBOT | F_MULTI); }
-        else flag_clear(d.flags + po, ci, m == 1 ? F_CIRC : m == 2 ? F_LEFT : m == 3 ? F_RIGHT : F_OBJ);
-        // restore the occupancy bit to static | object (dynamic stamps never survive a step)
-        bool base = (d.static_occ[(size_t)cx * d.c.Wb + (cy >> 5)] & bit) != 0;
-        if (m != 4) base = base || (d.flags[po + ci] & F_OBJ);
-        if (!base && (atomicAnd(occ, ~bit) & bit)) atomicSub(cz, 1u);
+        flag_clear(d.flags + po, ci, F_OBJ);
+        if (d.static_occ[(size_t)cx * d.c.Wb + (cy >> 5)] & bit) return;
+        atomicAnd(d.occ_all + wi, ~bit);
+        if (atomicAnd(d.base_occ + wi, ~bit) & bit) atomicSub(cz, 1u);
     }
 }
 
-__device__ __forceinline__ void stamp_points(const Dev& d, int s, const Tf2& t, const double* pts, int n, int mode, int id,
-                                             double offx, double offy) {
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        double bx = pts[2 * k], by = pts[2 * k + 1];
-        if (mode == 2 || mode == 3 || mode == 10 || mode == 11) {   // leg2base: identity rotation + leg origin (agent.cpp:815-837)
-            bx = bx + offx;
-            by = by + offy;
-        }
-        double wx, wy;
-        tf_apply(t, bx, by, wx, wy);
-        stamp_cell(d, s, world2cell_fast(wx, d.c.res, d.c.inv_res), world2cell_fast(wy, d.c.res, d.c.inv_res), mode, id);
+// Agent footprints.  The 0.01 m lattice puts 2-3 points into every 0.015 m cell, so a footprint is first reduced to
+// its set of cells in a shared-memory bitmap (rows x 32-cell words aligned with occ_all's words).  The planes are
+// then updated per group of 8 cells with fire-and-forget reductions only -- nothing waits for an L2 round trip
+// except the robots' flag words, whose previous value tells whether another robot already stamped the cell:
+//   stamp:   flags |= bits, rmin = id (plain store: with two robots on a cell F_MULTI makes rmin irrelevant),
+//            occ_all |= mask, coarse |= 1<<31
+//   unstamp: flags &= ~bits, occ_all = base_occ (every unstamping agent writes the same final word),
+//            coarse &= ~(1<<31)
+// mode: 0 robot(id), 1 ped body (circle), 2 left leg, 3 right leg; 8+ = unstamp of (mode-8)
+#define STAMP_THREADS 64
+struct StampBox { int cx0, wj0, nrow, wpr; };
+inline __host__ __device__ int stamp_rad_cells(double ext, double res) { return (int)ceil(ext / res) + 1; }
+inline __host__ __device__ int stamp_bitmap_words(int rad_cells) { return (2 * rad_cells + 1) * ((2 * rad_cells) / 32 + 2); }
+__device__ __forceinline__ StampBox stamp_box(const Dev& d, double x, double y, int rad_cells) {
+    const int ccx = world2cell(x, d.c.res), ccy = world2cell(y, d.c.res);
+    StampBox b;
+    b.cx0 = ccx - rad_cells; b.nrow = 2 * rad_cells + 1;
+    b.wj0 = (ccy - rad_cells) >> 5; b.wpr = ((ccy + rad_cells) >> 5) - b.wj0 + 1;
+    return b;
+}
+__device__ __forceinline__ void stamp_cells8(const Dev& d, int s, int cx, int cy0, unsigned m8, int mode, int id) {
+    // cells (cx, cy0 .. cy0+7) selected by m8; cy0 is a multiple of 8: one occ_all word, one coarse block, <= 3 flag words
+    if ((unsigned)cx >= (unsigned)d.c.H || cy0 < 0) return;
+    if (cy0 + 8 > d.c.W) m8 &= cy0 >= d.c.W ? 0u : (0xFFu >> (cy0 + 8 - d.c.W));
+    if (!m8) return;
+    const size_t po = (size_t)s * plane_cells(d.c);
+    const size_t ci0 = (size_t)cx * d.c.W + cy0;
+    const size_t wi = (size_t)s * d.c.H * d.c.Wb + (size_t)cx * d.c.Wb + (cy0 >> 5);
+    uint32_t* cz = d.coarse + (size_t)s * d.c.Hc * d.c.Wb + (size_t)(cx >> 5) * d.c.Wb + (cy0 >> 5);
+    const int m = mode & 7;
+    const unsigned fb = m == 0 ? F_ROBOT : m == 1 ? F_CIRC : m == 2 ? F_LEFT : F_RIGHT;
+    // spread the 8 cell bits over the (at most 3) aligned 32-bit words of the flags plane they fall into
+    const int a0 = (int)(ci0 & 3);
+    const unsigned long long sel = (unsigned long long)m8 << a0;              // bit k = byte k of the 12-byte window at ci0 - a0
+    unsigned wmask[3];
+#pragma unroll
+    for (int w = 0; w < 3; w++) {
+        const unsigned n4 = (unsigned)(sel >> (4 * w)) & 0xFu;
+        wmask[w] = ((n4 & 1u) | ((n4 & 2u) << 7) | ((n4 & 4u) << 14) | ((n4 & 8u) << 21)) * fb;
     }
+    unsigned* fw = reinterpret_cast<unsigned*>(d.flags + po + (ci0 - a0));
+    if (mode < 8) {
+        if (m == 0) {
+            unsigned old[3];
+#pragma unroll
+            for (int w = 0; w < 3; w++) old[w] = wmask[w] ? atomicOr(fw + w, wmask[w]) : 0u;
+#pragma unroll
+            for (int b = 0; b < 8; b++) if ((m8 >> b) & 1u) d.rmin[po + ci0 + b] = (unsigned short)id;
+#pragma unroll
+            for (int w = 0; w < 3; w++) {
+                const unsigned again = old[w] & wmask[w];                        // another robot set F_ROBOT here before us
+                if (again) atomicOr(fw + w, again * (F_MULTI / F_ROBOT));
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < 3; w++) if (wmask[w]) atomicOr(fw + w, wmask[w]);
+        }
+        atomicOr(d.occ_all + wi, m8 << (cy0 & 31));
+        atomicOr(cz, 0x80000000u);
+    } else {
+        const unsigned clr = m == 0 ? (F_MULTI / F_ROBOT + 1u) : 1u;            // robots also drop F_MULTI
+#pragma unroll
+        for (int w = 0; w < 3; w++) if (wmask[w]) atomicAnd(fw + w, ~(wmask[w] * clr));
+        d.occ_all[wi] = d.base_occ[wi];
+        atomicAnd(cz, 0x7FFFFFFFu);
+    }
+}
+__device__ __forceinline__ void stamp_part(const Dev& d, int s, const Tf2& t, const double* pts, int n, int mode, int id,
+                                           double offx, double offy, const StampBox& bx, uint32_t* bm) {
+    const int nw = bx.nrow * bx.wpr;
+    for (int k = threadIdx.x; k < nw; k += STAMP_THREADS) bm[k] = 0u;
+    __syncthreads();
+    const bool leg = (mode & 7) == 2 || (mode & 7) == 3;
+    for (int k = threadIdx.x; k < n; k += STAMP_THREADS) {
+        double px = pts[2 * k], py = pts[2 * k + 1];
+        if (leg) { px = px + offx; py = py + offy; }   // leg2base: identity rotation + leg origin (agent.cpp:815-837)
+        double wx, wy;
+        tf_apply(t, px, py, wx, wy);
+        const int cx = world2cell_fast(wx, d.c.res, d.c.inv_res), cy = world2cell_fast(wy, d.c.res, d.c.inv_res);
+        const int r = cx - bx.cx0, w = (cy >> 5) - bx.wj0;
+        if ((unsigned)r < (unsigned)bx.nrow && (unsigned)w < (unsigned)bx.wpr) atomicOr(&bm[r * bx.wpr + w], 1u << (cy & 31));
+        else stamp_cells8(d, s, cx, cy & ~7, 1u << (cy & 7), mode, id);   // cannot happen (the box bounds the footprint); still a valid write
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < 4 * nw; it += STAMP_THREADS) {
+        const int word = it >> 2, byte = it & 3;
+        const unsigned m8 = (bm[word] >> (8 * byte)) & 0xFFu;
+        if (!m8) continue;
+        const int r = word / bx.wpr, w = word - r * bx.wpr;
+        stamp_cells8(d, s, bx.cx0 + r, (bx.wj0 + w) * 32 + 8 * byte, m8, mode, id);
+    }
+    __syncthreads();
 }
 
 // grid = n_scenes * (R + P) CTAs; `unstamp` selects the inverse operation.
-#define STAMP_THREADS 64
 __global__ void __launch_bounds__(STAMP_THREADS) k_stamp_agents(Dev d, const int* scene_ids, int unstamp) {
+    extern __shared__ uint32_t bm[];     // stamp_bitmap_words(largest agent) words
     const int per = d.c.R + d.c.P;
     const int sl = blockIdx.x / per, a = blockIdx.x % per;
     const int s = scene_ids ? scene_ids[sl] : sl;
@@ -126,19 +187,20 @@ __global__ void __launch_bounds__(STAMP_THREADS) k_stamp_agents(Dev d, const int
     }
     if (!__syncthreads_or(rel)) return;
     const Tf2 t = tf_from_pose(x, y, yaw);
+    const StampBox bx = stamp_box(d, x, y, stamp_rad_cells(ext, d.c.res));
     if (is_robot) {
         const RobotType& ty = d.types[d.type_of[a]];
-        stamp_points(d, s, t, d.lattice_xy + 2 * (size_t)ty.pts_off, ty.n_pts, 0 + add, a, 0, 0);
+        stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)ty.pts_off, ty.n_pts, 0 + add, a, 0, 0, bx, bm);
     } else {
         const int idx = s * d.c.P + p;
         const int shape = d.ped_shape[p];
         if (shape == 0) {
-            stamp_points(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p], d.ped_pts_n[2 * p], 1 + add, p, 0, 0);
+            stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p], d.ped_pts_n[2 * p], 1 + add, p, 0, 0, bx, bm);
         } else if (shape == 2) {
-            stamp_points(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p], d.ped_pts_n[2 * p], 2 + add, p,
-                         PDF(d, PD_LLX, idx), PDF(d, PD_LLY, idx));
-            stamp_points(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p + 1], d.ped_pts_n[2 * p + 1], 3 + add, p,
-                         PDF(d, PD_RLX, idx), PDF(d, PD_RLY, idx));
+            stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p], d.ped_pts_n[2 * p], 2 + add, p,
+                       PDF(d, PD_LLX, idx), PDF(d, PD_LLY, idx), bx, bm);
+            stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p + 1], d.ped_pts_n[2 * p + 1], 3 + add, p,
+                       PDF(d, PD_RLX, idx), PDF(d, PD_RLY, idx), bx, bm);
         }   // rectangle pedestrians are never drawn (img_env.cpp:599-616 has no branch for them)
     }
 }
@@ -163,7 +225,7 @@ __global__ void k_stamp_objects(Dev d, const int* scene_ids, int unstamp) {
                 double px = m * resolution + ob[1], py = n * resolution + ob[2];
                 double wx, wy;
                 tf_apply(t, px, py, wx, wy);
-                stamp_cell(d, s, world2cell(wx, d.c.res), world2cell(wy, d.c.res), mode, 0);
+                stamp_object_cell(d, s, world2cell(wx, d.c.res), world2cell(wy, d.c.res), mode);
             }
         }
     } else if (shape == 1) {
@@ -174,7 +236,7 @@ __global__ void k_stamp_objects(Dev d, const int* scene_ids, int unstamp) {
             int m = x_min + k / ny, n = y_min + k % ny;
             double wx, wy;
             tf_apply(t, m * resolution, n * resolution, wx, wy);
-            stamp_cell(d, s, world2cell(wx, d.c.res), world2cell(wy, d.c.res), mode, 0);
+            stamp_object_cell(d, s, world2cell(wx, d.c.res), world2cell(wy, d.c.res), mode);
         }
     }
 }
@@ -647,11 +709,11 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         //      output column, so the horizontal pass evaluates its (<= 4) pixels on the fly: no pixel buffer.
         const uint32_t* own_mask = d.own_mask + (size_t)ty.own_mask_off;
         const uint32_t* dtab = d.dtab + (size_t)ty.dtab_off;
-        // value code of the needed pixel (rr, nc): 0 -> 0, 1 -> 100, 2 -> 200, 3 -> 255
-        auto pixel_code = [&](int rr, int nc) -> unsigned {
+        // value code of tap k of output column oc on needed row rr: 0 -> 0, 1 -> 100, 2 -> 200, 3 -> 255.
+        // e is the tap's dtab entry; the source column is only looked up on the rare fall-through path.
+        auto pixel_code = [&](unsigned e, int rr, const short* tp, int k) -> unsigned {
             unsigned code = 2u; bool own;
             if (c.use_laser) {
-                const unsigned e = __ldg(dtab + rr * c.ns + nc);
                 own = e >> 31;
                 const int kh = e & 0xFFF;
                 if (kh != 0xFFF) {
@@ -660,14 +722,14 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     if (i0 < hp) code = 3u;
                     else if (i0 == hp) code = 0u;
                     else {
-                        const int pr = need[rr], pc = need[nc];
+                        const int pr = need[rr], pc = need[tp[k]];
                         if (!(pr != (int)((key >> 11) & 2047) && pc != (int)(key & 2047))) {     // no shadow write: fall through to lower rays
                             const unsigned kp = __ldg(kpack + pr * vw + pc);
                             const int kl = kp >> 16;
-                            for (int k = kh - 1; k >= kl; k--) {
-                                const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
+                            for (int kk = kh - 1; kk >= kl; kk--) {
+                                const int i = ray_touch(ox, oy, rend[2 * kk], rend[2 * kk + 1], pr, pc);
                                 if (i < 0) continue;
-                                const unsigned key2 = hitkey[k];
+                                const unsigned key2 = hitkey[kk];
                                 const int hp2 = (int)(key2 >> 22);
                                 if (i < hp2) { code = 3u; break; }
                                 if (i == hp2) { code = 0u; break; }
@@ -677,7 +739,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     }
                 }
             } else {
-                const int pr = need[rr], pc = need[nc], full = pr * vw + pc;
+                const int pr = need[rr], pc = need[tp[k]], full = pr * vw + pc;
                 const bool o = (occ[pr * vwb + (pc >> 5)] >> (pc & 31)) & 1u;
                 const bool kn = (known[pr * vwb + (pc >> 5)] >> (pc & 31)) & 1u;
                 code = o ? 0u : (kn ? 3u : 2u);
@@ -724,15 +786,16 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 for (int q = tid; q < c.ns * HB_COLS; q += VIEW_THREADS) {
                     const int rr = q / HB_COLS, ocl = q % HB_COLS;
                     if (ocl >= nc) continue;
-                    const short* tp = d.cubic_tap + 4 * (cb + ocl); const short* cf = d.cubic_coef + 4 * (cb + ocl);
+                    const int oc = cb + ocl;
+                    const short* tp = d.cubic_tap + 4 * oc;
+                    const short4 cf = __ldg(reinterpret_cast<const short4*>(d.cubic_coef) + oc);
+                    uint4 e4 = make_uint4(0u, 0u, 0u, 0u);
+                    if (c.use_laser) e4 = __ldg(reinterpret_cast<const uint4*>(dtab) + (size_t)rr * c.img + oc);
                     int acc = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int w = cf[k];
-                        if (w == 0) continue;
-                        const unsigned code = pixel_code(rr, tp[k]);
-                        acc += (int)((0xFFC86400u >> (8 * code)) & 0xFFu) * w;
-                    }
+                    if (cf.x) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.x, rr, tp, 0))) & 0xFFu) * cf.x;
+                    if (cf.y) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.y, rr, tp, 1))) & 0xFFu) * cf.y;
+                    if (cf.z) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.z, rr, tp, 2))) & 0xFFu) * cf.z;
+                    if (cf.w) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.w, rr, tp, 3))) & 0xFFu) * cf.w;
                     hbuf[rr * HB_COLS + ocl] = acc;
                 }
                 __syncthreads();
