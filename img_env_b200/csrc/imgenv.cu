@@ -191,7 +191,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         }
     }
     c.n_types = (int)types.size();
-    std::vector<double> lattice; std::vector<short> ray_end, spans; std::vector<unsigned short> khi, klo; std::vector<uint32_t> own_mask, tile_fov, edge_px, dtab;
+    std::vector<double> lattice; std::vector<short> ray_end, spans; std::vector<unsigned short> khi, klo; std::vector<uint32_t> own_mask, tile_fov, edge_px, dtab, hstat;
     std::vector<RobotType> rts;
     for (auto& T : types) {
         T.t.pts_off = (int)lattice.size() / 2; lattice.insert(lattice.end(), T.lattice.begin(), T.lattice.end());
@@ -219,6 +219,22 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
                         if ((T.own_mask[full >> 5] >> (full & 31)) & 1u) e |= 1u << 31;
                         T.dtab[((size_t)rr * c.img + oc) * 4 + k] = e;
                     }
+            // hit-free shortcut of the same pass: ray interval of the taps' top rays and the sum when none of them hits
+            for (int rr = 0; rr < c.ns; rr++)
+                for (int oc = 0; oc < c.img; oc++) {
+                    uint32_t kmin = 0xFFFFu, kmax = 0; bool any = false; int sum = 0;
+                    for (int k = 0; k < 4; k++) {
+                        const int w = coef[4 * oc + k];
+                        if (w == 0) continue;
+                        const uint32_t e = T.dtab[((size_t)rr * c.img + oc) * 4 + k], kh = e & 0xFFFu;
+                        int val = 200;                                   // no ray passes: unknown
+                        if (kh != 0xFFFu) { val = 255; kmin = std::min(kmin, kh); kmax = std::max(kmax, kh); any = true; }
+                        if (e >> 31) val = 100;                          // own footprint
+                        sum += val * w;
+                    }
+                    if (!any) { kmin = 1; kmax = 0; }
+                    hstat.push_back(kmin | (kmax << 16)); hstat.push_back((uint32_t)sum);
+                }
         }
         T.t.dtab_off = (int)dtab.size(); dtab.insert(dtab.end(), T.dtab.begin(), T.dtab.end());
         T.t.n_own = 0; T.t.own_off = 0;
@@ -262,7 +278,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     UP(kpack, kpack) UP(grid, g) UP(static_occ, socc) UP(types, rts) UP(type_of, type_of) UP(lattice_xy, lattice) UP(ray_end, ray_end)
     UP(fov_spans, spans) UP(khi, khi) UP(klo, klo) UP(own_mask, own_mask) UP(need_idx, need_idx) UP(cubic_tap, tap)
     UP(cubic_coef, coef) UP(f16_lut, lut) UP(lim_v, lv) UP(lim_w, lw) UP(ped_shape, pshape) UP(ped_size, psize)
-    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(dtab, dtab) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(ped_ext, pext) UP(own_cells, own_dummy)
+    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(dtab, dtab) UP(hstat, hstat) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(ped_ext, pext) UP(own_cells, own_dummy)
 #undef UP
     size_t S = c.S;
     size_t pc = ((size_t)H * W + 3) & ~(size_t)3;

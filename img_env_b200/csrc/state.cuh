@@ -97,6 +97,7 @@ struct Dev {
     const uint32_t* tile_fov;     // per type: bit per 32x32 view tile (row-major, vwb per row) with any FOV pixel
     const uint32_t* edge_px;      // per type: FOV-edge pixels
     const uint32_t* dtab;         // per type [ns][img][4]: for tap k of output column oc on needed row rr: top ray (12b) | its step index there (10b) << 12 | own footprint << 31
+    const uint32_t* hstat;        // per type [ns][img][2]: (lowest | highest << 16) top ray over the output's taps, hit-free horizontal sum
     const short* need_idx;        // [ns] source row/col index of the k-th needed row/col
     const short* cubic_tap;       // [img][4] index into need_idx space (0..ns-1) of the 4 taps
     const short* cubic_coef;      // [img][4] fixed-point weights (x2048)

@@ -309,7 +309,7 @@ __device__ __forceinline__ int ray_touch(int ox, int oy, int ex, int ey, int pr,
 
 #define HB_COLS 16           // output columns per vertical-pass block (bounds the horizontal buffer)
 #define INV_MAX_BLOCKS 512   // 32x32-cell world blocks under the FOV; more -> forward (tile) rasterisation
-struct ViewLayout { size_t sh, regA, regB, hitkey, rays, need, spans, blocks, total; };
+struct ViewLayout { size_t sh, regA, regB, hpre, hitkey, rays, need, spans, blocks, total; };
 __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     ViewLayout L;
     size_t off = 0;
@@ -317,8 +317,8 @@ __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     size_t occ = (size_t)c.vh * c.vwb * 4 * (c.use_laser ? 1 : 2);
     size_t pedb = (size_t)c.img * c.img * 4 + (size_t)((c.P + 1) & ~1) * 8 + (size_t)c.P * 16 + (size_t)c.P * 4 + 16;
     L.regA = off; off += ((occ > pedb ? occ : pedb) + 15) & ~(size_t)15;
-    size_t bl = (size_t)(BL_CAP + BL2_CAP) * 4, hb = (size_t)c.ns * HB_COLS * 4;
-    L.regB = off; off += ((bl > hb ? bl : hb) + 15) & ~(size_t)15;
+    size_t bl = (size_t)(BL_CAP + BL2_CAP) * 4, hb = (((size_t)c.ns * HB_COLS * 4 + 15) & ~(size_t)15) + ((size_t)c.range_total + 1) * 2;
+    L.regB = off; L.hpre = off + (((size_t)c.ns * HB_COLS * 4 + 15) & ~(size_t)15); off += ((bl > hb ? bl : hb) + 15) & ~(size_t)15;
     L.hitkey = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
     L.rays = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
     L.need = off; off += ((size_t)c.ns * 2 + 15) & ~(size_t)15;
@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
     uint32_t* blist = reinterpret_cast<uint32_t*>(smem_raw + L.regB);
     uint32_t* blist2 = blist + BL_CAP;
     int* hbuf = reinterpret_cast<int*>(smem_raw + L.regB);
+    unsigned short* hpre = reinterpret_cast<unsigned short*>(smem_raw + L.hpre);   // after phase C: hpre[k] = #rays < k with a hit
     short* spans = reinterpret_cast<short*>(smem_raw + L.spans);
     uint32_t* blocks = reinterpret_cast<uint32_t*>(smem_raw + L.blocks);
     unsigned* hitkey = reinterpret_cast<unsigned*>(smem_raw + L.hitkey);
@@ -695,6 +696,21 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     const float wire = (float)hit;                         // AgentState.laser is float32[]
                     d.o_laser[(size_t)idx * c.range_total + k] = c.laser_norm ? (float)((double)wire / c.laser_max) : wire;   // yaml_env.py:440-444
                 }
+                // prefix counts of the rays that hit something: phase D/F asks "any hit among rays [a, b]?" in O(1)
+                const int per = (c.range_total + VIEW_THREADS - 1) / VIEW_THREADS;
+                const int k0 = min(tid * per, c.range_total), k1 = min(k0 + per, c.range_total);
+                int cnt = 0;
+                for (int k = k0; k < k1; k++) cnt += hitkey[k] != NOHIT;
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                if (lane == 31) sh->red[warp] = incl;      // the list counters in red[] are dead after the barrier above
+                __syncthreads();
+                int run = incl - cnt;
+                for (int w = 0; w < warp; w++) run += sh->red[w];
+                for (int k = k0; k < k1; k++) { hpre[k] = (unsigned short)run; run += hitkey[k] != NOHIT; }
+                if (k1 == c.range_total) hpre[k1] = (unsigned short)run;
+                __syncthreads();
             }
         }
 
@@ -790,7 +806,14 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     const short* tp = d.cubic_tap + 4 * oc;
                     const short4 cf = __ldg(reinterpret_cast<const short4*>(d.cubic_coef) + oc);
                     uint4 e4 = make_uint4(0u, 0u, 0u, 0u);
-                    if (c.use_laser) e4 = __ldg(reinterpret_cast<const uint4*>(dtab) + (size_t)rr * c.img + oc);
+                    if (c.use_laser) {
+                        // static shortcut: when none of the top rays of this output's taps hit anything, all of its source
+                        // pixels keep their hit-free value (free / own footprint / outside every ray) and the sum is a table entry
+                        const uint2 hs = __ldg(reinterpret_cast<const uint2*>(d.hstat) + (size_t)(ty.dtab_off >> 2) + (size_t)rr * c.img + oc);
+                        const int kmin = hs.x & 0xFFFFu, kmax = hs.x >> 16;
+                        if (kmax < kmin || hpre[kmax + 1] == hpre[kmin]) { hbuf[rr * HB_COLS + ocl] = (int)hs.y; continue; }
+                        e4 = __ldg(reinterpret_cast<const uint4*>(dtab) + (size_t)rr * c.img + oc);
+                    }
                     int acc = 0;
                     if (cf.x) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.x, rr, tp, 0))) & 0xFFu) * cf.x;
                     if (cf.y) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.y, rr, tp, 1))) & 0xFFu) * cf.y;
