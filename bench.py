@@ -40,7 +40,7 @@ WORKLOADS = {
     "c4": dict(desc="200 robots + 200 ervoscene pedestrians + 200 objects on one 7333^2 grid (image_big shape)", R=200, P=200,
                scene="ervoscene", n_obj=200, map_px=110, gres=1.0, lo=25.0, hi=85.0, max_ped=200, scenes=128),
     "c5": dict(desc="64 robots + 64 pedscene (SFM) pedestrians per scene, 1066^2 grid", R=64, P=64, scene="pedscene", n_obj=0,
-               map_px=160, gres=0.1, lo=2.5, hi=13.5, max_ped=64, scenes=256),
+               map_px=160, gres=0.1, lo=2.5, hi=13.5, max_ped=64, scenes=512),
 }
 
 

@@ -380,13 +380,16 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_apply(Dev d, const float* a
     }
 }
 
-// Tscene::moveAgent for every agent in index order (the order Tscene::moveAgents moves them): one thread per scene.
-__global__ void k_sfm_tree(Dev d) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= d.c.S) return;
+// Tscene::moveAgent for every agent in index order (the order Tscene::moveAgents moves them).  The walk is
+// sequential per scene and data dependent, so one scene = one warp with one working lane (32 scenes in a warp
+// would serialise their divergent walks); the in-tree flags are written back by all lanes.
+__global__ void __launch_bounds__(32) k_sfm_tree(Dev d) {
+    const int s = blockIdx.x;
     const QTreeView t = qt_view(d, s, d.sfm_newpos + (size_t)s * d.c.NA * 2);
-    for (int a = 0; a < d.c.NA; a++) qt_move(t, a);
-    for (int a = 0; a < d.c.NA; a++) d.sfm[((size_t)s * d.c.NA + a) * SFM_REC + 10] = qt_in_tree(t, a) ? 1.0 : 0.0;
+    if (threadIdx.x == 0) for (int a = 0; a < d.c.NA; a++) qt_move(t, a);
+    __syncwarp();
+    __threadfence_block();
+    for (int a = threadIdx.x; a < d.c.NA; a += 32) d.sfm[((size_t)s * d.c.NA + a) * SFM_REC + 10] = qt_in_tree(t, a) ? 1.0 : 0.0;
 }
 
 inline size_t dyn_smem_bytes(const Cfg& c) { return (size_t)c.NA * 2 * 8 + (size_t)c.R * 12 + 64; }

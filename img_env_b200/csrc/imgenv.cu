@@ -38,6 +38,9 @@ struct imgenv {
     float* stf_h = nullptr; float* stf_d = nullptr; size_t st_floats = 0;
     float* act_d = nullptr; uint8_t* alive_d = nullptr;
     size_t view_smem = 0, dyn_smem = 0, stamp_smem = 0;
+    // SFM only: the (sequential, latency-bound) quadtree update of step t runs on a side stream underneath the
+    // observation kernels and is joined before the next reader of the tree (next step's forces, reset)
+    cudaStream_t side = nullptr; cudaEvent_t ev_moved = nullptr, ev_tree = nullptr; bool tree_pending = false;
     // optional per-kernel CUDA-event timing (bench.py roofline): 5 events per profiled step
     std::vector<cudaEvent_t> evs; int prof_max = 0, prof_n = 0;
 };
@@ -106,6 +109,9 @@ extern "C" int imgenv_destroy(imgenv_t* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+    if (h->ev_moved) cudaEventDestroy(h->ev_moved);
+    if (h->ev_tree) cudaEventDestroy(h->ev_tree);
     for (auto& g : h->stage) {
         if (g.h) cudaFreeHost(g.h);
         if (g.ih) cudaFreeHost(g.ih);
@@ -346,6 +352,11 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         CK(cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming));
     }
 
+    if (c.scene_type == 1) {
+        CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_moved, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_tree, cudaEventDisableTiming));
+    }
     {   // shared-memory cell bitmap of k_stamp_agents: sized for the largest footprint box
         int words = 1;
         for (const auto& t : rts) words = std::max(words, stamp_bitmap_words(stamp_rad_cells(t.zone_rad * c.res, c.res)));
@@ -475,6 +486,7 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     if (n < 1 || n > c.S) return fail("imgenv_reset: bad scene count");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->tree_pending) { CK(cudaStreamWaitEvent(st, h->ev_tree, 0)); h->tree_pending = false; }
     {   // staging is double-buffered: wait only until the reset that last used this set has consumed it
         imgenv::Stage& g = h->stage[h->stage_i ^= 1];
         CK(cudaEventSynchronize(g.ev));
@@ -577,9 +589,16 @@ extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d
     if (ev) cudaEventRecord(ev[0], st);
     {
         const int nblk = dyn_nblk(c);
+        if (h->tree_pending) { CK(cudaStreamWaitEvent(st, h->ev_tree, 0)); h->tree_pending = false; }
         if (c.NA > 0) k_dyn_solve<<<c.S * nblk, DYN_THREADS, h->dyn_smem, st>>>(d, d_actions, d_alive);
         k_dyn_apply<<<c.S * nblk, DYN_THREADS, 0, st>>>(d, d_actions, d_alive, h->ped_yaw_mode);
-        if (c.scene_type == 1) k_sfm_tree<<<(c.S + 31) / 32, 32, 0, st>>>(d);
+        if (c.scene_type == 1) {   // quadtree maintenance (ped_scene.cpp:167-182 moveAgent) off the critical path
+            CK(cudaEventRecord(h->ev_moved, st));
+            CK(cudaStreamWaitEvent(h->side, h->ev_moved, 0));
+            k_sfm_tree<<<c.S, 32, 0, h->side>>>(d);
+            CK(cudaEventRecord(h->ev_tree, h->side));
+            h->tree_pending = true;
+        }
     }
     if (ev) cudaEventRecord(ev[1], st);
     return launch_observe(h, nullptr, c.S, 0, st, ev);
