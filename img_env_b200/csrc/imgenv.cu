@@ -38,9 +38,12 @@ struct imgenv {
     float* stf_h = nullptr; float* stf_d = nullptr; size_t st_floats = 0;
     float* act_d = nullptr; uint8_t* alive_d = nullptr;
     size_t view_smem = 0, dyn_smem = 0, stamp_smem = 0;
-    // SFM only: the (sequential, latency-bound) quadtree update of step t runs on a side stream underneath the
-    // observation kernels and is joined before the next reader of the tree (next step's forces, reset)
-    cudaStream_t side = nullptr; cudaEvent_t ev_moved = nullptr, ev_tree = nullptr; bool tree_pending = false;
+    // Side stream, forked after the agents have moved and joined before the call returns to the caller's stream:
+    // the pedestrian observation (k_ped_obs only reads poses) runs beside the stamp / view kernels.  SFM only: the
+    // sequential, latency-bound quadtree update of step t follows it there and is joined before the next reader of
+    // the tree (next step's forces, reset).
+    cudaStream_t side = nullptr; cudaEvent_t ev_moved = nullptr, ev_ped = nullptr, ev_tree = nullptr; bool tree_pending = false;
+    size_t ped_smem = 0;
     // optional per-kernel CUDA-event timing (bench.py roofline): 5 events per profiled step
     std::vector<cudaEvent_t> evs; int prof_max = 0, prof_n = 0;
 };
@@ -112,6 +115,7 @@ extern "C" int imgenv_destroy(imgenv_t* h) {
     if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
     if (h->ev_moved) cudaEventDestroy(h->ev_moved);
     if (h->ev_tree) cudaEventDestroy(h->ev_tree);
+    if (h->ev_ped) cudaEventDestroy(h->ev_ped);
     for (auto& g : h->stage) {
         if (g.h) cudaFreeHost(g.h);
         if (g.ih) cudaFreeHost(g.ih);
@@ -352,11 +356,13 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         CK(cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming));
     }
 
-    if (c.scene_type == 1) {
-        CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&h->ev_moved, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&h->ev_tree, cudaEventDisableTiming));
-    }
+    CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_moved, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_ped, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_tree, cudaEventDisableTiming));
+    h->ped_smem = ped_smem_bytes(c);
+    if (h->ped_smem > 200 * 1024) return fail("imgenv_create: too many pedestrians for the pedestrian observation kernel's shared memory");
+    CK(cudaFuncSetAttribute(k_ped_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ped_smem));
     {   // shared-memory cell bitmap of k_stamp_agents: sized for the largest footprint box
         int words = 1;
         for (const auto& t : rts) words = std::max(words, stamp_bitmap_words(stamp_rad_cells(t.zone_rad * c.res, c.res)));
@@ -467,12 +473,23 @@ __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, co
 
 static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int is_reset, cudaStream_t st, cudaEvent_t* ev = nullptr) {
     Dev& d = h->d; const Cfg& c = d.c;
+    // fork: pedestrian observation (+ SFM quadtree maintenance, ped_scene.cpp:167-182 moveAgent) on the side stream
+    CK(cudaEventRecord(h->ev_moved, st));
+    CK(cudaStreamWaitEvent(h->side, h->ev_moved, 0));
+    k_ped_obs<<<n_scenes * c.R, PED_THREADS, h->ped_smem, h->side>>>(d, d_scene_ids);
+    CK(cudaEventRecord(h->ev_ped, h->side));
+    if (!is_reset && c.scene_type == 1) {
+        k_sfm_tree<<<c.S, 32, 0, h->side>>>(d);
+        CK(cudaEventRecord(h->ev_tree, h->side));
+        h->tree_pending = true;
+    }
     k_stamp_agents<<<n_scenes * (c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(d, d_scene_ids, 0);
     if (ev) cudaEventRecord(ev[2], st);
     k_view<false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
     if (ev) cudaEventRecord(ev[3], st);
     k_stamp_agents<<<n_scenes * (c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(d, d_scene_ids, is_reset ? 1 : 2);    // 2: also step_++
     if (ev) cudaEventRecord(ev[4], st);
+    CK(cudaStreamWaitEvent(st, h->ev_ped, 0));      // join: every output of the call is ordered on the caller's stream
     CK(cudaGetLastError());
     return 0;
 }
@@ -576,7 +593,7 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     return 0;
 }
 
-extern "C" int imgenv_launches_per_step(const imgenv_t* h) { return !h ? 4 : (h->d.c.scene_type == 1 ? 6 : (h->d.c.NA > 0 ? 5 : 4)); }
+extern "C" int imgenv_launches_per_step(const imgenv_t* h) { return !h ? 5 : (h->d.c.scene_type == 1 ? 7 : (h->d.c.NA > 0 ? 6 : 5)); }
 
 extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d_alive, void* stream) {
     if (!h) return fail("imgenv_step: null handle");
@@ -592,13 +609,7 @@ extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d
         if (h->tree_pending) { CK(cudaStreamWaitEvent(st, h->ev_tree, 0)); h->tree_pending = false; }
         if (c.NA > 0) k_dyn_solve<<<c.S * nblk, DYN_THREADS, h->dyn_smem, st>>>(d, d_actions, d_alive);
         k_dyn_apply<<<c.S * nblk, DYN_THREADS, 0, st>>>(d, d_actions, d_alive, h->ped_yaw_mode);
-        if (c.scene_type == 1) {   // quadtree maintenance (ped_scene.cpp:167-182 moveAgent) off the critical path
-            CK(cudaEventRecord(h->ev_moved, st));
-            CK(cudaStreamWaitEvent(h->side, h->ev_moved, 0));
-            k_sfm_tree<<<c.S, 32, 0, h->side>>>(d);
-            CK(cudaEventRecord(h->ev_tree, h->side));
-            h->tree_pending = true;
-        }
+
     }
     if (ev) cudaEventRecord(ev[1], st);
     return launch_observe(h, nullptr, c.S, 0, st, ev);

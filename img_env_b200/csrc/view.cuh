@@ -315,8 +315,7 @@ __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     size_t off = 0;
     L.sh = off; off += (sizeof(ViewShared) + 15) & ~(size_t)15;
     size_t occ = (size_t)c.vh * c.vwb * 4 * (c.use_laser ? 1 : 2);
-    size_t pedb = (size_t)c.img * c.img * 4 + (size_t)((c.P + 1) & ~1) * 8 + (size_t)c.P * 16 + (size_t)c.P * 4 + 16;
-    L.regA = off; off += ((occ > pedb ? occ : pedb) + 15) & ~(size_t)15;
+    L.regA = off; off += (occ + 15) & ~(size_t)15;
     size_t bl = (size_t)(BL_CAP + BL2_CAP) * 4, hb = (((size_t)c.ns * HB_COLS * 4 + 15) & ~(size_t)15) + ((size_t)c.range_total + 1) * 2;
     L.regB = off; L.hpre = off + (((size_t)c.ns * HB_COLS * 4 + 15) & ~(size_t)15); off += ((bl > hb ? bl : hb) + 15) & ~(size_t)15;
     L.hitkey = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
@@ -355,11 +354,6 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
     unsigned* hitkey = reinterpret_cast<unsigned*>(smem_raw + L.hitkey);
     short* rend = reinterpret_cast<short*>(smem_raw + L.rays);
     short* need = reinterpret_cast<short*>(smem_raw + L.need);
-    // phase G aliases of region A
-    int* winner = reinterpret_cast<int*>(smem_raw + L.regA);
-    double* pkey = reinterpret_cast<double*>(smem_raw + L.regA + (((size_t)c.img * c.img * 4 + 15) & ~(size_t)15));
-    float* pobs = reinterpret_cast<float*>(pkey + ((c.P + 1) & ~1));
-    int* prank = reinterpret_cast<int*>(pobs + 4 * (size_t)c.P);
 
     if (tid == 0) {
         double x = RBF(d, RB_X, idx), y = RBF(d, RB_Y, idx), yaw = RBF(d, RB_YAW, idx);
@@ -799,9 +793,12 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             const float scale = 1.f / (2048.f * 2048.f);
             for (int cb = 0; cb < c.img; cb += HB_COLS) {
                 const int nc = min(HB_COLS, c.img - cb);
-                for (int q = tid; q < c.ns * HB_COLS; q += VIEW_THREADS) {
-                    const int rr = q / HB_COLS, ocl = q % HB_COLS;
-                    if (ocl >= nc) continue;
+                // a warp covers a compact patch of 8 needed rows x 4 output columns: few rays cross it, so the whole warp
+                // often takes the hit-free shortcut below
+                for (int q = tid; q < ((c.ns + 7) >> 3) * 8 * HB_COLS; q += VIEW_THREADS) {
+                    const int tile = q >> 5, l = q & 31;
+                    const int rr = (tile / (HB_COLS / 4)) * 8 + (l >> 2), ocl = (tile % (HB_COLS / 4)) * 4 + (l & 3);
+                    if (ocl >= nc || rr >= c.ns) continue;
                     const int oc = cb + ocl;
                     const short* tp = d.cubic_tap + 4 * oc;
                     const short4 cf = __ldg(reinterpret_cast<const short4*>(d.cubic_coef) + oc);
@@ -839,10 +836,9 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         }
     }
     if (DEBUG_FULL) return;
-    __syncthreads();     // region A (raster) is dead from here on: reuse it for the pedestrian observation
 
-    // ---- Phase G: state vector + pedestrian observation (img_env.cpp:547-587, yaml_env.py:392-481)
-    for (int k = tid; k < c.img * c.img; k += VIEW_THREADS) winner[k] = -1;
+    // ---- Phase G: state vector and the episode bookkeeping (img_env.cpp:547-587, yaml_env.py:316, 374-376, 467-471).
+    //      The pedestrian observation does not depend on the raster: k_ped_obs below, on its own stream.
     if (tid == 0) {
         double st[5];
         robot_state_vec(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx), RBF(d, RB_GX, idx), RBF(d, RB_GY, idx),
@@ -858,26 +854,52 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         d.o_arr[idx] = (uint8_t)arr;
         RBF(d, RB_DONE, idx) = is_reset ? 0.0 : (double)min(1, min(coll, 1) + arr);   // yaml_env.py:316, 374-376
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pedestrian observation of every robot (img_env.cpp:566-583 ped_info; yaml_env.py:392-466 _get_states /
+// _draw_ped_map): pedestrians in the robot frame, nearest first (stable sort), ped_vector_states, ped_min_dists
+// (NearbyPed persistence) and the 3 x img x img ped_maps where farther pedestrians overwrite nearer ones.
+// It only reads poses, so it runs beside the stamp / view kernels on the library's side stream.
+// ---------------------------------------------------------------------------------------------
+#define PED_THREADS 128
+inline size_t ped_smem_bytes(const Cfg& c) {
+    return (((size_t)c.img * c.img * 4 + 15) & ~(size_t)15) + (size_t)((c.P + 1) & ~1) * 8 + (size_t)c.P * 16 + (size_t)c.P * 4 + 16;
+}
+__global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene_ids) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Cfg& c = d.c;
+    const int tid = threadIdx.x;
+    const int sl = blockIdx.x / c.R, r = blockIdx.x % c.R;
+    const int s = scene_ids ? scene_ids[sl] : sl;
+    const int idx = s * c.R + r;
+    const RobotType& ty = d.types[d.type_of[r]];
+    int* winner = reinterpret_cast<int*>(smem_raw);
+    double* pkey = reinterpret_cast<double*>(smem_raw + (((size_t)c.img * c.img * 4 + 15) & ~(size_t)15));
+    float* pobs = reinterpret_cast<float*>(pkey + ((c.P + 1) & ~1));
+    int* prank = reinterpret_cast<int*>(pobs + 4 * (size_t)c.P);
+    const Tf2 world_base = tf_inv(tf_from_pose(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx)));
+    for (int k = tid; k < c.img * c.img; k += PED_THREADS) winner[k] = -1;
     float* pvs = d.o_pvs + (size_t)idx * c.pvs_len;
-    for (int k = tid; k < c.pvs_len; k += VIEW_THREADS) pvs[k] = k == 0 ? (float)c.P : 0.f;
-    for (int j = tid; j < c.P; j += VIEW_THREADS) {
+    for (int k = tid; k < c.pvs_len; k += PED_THREADS) pvs[k] = k == 0 ? (float)c.P : 0.f;
+    for (int j = tid; j < c.P; j += PED_THREADS) {
         int pi = s * c.P + j;
         double bx, by, bvx, bvy;
-        tf_apply(sh->world_base, PDF(d, PD_X, pi), PDF(d, PD_Y, pi), bx, by);
-        tf_rotate(sh->world_base, PDF(d, PD_VX, pi), PDF(d, PD_VY, pi), bvx, bvy);
+        tf_apply(world_base, PDF(d, PD_X, pi), PDF(d, PD_Y, pi), bx, by);
+        tf_rotate(world_base, PDF(d, PD_VX, pi), PDF(d, PD_VY, pi), bvx, bvy);
         float px = (float)bx, py = (float)by;
         pobs[4 * j] = px; pobs[4 * j + 1] = py; pobs[4 * j + 2] = (float)bvx; pobs[4 * j + 3] = (float)bvy;
         pkey[j] = (double)px * (double)px + (double)py * (double)py;
     }
     __syncthreads();
-    for (int j = tid; j < c.P; j += VIEW_THREADS) {   // stable rank == python's list.sort(key=...)
+    for (int j = tid; j < c.P; j += PED_THREADS) {   // stable rank == python's list.sort(key=...)
         double kj = pkey[j];
         int rk = 0;
         for (int i = 0; i < c.P; i++) rk += (pkey[i] < kj) || (pkey[i] == kj && i < j);
         prank[j] = rk;
     }
     __syncthreads();
-    for (int j = tid; j < c.P; j += VIEW_THREADS) {
+    for (int j = tid; j < c.P; j += PED_THREADS) {
         int q = prank[j];
         double px = pobs[4 * j], py = pobs[4 * j + 1];
         double ped_r = d.ped_r_round[j];
@@ -907,7 +929,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
     float* pm = d.o_pmap + (size_t)idx * 3 * c.img * c.img;
     const int npm = c.img * c.img;
     for (int ch = 0; ch < 3; ch++)
-        for (int cell = tid; cell < npm; cell += VIEW_THREADS) {
+        for (int cell = tid; cell < npm; cell += PED_THREADS) {
             int wv = winner[cell];
             float v = 0.f;
             if (wv >= 0) { int j = wv & 0xFFFF; v = ch == 0 ? 1.0f : pobs[4 * j + 1 + ch]; }
