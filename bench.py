@@ -304,9 +304,12 @@ def run_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     view_ms = kms["k_view"]
     achieved = (B * S * R) / (view_ms * 1e-3) / 1e9 if view_ms > 0 else None
+    # bytes k_view itself moves: everything except the pedestrian observation, which k_ped_obs writes concurrently
+    B_ped = 3 * sim.spec["ped_image_size"][0] ** 2 * 4 + 4 * sim.pvs_len + 4
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    try:   # measured per robot-step by ncu (profiles/): scaled to this launch's robot count
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        traffic = float(tj["bytes_per_robot_step"]) * S * R
     except Exception:
         pass
     out = {
@@ -325,6 +328,11 @@ def run_b200(args):
         "kernel_ms": {k: round(v, 4) for k, v in kms.items()},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "kernel": "k_view", "bytes_per_robot_step": B, "robot_steps_per_launch": S * R,
+                     "kernel_own_bytes_per_robot_step": B - B_ped,
+                     "step_frac": (B * S * R) / (ms / K * 1e-3) / 1e9 / peak,
+                     "note": "achieved = SURVEY 8(d) bytes per robot-step x robots per launch / k_view's CUDA-event time; the pedestrian "
+                             "part of those bytes is written by k_ped_obs, which runs concurrently on the side stream inside that window; "
+                             "step_frac = the same bytes over the whole step time (all kernels)",
                      "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s"},
         "clocks": clocks,
     }
