@@ -934,3 +934,40 @@ extern "C" int imgenv_debug_global_map(imgenv_t* h, int32_t scene, int32_t self,
     if (e != cudaSuccess) return fail(std::string("imgenv_debug_global_map: ") + cudaGetErrorString(e));
     return 0;
 }
+
+// Invariant check for the tests (SURVEY §8c "size-independent properties"): between calls no agent is stamped, so in
+// every scene occ_all == base_occ, no dynamic flag bit is set, no block carries the "stamped this step" mark and the
+// block counts equal the popcount of base_occ.  out[4] = number of violating occ words, flag bytes, block marks, block counts.
+__global__ void k_debug_check_planes(Dev d, unsigned long long* out) {
+    const size_t wpp = (size_t)d.c.H * d.c.Wb, pcs = plane_cells(d.c), nb = (size_t)d.c.Hc * d.c.Wb;
+    const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long a = 0, b = 0, c2 = 0, e = 0;
+    for (size_t i = t0; i < wpp * d.c.S; i += stride) a += d.occ_all[i] != d.base_occ[i];
+    for (size_t i = t0; i < pcs * d.c.S; i += stride) b += (d.flags[i] & ~F_OBJ) != 0;
+    for (size_t i = t0; i < nb * d.c.S; i += stride) {
+        c2 += (d.coarse[i] >> 31) != 0;
+        const size_t s = i / nb, blk = i % nb; const int I = (int)(blk / d.c.Wb), J = (int)(blk % d.c.Wb);
+        unsigned cnt = 0;
+        for (int rr = 32 * I; rr < min(32 * I + 32, d.c.H); rr++) cnt += __popc(d.base_occ[s * wpp + (size_t)rr * d.c.Wb + J]);
+        e += (d.coarse[i] & 0x7FFFFFFFu) != cnt;
+    }
+    if (a) atomicAdd(out + 0, a);
+    if (b) atomicAdd(out + 1, b);
+    if (c2) atomicAdd(out + 2, c2);
+    if (e) atomicAdd(out + 3, e);
+}
+extern "C" int imgenv_debug_check_planes(imgenv_t* h, int64_t* out4, void* stream) {
+    if (!h || !out4) return fail("imgenv_debug_check_planes: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* buf = nullptr;
+    CK(cudaMalloc((void**)&buf, 32));
+    CK(cudaMemsetAsync(buf, 0, 32, st));
+    k_debug_check_planes<<<1184, 256, 0, st>>>(h->d, buf);
+    unsigned long long r[4];
+    cudaError_t e = cudaMemcpyAsync(r, buf, 32, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(std::string("imgenv_debug_check_planes: ") + cudaGetErrorString(e));
+    for (int k = 0; k < 4; k++) out4[k] = (int64_t)r[k];
+    return 0;
+}

@@ -39,7 +39,7 @@ EXPORTS = ["imgenv_create", "imgenv_destroy", "imgenv_bind_outputs", "imgenv_res
            "imgenv_solver_agents", "imgenv_view_dims", "imgenv_launches_per_step",
            "imgenv_algorithmic_bytes_per_robot_step", "imgenv_last_error", "imgenv_version",
            "imgenv_sampler_create", "imgenv_sampler_destroy", "imgenv_sampler_seed", "imgenv_sampler_sample", "imgenv_sampler_draw",
-           "imgenv_reset_sampled"]
+           "imgenv_reset_sampled", "imgenv_debug_check_planes"]
 
 
 def load_library(path=None):
@@ -224,6 +224,12 @@ class BatchedSim:
         ids = np.ascontiguousarray(scene_ids if scene_ids is not None else np.arange(self.S), dtype=np.int32)
         self._check(self.lib.imgenv_reset_sampled(self.h, sampler.h, ids.size, _ptr(ids, C.c_int32), int(ignore_obstacle), self._stream()))
         return self.out
+
+    def debug_check_planes(self):
+        """-> (occ words, flag bytes, block marks, block counts) violating 'no agent is stamped between calls'."""
+        out = np.zeros(4, np.int64)
+        self._check(self.lib.imgenv_debug_check_planes(self.h, _ptr(out, C.c_int64), self._stream()))
+        return tuple(int(x) for x in out)
 
     def step(self, actions, alive=None):
         """actions: float32 CUDA tensor [S,R,3] (v, w, beep); alive: uint8 CUDA tensor [S,R] or None."""

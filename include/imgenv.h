@@ -142,6 +142,9 @@ int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* stats_out, 
 /* Debug raster: the composited byte map of one scene, u8 [H][W] to host. self >= 0: robot self's
  * global_map_ (img_env.cpp:623-628); self == -1: peds_map_ (img_env.cpp:594-618); self == -2: obs_map_ (img_env.cpp:167-187). */
 int imgenv_debug_global_map(imgenv_t* h, int32_t scene, int32_t self, uint8_t* host_out, void* stream);
+/* Invariant check (tests): between calls no agent is stamped in the per-scene planes. out4 = number of occupancy words,
+ * flag bytes, block marks and block counts that violate it (all 0 when healthy). */
+int imgenv_debug_check_planes(imgenv_t* h, int64_t* out4, void* stream);
 /* ped_min_dists persistence (NearbyPed, reset_helper.py:85-99) and dones are library state. */
 int imgenv_solver_agents(const imgenv_t* h);   /* P + R' */
 int imgenv_view_dims(const imgenv_t* h, int32_t* vh, int32_t* vw);
