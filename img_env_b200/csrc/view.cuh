@@ -297,6 +297,28 @@ __device__ __forceinline__ int ray_touch(int ox, int oy, int ex, int ey, int pr,
     }
 }
 
+// Rare continuation of the laser_map pixel rule (phase D): the pixel lies behind its top ray's hit and was not shadow
+// written by it, so the rays below (kh-1 .. kl) decide, highest first.  Out of line to keep the kernel's hot loop small.
+__device__ __noinline__ unsigned pixel_code_below(const unsigned* hitkey, const short* rend, int ox, int oy, int pr, int pc, int kh, int kl) {
+    for (int kk = kh - 1; kk >= kl; kk--) {
+        const int i = ray_touch(ox, oy, rend[2 * kk], rend[2 * kk + 1], pr, pc);
+        if (i < 0) continue;
+        const unsigned key2 = hitkey[kk];
+        const int hp2 = (int)(key2 >> 22);
+        if (i < hp2) return 3u;
+        if (i == hp2) return 0u;
+        if (pr != (int)((key2 >> 11) & 2047) && pc != (int)(key2 & 2047)) return 2u;
+    }
+    return 2u;
+}
+// Ray-hit candidates of one raster cell, resolved on the spot (only when the shared-memory lists are full).
+__device__ __noinline__ void cell_rays_inline(unsigned* hitkey, const short* rend, int ox, int oy, int pr, int pc, int kl, int kh) {
+    for (int k = kl; k <= kh; k++) {
+        const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
+        if (i >= 0) atomicMin(&hitkey[k], ((unsigned)i << 22) | ((unsigned)pr << 11) | (unsigned)pc);
+    }
+}
+
 // Shared-memory plan (bytes for the canonical 400x400 view / 1000 rays / 48x48 outputs):
 //   region A  occ raster 400*13*4 = 20.8 KB   (phases B-C)   | later: ped map winners + pedestrian scratch (phase G)
 //   region B  boundary-cell list 24 KB        (phase C)       | later: horizontal resize buffer 144*48*4 = 27.6 KB (phase F)
@@ -308,6 +330,7 @@ __device__ __forceinline__ int ray_touch(int ox, int oy, int ex, int ey, int pr,
 #define NOHIT 0xFFFFFFFFu
 
 #define HB_COLS 16           // output columns per vertical-pass block (bounds the horizontal buffer)
+#define INV_EPS 0.004f       // band around a cell edge inside which the inverse rasterisation runs the exact forward map
 #define INV_MAX_BLOCKS 512   // 32x32-cell world blocks under the FOV; more -> forward (tile) rasterisation
 struct ViewLayout { size_t sh, regA, regB, hpre, hitkey, rays, need, spans, blocks, total; };
 __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
@@ -446,7 +469,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             const bool heavy = kh - (int)(kp >> 16) + 1 > BL_HEAVY;
             const int p = atomicAdd(heavy ? n_list2 : n_list, 1);
             if (p < (heavy ? BL2_CAP : BL_CAP)) (heavy ? blist2 : blist)[p] = (unsigned)full;
-            else cell_rays(full, kp, 0, 1);                                // list full: resolve this cell right here
+            else cell_rays_inline(hitkey, rend, ox, oy, full / vw, full % vw, (int)(kp >> 16), kh);   // list full: resolve this cell right here
         };
         const int n_trow = (vh + 31) >> 5, n_tiles = n_trow * vwb;
         // (1) World -> view ("inverse") rasterisation, used when lasers are on: only raster cells that can be the
@@ -494,6 +517,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             const int X0 = sh->wbb[0], X1 = sh->wbb[1], Y0 = sh->wbb[2], Y1 = sh->wbb[3];
             const int zx = sh->zc[0], zy = sh->zc[1], zr = ty.zone_rad;
             const float i00 = (float)sh->inv[0], i01 = (float)sh->inv[1], i10 = (float)sh->inv[2], i11 = (float)sh->inv[3];
+            const float f00 = (float)sh->view_world.m00, f01 = (float)sh->view_world.m01, f10 = (float)sh->view_world.m10, f11 = (float)sh->view_world.m11;
             // each warp takes 32 words (one per lane), then expands their candidate bits over all lanes
             // batches of 32 words are handed out dynamically: dense world blocks make the work per batch very uneven
             for (;;) {
@@ -546,12 +570,20 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     const int cY = cbj * 32 + (int)__fns(m, 0, n + 1);
                     const float u = (float)((double)cX - sh->org[0]), v = (float)((double)cY - sh->org[1]);
                     const float qi = i00 * u + i01 * v, qj = i10 * u + i11 * v;
-                    const int ia = max((int)ceilf(qi - 0.72f), 0), ib = min((int)floorf(qi + 0.72f), vh - 1);
-                    const int ja = max((int)ceilf(qj - 0.72f), 0), jb = min((int)floorf(qj + 0.72f), vw - 1);
-                    for (int i = ia; i <= ib; i++) {
+                    // Pixel (i,j) maps to this cell iff M*((i,j) - q) lies in the unit square around the cell centre (M =
+                    // rotation of view_world).  The float test decides all pixels farther than INV_EPS from the square's
+                    // edge; only the others run the exact forward map.  |q| < 2^10 so the float error is < 1e-3 cell.
+                    const int ia = (int)ceilf(qi - 0.72f), ja = (int)ceilf(qj - 0.72f);
+#pragma unroll 1
+                    for (int t = 0; t < 4; t++) {
+                        const int i = ia + (t >> 1), j = ja + (t & 1);
+                        const float du = (float)i - qi, dv = (float)j - qj;
+                        const float ex = fabsf(f00 * du + f01 * dv), ey = fabsf(f10 * du + f11 * dv);
+                        if (fmaxf(ex, ey) > 0.5f + INV_EPS) continue;
+                        if ((unsigned)i >= (unsigned)vh || (unsigned)j >= (unsigned)vw) continue;
                         const int a0 = spans[i * 4 + 0], a1 = spans[i * 4 + 1], b0 = spans[i * 4 + 2], b1 = spans[i * 4 + 3];
-                        for (int j = ja; j <= jb; j++) {
-                            if (!((j >= a0 && j < a1) || (j >= b0 && j < b1))) continue;
+                        if (!((j >= a0 && j < a1) || (j >= b0 && j < b1))) continue;
+                        if (fmaxf(ex, ey) > 0.5f - INV_EPS) {
                             const long long tx = sh->cx + (long long)i * sh->ax + (long long)j * sh->bx;
                             const long long tyy = sh->cy + (long long)i * sh->ay + (long long)j * sh->by;
                             int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
@@ -561,9 +593,9 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                                 cx = world2cell(wx, c.res); cy = world2cell(wy, c.res);
                             }
                             if (cx != cX || cy != cY) continue;
-                            if (i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1 && !(global_value(d, s, r, cX, cY) < 250)) continue;
-                            if (!(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31)))) push_cell(i * vw + j);
                         }
+                        if (i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1 && !(global_value(d, s, r, cX, cY) < 250)) continue;
+                        if (!(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31)))) push_cell(i * vw + j);
                     }
                 }
             }
@@ -735,16 +767,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                         const int pr = need[rr], pc = need[tp[k]];
                         if (!(pr != (int)((key >> 11) & 2047) && pc != (int)(key & 2047))) {     // no shadow write: fall through to lower rays
                             const unsigned kp = __ldg(kpack + pr * vw + pc);
-                            const int kl = kp >> 16;
-                            for (int kk = kh - 1; kk >= kl; kk--) {
-                                const int i = ray_touch(ox, oy, rend[2 * kk], rend[2 * kk + 1], pr, pc);
-                                if (i < 0) continue;
-                                const unsigned key2 = hitkey[kk];
-                                const int hp2 = (int)(key2 >> 22);
-                                if (i < hp2) { code = 3u; break; }
-                                if (i == hp2) { code = 0u; break; }
-                                if (pr != (int)((key2 >> 11) & 2047) && pc != (int)(key2 & 2047)) { code = 2u; break; }
-                            }
+                            code = pixel_code_below(hitkey, rend, ox, oy, pr, pc, kh, (int)(kp >> 16));
                         }
                     }
                 }
