@@ -289,6 +289,25 @@ def run_b200(args):
     if dist:
         tt = torch.tensor([full_s], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); full_s = float(tt.item())
 
+    # ---- N > 1: the same steps with the State of every rank delivered to the learner GPU (rank 0) over NVLink
+    gather = None
+    if dist and args.gather:
+        from img_env_b200.parallel import ObservationGatherer
+        gat = ObservationGatherer(sim.out, dst=0)
+        kg = max(2, min(K, 10))
+        step(0); gat(sim.out)
+        torch.cuda.synchronize(); dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for t in range(kg):
+            step(t); gat(sim.out)
+        g1.record()
+        torch.cuda.synchronize()
+        tg = torch.tensor([g0.elapsed_time(g1)], device="cuda"); dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather = {"value": world * S * R * kg / (float(tg.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(tg.item()) / kg,
+                  "bytes_to_learner_per_step": int(gat.bytes_to_learner),
+                  "note": "sim + point-to-point delivery of all nine State tensors of every rank to rank 0 (NCCL isend/irecv "
+                          "over NVLink); not part of the headline metric"}
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -336,6 +355,8 @@ def run_b200(args):
                      "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s"},
         "clocks": clocks,
     }
+    if gather:
+        out["gather_to_learner"] = gather
     if world == 1 and not args.no_cpu_baseline:
         try:
             ref = run_reference(args.workload, steps=2, warmup=0, budget_s=25.0 * 8)
@@ -381,6 +402,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--scenes", type=int, default=0, help="scenes per GPU (default: workload-specific)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="N > 1: also time sim + delivery of the State to rank 0")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -29,24 +29,51 @@ def reduce_max(value, device=None, group=None):
     return float(t.item())
 
 
+class ObservationGatherer:
+    """Delivers every rank's State tensors ([S_local, R, ...]) to the learner rank `dst`, concatenated along the
+    scene axis in rank order.  Point-to-point sends straight into slices of persistent buffers on
+    `dst` (one batched isend/irecv group per call): only the learner's NVLink ingress carries data, nothing is
+    gathered to ranks that do not need it and there is no concatenation copy.  Works on NCCL (device tensors over
+    NVLink/NVSwitch) and gloo (CPU tests); shard sizes may differ per rank."""
+
+    def __init__(self, out, dst=0, group=None):
+        self.dst, self.group = dst, group
+        self.active = dist.is_available() and dist.is_initialized()
+        if not self.active:
+            return
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        n_local = next(iter(out.values())).shape[0]
+        sizes = [None] * self.world
+        dist.all_gather_object(sizes, int(n_local), group=group)
+        self.sizes = sizes
+        self.offsets = [sum(sizes[:r]) for r in range(self.world)]
+        self.buf = None
+        if self.rank == dst:
+            self.buf = {k: torch.empty((sum(sizes),) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device) for k, v in out.items()}
+        self.bytes_to_learner = sum(v[:1].numel() * v.element_size() for v in out.values()) * (sum(sizes) - sizes[dst])
+
+    def __call__(self, out):
+        """-> dict of gathered tensors on `dst` (persistent buffers, overwritten by the next call), None elsewhere."""
+        if not self.active:
+            return out
+        ops = []
+        if self.rank == self.dst:
+            for k, v in out.items():
+                for src in range(self.world):
+                    sl = self.buf[k][self.offsets[src]: self.offsets[src] + self.sizes[src]]
+                    if src == self.rank:
+                        sl.copy_(v)
+                    elif self.sizes[src]:
+                        ops.append(dist.P2POp(dist.irecv, sl, src, group=self.group))
+        elif self.sizes[self.rank]:
+            ops = [dist.P2POp(dist.isend, v.contiguous(), self.dst, group=self.group) for v in out.values()]
+        for req in (dist.batch_isend_irecv(ops) if ops else []):
+            req.wait()
+        return self.buf if self.rank == self.dst else None
+
+
 def gather_observations(out, dst=0, group=None):
-    """Delivers every rank's State tensors ([S_local, R, ...]) to rank `dst`, concatenated along the scene
-    axis in rank order.  Returns the dict on `dst`, None elsewhere.  Uses all_gather over NVLink/NVSwitch
-    when the backend is NCCL (equal shard sizes required), gather on gloo."""
+    """One-shot form of ObservationGatherer (allocates the destination buffers on every call)."""
     if not (dist.is_available() and dist.is_initialized()):
         return out
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    res = {}
-    for k, v in out.items():
-        v = v.contiguous()
-        if dist.get_backend(group) == "nccl":
-            buf = [torch.empty_like(v) for _ in range(world)]
-            dist.all_gather(buf, v, group=group)
-            if rank == dst:
-                res[k] = torch.cat(buf, 0)
-        else:
-            buf = [torch.empty_like(v) for _ in range(world)] if rank == dst else None
-            dist.gather(v, buf, dst=dst, group=group)
-            if rank == dst:
-                res[k] = torch.cat(buf, 0)
-    return res if rank == dst else None
+    return ObservationGatherer(out, dst=dst, group=group)(out)

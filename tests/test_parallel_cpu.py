@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from img_env_b200.parallel import gather_observations, owner_of, reduce_max, shard_scenes
+from img_env_b200.parallel import ObservationGatherer, gather_observations, owner_of, reduce_max, shard_scenes
 
 
 def test_shards_partition_all_scenes():
@@ -28,6 +28,18 @@ def _worker(rank, world, port, q):
     start, n = shard_scenes(6, world, rank)
     out = {"lasers": torch.full((n, 2, 5), float(rank)), "is_collisions": torch.arange(start, start + n, dtype=torch.int8)[:, None].repeat(1, 2)}
     g = gather_observations(out, dst=0)
+    # persistent gatherer, unequal shards (7 scenes -> 4 + 3), delivered to rank 1, called twice
+    s7, n7 = shard_scenes(7, world, rank)
+    o7 = {"step_ds": torch.arange(s7, s7 + n7, dtype=torch.float32)[:, None].repeat(1, 3)}
+    gat = ObservationGatherer(o7, dst=1)
+    for rep in range(2):
+        o7["step_ds"] += 100.0
+        g7 = gat(o7)
+        if rank == 1:
+            assert g7["step_ds"][:, 0].tolist() == [100.0 * (rep + 1) + i for i in range(7)]
+            assert gat.bytes_to_learner == 4 * 3 * 4
+        else:
+            assert g7 is None
     m = reduce_max(10.0 + rank)
     if rank == 0:
         q.put((g["lasers"][:, 0, 0].tolist(), g["is_collisions"][:, 0].tolist(), m))
