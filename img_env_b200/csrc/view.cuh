@@ -412,11 +412,12 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         }
     }
     {   // static tables into shared memory
-        const short* g_rend = d.ray_end + 2 * (size_t)ty.ray_off;
-        for (int k = tid; k < 2 * c.range_total; k += VIEW_THREADS) rend[k] = g_rend[k];
+        // one ray end = 2 shorts, one row of FOV spans = 4 shorts: copied as 4- and 8-byte words
+        const int* g_rend = reinterpret_cast<const int*>(d.ray_end + 2 * (size_t)ty.ray_off);
+        for (int k = tid; k < c.range_total; k += VIEW_THREADS) reinterpret_cast<int*>(rend)[k] = __ldg(g_rend + k);
         for (int k = tid; k < c.ns; k += VIEW_THREADS) need[k] = d.need_idx[k];
-        const short* g_spans = d.fov_spans + (size_t)ty.span_off;
-        for (int k = tid; k < 4 * vh; k += VIEW_THREADS) spans[k] = g_spans[k];
+        const int2* g_spans = reinterpret_cast<const int2*>(d.fov_spans + (size_t)ty.span_off);
+        for (int k = tid; k < vh; k += VIEW_THREADS) reinterpret_cast<int2*>(spans)[k] = __ldg(g_spans + k);
         for (int k = tid; k < c.range_total; k += VIEW_THREADS) hitkey[k] = NOHIT;
     }
     __syncthreads();
