@@ -20,6 +20,19 @@
 #include "state.cuh"
 
 namespace ht {
+// bounding circle of a footprint lattice for the stamping kernel's cell bitmap: centre of the bounding box (m) and the
+// radius in cells of the farthest point from it, + 2 cells (rounding of the centre and of the points)
+inline void bounding_circle(const std::vector<double>& pts, double res, double out[3]) {
+    out[0] = out[1] = 0; out[2] = 2;
+    if (pts.empty()) return;
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (size_t k = 0; k + 1 < pts.size(); k += 2) { x0 = std::min(x0, pts[k]); x1 = std::max(x1, pts[k]); y0 = std::min(y0, pts[k + 1]); y1 = std::max(y1, pts[k + 1]); }
+    out[0] = 0.5 * (x0 + x1); out[1] = 0.5 * (y0 + y1);
+    double r = 0;
+    for (size_t k = 0; k + 1 < pts.size(); k += 2) r = std::max(r, hypot(pts[k] - out[0], pts[k + 1] - out[1]));
+    out[2] = ceil(r / res) + 2;
+}
+
 
 inline double f32(double x) { return (double)(float)x; }
 
@@ -166,6 +179,8 @@ inline std::string build_type(const Cfg& c, const double* desc, double view_angl
         double rmax = 0;
         for (int k = 0; k < T.t.n_pts; k++) rmax = std::max(rmax, sqrt(T.lattice[2 * k] * T.lattice[2 * k] + T.lattice[2 * k + 1] * T.lattice[2 * k + 1]));
         T.t.zone_rad = (int)ceil(rmax / c.res) + 5;
+        double bc[3]; bounding_circle(T.lattice, c.res, bc);
+        T.t.stamp_cx = bc[0]; T.t.stamp_cy = bc[1]; T.t.stamp_rad = (int)bc[2];
     }
     // per-pixel highest / lowest touching ray: walk every ray over its full static cell sequence
     T.khi.assign(npx, 0xFFFF); T.klo.assign(npx, 0xFFFF);

@@ -254,7 +254,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     std::vector<int> pshape(c.P), poff(2 * (size_t)c.P, 0), pn(2 * (size_t)c.P, 0);
     std::vector<double> psize(6 * (size_t)c.P), pmax(c.P), prr(c.P);
     std::vector<float> prw(c.P);
-    std::vector<double> pext(std::max(c.P, 1), 0.0);
+    std::vector<double> pext(std::max(c.P, 1), 0.0), ppart(6 * (size_t)std::max(c.P, 1), 0.0);
     for (int p = 0; p < c.P; p++) {
         const double* q = ped_desc + 8 * (size_t)p;
         pshape[p] = (int)q[0];
@@ -271,6 +271,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
                                      : hypot(std::max(std::max(fabs(z[0]), fabs(z[3])), 0.3), std::max(fabs(z[1]), fabs(z[4]))) + std::max(z[2], z[5]);
             pext[p] += 3 * c.res;
         }
+        ht::bounding_circle(a, c.res, ppart.data() + 6 * p); ht::bounding_circle(b, c.res, ppart.data() + 6 * p + 3);
         poff[2 * p] = (int)lattice.size() / 2; pn[2 * p] = (int)a.size() / 2; lattice.insert(lattice.end(), a.begin(), a.end());
         poff[2 * p + 1] = (int)lattice.size() / 2; pn[2 * p + 1] = (int)b.size() / 2; lattice.insert(lattice.end(), b.begin(), b.end());
     }
@@ -288,7 +289,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     UP(kpack, kpack) UP(grid, g) UP(static_occ, socc) UP(types, rts) UP(type_of, type_of) UP(lattice_xy, lattice) UP(ray_end, ray_end)
     UP(fov_spans, spans) UP(khi, khi) UP(klo, klo) UP(own_mask, own_mask) UP(need_idx, need_idx) UP(cubic_tap, tap)
     UP(cubic_coef, coef) UP(f16_lut, lut) UP(lim_v, lv) UP(lim_w, lw) UP(ped_shape, pshape) UP(ped_size, psize)
-    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(dtab, dtab) UP(hstat, hstat) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(ped_ext, pext) UP(own_cells, own_dummy)
+    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(dtab, dtab) UP(hstat, hstat) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(ped_ext, pext) UP(ped_part, ppart) UP(own_cells, own_dummy)
 #undef UP
     size_t S = c.S;
     size_t pc = ((size_t)H * W + 3) & ~(size_t)3;
@@ -365,8 +366,8 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     CK(cudaFuncSetAttribute(k_ped_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ped_smem));
     {   // shared-memory cell bitmap of k_stamp_agents: sized for the largest footprint box
         int words = 1;
-        for (const auto& t : rts) words = std::max(words, stamp_bitmap_words(stamp_rad_cells(t.zone_rad * c.res, c.res)));
-        for (int p = 0; p < c.P; p++) words = std::max(words, stamp_bitmap_words(stamp_rad_cells(pext[p], c.res)));
+        for (const auto& t : rts) words = std::max(words, stamp_bitmap_words(t.stamp_rad));
+        for (int p = 0; p < 2 * c.P; p++) words = std::max(words, stamp_bitmap_words((int)ppart[3 * p + 2]));
         h->stamp_smem = (size_t)words * 4;
         if (h->stamp_smem > 200 * 1024) return fail("imgenv_create: an agent footprint is too large for the stamping kernel");
         CK(cudaFuncSetAttribute(k_stamp_agents, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stamp_smem));

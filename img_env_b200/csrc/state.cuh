@@ -52,6 +52,7 @@ struct RobotType {
     int edge_off, n_edge; // FOV pixels with an 8-neighbour outside the FOV (u32 row<<16|col), always evaluated forward
     int fov_r0, fov_r1, fov_c0, fov_c1;   // bounding box (inclusive) of the FOV pixels in the view raster
     int dtab_off;         // offset into dtab (ns*img*4 u32)
+    double stamp_cx, stamp_cy; int stamp_rad;   // footprint lattice: centre (base frame, m) and radius (cells, incl. margin) of its bounding circle
     int zone_rad;         // world cells around the robot's position inside which a set occ_all bit may be its own stamp
     double size_last;     // python: robots[i].size[-1]
     double sensor_x, sensor_y;
@@ -111,6 +112,7 @@ struct Dev {
     const float* ped_r_wire;      // [P] float32 r_ = sizes_[2]
     const int* ped_pts_off;       // [P][2] lattice offsets (body or left leg, right leg)
     const int* ped_pts_n;         // [P][2]
+    const double* ped_part;       // [P][2][3] per stamped part (body / left leg, right leg): bounding circle centre x, y (m) and radius (cells)
     const double* ped_ext;        // [P] bound on the distance from the pedestrian position to any cell it stamps
     // per scene planes
     uint32_t* occ_all;            // [S][H][Wb] static | reset objects | this step's agent stamps

@@ -135,7 +135,10 @@ __device__ __forceinline__ void stamp_cells8(const Dev& d, int s, int cx, int cy
     }
 }
 __device__ __forceinline__ void stamp_part(const Dev& d, int s, const Tf2& t, const double* pts, int n, int mode, int id,
-                                           double offx, double offy, const StampBox& bx, uint32_t* bm) {
+                                           double offx, double offy, double ccx, double ccy, int rad_cells, uint32_t* bm) {
+    double bwx, bwy;
+    tf_apply(t, ccx + offx, ccy + offy, bwx, bwy);      // world position of the part's bounding-circle centre
+    const StampBox bx = stamp_box(d, bwx, bwy, rad_cells);
     const int nw = bx.nrow * bx.wpr;
     for (int k = threadIdx.x; k < nw; k += STAMP_THREADS) bm[k] = 0u;
     __syncthreads();
@@ -187,20 +190,20 @@ __global__ void __launch_bounds__(STAMP_THREADS) k_stamp_agents(Dev d, const int
     }
     if (!__syncthreads_or(rel)) return;
     const Tf2 t = tf_from_pose(x, y, yaw);
-    const StampBox bx = stamp_box(d, x, y, stamp_rad_cells(ext, d.c.res));
     if (is_robot) {
         const RobotType& ty = d.types[d.type_of[a]];
-        stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)ty.pts_off, ty.n_pts, 0 + add, a, 0, 0, bx, bm);
+        stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)ty.pts_off, ty.n_pts, 0 + add, a, 0, 0, ty.stamp_cx, ty.stamp_cy, ty.stamp_rad, bm);
     } else {
         const int idx = s * d.c.P + p;
         const int shape = d.ped_shape[p];
+        const double* pc = d.ped_part + 6 * (size_t)p;
         if (shape == 0) {
-            stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p], d.ped_pts_n[2 * p], 1 + add, p, 0, 0, bx, bm);
+            stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p], d.ped_pts_n[2 * p], 1 + add, p, 0, 0, pc[0], pc[1], (int)pc[2], bm);
         } else if (shape == 2) {
             stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p], d.ped_pts_n[2 * p], 2 + add, p,
-                       PDF(d, PD_LLX, idx), PDF(d, PD_LLY, idx), bx, bm);
+                       PDF(d, PD_LLX, idx), PDF(d, PD_LLY, idx), pc[0], pc[1], (int)pc[2], bm);
             stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p + 1], d.ped_pts_n[2 * p + 1], 3 + add, p,
-                       PDF(d, PD_RLX, idx), PDF(d, PD_RLY, idx), bx, bm);
+                       PDF(d, PD_RLX, idx), PDF(d, PD_RLY, idx), pc[3], pc[4], (int)pc[5], bm);
         }   // rectangle pedestrians are never drawn (img_env.cpp:599-616 has no branch for them)
     }
 }
