@@ -113,7 +113,7 @@ class ClockSampler:
 # reference arm / cpu baseline (TEST INFRASTRUCTURE: the only place bench.py touches oracle/)
 # --------------------------------------------------------------------------------------------
 def _ref_worker(args):
-    wname, seed, warmup, steps, barrier_dir, nproc, rank = args
+    wname, seed, warmup, steps, barrier_dir, nproc, rank, target_s = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     import cv2
     cv2.setNumThreads(1)
@@ -145,13 +145,14 @@ def _ref_worker(args):
     while len([f for f in os.listdir(barrier_dir) if f.startswith("ready")]) < nproc and time.time() - t_wait < 600:
         time.sleep(0.01)
     t0 = time.time()
-    for _ in range(steps):
-        one_step()
+    done = 0
+    while done < steps or (target_s > 0 and time.time() - t0 < target_s):     # target_s: sample sized by time, not by steps
+        one_step(); done += 1
     t1 = time.time()
-    return t0, t1, R
+    return t0, t1, R * done
 
 
-def run_reference(wname, steps, warmup, procs=None, budget_s=200.0):
+def run_reference(wname, steps, warmup, procs=None, budget_s=200.0, target_s=0.0):
     """Times oracle/_ref (+ restated Python post-processing), one scene per process."""
     import multiprocessing as mp
     import tempfile
@@ -174,13 +175,25 @@ def run_reference(wname, steps, warmup, procs=None, budget_s=200.0):
     est = w["R"] * (0.012 + 1.2e-9 * (w["map_px"] * w["gres"] / 0.015) ** 2 * 0.35) + 0.05
     steps_eff = max(1, min(steps, int(budget_s / est) - warmup))
     warm_eff = max(0, min(warmup, max(0, int(0.25 * budget_s / est))))
+    if w["scene"] == "pedscene" and w["R"] >= 9:
+        # libpedsim's quadtree recurses without bound once 9 agents share a point: the node's robots are all constructed at
+        # (0,0) (pedscene.h:53-56), so the reference crashes on this configuration
+        return dict(unavailable="the reference node cannot run pedscene with >= 9 robots (quadtree stack overflow)")
     ctx = mp.get_context("spawn")
     with tempfile.TemporaryDirectory() as bd:
-        with ctx.Pool(procs) as pool:
-            res = pool.map(_ref_worker, [(wname, 1000 + i, warm_eff, steps_eff, bd, procs, i) for i in range(procs)])
+        pool = ctx.Pool(procs)
+        try:      # a crashed worker would make a plain map() wait forever
+            res = pool.map_async(_ref_worker, [(wname, 1000 + i, warm_eff, steps_eff, bd, procs, i, target_s) for i in range(procs)]).get(
+                timeout=2.0 * budget_s + 120.0)
+        except Exception as e:
+            pool.terminate()
+            return dict(unavailable="reference workers failed or timed out: %s" % type(e).__name__)
+        finally:
+            pool.terminate()
     t0 = min(r[0] for r in res); t1 = max(r[1] for r in res)
-    total = sum(r[2] for r in res) * steps_eff
-    return dict(value=total / (t1 - t0), seconds=t1 - t0, procs=procs, steps=steps_eff, warmup=warm_eff, robot_steps=total)
+    total = sum(r[2] for r in res)
+    return dict(value=total / (t1 - t0), seconds=t1 - t0, procs=procs, steps=int(round(total / max(1, sum(1 for _ in res)) / w["R"])),
+                warmup=warm_eff, robot_steps=total)
 
 
 # --------------------------------------------------------------------------------------------
@@ -359,8 +372,10 @@ def run_b200(args):
         out["gather_to_learner"] = gather
     if world == 1 and not args.no_cpu_baseline:
         try:
-            ref = run_reference(args.workload, steps=2, warmup=0, budget_s=25.0 * 8)
-            if ref:
+            ref = run_reference(args.workload, steps=2, warmup=1, budget_s=25.0 * 8, target_s=12.0)
+            if ref and "unavailable" in ref:
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": ref["unavailable"]}
+            elif ref:
                 out["cpu_baseline"] = {"value": ref["value"], "unit": UNIT, "cores": ref["procs"], "kind": "reference",
                                        "sample": "%d scene(s) of this workload (one per process, oracle/_ref = unmodified reference node + "
                                                  "restated Python post-processing), %d timed step(s), %.1f s" %
@@ -380,6 +395,9 @@ def run_reference_arm(args):
     ref = run_reference(args.workload, steps=args.steps, warmup=args.warmup, budget_s=200.0)
     if ref is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libimgenv_ref.so is not built"}))
+        return
+    if "unavailable" in ref:
+        print(json.dumps({"impl": "reference", "unavailable": ref["unavailable"]}))
         return
     out = {"impl": "reference", "metric": METRIC, "value": ref["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": ref["steps"],
            "steps_requested": args.steps, "warmup": ref["warmup"], "ms_per_step": 1e3 * ref["seconds"] / ref["steps"],
