@@ -920,9 +920,12 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
     }
     __syncthreads();
     for (int j = tid; j < c.P; j += PED_THREADS) {   // stable rank == python's list.sort(key=...)
-        double kj = pkey[j];
+        const double kj = pkey[j];
+        const int jb = j - (tid & 31);       // a warp ranks 32 consecutive pedestrians: ties only need care inside that group
         int rk = 0;
-        for (int i = 0; i < c.P; i++) rk += (pkey[i] < kj) || (pkey[i] == kj && i < j);
+        for (int i = 0; i < jb; i++) rk += pkey[i] <= kj;
+        for (int i = jb; i < min(jb + 32, c.P); i++) rk += (pkey[i] < kj) || (pkey[i] == kj && i < j);
+        for (int i = jb + 32; i < c.P; i++) rk += pkey[i] < kj;
         prank[j] = rk;
     }
     __syncthreads();
