@@ -348,6 +348,11 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_apply(Dev d, const float* a
         PDF(d, PD_VX, pi) = tv[0]; PDF(d, PD_VY, pi) = tv[1];
         ped_gait(d, pi, a);
     }
+    if (d.rec_T > 0 && a < c.P && d.step_no[s] < (unsigned long long)d.rec_T) {   // eps_res_msg.peds_res (img_env.cpp:355-357)
+        const int pi = s * c.P + a;
+        double* o = d.rec_pd + (((size_t)s * d.rec_T + (size_t)d.step_no[s]) * c.P + a) * 5;
+        o[0] = PDF(d, PD_X, pi); o[1] = PDF(d, PD_Y, pi); o[2] = PDF(d, PD_YAW, pi); o[3] = PDF(d, PD_VX, pi); o[4] = PDF(d, PD_VY, pi);
+    }
     // ---- robots (img_env.cpp:388-419). Robot j is handled by the thread that (if the robots are solver
     // agents) also updated solver agent P + j, so the solver write above is ordered before the overwrite below.
     const bool robots_in_solver = c.relation == 1 && c.NA > 0;
@@ -366,6 +371,12 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_apply(Dev d, const float* a
             RBF(d, RB_L0V, idx) = rk.l0v; RBF(d, RB_L0W, idx) = rk.l0w; RBF(d, RB_L1V, idx) = rk.l1v; RBF(d, RB_L1W, idx) = rk.l1w;
             RBF(d, RB_VX, idx) = rk.vx; RBF(d, RB_VY, idx) = rk.vy;
             RBF(d, RB_ARR, idx) = rk.arrive ? 1.0 : 0.0;
+        }
+        if (d.rec_T > 0 && d.step_no[s] < (unsigned long long)d.rec_T) {   // eps_res_msg.robots_res (img_env.cpp:397-408; alive steps only)
+            double* o = d.rec_rb + (((size_t)s * d.rec_T + (size_t)d.step_no[s]) * c.R + j) * 6;
+            const float* ac = actions + (size_t)idx * 3;
+            o[0] = RBF(d, RB_X, idx); o[1] = RBF(d, RB_Y, idx); o[2] = RBF(d, RB_YAW, idx); o[3] = (double)ac[0]; o[4] = (double)ac[1];
+            o[5] = robot_alive(d, alive, idx) ? 1.0 : 0.0;
         }
         if (robots_in_solver) {   // setRobotPos
             int ag = c.P + j;

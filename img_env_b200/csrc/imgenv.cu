@@ -112,6 +112,8 @@ extern "C" int imgenv_destroy(imgenv_t* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->d.rec_rb) cudaFree(h->d.rec_rb);
+    if (h->d.rec_pd) cudaFree(h->d.rec_pd);
     if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
     if (h->ev_moved) cudaEventDestroy(h->ev_moved);
     if (h->ev_tree) cudaEventDestroy(h->ev_tree);
@@ -970,5 +972,38 @@ extern "C" int imgenv_debug_check_planes(imgenv_t* h, int64_t* out4, void* strea
     cudaFree(buf);
     if (e != cudaSuccess) return fail(std::string("imgenv_debug_check_planes: ") + cudaGetErrorString(e));
     for (int k = 0; k < 4; k++) out4[k] = (int64_t)r[k];
+    return 0;
+}
+
+// Episode record (EpRes.msg: per step the pose and request speeds of every alive robot, pose and velocity of every
+// pedestrian; img_env.cpp:355-357, 397-408, 527-545).  The obs_map image of the message is imgenv_debug_global_map(scene, -2).
+extern "C" int imgenv_record_enable(imgenv_t* h, int32_t max_steps) {
+    if (!h || max_steps < 0) return fail("imgenv_record_enable: bad argument");
+    Dev& d = h->d; const Cfg& c = d.c;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    if (d.rec_rb) { cudaFree(d.rec_rb); d.rec_rb = nullptr; }
+    if (d.rec_pd) { cudaFree(d.rec_pd); d.rec_pd = nullptr; }
+    d.rec_T = 0;
+    if (max_steps == 0) return 0;
+    CK(cudaMalloc((void**)&d.rec_rb, std::max<size_t>(1, (size_t)c.S * max_steps * c.R * 6) * 8));
+    CK(cudaMalloc((void**)&d.rec_pd, std::max<size_t>(1, (size_t)c.S * max_steps * c.P * 5) * 8));
+    d.rec_T = max_steps;
+    return 0;
+}
+extern "C" int imgenv_record_fetch(imgenv_t* h, int32_t scene, int32_t* n_steps, double* robots, double* peds, void* stream) {
+    if (!h || !n_steps) return fail("imgenv_record_fetch: null argument");
+    Dev& d = h->d; const Cfg& c = d.c;
+    if (d.rec_T <= 0) return fail("imgenv_record_fetch: recording is not enabled (imgenv_record_enable)");
+    if (scene < 0 || scene >= c.S) return fail("imgenv_record_fetch: bad scene");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, d.step_no + scene, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int T = (int)std::min<unsigned long long>(n, (unsigned long long)d.rec_T);
+    *n_steps = T;
+    if (T > 0 && robots) CK(cudaMemcpyAsync(robots, d.rec_rb + (size_t)scene * d.rec_T * c.R * 6, (size_t)T * c.R * 6 * 8, cudaMemcpyDeviceToHost, st));
+    if (T > 0 && peds && c.P) CK(cudaMemcpyAsync(peds, d.rec_pd + (size_t)scene * d.rec_T * c.P * 5, (size_t)T * c.P * 5 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return 0;
 }

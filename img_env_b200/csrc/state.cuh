@@ -130,6 +130,10 @@ struct Dev {
     double* obs;                  // [S][max_obs][8]: shape, size[4], x, y, yaw
     int* n_obs;                   // [S]
     unsigned long long* step_no;  // [S]
+    // optional episode record (EpRes, img_env.cpp:355-357, 397-408): rec_T > 0 enables it
+    double* rec_rb;               // [S][rec_T][R][6] x, y, yaw, v, w (request values), alive
+    double* rec_pd;               // [S][rec_T][P][5] x, y, yaw, vx, vy
+    int rec_T;
     // solver state
     float* rvo_pos; float* rvo_vel;         // [S][NA][2]
     float* rvo_nvel;                        // [S][NA][2] new velocities (scratch between solve and apply)

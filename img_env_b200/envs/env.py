@@ -34,6 +34,9 @@ class ImageEnv:
             self.sampler = NativeSampler(sampler_desc(cfg), num_scenes=self.num_scenes, seed=int(cfg.get("sampler_seed", random.getrandbits(62))),
                                          max_obs=self.spec["max_obstacles"], max_traj=self.spec["max_traj"])
         self._ignore_obstacle = int(bool(cfg["ped_sim"].get("ignore_obstacle", False)))
+        self._record_steps = int(cfg.get("record_steps", 0))
+        if self._record_steps:
+            self.sim.record_enable(self._record_steps)
         self.dones = None
         self._act = torch.zeros(self.num_scenes, self.robot_total, 3, dtype=torch.float32, device=self.sim.device)
 
@@ -96,8 +99,19 @@ class ImageEnv:
         self.dones = (coll.clamp(-1, 1) + arr).clamp(0, 1)               # yaml_env.py:374-376
         return state, rewards, self.dones.clone(), {"dones_info": torch.zeros_like(self.dones)}
 
-    def end_ep(self, robot_res=None):
-        return True                        # EpRes logging is out of scope
+    def end_ep(self, robot_res=None, scene=0):
+        """yaml_env.py:379-390 / img_env.cpp:527-545.  The node publishes an EpRes message (poses and speeds of the episode);
+        with cfg['record_steps'] > 0 the same record is returned for `scene` (None -> every scene) instead of True."""
+        if not self._record_steps:
+            return True
+        scenes = range(self.num_scenes) if scene is None else [scene]
+        out = []
+        for sc in scenes:
+            rec = self.sim.record_fetch(sc)
+            rec["result"] = list(robot_res) if robot_res is not None else None
+            rec["resolution"], rec["step_hz"], rec["env_name"] = self.spec["scalars"][0], self.control_hz, self.env_name
+            out.append(rec)
+        return out if scene is None else out[0]
 
     def close(self):
         self.sim.close()

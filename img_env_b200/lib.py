@@ -39,7 +39,8 @@ EXPORTS = ["imgenv_create", "imgenv_destroy", "imgenv_bind_outputs", "imgenv_res
            "imgenv_solver_agents", "imgenv_view_dims", "imgenv_launches_per_step",
            "imgenv_algorithmic_bytes_per_robot_step", "imgenv_last_error", "imgenv_version",
            "imgenv_sampler_create", "imgenv_sampler_destroy", "imgenv_sampler_seed", "imgenv_sampler_sample", "imgenv_sampler_draw",
-           "imgenv_reset_sampled", "imgenv_debug_check_planes"]
+           "imgenv_reset_sampled", "imgenv_debug_check_planes",
+           "imgenv_record_enable", "imgenv_record_fetch"]
 
 
 def load_library(path=None):
@@ -224,6 +225,19 @@ class BatchedSim:
         ids = np.ascontiguousarray(scene_ids if scene_ids is not None else np.arange(self.S), dtype=np.int32)
         self._check(self.lib.imgenv_reset_sampled(self.h, sampler.h, ids.size, _ptr(ids, C.c_int32), int(ignore_obstacle), self._stream()))
         return self.out
+
+    def record_enable(self, max_steps):
+        """Episode record (EpRes.msg): keep the poses / speeds of the next `max_steps` steps after every reset; 0 disables."""
+        self._check(self.lib.imgenv_record_enable(self.h, int(max_steps)))
+        self._rec_T = int(max_steps)
+
+    def record_fetch(self, scene):
+        """-> dict(robots[T,R,6] = x, y, yaw, v, w, alive; peds[T,P,5] = x, y, yaw, vx, vy) of `scene` since its last reset."""
+        T = getattr(self, "_rec_T", 0)
+        rb = np.zeros((max(T, 1), self.R, 6)); pd = np.zeros((max(T, 1), max(self.P, 1), 5))
+        n = C.c_int32(0)
+        self._check(self.lib.imgenv_record_fetch(self.h, int(scene), C.byref(n), _ptr(rb), _ptr(pd), self._stream()))
+        return dict(robots=rb[: n.value], peds=pd[: n.value, : self.P])
 
     def debug_check_planes(self):
         """-> (occ words, flag bytes, block marks, block counts) violating 'no agent is stamped between calls'."""

@@ -142,6 +142,12 @@ int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* stats_out, 
 /* Debug raster: the composited byte map of one scene, u8 [H][W] to host. self >= 0: robot self's
  * global_map_ (img_env.cpp:623-628); self == -1: peds_map_ (img_env.cpp:594-618); self == -2: obs_map_ (img_env.cpp:167-187). */
 int imgenv_debug_global_map(imgenv_t* h, int32_t scene, int32_t self, uint8_t* host_out, void* stream);
+/* Episode record (EpRes.msg; img_env.cpp:355-357, 397-408, 527-545): once enabled, every step stores per scene the pose and
+ * request speeds of every robot (robots[t][R][6] = x, y, yaw, v, w, alive -- the node only appends alive robots) and the pose
+ * and velocity of every pedestrian (peds[t][P][5] = x, y, yaw, vx, vy), up to max_steps steps after the scene's last reset.
+ * max_steps = 0 disables and frees.  fetch copies the steps recorded since the last reset of `scene` to host arrays. */
+int imgenv_record_enable(imgenv_t* h, int32_t max_steps);
+int imgenv_record_fetch(imgenv_t* h, int32_t scene, int32_t* n_steps, double* robots, double* peds, void* stream);
 /* Invariant check (tests): between calls no agent is stamped in the per-scene planes. out4 = number of occupancy words,
  * flag bytes, block marks and block counts that violate it (all 0 when healthy). */
 int imgenv_debug_check_planes(imgenv_t* h, int64_t* out4, void* stream);

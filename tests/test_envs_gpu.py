@@ -99,3 +99,38 @@ def test_native_sampler_reset_equals_python_sampler_reset():
     s1 = e.reset(scene_ids=[1, 3])
     assert torch.equal(s1.vector_states[[0, 2]], keep[[0, 2]]) and not torch.equal(s1.vector_states[[1, 3]], keep[[1, 3]])
     e.close()
+
+
+def test_episode_record_matches_stepwise_state():
+    """EpRes-style episode record (img_env.cpp:355-357, 397-408): the recorded poses / speeds of a scene equal the state read
+    back after every step, restart at a reset of that scene only, and rows of robots that are not alive are flagged."""
+    import torch
+    from helpers import build_spec, make_reset, random_actions
+    from img_env_b200.lib import BatchedSim
+    spec = build_spec(base_cfg(R=2, P=3, scene="rvoscene", n_obj=2))
+    rng = np.random.default_rng(3)
+    sim = BatchedSim(spec, num_scenes=2, ped_yaw_mode=1)
+    sim.record_enable(6)
+    sim.reset([make_reset(spec, rng) for _ in range(2)])
+    want_rb, want_pd, acts = [], [], []
+    alive = np.ones((2, 2), np.uint8); alive[1, 1] = 0
+    for t in range(8):                           # two more steps than the record holds
+        a = np.stack([random_actions(2, rng) for _ in range(2)]).astype(np.float32)
+        sim.step(torch.from_numpy(a).cuda(), torch.from_numpy(alive).cuda())
+        rb, pd, _ = sim.get_internal()
+        want_rb.append(rb.copy()); want_pd.append(pd.copy()); acts.append(a)
+    rec = sim.record_fetch(1)
+    assert rec["robots"].shape == (6, 2, 6) and rec["peds"].shape == (6, 3, 5)
+    for t in range(6):
+        assert np.array_equal(rec["robots"][t, :, :3], want_rb[t][1][:, :3])
+        assert np.array_equal(rec["robots"][t, :, 3:5], acts[t][1][:, :2].astype(np.float64))
+        assert rec["robots"][t, :, 5].tolist() == [1.0, 0.0]
+        assert np.array_equal(rec["peds"][t, :, :2], want_pd[t][1][:, :2]) and np.array_equal(rec["peds"][t, :, 3:5], want_pd[t][1][:, 6:8])
+    sim.reset([make_reset(spec, rng)], scene_ids=[0])          # scene 0 restarts its record, scene 1 keeps it
+    assert sim.record_fetch(0)["robots"].shape[0] == 0 and sim.record_fetch(1)["robots"].shape[0] == 6
+    sim.step(torch.from_numpy(acts[0]).cuda())
+    assert sim.record_fetch(0)["robots"].shape[0] == 1
+    sim.record_enable(0)
+    with pytest.raises(RuntimeError):
+        sim.record_fetch(0)
+    sim.close()
