@@ -249,7 +249,6 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
                 }
         }
         T.t.dtab_off = (int)dtab.size(); dtab.insert(dtab.end(), T.dtab.begin(), T.dtab.end());
-        T.t.n_own = 0; T.t.own_off = 0;
         rts.push_back(T.t);
     }
     // pedestrians
@@ -282,16 +281,15 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     std::vector<uint8_t> g(grid, grid + (size_t)H * W);
     std::vector<uint32_t> socc((size_t)H * c.Wb, 0u);
     for (int i = 0; i < H; i++) for (int j = 0; j < W; j++) if (grid[(size_t)i * W + j] < 250) socc[(size_t)i * c.Wb + (j >> 5)] |= 1u << (j & 31);
-    std::vector<int> own_dummy(1, 0);
 
     Dev& d = h->d;
 #define UP(field, vec) if (dupload(h, &d.field, vec)) return -1;
     std::vector<uint32_t> kpack(khi.size());
     for (size_t k = 0; k < khi.size(); k++) kpack[k] = (uint32_t)khi[k] | ((uint32_t)klo[k] << 16);
     UP(kpack, kpack) UP(grid, g) UP(static_occ, socc) UP(types, rts) UP(type_of, type_of) UP(lattice_xy, lattice) UP(ray_end, ray_end)
-    UP(fov_spans, spans) UP(khi, khi) UP(klo, klo) UP(own_mask, own_mask) UP(need_idx, need_idx) UP(cubic_tap, tap)
+    UP(fov_spans, spans) UP(own_mask, own_mask) UP(need_idx, need_idx) UP(cubic_tap, tap)
     UP(cubic_coef, coef) UP(f16_lut, lut) UP(lim_v, lv) UP(lim_w, lw) UP(ped_shape, pshape) UP(ped_size, psize)
-    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(dtab, dtab) UP(hstat, hstat) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_r_wire, prw) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(ped_ext, pext) UP(ped_part, ppart) UP(own_cells, own_dummy)
+    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(dtab, dtab) UP(hstat, hstat) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(ped_ext, pext) UP(ped_part, ppart)
 #undef UP
     size_t S = c.S;
     size_t pc = ((size_t)H * W + 3) & ~(size_t)3;

@@ -40,13 +40,11 @@ struct Limiter {
 struct RobotType {
     int n_pts;            // footprint lattice points (agent.cpp:18-62)
     int pts_off;          // offset into lattice_xy (double2 units)
-    int n_own;            // own-footprint cells in the view raster (static: base2view is pose independent)
-    int own_off;          // offset into own_cells (int: row*vw+col)
     int org_x, org_y;     // laser origin cell (agent.cpp:366-369)
     int ray_off;          // offset into ray_end (short2 units), range_total entries
     int span_off;         // offset into fov_spans (vh * MAX_SPANS * 2 shorts)
     int zone_r0, zone_r1, zone_c0, zone_c1;  // view-raster box where the robot's own footprint may be the only stamp
-    int khi_off;          // offset into khi/klo tables (ns*ns entries)
+    int khi_off;          // offset into kpack (vh*vw entries per type)
     int own_mask_off;     // offset into own_mask (vh*vw bits, u32 words)
     int tile_off;         // offset into tile_fov (u32 words): bit per 32x32 view tile that contains FOV pixels
     int edge_off, n_edge; // FOV pixels with an 8-neighbour outside the FOV (u32 row<<16|col), always evaluated forward
@@ -88,11 +86,8 @@ struct Dev {
     const RobotType* types;       // [n_types]
     const int* type_of;           // [R]
     const double* lattice_xy;     // packed (x,y) pairs
-    const int* own_cells;
     const short* ray_end;         // (x2,y2) pairs
     const short* fov_spans;       // per type: [vh][MAX_SPANS][2] (c0,c1 exclusive), -1 = none
-    const unsigned short* khi;    // per type [ns*ns]: highest ray index touching the needed pixel (0xFFFF none)
-    const unsigned short* klo;    //                   lowest
     const uint32_t* kpack;        // khi | klo << 16 (one load per pixel)
     const uint32_t* own_mask;     // per type: bit per view pixel = own footprint cell
     const uint32_t* tile_fov;     // per type: bit per 32x32 view tile (row-major, vwb per row) with any FOV pixel
@@ -109,7 +104,6 @@ struct Dev {
     const double* ped_size;       // [P][6] (float32 widened)
     const double* ped_maxspeed;   // [P]
     const double* ped_r_round;    // [P] python round(r_,2)
-    const float* ped_r_wire;      // [P] float32 r_ = sizes_[2]
     const int* ped_pts_off;       // [P][2] lattice offsets (body or left leg, right leg)
     const int* ped_pts_n;         // [P][2]
     const double* ped_part;       // [P][2][3] per stamped part (body / left leg, right leg): bounding circle centre x, y (m) and radius (cells)

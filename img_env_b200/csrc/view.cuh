@@ -322,11 +322,13 @@ __device__ __noinline__ void cell_rays_inline(unsigned* hitkey, const short* ren
     }
 }
 
-// Shared-memory plan (bytes for the canonical 400x400 view / 1000 rays / 48x48 outputs):
-//   region A  occ raster 400*13*4 = 20.8 KB   (phases B-C)   | later: ped map winners + pedestrian scratch (phase G)
-//   region B  boundary-cell list 24 KB        (phase C)       | later: horizontal resize buffer 144*48*4 = 27.6 KB (phase F)
-//   (no pixel buffer: the laser_map values are evaluated inside the horizontal resize pass)
-//   hitkey    range_total*4, ray end cells range_total*4, needed-line indices
+// Shared-memory plan of k_view (bytes for the canonical 400x400 view / 1000 rays / 48x48 outputs; 48 KB -> 4 CTAs per SM):
+//   region A  occupancy raster 400*13*4 = 20.8 KB (x2 with lasers off: + the "known" plane)            phases B-D
+//   region B  ray-hit candidate lists (BL_CAP + BL2_CAP)*4 = 13.3 KB                                     phases B-C
+//             later: horizontal resize buffer ns*HB_COLS*4 = 9.2 KB + hit prefix counts 2 KB            phases D-F
+//   hitkey    range_total*4 (first hit per ray), ray end cells range_total*4, needed-line indices, FOV spans vh*8,
+//             list of occupied world blocks under the FOV INV_MAX_BLOCKS*4
+//   (no 400x400 pixel buffer: the laser_map values are evaluated inside the horizontal resize pass)
 #define BL_CAP 3072          // candidate cells kept in shared memory; further cells are resolved inline by their finder
 #define BL2_CAP 256          // cells touched by many rays (close to the origin): processed warp-cooperatively
 #define BL_HEAVY 24
