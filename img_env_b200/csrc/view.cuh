@@ -580,16 +580,25 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     // rotation of view_world).  The float test decides all pixels farther than INV_EPS from the square's
                     // edge; only the others run the exact forward map.  |q| < 2^10 so the float error is < 1e-3 cell.
                     const int ia = (int)ceilf(qi - 0.72f), ja = (int)ceilf(qj - 0.72f);
-#pragma unroll 1
-                    for (int t = 0; t < 4; t++) {
+                    // cheap part for the 2 x 2 window at once (M*d is linear: the four offsets share two products), ...
+                    const float du0 = (float)ia - qi, dv0 = (float)ja - qj;
+                    const float x00 = f00 * du0 + f01 * dv0, y00 = f10 * du0 + f11 * dv0;
+                    float e4[4];
+                    e4[0] = fmaxf(fabsf(x00), fabsf(y00));
+                    e4[1] = fmaxf(fabsf(x00 + f01), fabsf(y00 + f11));
+                    e4[2] = fmaxf(fabsf(x00 + f00), fabsf(y00 + f10));
+                    e4[3] = fmaxf(fabsf(x00 + f00 + f01), fabsf(y00 + f10 + f11));
+                    unsigned live = (e4[0] <= 0.5f + INV_EPS ? 1u : 0u) | (e4[1] <= 0.5f + INV_EPS ? 2u : 0u) |
+                                    (e4[2] <= 0.5f + INV_EPS ? 4u : 0u) | (e4[3] <= 0.5f + INV_EPS ? 8u : 0u);
+                    // ... then the (usually one) surviving pixel
+                    while (live) {
+                        const int t = __ffs(live) - 1; live &= live - 1;
                         const int i = ia + (t >> 1), j = ja + (t & 1);
-                        const float du = (float)i - qi, dv = (float)j - qj;
-                        const float ex = fabsf(f00 * du + f01 * dv), ey = fabsf(f10 * du + f11 * dv);
-                        if (fmaxf(ex, ey) > 0.5f + INV_EPS) continue;
+                        const float em = t == 0 ? e4[0] : t == 1 ? e4[1] : t == 2 ? e4[2] : e4[3];
                         if ((unsigned)i >= (unsigned)vh || (unsigned)j >= (unsigned)vw) continue;
                         const int a0 = spans[i * 4 + 0], a1 = spans[i * 4 + 1], b0 = spans[i * 4 + 2], b1 = spans[i * 4 + 3];
                         if (!((j >= a0 && j < a1) || (j >= b0 && j < b1))) continue;
-                        if (fmaxf(ex, ey) > 0.5f - INV_EPS) {
+                        if (em > 0.5f - INV_EPS) {
                             const long long tx = sh->cx + (long long)i * sh->ax + (long long)j * sh->bx;
                             const long long tyy = sh->cy + (long long)i * sh->ay + (long long)j * sh->by;
                             int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
