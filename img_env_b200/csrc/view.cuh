@@ -523,6 +523,8 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             const int X0 = sh->wbb[0], X1 = sh->wbb[1], Y0 = sh->wbb[2], Y1 = sh->wbb[3];
             const int zx = sh->zc[0], zy = sh->zc[1], zr = ty.zone_rad;
             const float i00 = (float)sh->inv[0], i01 = (float)sh->inv[1], i10 = (float)sh->inv[2], i11 = (float)sh->inv[3];
+            const int orgi0 = (int)floor(sh->org[0]), orgi1 = (int)floor(sh->org[1]);
+            const float orgf0 = (float)(sh->org[0] - orgi0), orgf1 = (float)(sh->org[1] - orgi1);
             const float f00 = (float)sh->view_world.m00, f01 = (float)sh->view_world.m01, f10 = (float)sh->view_world.m10, f11 = (float)sh->view_world.m11;
             // each warp takes 32 words (one per lane), then expands their candidate bits over all lanes
             // batches of 32 words are handed out dynamically: dense world blocks make the work per batch very uneven
@@ -574,7 +576,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     const int cX = __shfl_sync(0xffffffffu, X, src), cbj = __shfl_sync(0xffffffffu, bj, src);
                     if (k >= total) continue;
                     const int cY = cbj * 32 + (int)__fns(m, 0, n + 1);
-                    const float u = (float)((double)cX - sh->org[0]), v = (float)((double)cY - sh->org[1]);
+                    const float u = (float)(cX - orgi0) - orgf0, v = (float)(cY - orgi1) - orgf1;      // cell - org, exact integer part
                     const float qi = i00 * u + i01 * v, qj = i10 * u + i11 * v;
                     // Pixel (i,j) maps to this cell iff M*((i,j) - q) lies in the unit square around the cell centre (M =
                     // rotation of view_world).  The float test decides all pixels farther than INV_EPS from the square's
