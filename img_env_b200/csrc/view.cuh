@@ -460,22 +460,22 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         // a newly set raster cell goes straight to the ray-hit candidate lists (phase C)
         // every ray of [k0, k0+kstep, ...] within the cell's static ray interval that really passes through it
         // keeps the minimum step: hitkey[k] = min(step << 22 | cell)
-        auto cell_rays = [&](int full, unsigned kp, int k0, int kstep) {
-            const int pr = full / vw, pc = full - pr * vw;
+        auto cell_rays = [&](unsigned cell, unsigned kp, int k0, int kstep) {      // cell = row << 16 | col
+            const int pr = (int)(cell >> 16), pc = (int)(cell & 0xFFFFu);
             const int kh = kp & 0xFFFF, kl = kp >> 16;
             for (int k = kl + k0; k <= kh; k += kstep) {
                 const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
                 if (i >= 0) atomicMin(&hitkey[k], hit_key(i, pr, pc));
             }
         };
-        auto push_cell = [&](int full) {
-            const unsigned kp = __ldg(kpack + full);
+        auto push_cell = [&](int pr, int pc) {
+            const unsigned kp = __ldg(kpack + pr * vw + pc);
             const int kh = kp & 0xFFFF;
             if (kh == 0xFFFF) return;                                      // no ray passes through this cell
             const bool heavy = kh - (int)(kp >> 16) + 1 > BL_HEAVY;
             const int p = atomicAdd(heavy ? n_list2 : n_list, 1);
-            if (p < (heavy ? BL2_CAP : BL_CAP)) (heavy ? blist2 : blist)[p] = (unsigned)full;
-            else cell_rays_inline(hitkey, rend, ox, oy, full / vw, full % vw, (int)(kp >> 16), kh);   // list full: resolve this cell right here
+            if (p < (heavy ? BL2_CAP : BL_CAP)) (heavy ? blist2 : blist)[p] = ((unsigned)pr << 16) | (unsigned)pc;
+            else cell_rays_inline(hitkey, rend, ox, oy, pr, pc, (int)(kp >> 16), kh);   // list full: resolve this cell right here
         };
         const int n_trow = (vh + 31) >> 5, n_tiles = n_trow * vwb;
         // (1) World -> view ("inverse") rasterisation, used when lasers are on: only raster cells that can be the
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 if ((unsigned)cx < H && (unsigned)cy < W) {
                     bool o = (__ldg(occ_all + (unsigned)cx * Wb + ((unsigned)cy >> 5)) >> (cy & 31)) & 1u;
                     if (o && i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1) o = global_value(d, s, r, cx, cy) < 250;
-                    if (o && !(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31)))) push_cell(i * vw + j);
+                    if (o && !(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31)))) push_cell(i, j);
                 }
             }
             // occupied world words -> candidate cells -> view pixels
@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                             if (cx != cX || cy != cY) continue;
                         }
                         if (i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1 && !(global_value(d, s, r, cX, cY) < 250)) continue;
-                        if (!(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31)))) push_cell(i * vw + j);
+                        if (!(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31)))) push_cell(i, j);
                     }
                 }
             }
@@ -717,15 +717,14 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     const int b = __ffs(bnd) - 1; bnd &= bnd - 1;
                     const int col = wj * 32 + b;
                     if (col >= vw) break;
-                    const int full = i * vw + col;
-                    push_cell(full);
+                    push_cell(i, col);
                 }
             }
             __syncthreads();
             const int nl = min(sh->red[0], BL_CAP), nl2 = min(sh->red[1], BL2_CAP);
             if (d.dbg_stats && tid == 0) { int* st = d.dbg_stats + 4 * (size_t)idx; st[0] = sh->red[2] + sh->red[3]; st[1] = sh->red[0]; st[2] = sh->red[1]; st[3] = sh->red[0] > BL_CAP || sh->red[1] > BL2_CAP; }
-            for (int q = tid; q < nl; q += VIEW_THREADS) { const int full = blist[q]; cell_rays(full, __ldg(kpack + full), 0, 1); }
-            for (int q = warp; q < nl2; q += VIEW_THREADS / 32) { const int full = blist2[q]; cell_rays(full, __ldg(kpack + full), lane, 32); }
+            for (int q = tid; q < nl; q += VIEW_THREADS) { const unsigned cell = blist[q]; cell_rays(cell, __ldg(kpack + (cell >> 16) * vw + (cell & 0xFFFFu)), 0, 1); }
+            for (int q = warp; q < nl2; q += VIEW_THREADS / 32) { const unsigned cell = blist2[q]; cell_rays(cell, __ldg(kpack + (cell >> 16) * vw + (cell & 0xFFFFu)), lane, 32); }
             __syncthreads();
             if (!DEBUG_FULL) {
                 for (int k = tid; k < c.range_total; k += VIEW_THREADS) {
