@@ -154,11 +154,12 @@ __device__ __forceinline__ void stamp_part(const Dev& d, int s, const Tf2& t, co
         else stamp_cells8(d, s, cx, cy & ~7, 1u << (cy & 7), mode, id);   // cannot happen (the box bounds the footprint); still a valid write
     }
     __syncthreads();
+    const unsigned inv_wpr = (65536u + bx.wpr - 1) / bx.wpr;     // word / wpr == (word * inv_wpr) >> 16 for word < 8192, wpr <= 12 (checked exhaustively)
     for (int it = threadIdx.x; it < 4 * nw; it += STAMP_THREADS) {
         const int word = it >> 2, byte = it & 3;
         const unsigned m8 = (bm[word] >> (8 * byte)) & 0xFFu;
         if (!m8) continue;
-        const int r = word / bx.wpr, w = word - r * bx.wpr;
+        const int r = bx.wpr <= 12 && nw < 8192 ? (int)(((unsigned)word * inv_wpr) >> 16) : word / bx.wpr, w = word - r * bx.wpr;
         stamp_cells8(d, s, bx.cx0 + r, (bx.wj0 + w) * 32 + 8 * byte, m8, mode, id);
     }
     __syncthreads();
