@@ -833,30 +833,35 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             const float scale = 1.f / (2048.f * 2048.f);
             for (int cb = 0; cb < c.img; cb += HB_COLS) {
                 const int nc = min(HB_COLS, c.img - cb);
-                // a warp covers a compact patch of 8 needed rows x 4 output columns: few rays cross it, so the whole warp
-                // often takes the hit-free shortcut below
-                for (int q = tid; q < ((c.ns + 7) >> 3) * 8 * HB_COLS; q += VIEW_THREADS) {
-                    const int tile = q >> 5, l = q & 31;
-                    const int rr = (tile / (HB_COLS / 4)) * 8 + (l >> 2), ocl = (tile % (HB_COLS / 4)) * 4 + (l & 3);
-                    if (ocl >= nc || rr >= c.ns) continue;
+                // A warp covers a compact patch of 8 needed rows x 4 output columns (few rays cross it, so the whole warp often
+                // takes the hit-free shortcut below); with 8 warps and 16 columns per block a thread keeps its output column
+                // and walks down the needed rows in steps of 16.
+                static_assert(VIEW_THREADS == 256 && HB_COLS == 16, "item mapping of the horizontal resize pass");
+                const int ocl = (warp & 3) * 4 + (lane & 3);
+                if (ocl < nc) {
                     const int oc = cb + ocl;
                     const short* tp = d.cubic_tap + 4 * oc;
                     const short4 cf = __ldg(reinterpret_cast<const short4*>(d.cubic_coef) + oc);
-                    uint4 e4 = make_uint4(0u, 0u, 0u, 0u);
-                    if (c.use_laser) {
-                        // static shortcut: when none of the top rays of this output's taps hit anything, all of its source
-                        // pixels keep their hit-free value (free / own footprint / outside every ray) and the sum is a table entry
-                        const uint2 hs = __ldg(reinterpret_cast<const uint2*>(d.hstat) + (size_t)(ty.dtab_off >> 2) + (size_t)rr * c.img + oc);
-                        const int kmin = hs.x & 0xFFFFu, kmax = hs.x >> 16;
-                        if (kmax < kmin || hpre[kmax + 1] == hpre[kmin]) { hbuf[rr * HB_COLS + ocl] = (int)hs.y; continue; }
-                        e4 = __ldg(reinterpret_cast<const uint4*>(dtab) + (size_t)rr * c.img + oc);
+                    const int rr0 = (warp >> 2) * 8 + (lane >> 2);
+                    const uint2* hsp = reinterpret_cast<const uint2*>(d.hstat) + (size_t)(ty.dtab_off >> 2) + oc;
+                    const uint4* dtp = reinterpret_cast<const uint4*>(dtab) + oc;
+                    for (int rr = rr0; rr < c.ns; rr += 16) {
+                        uint4 e4 = make_uint4(0u, 0u, 0u, 0u);
+                        if (c.use_laser) {
+                            // static shortcut: when none of the top rays of this output's taps hit anything, all of its source
+                            // pixels keep their hit-free value (free / own footprint / outside every ray) and the sum is a table entry
+                            const uint2 hs = __ldg(hsp + rr * c.img);
+                            const int kmin = hs.x & 0xFFFFu, kmax = hs.x >> 16;
+                            if (kmax < kmin || hpre[kmax + 1] == hpre[kmin]) { hbuf[rr * HB_COLS + ocl] = (int)hs.y; continue; }
+                            e4 = __ldg(dtp + rr * c.img);
+                        }
+                        int acc = 0;
+                        if (cf.x) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.x, rr, tp, 0))) & 0xFFu) * cf.x;
+                        if (cf.y) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.y, rr, tp, 1))) & 0xFFu) * cf.y;
+                        if (cf.z) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.z, rr, tp, 2))) & 0xFFu) * cf.z;
+                        if (cf.w) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.w, rr, tp, 3))) & 0xFFu) * cf.w;
+                        hbuf[rr * HB_COLS + ocl] = acc;
                     }
-                    int acc = 0;
-                    if (cf.x) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.x, rr, tp, 0))) & 0xFFu) * cf.x;
-                    if (cf.y) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.y, rr, tp, 1))) & 0xFFu) * cf.y;
-                    if (cf.z) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.z, rr, tp, 2))) & 0xFFu) * cf.z;
-                    if (cf.w) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.w, rr, tp, 3))) & 0xFFu) * cf.w;
-                    hbuf[rr * HB_COLS + ocl] = acc;
                 }
                 __syncthreads();
                 for (int q = tid; q < c.img * HB_COLS; q += VIEW_THREADS) {
