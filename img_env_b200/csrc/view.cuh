@@ -867,10 +867,10 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 for (int q = tid; q < c.img * HB_COLS; q += VIEW_THREADS) {
                     const int orow = q / HB_COLS, ocl = q % HB_COLS;
                     if (ocl >= nc) continue;
-                    const short* tp = d.cubic_tap + 4 * orow; const short* cf = d.cubic_coef + 4 * orow;
-                    const float b0 = cf[0] * scale, b1 = cf[1] * scale, b2 = cf[2] * scale, b3 = cf[3] * scale;
-                    const float s0 = (float)hbuf[tp[0] * HB_COLS + ocl], s1 = (float)hbuf[tp[1] * HB_COLS + ocl];
-                    const float s2 = (float)hbuf[tp[2] * HB_COLS + ocl], s3 = (float)hbuf[tp[3] * HB_COLS + ocl];
+                    const short4 tp = __ldg(reinterpret_cast<const short4*>(d.cubic_tap) + orow), cf = __ldg(reinterpret_cast<const short4*>(d.cubic_coef) + orow);
+                    const float b0 = cf.x * scale, b1 = cf.y * scale, b2 = cf.z * scale, b3 = cf.w * scale;
+                    const float s0 = (float)hbuf[tp.x * HB_COLS + ocl], s1 = (float)hbuf[tp.y * HB_COLS + ocl];
+                    const float s2 = (float)hbuf[tp.z * HB_COLS + ocl], s3 = (float)hbuf[tp.w * HB_COLS + ocl];
                     const float v = fmaf(s0, b0, fmaf(s1, b1, fmaf(s2, b2, s3 * b3)));
                     int iv = __float2int_rn(v);
                     iv = min(255, max(0, iv));
