@@ -301,6 +301,16 @@ __device__ __forceinline__ int ray_touch(int ox, int oy, int ex, int ey, int pr,
     }
 }
 
+// position of the n-th (0-based) set bit of m; m has more than n bits set.  (The generic __fns intrinsic costs ~55 instructions.)
+__device__ __forceinline__ int nth_set_bit(unsigned m, int n) {
+    int pos = 0, c;
+    c = __popc(m & 0xFFFFu); if (n >= c) { n -= c; pos = 16; m >>= 16; }
+    c = __popc(m & 0xFFu);   if (n >= c) { n -= c; pos += 8; m >>= 8; }
+    c = __popc(m & 0xFu);    if (n >= c) { n -= c; pos += 4; m >>= 4; }
+    c = __popc(m & 0x3u);    if (n >= c) { n -= c; pos += 2; m >>= 2; }
+    return pos + (n >= (int)(m & 1u) ? 1 : 0);
+}
+
 // Rare continuation of the laser_map pixel rule (phase D): the pixel lies behind its top ray's hit and was not shadow
 // written by it, so the rays below (kh-1 .. kl) decide, highest first.  Out of line to keep the kernel's hot loop small.
 __device__ __noinline__ unsigned pixel_code_below(const unsigned* hitkey, const short* rend, int ox, int oy, int pr, int pc, int kh, int kl) {
@@ -436,7 +446,8 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             const double* pts = d.lattice_xy + 2 * (size_t)ty.pts_off;
             for (int k = tid; k < ty.n_pts; k += VIEW_THREADS) {
                 double wx, wy;
-                tf_apply(sh->base_world, pts[2 * k], pts[2 * k + 1], wx, wy);
+                const double2 pt = __ldg(reinterpret_cast<const double2*>(pts) + k);
+                tf_apply(sh->base_world, pt.x, pt.y, wx, wy);
                 int cx = world2cell_fast(wx, c.res, c.inv_res), cy = world2cell_fast(wy, c.res, c.inv_res);
                 if ((unsigned)cx < (unsigned)c.H && (unsigned)cy < (unsigned)c.W) {
                     int v = global_value(d, s, r, cx, cy);
@@ -576,7 +587,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     const unsigned m = __shfl_sync(0xffffffffu, cand, src);
                     const int cX = __shfl_sync(0xffffffffu, X, src), cbj = __shfl_sync(0xffffffffu, bj, src);
                     if (k >= total) continue;
-                    const int cY = cbj * 32 + (int)__fns(m, 0, n + 1);
+                    const int cY = cbj * 32 + nth_set_bit(m, n);
                     const float u = (float)(cX - orgi0) - orgf0, v = (float)(cY - orgi1) - orgf1;      // cell - org, exact integer part
                     const float qi = i00 * u + i01 * v, qj = i10 * u + i11 * v;
                     // Pixel (i,j) maps to this cell iff M*((i,j) - q) lies in the unit square around the cell centre (M =
