@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     }
                     const int n = k - __shfl_sync(0xffffffffu, excl, src);
                     const unsigned m = __shfl_sync(0xffffffffu, cand, src);
-                    const int cX = __shfl_sync(0xffffffffu, X, src), cbj = __shfl_sync(0xffffffffu, bj, src);
+                    const int cX = X - lane + src, cbj = bj;      // a batch is the 32 rows of one block: row = first row + lane, same word column
                     if (k >= total) continue;
                     const int cY = cbj * 32 + nth_set_bit(m, n);
                     const float u = (float)(cX - orgi0) - orgf0, v = (float)(cY - orgi1) - orgf1;      // cell - org, exact integer part
