@@ -152,7 +152,7 @@ def _ref_worker(args):
     return t0, t1, R * done
 
 
-def run_reference(wname, steps, warmup, procs=None, budget_s=200.0, target_s=0.0):
+def run_reference(wname, steps, warmup, procs=None, budget_s=200.0, target_s=0.0, hard_timeout=None):
     """Times oracle/_ref (+ restated Python post-processing), one scene per process."""
     import multiprocessing as mp
     import tempfile
@@ -184,7 +184,7 @@ def run_reference(wname, steps, warmup, procs=None, budget_s=200.0, target_s=0.0
         pool = ctx.Pool(procs)
         try:      # a crashed worker would make a plain map() wait forever
             res = pool.map_async(_ref_worker, [(wname, 1000 + i, warm_eff, steps_eff, bd, procs, i, target_s) for i in range(procs)]).get(
-                timeout=2.0 * budget_s + 120.0)
+                timeout=hard_timeout or (2.0 * budget_s + 120.0))
         except Exception as e:
             pool.terminate()
             return dict(unavailable="reference workers failed or timed out: %s" % type(e).__name__)
@@ -372,7 +372,7 @@ def run_b200(args):
         out["gather_to_learner"] = gather
     if world == 1 and not args.no_cpu_baseline:
         try:
-            ref = run_reference(args.workload, steps=2, warmup=1, budget_s=25.0 * 8, target_s=12.0)
+            ref = run_reference(args.workload, steps=2, warmup=1, budget_s=25.0 * 8, target_s=12.0, hard_timeout=240.0)
             if ref and "unavailable" in ref:
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": ref["unavailable"]}
             elif ref:
