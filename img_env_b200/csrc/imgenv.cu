@@ -65,6 +65,12 @@ template <class T> static int dupload(imgenv* h, const T** p, const std::vector<
     return 0;
 }
 
+// fn(i) for every listed scene; returns the first error message or nullptr
+template <class F> static const char* for_scenes(int n, F fn) {
+    for (int i = 0; i < n; i++) if (const char* e = fn(i)) return e;
+    return nullptr;
+}
+
 extern "C" const char* imgenv_last_error(void) { return g_err.c_str(); }
 extern "C" const char* imgenv_version(void) { return "img_env_b200 0.1 (sm_100a)"; }
 // host-only helpers exported for CPU-side table checks (tests/test_tables.py)
@@ -516,15 +522,15 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     size_t iper = (size_t)5 + c.P + 3 * (size_t)d.max_verts;
     size_t fper = (size_t)8 * d.max_verts;
     memset(h->st_h, 0, dper * n * 8); memset(h->sti_h, 0, iper * n * 4); memset(h->stf_h, 0, fper * n * 4);
-    for (int sl = 0; sl < n; sl++) {
+    auto pack_scene = [&](int sl) -> const char* {
         int s = scene_ids ? scene_ids[sl] : sl;
-        if (s < 0 || s >= c.S) return fail("imgenv_reset: scene id out of range");
+        if (s < 0 || s >= c.S) return "imgenv_reset: scene id out of range";
         double* D = h->st_h + dper * sl; int* I = h->sti_h + iper * sl; float* Fp = h->stf_h + fper * sl;
         double* o_obs = D; double* o_rob = o_obs + 8 * (size_t)c.max_obs; double* o_ped = o_rob + 5 * (size_t)c.R;
         double* o_traj = o_ped + 5 * (size_t)c.P; double* o_seg = o_traj + 3 * (size_t)c.max_traj * c.P;
         double* o_trajv = o_seg + 4 * (size_t)c.max_obs;
         int no = n_obs ? n_obs[sl] : 0;
-        if (no < 0 || no > c.max_obs) return fail("imgenv_reset: too many obstacles for max_obstacles");
+        if (no < 0 || no > c.max_obs) return "imgenv_reset: too many obstacles for max_obstacles";
         I[0] = s; I[1] = no;
         std::vector<ht::RvoObst> robst; int nseg = 0;
         for (int k = 0; k < no; k++) {
@@ -551,7 +557,7 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
             std::vector<int> list(robst.size());
             for (size_t k = 0; k < list.size(); k++) list[k] = (int)k;
             root = ht::rvo_build_tree(robst, nodes, list);
-            if ((int)robst.size() > d.max_verts || (int)nodes.size() > d.max_verts) return fail("imgenv_reset: obstacle k-d tree exceeds max_verts");
+            if ((int)robst.size() > d.max_verts || (int)nodes.size() > d.max_verts) return "imgenv_reset: obstacle k-d tree exceeds max_verts";
             for (size_t k = 0; k < robst.size(); k++) {
                 float* v = Fp + 8 * k;
                 v[0] = robst[k].px; v[1] = robst[k].py; v[2] = robst[k].dx; v[3] = robst[k].dy; v[4] = (float)robst[k].convex;
@@ -571,12 +577,14 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
             double* o = o_ped + 5 * p;
             o[0] = q[0]; o[1] = q[1]; o[2] = ht::yaw_from_quaternion(q[2], q[3], q[4], q[5]); o[3] = q[6]; o[4] = q[7];
             int tl = traj_len ? traj_len[(size_t)sl * c.P + p] : 0;
-            if (tl < 1 || tl > c.max_traj) return fail("imgenv_reset: pedestrian trajectory length must be in [1, max_traj]");
+            if (tl < 1 || tl > c.max_traj) return "imgenv_reset: pedestrian trajectory length must be in [1, max_traj]";
             I[5 + p] = tl;
             for (int k = 0; k < 3 * tl; k++) o_traj[(size_t)p * c.max_traj * 3 + k] = traj[((size_t)sl * c.P + p) * c.max_traj * 3 + k];
             if (c.scene_type == 4) for (int k = 0; k < 3 * tl; k++) o_trajv[(size_t)p * c.max_traj * 3 + k] = traj_v[((size_t)sl * c.P + p) * c.max_traj * 3 + k];
         }
-    }
+        return nullptr;
+    };
+    if (const char* e = for_scenes(n, pack_scene)) return fail(e);
     CK(cudaMemcpyAsync(h->st_d, h->st_h, dper * n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->sti_d, h->sti_h, iper * n * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->stf_d, h->stf_h, fper * n * 4, cudaMemcpyHostToDevice, st));
@@ -724,13 +732,20 @@ extern "C" int imgenv_sampler_sample(imgenv_sampler_t* w, int32_t n, const int32
     const sampler::Sampler& S = w->s;
     if ((int)S.objects.size() > max_obs) return fail("imgenv_sampler_sample: more objects than max_obs");
     if (S.P > 0 && max_traj < 2) return fail("imgenv_sampler_sample: max_traj must be >= 2");
+    std::vector<char> seen(S.rng.size(), 0);
     for (int i = 0; i < n; i++) {
         const int sc = scene_ids ? scene_ids[i] : i;
         if (sc < 0 || sc >= (int)S.rng.size()) return fail("imgenv_sampler_sample: scene id out of range");
+        if (seen[sc]) return fail("imgenv_sampler_sample: duplicate scene id");
+        seen[sc] = 1;
+    }
+    for_scenes(n, [&](int i) -> const char* {
+        const int sc = scene_ids ? scene_ids[i] : i;
         n_obs[i] = (int)S.objects.size();
         sampler::sample_scene(S, w->s.rng[sc], obs + (size_t)i * max_obs * 11, robots + (size_t)i * S.R * 8, peds + (size_t)i * S.P * 8,
                               traj_len + (size_t)i * S.P, traj + (size_t)i * S.P * max_traj * 3, max_traj);
-    }
+        return nullptr;
+    });
     return 0;
 }
 // Debug: the raw double stream of one scene's generator (tests pin it against CPython's random module).
