@@ -295,7 +295,8 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     UP(kpack, kpack) UP(grid, g) UP(static_occ, socc) UP(types, rts) UP(type_of, type_of) UP(lattice_xy, lattice) UP(ray_end, ray_end)
     UP(fov_spans, spans) UP(own_mask, own_mask) UP(need_idx, need_idx) UP(cubic_tap, tap)
     UP(cubic_coef, coef) UP(f16_lut, lut) UP(lim_v, lv) UP(lim_w, lw) UP(ped_shape, pshape) UP(ped_size, psize)
-    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(dtab, dtab) UP(hstat, hstat) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_pts_off, poff) UP(ped_pts_n, pn) UP(ped_ext, pext) UP(ped_part, ppart)
+    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(dtab, dtab) UP(hstat, hstat) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_pts_off, poff)
+    UP(ped_pts_n, pn) UP(ped_ext, pext) UP(ped_part, ppart)
 #undef UP
     size_t S = c.S;
     size_t pc = ((size_t)H * W + 3) & ~(size_t)3;
@@ -304,7 +305,8 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     AL(occ_all, S * H * c.Wb) AL(base_occ, S * H * c.Wb) AL(flags, S * pc) AL(rmin, S * pc) AL(coarse, S * c.Hc * c.Wb)
     AL(rb, (size_t)RB_FIELDS * S * c.R) AL(pd, (size_t)PD_FIELDS * S * c.P)
     AL(traj, S * c.P * c.max_traj * 3) AL(traj_v, c.scene_type == 4 ? S * c.P * c.max_traj * 3 : 1) AL(traj_len, S * c.P) AL(obs, S * c.max_obs * 8) AL(n_obs, S) AL(step_no, S)
-    AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_nvel, S * c.NA * 2) AL(sfm_force, c.scene_type == 1 ? S * c.NA * 12 : 1) AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 3)
+    AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_nvel, S * c.NA * 2) AL(sfm_force, c.scene_type == 1 ? S * c.NA * 12 : 1)
+    AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 3)
     AL(rvo_counts, S * 2) AL(sfm, S * c.NA * SFM_REC) AL(sfm_obs, S * c.max_obs * 4) AL(sfm_nobs, S)
     AL(sfm_wp, S * c.P * (1 + c.max_traj) * 3)
     {
@@ -473,7 +475,10 @@ __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, co
             rec[7] = 0; rec[8] = -1; rec[9] = 0;
             double* wp = d.sfm_wp + (size_t)pi * (1 + c.max_traj) * 3;
             wp[0] = q[3]; wp[1] = q[4]; wp[2] = 1.0;
-            for (int k = 0; k < tl[p]; k++) { wp[3 + 3 * k] = traj[((size_t)p * c.max_traj + k) * 3]; wp[4 + 3 * k] = traj[((size_t)p * c.max_traj + k) * 3 + 1]; wp[5 + 3 * k] = traj[((size_t)p * c.max_traj + k) * 3 + 2]; }
+            for (int k = 0; k < tl[p]; k++) {
+                const double* tk = traj + ((size_t)p * c.max_traj + k) * 3;
+                wp[3 + 3 * k] = tk[0]; wp[4 + 3 * k] = tk[1]; wp[5 + 3 * k] = tk[2];
+            }
         }
     }
 }
@@ -689,7 +694,10 @@ extern "C" int imgenv_sampler_create(const double* desc, int64_t n_desc, int32_t
     S.R = (int)desc[0]; S.P = (int)desc[1]; const int nobj = (int)desc[2];
     S.circle_lo = desc[3]; S.circle_hi = desc[4]; S.target_min_dist = desc[5]; S.go_back = (int)desc[6];
     if (S.R < 0 || S.P < 0 || nobj < 0 || S.go_back < 0 || S.go_back > 2 ||
-        n_desc != SAMPLER_HDR + (int64_t)(S.R + S.P) * SAMPLER_AGENT_REC + (int64_t)nobj * SAMPLER_OBJ_REC) { delete w; return fail("imgenv_sampler_create: descriptor size does not match its header"); }
+        n_desc != SAMPLER_HDR + (int64_t)(S.R + S.P) * SAMPLER_AGENT_REC + (int64_t)nobj * SAMPLER_OBJ_REC) {
+        delete w;
+        return fail("imgenv_sampler_create: descriptor size does not match its header");
+    }
     const double* q = desc + SAMPLER_HDR;
     auto pose = [&](sampler::PoseSpec& ps) {
         ps.type = (int)q[0]; ps.n_multi = (int)q[1]; ps.len = (int)q[2];
@@ -703,7 +711,11 @@ extern "C" int imgenv_sampler_create(const double* desc, int64_t n_desc, int32_t
         // configurations on which the reference's loop never terminates (reset_helper.py:222-305): a begin pose that is
         // not sampled ('range') next to a sampled target leaves reset_init True forever; 'view_plus' keeps a stale pose.
         const bool fixed_b = a.begin.type & (sampler::T_EQ_FIX | sampler::T_EQ_RAND_ANGLE), fixed_t = a.target.type & (sampler::T_EQ_FIX | sampler::T_EQ_RAND_ANGLE);
-        if (!(fixed_b && fixed_t) && !(a.begin.type & sampler::T_RANGE)) { delete w; return fail("imgenv_sampler_create: begin_poses_type must be a 'range' type unless begin and target are both fixed (the reference loops forever)"); }
+        if (!(fixed_b && fixed_t) && !(a.begin.type & sampler::T_RANGE)) {
+            delete w;
+            return fail("imgenv_sampler_create: begin_poses_type must be a 'range' type unless begin and target are both fixed "
+                        "(the reference loops forever)");
+        }
         if (!fixed_t && !(a.target.type & (sampler::T_RANGE | sampler::T_CIRCLE_FIX))) { delete w; return fail("imgenv_sampler_create: unknown target_poses_type"); }
         if (a.target.type & sampler::T_PLUS) { delete w; return fail("imgenv_sampler_create: 'view_plus' targets are not implemented by the reference"); }
         S.agents.push_back(a);

@@ -734,7 +734,11 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             }
             __syncthreads();
             const int nl = min(sh->red[0], BL_CAP), nl2 = min(sh->red[1], BL2_CAP);
-            if (d.dbg_stats && tid == 0) { int* st = d.dbg_stats + 4 * (size_t)idx; st[0] = sh->red[2] + sh->red[3]; st[1] = sh->red[0]; st[2] = sh->red[1]; st[3] = sh->red[0] > BL_CAP || sh->red[1] > BL2_CAP; }
+            if (d.dbg_stats && tid == 0) {
+                int* st = d.dbg_stats + 4 * (size_t)idx;
+                st[0] = sh->red[2] + sh->red[3]; st[1] = sh->red[0]; st[2] = sh->red[1];
+                st[3] = sh->red[0] > BL_CAP || sh->red[1] > BL2_CAP;
+            }
             for (int q = tid; q < nl; q += VIEW_THREADS) { const unsigned cell = blist[q]; cell_rays(cell, __ldg(kpack + (cell >> 16) * vw + (cell & 0xFFFFu)), 0, 1); }
             for (int q = warp; q < nl2; q += VIEW_THREADS / 32) { const unsigned cell = blist2[q]; cell_rays(cell, __ldg(kpack + (cell >> 16) * vw + (cell & 0xFFFFu)), lane, 32); }
             __syncthreads();
