@@ -73,3 +73,25 @@ def test_spec_follows_reference_request_building():
     assert build_spec(cfg, opt_in_beep=True)["scalars"][17] == 1.0
     assert list(spec["ped_desc"][0][:7]) == [2, 0, 0.1, 0.1, 0, -0.1, 0.1]   # leg: right = (x, -y, r), reset_helper.py:399-403
     assert spec["robot_size_last"] == [0.17, 0.17]
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof / offsetof of imgenv_config and imgenv_outputs as a C compiler sees include/imgenv.h == the ctypes mirror."""
+    import ctypes as C
+    import subprocess
+    from img_env_b200.lib import ImgenvConfig, ImgenvOutputs
+    src = tmp_path / "layout.c"
+    fields_cfg = [f[0] for f in ImgenvConfig._fields_]
+    fields_out = [f[0] for f in ImgenvOutputs._fields_]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "imgenv.h"', 'int main(void) {',
+             '  printf("%zu %zu\\n", sizeof(imgenv_config), sizeof(imgenv_outputs));']
+    lines += ['  printf("%%zu\\n", offsetof(imgenv_config, %s));' % f for f in fields_cfg]
+    lines += ['  printf("%%zu\\n", offsetof(imgenv_outputs, %s));' % f for f in fields_out]
+    lines += ['  return 0; }']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(got[0]), int(got[1])] == [C.sizeof(ImgenvConfig), C.sizeof(ImgenvOutputs)]
+    want = [getattr(ImgenvConfig, f).offset for f in fields_cfg] + [getattr(ImgenvOutputs, f).offset for f in fields_out]
+    assert [int(x) for x in got[2:]] == want
