@@ -95,3 +95,22 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     assert [int(got[0]), int(got[1])] == [C.sizeof(ImgenvConfig), C.sizeof(ImgenvOutputs)]
     want = [getattr(ImgenvConfig, f).offset for f in fields_cfg] + [getattr(ImgenvOutputs, f).offset for f in fields_out]
     assert [int(x) for x in got[2:]] == want
+
+
+def test_header_is_plain_c_and_links(tmp_path, lib):
+    """include/imgenv.h compiles as strict C99 and a C program links against the shared library (no torch, no C++)."""
+    import subprocess
+    from img_env_b200.lib import LIB_PATH
+    src = tmp_path / "client.c"
+    src.write_text('#include <stdio.h>\n#include "imgenv.h"\n'
+                   'int main(void) { imgenv_t* h = 0; imgenv_config cfg = {0};\n'
+                   '  printf("%s\\n", imgenv_version());\n'
+                   '  int rc = imgenv_create(&cfg, 0, 0, 0, 0, 0, 0, 0, &h);   /* null arguments: must fail cleanly */\n'
+                   '  printf("%d %s\\n", rc, imgenv_last_error());\n'
+                   '  return rc < 0 ? 0 : 1; }\n')
+    exe = tmp_path / "client"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src),
+                    LIB_PATH, "-Wl,-rpath," + os.path.dirname(LIB_PATH)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "img_env_b200" in r.stdout and "null argument" in r.stdout
