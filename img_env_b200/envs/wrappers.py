@@ -181,7 +181,7 @@ class MultiRobotCleanWrapper(Wrapper):
         state, reward, done, info = self.env.step(action)
         if self.is_clean is None:
             self.is_clean = _zeros_like(done) == 0
-        clean = self.is_clean.clone() if _is_torch(self.is_clean) else self.is_clean.copy()
+        clean = self.is_clean          # never mutated in place: every update below rebinds self.is_clean to a new array
         info["is_clean"] = clean
         reward = _where(clean, reward, _zeros_like(reward))
         if "speeds" in info:
@@ -222,8 +222,8 @@ class StateBatchWrapper(Wrapper):
         else:
             m = reset_mask.reshape((-1,) + (1,) * (q.ndim - 1))
             q = _where(m, _cat([_zeros_like(q[:, 1:]), t1], 1), q)
-        self.q[name] = q
-        return q.clone() if _is_torch(q) else q.copy()
+        self.q[name] = q               # a fresh array every call (cat / where): the caller may keep the returned one
+        return q
 
     def batch_state(self, state, reset_mask=None):
         state.sensor_maps = self._concate("sensor_maps", state.sensor_maps, reset_mask)
