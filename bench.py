@@ -130,13 +130,18 @@ def _ref_worker(args):
     alive = np.ones(R, np.uint8)
     rb, pd = ref.get_internal()
 
+    core = [0.0]
+
     def one_step():
         # keep every robot alive (same rule as the GPU arm: clear the collision/arrival flags)
         rb_, pd_ = ref.get_internal()
         rb_[:, 12] = 0; rb_[:, 13] = 0
         ref.set_internal(rb_, None)
-        st = ref.step(random_actions(R, rng), alive)
-        post.get_states(st)
+        acts = random_actions(R, rng)
+        tc = time.time()
+        st = ref.step(acts, alive)                 # (A) the C++ node core: ImgEnv::_step incl. get_states
+        core[0] += time.time() - tc
+        post.get_states(st)                        # (B) adds the restated yaml_env.py post-processing
     for _ in range(warmup):
         one_step()
     # file barrier so all workers time the same interval
@@ -144,12 +149,13 @@ def _ref_worker(args):
     t_wait = time.time()
     while len([f for f in os.listdir(barrier_dir) if f.startswith("ready")]) < nproc and time.time() - t_wait < 600:
         time.sleep(0.01)
+    core[0] = 0.0
     t0 = time.time()
     done = 0
     while done < steps or (target_s > 0 and time.time() - t0 < target_s):     # target_s: sample sized by time, not by steps
         one_step(); done += 1
     t1 = time.time()
-    return t0, t1, R * done
+    return t0, t1, R * done, core[0]
 
 
 def run_reference(wname, steps, warmup, procs=None, budget_s=200.0, target_s=0.0, hard_timeout=None):
@@ -192,8 +198,9 @@ def run_reference(wname, steps, warmup, procs=None, budget_s=200.0, target_s=0.0
             pool.terminate()
     t0 = min(r[0] for r in res); t1 = max(r[1] for r in res)
     total = sum(r[2] for r in res)
+    core_s = sum(r[3] for r in res) / len(res)          # mean seconds a worker spent inside the node during the timed steps
     return dict(value=total / (t1 - t0), seconds=t1 - t0, procs=procs, steps=int(round(total / max(1, sum(1 for _ in res)) / w["R"])),
-                warmup=warm_eff, robot_steps=total)
+                warmup=warm_eff, robot_steps=total, core_value=total / core_s if core_s > 0 else None)
 
 
 # --------------------------------------------------------------------------------------------
@@ -379,7 +386,8 @@ def run_b200(args):
                 out["cpu_baseline"] = {"value": ref["value"], "unit": UNIT, "cores": ref["procs"], "kind": "reference",
                                        "sample": "%d scene(s) of this workload (one per process, oracle/_ref = unmodified reference node + "
                                                  "restated Python post-processing), %d timed step(s), %.1f s" %
-                                                 (ref["procs"], ref["steps"], ref["seconds"])}
+                                                 (ref["procs"], ref["steps"], ref["seconds"]),
+                                       "node_core_value": ref["core_value"]}
         except Exception as e:   # the baseline is informative; never lose the GPU line
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
     print(json.dumps(out))
@@ -405,7 +413,10 @@ def run_reference_arm(args):
            "config": {"workload": args.workload + ": " + w["desc"], "scenes": ref["procs"], "robots_per_scene": w["R"],
                       "peds_per_scene": w["P"], "note": "bounded sample: one scene per host process (the reference's own parallelism)"},
            "cpu_baseline": {"value": ref["value"], "unit": UNIT, "cores": ref["procs"], "kind": "reference",
-                            "sample": "%d scene(s), %d timed step(s), %.1f s" % (ref["procs"], ref["steps"], ref["seconds"])},
+                            "sample": "%d scene(s), %d timed step(s), %.1f s" % (ref["procs"], ref["steps"], ref["seconds"]),
+                            "node_core_value": ref["core_value"],
+                            "note": "value = end-to-end State (C++ node + restated yaml_env.py post-processing, BASELINE.md 3B); "
+                                    "node_core_value = the C++ node alone (3A)"},
            "e2e": {"value": ref["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
