@@ -24,38 +24,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "robot-steps/s (48x48 sensor+ped maps, lasers)"
 UNIT = "robot-steps/s"
 
-WORKLOADS = {
-    # SURVEY.md §8(d) synthetic inputs; shapes of BASELINE.json configs[0..4]
-    "c1": dict(desc="test.yaml shape: 1 robot, 4 reset objects, no pedestrians, 733^2 grid", R=1, P=0, scene="rvoscene", n_obj=4,
-               map_px=110, gres=0.1, lo=2.5, hi=8.5, max_ped=10, scenes=8192),
-    "c2": dict(desc="8-robot circle crossing (image_circle_fix_8 shape), 733^2 grid", R=8, P=0, scene="rvoscene", n_obj=0,
-               map_px=110, gres=0.1, lo=3.5, hi=7.5, max_ped=10, scenes=1024),
-    "c3": dict(desc="1 robot + 20 ORCA pedestrians (rvoscene), 733^2 grid", R=1, P=20, scene="rvoscene", n_obj=4, map_px=110,
-               gres=0.1, lo=2.5, hi=8.5, max_ped=20, scenes=8192),
-    "c4": dict(desc="200 robots + 200 ervoscene pedestrians + 200 objects on one 7333^2 grid (image_big shape)", R=200, P=200,
-               scene="ervoscene", n_obj=200, map_px=110, gres=1.0, lo=25.0, hi=85.0, max_ped=200, scenes=128),
-    "c5": dict(desc="64 robots + 64 pedscene (SFM) pedestrians per scene, 1066^2 grid", R=64, P=64, scene="pedscene", n_obj=0,
-               map_px=160, gres=0.1, lo=2.5, hi=13.5, max_ped=64, scenes=512),
-}
-
-
-def make_cfg(w):
-    from helpers import base_cfg, synthetic_map
-    cfg = base_cfg(R=w["R"], P=w["P"], scene=w["scene"], n_obj=w["n_obj"], max_ped=w["max_ped"],
-                   image=synthetic_map(w["map_px"], blocks=True, seed=7))
-    cfg["global_map"]["resolution"] = w["gres"]
-    return cfg
-
-
-def make_resets(spec, w, n, seed):
-    from helpers import make_reset
-    rng = np.random.default_rng(seed)
-    return [make_reset(spec, rng, n_obj=w["n_obj"], lo=w["lo"], hi=w["hi"]) for _ in range(n)]
+from img_env_b200.scenarios import WORKLOADS, make_cfg, make_resets, random_actions, workload_map  # noqa: E402
 
 
 # --------------------------------------------------------------------------------------------
@@ -119,7 +92,6 @@ def _ref_worker(args):
     cv2.setNumThreads(1)
     from img_env_b200.spec import build_spec
     from oracle.pyref import RefEnv, PyPost
-    from helpers import random_actions
     w = WORKLOADS[wname]
     spec = build_spec(make_cfg(w))
     rs = make_resets(spec, w, 1, seed)[0]
@@ -211,7 +183,6 @@ def run_b200(args):
     from img_env_b200.build import build
     from img_env_b200.spec import build_spec
     from img_env_b200.lib import BatchedSim
-    from helpers import random_actions
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -322,9 +322,13 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_apply(Dev d, const float* a
             const double* f = d.sfm_force + ((size_t)s * c.NA + a) * 12;
             SfmForces F;
             F.desired = v3(f[0], f[1], f[2]); F.social = v3(f[3], f[4], f[5]); F.obstacle = v3(f[6], f[7], f[8]); F.lookahead = v3(f[9], f[10], f[11]);
+            // scene->moveAgent(this) runs inside Tagent::move, agent by agent: a leaf that splits while agent i moves re-sorts its
+            // members by their CURRENT positions -- already moved for j < i, not yet for j > i.  k_sfm_tree therefore gets both
+            // the pre-move position (robots: the pose setRobotPos wrote after the previous step) and the post-move one.
+            double* tp = d.sfm_newpos + ((size_t)s * c.NA + a) * 4;
+            tp[2] = rec[0]; tp[3] = rec[1];
             sfm_move(d, s, rec, F, c.step_hz);
-            // scene->moveAgent(this) needs the post-move position (robots are overwritten below): k_sfm_tree
-            d.sfm_newpos[((size_t)s * c.NA + a) * 2] = rec[0]; d.sfm_newpos[((size_t)s * c.NA + a) * 2 + 1] = rec[1];
+            tp[0] = rec[0]; tp[1] = rec[1];
             if (a < c.P) {
                 int pi = s * c.P + a;
                 PDF(d, PD_LX, pi) = PDF(d, PD_X, pi); PDF(d, PD_LY, pi) = PDF(d, PD_Y, pi); PDF(d, PD_LYAW, pi) = PDF(d, PD_YAW, pi);
@@ -396,8 +400,12 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_apply(Dev d, const float* a
 // would serialise their divergent walks); the in-tree flags are written back by all lanes.
 __global__ void __launch_bounds__(32) k_sfm_tree(Dev d) {
     const int s = blockIdx.x;
-    const QTreeView t = qt_view(d, s, d.sfm_newpos + (size_t)s * d.c.NA * 2);
-    if (threadIdx.x == 0) for (int a = 0; a < d.c.NA; a++) qt_move(t, a);
+    double* np = d.sfm_newpos + (size_t)s * d.c.NA * 4;            // [NA][4] new x, y, old x, y
+    double* cur = d.sfm_treepos + (size_t)s * d.c.NA * 2;          // positions as Tagent::getPosition() would return them right now
+    for (int a = threadIdx.x; a < d.c.NA; a += 32) { cur[2 * a] = np[4 * a + 2]; cur[2 * a + 1] = np[4 * a + 3]; }
+    __syncwarp();
+    const QTreeView t = qt_view(d, s, cur);
+    if (threadIdx.x == 0) for (int a = 0; a < d.c.NA; a++) { cur[2 * a] = np[4 * a]; cur[2 * a + 1] = np[4 * a + 1]; qt_move(t, a); }
     __syncwarp();
     __threadfence_block();
     for (int a = threadIdx.x; a < d.c.NA; a += 32) d.sfm[((size_t)s * d.c.NA + a) * SFM_REC + 10] = qt_in_tree(t, a) ? 1.0 : 0.0;

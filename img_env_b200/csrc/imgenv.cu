@@ -84,6 +84,21 @@ extern "C" int imgenv_cubic_tables(int src, int dst, short* need_idx, int* ns, s
 }
 extern "C" double imgenv_yaw_from_quaternion(double x, double y, double z, double w) { return ht::yaw_from_quaternion(x, y, z, w); }
 extern "C" int imgenv_set_ped_yaw_mode(imgenv_t* h, int mode) { if (!h) return fail("null handle"); h->ped_yaw_mode = mode; return 0; }
+// SpeedLimiter(msg) never assigns min_jerk (speed_limit.cpp:56-65): the node clamps with whatever its stack held.  The library
+// defaults to min_jerk = max_jerk = msg.min_jerk; tests pin the value the reference build actually reads.  min_jerk[R][2] = lin, ang.
+extern "C" int imgenv_debug_set_min_jerk(imgenv_t* h, const double* min_jerk) {
+    if (!h || !min_jerk) return fail("imgenv_debug_set_min_jerk: null argument");
+    const int R = h->d.c.R;
+    std::vector<Limiter> lv(R), lw(R);
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(lv.data(), h->d.lim_v, sizeof(Limiter) * R, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lw.data(), h->d.lim_w, sizeof(Limiter) * R, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < R; r++) { lv[r].min_j = min_jerk[2 * r]; lw[r].min_j = min_jerk[2 * r + 1]; }
+    CK(cudaMemcpy(const_cast<Limiter*>(h->d.lim_v), lv.data(), sizeof(Limiter) * R, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(const_cast<Limiter*>(h->d.lim_w), lw.data(), sizeof(Limiter) * R, cudaMemcpyHostToDevice));
+    return 0;
+}
 
 __global__ void k_init_state(Dev d) {
     size_t wpp = (size_t)d.c.H * d.c.Wb;
@@ -312,7 +327,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     {
         const bool sf = c.scene_type == 1;
         AL(qt_nodes, sf ? S : 1) AL(qt_box, sf ? S * QT_MAX_NODES * 4 : 1) AL(qt_child0, sf ? S * QT_MAX_NODES : 1) AL(qt_count, sf ? S * QT_MAX_NODES : 1)
-        AL(qt_leaf, sf ? S * c.NA * QT_LEAVES : 1) AL(qt_hash, sf ? S * c.NA : 1) AL(sfm_newpos, sf ? S * c.NA * 2 : 1)
+        AL(qt_leaf, sf ? S * c.NA * QT_LEAVES : 1) AL(qt_hash, sf ? S * c.NA : 1) AL(sfm_newpos, sf ? S * c.NA * 4 : 1) AL(sfm_treepos, sf ? S * c.NA * 2 : 1)
     }
 #undef AL
     {   // SFM start-up state of a fresh reference process (pedscene.h:58-83): per Tagent one N(1.2,0.2) draw from a
@@ -523,6 +538,15 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     }
     using ht::f32;
     if (c.scene_type == 4 && !traj_v) return fail("imgenv_reset: dataset replay needs traj_v");
+    if (scene_ids) {   // two records for one scene would race in k_apply_reset / the object stamps
+        std::vector<char> seen(c.S, 0);
+        for (int sl = 0; sl < n; sl++) {
+            const int s = scene_ids[sl];
+            if (s < 0 || s >= c.S) return fail("imgenv_reset: scene id out of range");
+            if (seen[s]) return fail("imgenv_reset: duplicate scene id");
+            seen[s] = 1;
+        }
+    }
     size_t dper = (size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 6 * (size_t)c.max_traj * c.P + 4 * c.max_obs;
     size_t iper = (size_t)5 + c.P + 3 * (size_t)d.max_verts;
     size_t fper = (size_t)8 * d.max_verts;

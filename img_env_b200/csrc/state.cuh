@@ -146,7 +146,8 @@ struct Dev {
     int* qt_child0; int* qt_count;          // [S][QT_MAX_NODES]
     int* qt_leaf;                           // [S][NA][4]
     int* qt_hash;                           // [S][NA]
-    double* sfm_newpos;                     // [S][NA][2] post-move positions handed to the tree update
+    double* sfm_newpos;                     // [S][NA][4] post-move and pre-move positions handed to the tree update
+    double* sfm_treepos;                    // [S][NA][2] scratch of the tree update: every agent's position "right now"
     const double* sfm_vmax0;                // [NA] initial vmax (Tagent(): N(1.2,0.2), setVmax for pedestrians)
     // outputs
     float* o_vec; uint16_t* o_sensor; int8_t* o_coll; uint8_t* o_arr; float* o_laser;

@@ -17,10 +17,12 @@ def make_env(cfg, **kwargs):
         cfg = read_yaml(cfg)
     if cfg.get("env_type", "robot_nav") != "robot_nav":
         raise ValueError("only env_type 'robot_nav' (ImageEnv) is implemented; gazebo/real envs are out of scope")
-    env = ImageEnv(cfg, **kwargs)
     from .wrappers import wrapper_dict
+    unknown = [name for name in cfg.get("wrapper", []) if name not in wrapper_dict]
+    if unknown:      # the reference raises KeyError (envs/__init__.py:29); a typo must not silently change reward / done semantics
+        raise ValueError("unknown wrapper(s) %s; known: %s" % (unknown, sorted(wrapper_dict)))
+    env = ImageEnv(cfg, **kwargs)
     for name in cfg.get("wrapper", []):
-        if name in wrapper_dict:
-            env = wrapper_dict[name](env, cfg)
+        env = wrapper_dict[name](env, cfg)
     cfg["node_id"] = cfg.get("node_id", 0) + 1
     return env

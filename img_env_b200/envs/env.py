@@ -14,8 +14,13 @@ from .state import ImageState
 
 
 class ImageEnv:
-    def __init__(self, cfg: dict, num_scenes=None, device=0, numpy_state=False, map_dir=None):
+    def __init__(self, cfg: dict, num_scenes=None, device=0, numpy_state=False, map_dir=None, copy_state=None):
+        """copy_state (default True, or cfg['copy_state']): every reset()/step() returns FRESH tensors, like the reference's
+        fresh numpy arrays, so a State kept by the caller (replay buffer: obs vs next_obs) does not change under it.
+        copy_state=False returns views of the library's persistent output buffers, which the next reset()/step() overwrites
+        in place -- zero-copy for consumers that use the State before stepping again."""
         import torch
+        self.copy_state = bool(cfg.get("copy_state", True) if copy_state is None else copy_state)
         self.torch = torch
         self.cfg = cfg
         self._init_static_param(cfg)
@@ -65,11 +70,42 @@ class ImageEnv:
             return ImageState(f["vector_states"].astype(np.float64), f["sensor_maps"], f["is_collisions"].astype(np.int64),
                               f["is_arrives"].astype(bool), f["lasers"].astype(np.float64), f["ped_vector_states"], f["ped_maps"],
                               f["step_ds"].astype(np.float64), f["ped_min_dists"].astype(np.float64))
+        if self.copy_state:
+            flat = {k: v.clone() for k, v in flat.items()}
         return ImageState(**flat)
+
+    def _dataset_resets(self, ids, datas):
+        """EnvPos.init_ped_dataset (reset_helper.py:417-434) on top of a sampled episode: per pedestrian T rows of
+        (x, y, yaw, vx, vy) replace its start pose and trajectory (yaml_env.py:245-247)."""
+        if datas is None:
+            raise ValueError("ped_sim.type 'dataset' replays recorded trajectories: pass reset(cur_ped_pos_v_datas=array[P,T,5]) "
+                             "(or [n_scenes,P,T,5]) as the reference's PedTrajectoryDatasetWrapper does (yaml_env.py:245-247)")
+        from ..spec import rpy_to_q
+        d = np.asarray(datas, dtype=np.float64)
+        if d.ndim == 3:
+            d = np.broadcast_to(d, (len(ids),) + d.shape)
+        P, T = self.ped_total, d.shape[2]
+        if d.shape[0] != len(ids) or d.shape[1] != P or d.shape[3] != 5 or T > self.spec["max_traj"]:
+            raise ValueError("cur_ped_pos_v_datas must be [P=%d, T<=%d, 5] per scene, got %s" % (P, self.spec["max_traj"], d.shape))
+        out = []
+        for k, s in enumerate(ids):
+            rs = self.env_pose[s].reset()
+            rs["peds"] = np.array(rs["peds"], dtype=np.float64).reshape(P, 8)
+            traj = np.zeros((P, T, 3)); trajv = np.zeros((P, T, 3))
+            for p in range(P):
+                traj[p] = d[k, p, :, :3]
+                trajv[p, :, :2] = d[k, p, :, 3:5]
+                rs["peds"][p, :2] = d[k, p, 0, :2]
+                rs["peds"][p, 2:6] = rpy_to_q(d[k, p, 0, 2])
+            rs["traj"], rs["traj_v"], rs["traj_len"] = traj, trajv, np.full(P, T, np.int32)
+            out.append(rs)
+        return out
 
     def reset(self, scene_ids=None, **kwargs):
         ids = list(range(self.num_scenes)) if scene_ids is None else list(scene_ids)
-        if self.sampler is not None:
+        if self.spec["scene_type"] == "dataset":
+            self.sim.reset(self._dataset_resets(ids, kwargs.get("cur_ped_pos_v_datas")), scene_ids=ids)
+        elif self.sampler is not None:
             self.sim.reset_sampled(self.sampler, ids, self._ignore_obstacle)
         else:
             self.sim.reset([self.env_pose[s].reset() for s in ids], scene_ids=ids)

@@ -116,7 +116,10 @@ class StatePedVectorWrapper(ObservationWrapper):
     std = [6.0, 6.0, 0.6, 0.9, 0.50, 0.5, 6.0]
 
     def observation(self, state):
+        # out of place: in torch mode ped_vector_states may be a view of the library's output buffer, and rows of scenes that
+        # a partial reset did not touch would otherwise be normalised a second time
         p = state.ped_vector_states
+        p = p.clone() if _is_torch(p) else np.array(p, copy=True)
         n = p.shape[0]
         k = (p.shape[1] - 1) // 7
         body = p[:, 1:1 + 7 * k].reshape(n, k, 7)
@@ -130,6 +133,7 @@ class StatePedVectorWrapper(ObservationWrapper):
             idx = np.arange(k)[None, :] < p[:, :1]
             norm = ((body.astype(np.float64) - np.array(self.avg)) / np.array(self.std)).astype(p.dtype)
             p[:, 1:1 + 7 * k] = np.where(idx[..., None], norm, body).reshape(n, 7 * k)
+        state.ped_vector_states = p
         return state
 
 
@@ -145,10 +149,25 @@ class VelActionWrapper(Wrapper):
         else:
             self.clip_range = cfg["continuous_actions"]
 
+    def _action_torch(self, actions):
+        import torch
+        actions = actions.detach()
+        if self.discrete and actions.ndim == 1:
+            if getattr(self, "_table_t", None) is None or self._table_t.device != actions.device:
+                self._table_t = torch.as_tensor(self.table, device=actions.device)
+            return self._table_t[actions.long()]
+        out = torch.zeros((actions.shape[0], 3), dtype=torch.float32, device=actions.device)
+        if self.discrete:
+            out[:, : actions.shape[1]] = actions
+        else:
+            for i in range(actions.shape[1]):
+                out[:, i] = actions[:, i].clamp(self.clip_range[i][0], self.clip_range[i][1])
+        return out
+
     def action(self, actions):
-        """-> float32 array [N, 3] of (v, w, beep)"""
+        """-> float32 array [N, 3] of (v, w, beep); torch actions stay on their device (no host round trip)"""
         if _is_torch(actions):
-            actions = actions.detach().cpu().numpy()
+            return self._action_torch(actions)
         actions = np.asarray(actions)
         if self.discrete:
             if actions.ndim == 1:
@@ -163,7 +182,7 @@ class VelActionWrapper(Wrapper):
     def step(self, action):
         a = self.action(action)
         state, reward, done, info = self.env.step(a)
-        info["speeds"] = a[:, :2].astype(np.float64)
+        info["speeds"] = _f64(a[:, :2])
         return state, reward, done, info
 
     def reverse_action(self, actions):
@@ -185,8 +204,13 @@ class MultiRobotCleanWrapper(Wrapper):
         info["is_clean"] = clean
         reward = _where(clean, reward, _zeros_like(reward))
         if "speeds" in info:
-            c = clean.cpu().numpy() if _is_torch(clean) else clean
-            info["speeds"] = np.where(c[:, None], info["speeds"], 0.0)
+            sp = info["speeds"]
+            if _is_torch(sp) != _is_torch(clean):       # actions and state live in different array families
+                sp = sp.cpu().numpy() if _is_torch(sp) else sp
+                c = clean.cpu().numpy() if _is_torch(clean) else clean
+                info["speeds"] = np.where(c[:, None], sp, 0.0)
+            else:
+                info["speeds"] = _where(clean[:, None], sp, _zeros_like(sp))
         self.is_clean = _where(done > 0, _zeros_like(clean), clean)
         return state, reward, done, info
 
@@ -282,11 +306,14 @@ class NeverStopWrapper(Wrapper):
     def step(self, action):
         states, reward, done, info = self.env.step(action)
         ad = info["all_down"]
-        ad = ad.cpu().numpy() if _is_torch(ad) else np.asarray(ad)
         r = self._robots_per_scene()
-        scenes = [s for s in range(len(ad) // r) if ad[s * r]]
+        per_scene = ad.reshape(-1, r)[:, 0]
+        if _is_torch(per_scene):        # one small read per step; the scene list is only fetched when something ended
+            scenes = per_scene.nonzero().flatten().tolist() if bool(per_scene.any()) else []
+        else:
+            scenes = np.flatnonzero(np.asarray(per_scene)).tolist()
         if scenes:
-            if len(scenes) == len(ad) // r:
+            if len(scenes) == per_scene.shape[0]:
                 states = self.env.reset(**{k: v for k, v in info.items() if k == "dones_info"})
             else:
                 states = self.env.reset(scene_ids=scenes, row_mask=info["all_down"])

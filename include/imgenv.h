@@ -151,6 +151,11 @@ int imgenv_record_fetch(imgenv_t* h, int32_t scene, int32_t* n_steps, double* ro
 /* Invariant check (tests): between calls no agent is stamped in the per-scene planes. out4 = number of occupancy words,
  * flag bytes, block marks and block counts that violate it (all 0 when healthy). */
 int imgenv_debug_check_planes(imgenv_t* h, int64_t* out4, void* stream);
+/* Test hook: the node's SpeedLimiter(msg) leaves min_jerk unassigned (speed_limit.cpp:56-65) and clamps with whatever its
+ * stack held; the library defaults to min_jerk = max_jerk = msg.min_jerk.  min_jerk[R][2] (linear, angular) overrides it. */
+int imgenv_debug_set_min_jerk(imgenv_t* h, const double* min_jerk);
+/* Pedestrian yaw the node reads from an unassigned local (img_env.cpp:346-349): 0 keep, 1 zero (this build of the node), 2 heading. */
+int imgenv_set_ped_yaw_mode(imgenv_t* h, int mode);
 /* ped_min_dists persistence (NearbyPed, reset_helper.py:85-99) and dones are library state. */
 int imgenv_solver_agents(const imgenv_t* h);   /* P + R' */
 int imgenv_view_dims(const imgenv_t* h, int32_t* vh, int32_t* vw);

@@ -56,8 +56,11 @@ def _lib(prefix="ref_"):
         lib = C.CDLL(ref_lib_path() if prefix == "ref_" else port_lib_path())
         getattr(lib, prefix + "create").restype = C.c_void_p
         for name in ("destroy", "get_states", "get_internal", "set_internal", "rvo_get",
-                     "rvo_set", "rvo_get_obstacles", "sfm_get", "sfm_set_pv", "get_map"):
-            getattr(lib, prefix + name).restype = None
+                     "rvo_set", "rvo_get_obstacles", "sfm_get", "sfm_set_pv", "get_map", "get_jerk_limits"):
+            try:
+                getattr(lib, prefix + name).restype = None
+            except AttributeError:      # accessor only one of the two libraries has
+                pass
         _LIBS[prefix] = _Prefixed(lib, prefix)
     return _LIBS[prefix]
 
@@ -154,6 +157,13 @@ class RefEnv:
         rb = _dbl(rb) if rb is not None else None
         pd = _dbl(pd) if pd is not None else None
         self.lib.set_internal(self.h, _p(rb, C.c_double), _p(pd, C.c_double))
+
+    def jerk_limits(self):
+        """[R,4] = (lin min_jerk, lin max_jerk, ang min_jerk, ang max_jerk) as the node's robots hold them (min_jerk is
+        never assigned by SpeedLimiter(msg), speed_limit.cpp:56-65)."""
+        out = np.zeros((self.R, 4))
+        self.lib.get_jerk_limits(self.h, _p(out, C.c_double))
+        return out
 
     def rvo_get(self):
         n = self.lib.rvo_num_agents(self.h)

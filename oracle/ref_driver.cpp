@@ -231,6 +231,17 @@ void ref_get_internal(void* h, double* robot, double* ped) {
         o[17] = a.cur_traj_index_; o[18] = 0; o[19] = 0;
     }
 }
+// (min_jerk, max_jerk) of the linear and angular limiter as the node's robots hold them: SpeedLimiter(msg) never assigns
+// min_jerk (speed_limit.cpp:56-65), so it is whatever the stack held.  out[R][4] = lin min, lin max, ang min, ang max.
+void ref_get_jerk_limits(void* h, double* out) {
+    Ref* r = static_cast<Ref*>(h);
+    ImgEnv& e = r->svc.ImgEnv_env;
+    for (int i = 0; i < r->R; i++) {
+        Agent& a = e.robots_[i];
+        out[4 * i] = a.limiter_lin_.min_jerk; out[4 * i + 1] = a.limiter_lin_.max_jerk;
+        out[4 * i + 2] = a.limiter_ang_.min_jerk; out[4 * i + 3] = a.limiter_ang_.max_jerk;
+    }
+}
 void ref_set_internal(void* h, const double* robot, const double* ped) {
     Ref* r = static_cast<Ref*>(h);
     ImgEnv& e = r->svc.ImgEnv_env;

@@ -134,3 +134,94 @@ def test_episode_record_matches_stepwise_state():
     with pytest.raises(RuntimeError):
         sim.record_fetch(0)
     sim.close()
+
+
+def test_state_is_not_aliased_across_steps():
+    """a State kept by the caller must not change under it when the env steps again (the reference returns
+    fresh numpy arrays); copy_state=False opts into zero-copy views of the library's output buffers."""
+    import torch
+    from img_env_b200.envs import ImageEnv
+    random.seed(6)
+    env = ImageEnv(_cfg(), num_scenes=2)
+    s0 = env.reset()
+    keep = {f: getattr(s0, f).clone() for f in s0.FIELDS}
+    a = torch.tensor([[0.5, 0.3], [0.4, -0.5]], device="cuda")
+    s1, *_ = env.step(a)
+    s2, *_ = env.step(a)
+    for f in s0.FIELDS:
+        assert torch.equal(getattr(s0, f), keep[f]), "%s of the reset State changed after step()" % f
+    assert not torch.equal(s1.ped_maps, s2.ped_maps) or not torch.equal(s1.lasers, s2.lasers)
+    assert s1.ped_maps.data_ptr() != s2.ped_maps.data_ptr()
+    env.close()
+    env = ImageEnv(_cfg(), num_scenes=2, copy_state=False)
+    s0 = env.reset(); s1, *_ = env.step(a)
+    assert s0.ped_maps.data_ptr() == s1.ped_maps.data_ptr()       # documented: views of the bound output tensors
+    env.close()
+
+
+def test_ped_vector_wrapper_with_partial_auto_reset_normalises_once():
+    """StatePedVectorWrapper under NeverStopWrapper's per-scene reset: rows of scenes that were not reset hold
+    values normalised exactly once."""
+    import torch
+    from img_env_b200.envs import make_env
+    from img_env_b200.envs.wrappers import StatePedVectorWrapper
+    random.seed(7)
+    cfg = _cfg()
+    cfg["wrapper"] = ["StatePedVectorWrapper"]
+    env = make_env(cfg, num_scenes=3)
+    env.reset()
+    a = torch.tensor([[0.3, 0.1]] * 3, device="cuda")
+    s, *_ = env.step(a)
+    raw = env.env.sim.out["ped_vector_states"].reshape(3, -1).clone()          # what the library wrote (un-normalised)
+    s2 = env.reset(scene_ids=[1])                                               # partial reset re-observes scene 1 only
+    raw_after = env.env.sim.out["ped_vector_states"].reshape(3, -1)
+    assert torch.equal(raw_after[[0, 2]], raw[[0, 2]]), "library rows of untouched scenes must stay raw"
+    k = (raw.shape[1] - 1) // 7
+    avg = torch.tensor(StatePedVectorWrapper.avg, dtype=torch.float64, device="cuda"); std = torch.tensor(StatePedVectorWrapper.std, dtype=torch.float64, device="cuda")
+    want = raw_after.clone()
+    body = want[:, 1:].reshape(3, k, 7)
+    idx = torch.arange(k, device="cuda")[None, :] < want[:, :1]
+    want[:, 1:] = torch.where(idx[..., None], ((body.double() - avg) / std).float(), body).reshape(3, 7 * k)
+    assert torch.allclose(s2.ped_vector_states, want)
+    env.close()
+
+
+def test_make_env_rejects_unknown_wrapper_and_reset_rejects_duplicate_scenes():
+    from img_env_b200.envs import make_env, ImageEnv
+    cfg = _cfg(); cfg["wrapper"] = ["VelActionWrapper", "NoSuchWrapper"]
+    with pytest.raises(ValueError, match="NoSuchWrapper"):
+        make_env(cfg, num_scenes=1)
+    random.seed(8)
+    env = ImageEnv(_cfg(), num_scenes=3)
+    env.reset()
+    with pytest.raises(RuntimeError, match="duplicate scene id"):
+        env.reset(scene_ids=[1, 1])
+    env.close()
+
+
+def test_dataset_scenes_through_the_gym_api():
+    """ped_sim.type 'dataset': reset(cur_ped_pos_v_datas=...) as PedTrajectoryDatasetWrapper calls it (yaml_env.py:245-247)."""
+    import torch
+    from img_env_b200.envs import ImageEnv
+    random.seed(9)
+    cfg = _cfg()
+    cfg["ped_sim"]["type"] = "dataset"; cfg["ped_sim"]["max_traj"] = 6
+    env = ImageEnv(cfg, num_scenes=2, numpy_state=True)
+    with pytest.raises(ValueError, match="cur_ped_pos_v_datas"):
+        env.reset()
+    P, T = cfg["ped_sim"]["total"], 6
+    rng = np.random.default_rng(1)
+    datas = np.zeros((P, T, 5))
+    for p in range(P):
+        pos = rng.uniform(3, 7, 2)
+        for t in range(T):
+            v = rng.uniform(-0.5, 0.5, 2)
+            datas[p, t] = [pos[0], pos[1], np.arctan2(v[1], v[0]), v[0], v[1]]
+            pos = pos + 0.4 * v
+    env.reset(cur_ped_pos_v_datas=datas)
+    for t in range(3):
+        env.step(np.array([[0.2, 0.0], [0.3, 0.1]], np.float32))
+        rb, pd, _ = env.sim.get_internal()
+        assert np.allclose(pd[0][:, :2], datas[:, t, :2]) and np.allclose(pd[1][:, 6:8], datas[:, t, 3:5])
+    env.close()
+    del torch

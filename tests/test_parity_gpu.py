@@ -15,19 +15,21 @@ def _to_np(out, s):
 
 
 def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False, n_obj=None, lo=2.5, hi=8.5,
-                 check_view=True, tree_sync="once", ylo=None, yhi=None):
+                 check_view=True, tree_sync="once", ylo=None, yhi=None, map_dir=None, resets=None, action_fn=None):
     import torch
     from img_env_b200.lib import BatchedSim
     from oracle.pyref import RefEnv, PyPost, have_ref
     if not have_ref():
         pytest.skip("oracle/_ref/libimgenv_ref.so not built")
-    spec = build_spec(cfg, opt_in_beep=opt_in_beep)
+    spec = build_spec(cfg, map_dir=map_dir, opt_in_beep=opt_in_beep)
     R = spec["R"]
     rng = np.random.default_rng(seed)
     sim = BatchedSim(spec, num_scenes=S, ped_yaw_mode=1)
     refs = [RefEnv(spec) for _ in range(S)]
     posts = [PyPost(spec) for _ in range(S)]
-    if spec["scene_type"] == "dataset":
+    if resets is not None:
+        resets = resets(spec, rng) if callable(resets) else resets
+    elif spec["scene_type"] == "dataset":
         resets = [make_dataset_reset(spec, rng, T=spec["max_traj"], lo=lo, hi=hi) for _ in range(S)]
     else:
         resets = [make_reset(spec, rng, n_obj=n_obj, lo=lo, hi=hi, ylo=ylo, yhi=yhi) for _ in range(S)]
@@ -50,7 +52,7 @@ def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False
             sim.sfm_tree_set(*refs[s].sfm_tree(), scene=s)
     dones = np.zeros((S, R), np.int64)
     for t in range(steps):
-        acts = np.stack([random_actions(R, rng, beep=beep) for _ in range(S)])
+        acts = np.stack([(action_fn(R, rng, t) if action_fn else random_actions(R, rng, beep=beep)) for _ in range(S)])
         alive = (dones == 0).astype(np.uint8)
         if sync:   # put the product into the node's exact pre-step state
             rbs, pds, svs = [], [], []
