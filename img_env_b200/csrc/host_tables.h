@@ -75,7 +75,7 @@ struct TypeTables {
     std::vector<short> ray_end;
     std::vector<short> spans;
     std::vector<unsigned short> khi, klo;
-    std::vector<uint32_t> own_mask, tile_fov, edge_px, dtab;
+    std::vector<uint32_t> own_mask, tile_fov, edge_px, edge_tiles, dtab, ostat;
 };
 
 // desc: shape, size[4], sensor_cfg[2] (already float32-widened)
@@ -158,6 +158,11 @@ inline std::string build_type(const Cfg& c, const double* desc, double view_angl
                     }
                 if (edge || (i == T.t.org_x && j == T.t.org_y)) T.edge_px.push_back(((uint32_t)i << 16) | (uint32_t)j);   // + the laser origin (no predecessor)
             }
+        // 16x16-pixel view tiles that hold such a pixel: a footprint record whose view-space bounding box (+3 px) touches one
+        // of them contributes all of its cells to the raster, not only its candidate cells (view.cuh, phase B)
+        const int etw = (c.vw + 15) / 16, eth = (c.vh + 15) / 16;
+        T.edge_tiles.assign(((size_t)etw * eth + 31) / 32, 0u);
+        for (uint32_t ep : T.edge_px) { const int t = (int)(ep >> 16) / 16 * etw + (int)(ep & 0xFFFF) / 16; T.edge_tiles[t >> 5] |= 1u << (t & 31); }
     }
     // own footprint cells in the view raster: draw(view_map_, 100, "view_map", bbox_) agent.cpp:503
     size_t npx = (size_t)c.vh * c.vw;
@@ -212,6 +217,32 @@ inline std::string build_type(const Cfg& c, const double* desc, double view_angl
         }
     }
     return "";
+}
+
+// Static-map tables for the observation kernel: cand = occupied cells (value < 250) that have a free cell within their 5x5
+// neighbourhood or lie within 2 cells of the map border -- the only static cells a laser ray can hit first (view.cuh,
+// phase B); crow / orow = per 32x32-cell block the mask of rows that hold a cand / occupied bit.
+inline void static_planes(const std::vector<uint32_t>& occ, int H, int Wb, std::vector<uint32_t>& cand, std::vector<uint32_t>& crow,
+                          std::vector<uint32_t>& orow) {
+    const int Hc = (H + 31) / 32;
+    cand.assign((size_t)H * Wb, 0u); crow.assign((size_t)Hc * Wb, 0u); orow.assign((size_t)Hc * Wb, 0u);
+    for (int X = 0; X < H; X++)
+        for (int bj = 0; bj < Wb; bj++) {
+            const uint32_t w = occ[(size_t)X * Wb + bj];
+            if (!w) continue;
+            uint32_t interior = 0xffffffffu;
+            for (int dr = -2; dr <= 2 && interior; dr++) {
+                const int Xr = X + dr;
+                if (Xr < 0 || Xr >= H) { interior = 0; break; }
+                const uint32_t* rp = occ.data() + (size_t)Xr * Wb + bj;
+                const uint32_t wc = rp[0], wl = bj > 0 ? rp[-1] : 0u, wr = bj + 1 < Wb ? rp[1] : 0u;
+                interior &= wc & ((wc << 1) | (wl >> 31)) & ((wc << 2) | (wl >> 30)) & ((wc >> 1) | (wr << 31)) & ((wc >> 2) | (wr << 30));
+            }
+            const uint32_t cw = w & ~interior;
+            cand[(size_t)X * Wb + bj] = cw;
+            orow[(size_t)(X >> 5) * Wb + bj] |= 1u << (X & 31);
+            if (cw) crow[(size_t)(X >> 5) * Wb + bj] |= 1u << (X & 31);
+        }
 }
 
 // cv::resize INTER_CUBIC coefficient tables for a square src -> dst (OpenCV imgproc/resize.cpp)

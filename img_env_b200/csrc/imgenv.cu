@@ -11,6 +11,7 @@
 #include "../../include/imgenv.h"
 #include "state.cuh"
 #include "kin.cuh"
+#include "foot.cuh"
 #include "view.cuh"
 #include "dyn.cuh"
 #include "host_tables.h"
@@ -37,14 +38,14 @@ struct imgenv {
     int* sti_h = nullptr; int* sti_d = nullptr; size_t st_ints = 0;
     float* stf_h = nullptr; float* stf_d = nullptr; size_t st_floats = 0;
     float* act_d = nullptr; uint8_t* alive_d = nullptr;
-    size_t view_smem = 0, dyn_smem = 0, stamp_smem = 0;
+    size_t view_smem = 0, dyn_smem = 0, foot_smem = 0, obj_smem = 0;
     // Side stream, forked after the agents have moved and joined before the call returns to the caller's stream:
     // the pedestrian observation (k_ped_obs only reads poses) runs beside the stamp / view kernels.  SFM only: the
     // sequential, latency-bound quadtree update of step t follows it there and is joined before the next reader of
     // the tree (next step's forces, reset).
     cudaStream_t side = nullptr; cudaEvent_t ev_moved = nullptr, ev_ped = nullptr, ev_tree = nullptr; bool tree_pending = false;
     size_t ped_smem = 0;
-    // optional per-kernel CUDA-event timing (bench.py roofline): 5 events per profiled step
+    // optional per-kernel CUDA-event timing (bench.py roofline): 4 events per profiled step
     std::vector<cudaEvent_t> evs; int prof_max = 0, prof_n = 0;
 };
 
@@ -101,19 +102,9 @@ extern "C" int imgenv_debug_set_min_jerk(imgenv_t* h, const double* min_jerk) {
 }
 
 __global__ void k_init_state(Dev d) {
-    size_t wpp = (size_t)d.c.H * d.c.Wb;
-    size_t n = wpp * d.c.S;
     size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = t0; i < n; i += stride) { d.occ_all[i] = d.static_occ[i % wpp]; d.base_occ[i] = d.static_occ[i % wpp]; }
-    size_t pc = (((size_t)d.c.H * d.c.W + 3) & ~(size_t)3) * d.c.S;
-    for (size_t i = t0; i < pc; i += stride) { d.rmin[i] = RMIN_EMPTY; d.flags[i] = 0; }
-    size_t nb = (size_t)d.c.Hc * d.c.Wb;
-    for (size_t i = t0; i < nb * d.c.S; i += stride) {       // coarse[s][I][J] = popcount of the static bits of the block
-        size_t b = i % nb; int I = (int)(b / d.c.Wb), J = (int)(b % d.c.Wb);
-        unsigned cnt = 0;
-        for (int rr = 32 * I; rr < min(32 * I + 32, d.c.H); rr++) cnt += __popc(d.static_occ[(size_t)rr * d.c.Wb + J]);
-        d.coarse[i] = cnt;
-    }
+    size_t nh = (size_t)d.c.S * d.c.NP;
+    for (size_t i = t0; i < nh; i += stride) d.foot_hdr[i] = make_int4(0, 0, 0, 0);      // no footprint record yet
     size_t nr = (size_t)d.c.S * d.c.R;
     for (size_t i = t0; i < nr; i += stride) {
         d.rb[(size_t)RB_PREVD * nr + i] = nan("");
@@ -176,6 +167,9 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     c.laser_norm = cfg->laser_norm;
     c.max_obs = std::max(cfg->max_obstacles, 1); c.max_traj = std::max(cfg->max_traj, 1);
     c.seed = cfg->seed;
+    const double max_obj_r = cfg->max_object_radius > 0 ? cfg->max_object_radius : 0.75;
+    c.obj_rad = object_rad_cells(max_obj_r, c.res);
+    c.obj_cap = stamp_bitmap_words(c.obj_rad);
     if (c.vh != c.vw) return fail("imgenv_create: only square view maps are supported");
     if (c.vh > 1022) return fail("imgenv_create: view raster larger than 1022x1022 cells is not supported");
     if (cfg->ped_image_size != cfg->image_size) return fail("imgenv_create: ped_image_size must equal image_size");
@@ -224,7 +218,8 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         }
     }
     c.n_types = (int)types.size();
-    std::vector<double> lattice; std::vector<short> ray_end, spans; std::vector<unsigned short> khi, klo; std::vector<uint32_t> own_mask, tile_fov, edge_px, dtab, hstat;
+    std::vector<double> lattice; std::vector<short> ray_end, spans; std::vector<unsigned short> khi, klo; std::vector<uint32_t> own_mask, tile_fov, edge_px, edge_tiles, dtab, ostat;
+    std::vector<uint16_t> lut(256); ht::f16_lut(lut.data());
     std::vector<RobotType> rts;
     for (auto& T : types) {
         T.t.pts_off = (int)lattice.size() / 2; lattice.insert(lattice.end(), T.lattice.begin(), T.lattice.end());
@@ -234,6 +229,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         T.t.own_mask_off = (int)own_mask.size(); own_mask.insert(own_mask.end(), T.own_mask.begin(), T.own_mask.end());
         T.t.tile_off = (int)tile_fov.size(); tile_fov.insert(tile_fov.end(), T.tile_fov.begin(), T.tile_fov.end());
         T.t.edge_off = (int)edge_px.size(); T.t.n_edge = (int)T.edge_px.size(); edge_px.insert(edge_px.end(), T.edge_px.begin(), T.edge_px.end());
+        T.t.etile_off = (int)edge_tiles.size(); edge_tiles.insert(edge_tiles.end(), T.edge_tiles.begin(), T.edge_tiles.end());
         {   // per (needed row, output column, tap) table for the laser_map reconstruction fused into the horizontal
             // cubic pass (view.cuh phase D/F): one 16-byte load gives a thread the four source pixels of its output.
             T.dtab.assign((size_t)c.ns * c.img * 4, 0u);
@@ -252,23 +248,40 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
                         if ((T.own_mask[full >> 5] >> (full & 31)) & 1u) e |= 1u << 31;
                         T.dtab[((size_t)rr * c.img + oc) * 4 + k] = e;
                     }
-            // hit-free shortcut of the same pass: ray interval of the taps' top rays and the sum when none of them hits
-            for (int rr = 0; rr < c.ns; rr++)
+            // Per OUTPUT pixel of the resize (its <= 16 source pixels belong to it alone: the scale 8.33 exceeds the 4 taps): the
+            // interval of the source pixels' top rays and the float16 value the pixel takes when none of those rays hits
+            // anything (free / own footprint / outside every ray), evaluated with the arithmetic of view.cuh phase F.
+            const int npx = c.img * c.img;
+            T.ostat.assign((size_t)npx + (npx + 1) / 2, 0u);
+            uint16_t* oval = reinterpret_cast<uint16_t*>(T.ostat.data() + npx);
+            const float scale = 1.f / (2048.f * 2048.f);
+            for (int orow = 0; orow < c.img; orow++)
                 for (int oc = 0; oc < c.img; oc++) {
-                    uint32_t kmin = 0xFFFFu, kmax = 0; bool any = false; int sum = 0;
-                    for (int k = 0; k < 4; k++) {
-                        const int w = coef[4 * oc + k];
-                        if (w == 0) continue;
-                        const uint32_t e = T.dtab[((size_t)rr * c.img + oc) * 4 + k], kh = e & 0xFFFu;
-                        int val = 200;                                   // no ray passes: unknown
-                        if (kh != 0xFFFu) { val = 255; kmin = std::min(kmin, kh); kmax = std::max(kmax, kh); any = true; }
-                        if (e >> 31) val = 100;                          // own footprint
-                        sum += val * w;
+                    uint32_t kmin = 0xFFFFu, kmax = 0; bool any = false; float sv[4];
+                    for (int t = 0; t < 4; t++) {
+                        const int rr = tap[4 * orow + t];
+                        int sum = 0;
+                        for (int k = 0; k < 4; k++) {
+                            const int w = coef[4 * oc + k];
+                            if (w == 0) continue;
+                            const uint32_t e = T.dtab[((size_t)rr * c.img + oc) * 4 + k], kh = e & 0xFFFu;
+                            int val = 200;                                   // no ray passes: unknown
+                            if (kh != 0xFFFu) { val = 255; if (coef[4 * orow + t] != 0) { kmin = std::min(kmin, kh); kmax = std::max(kmax, kh); any = true; } }
+                            if (e >> 31) val = 100;                          // own footprint
+                            sum += val * w;
+                        }
+                        sv[t] = (float)sum;
                     }
                     if (!any) { kmin = 1; kmax = 0; }
-                    hstat.push_back(kmin | (kmax << 16)); hstat.push_back((uint32_t)sum);
+                    const float b0 = coef[4 * orow + 0] * scale, b1 = coef[4 * orow + 1] * scale, b2 = coef[4 * orow + 2] * scale, b3 = coef[4 * orow + 3] * scale;
+                    const float v = fmaf(sv[0], b0, fmaf(sv[1], b1, fmaf(sv[2], b2, sv[3] * b3)));
+                    int iv = (int)lrintf(v);
+                    iv = std::min(255, std::max(0, iv));
+                    T.ostat[(size_t)orow * c.img + oc] = kmin | (kmax << 16);
+                    oval[(size_t)orow * c.img + oc] = lut[iv];
                 }
         }
+        T.t.ostat_off = (int)ostat.size(); ostat.insert(ostat.end(), T.ostat.begin(), T.ostat.end());
         T.t.dtab_off = (int)dtab.size(); dtab.insert(dtab.end(), T.dtab.begin(), T.dtab.end());
         rts.push_back(T.t);
     }
@@ -298,11 +311,26 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         poff[2 * p + 1] = (int)lattice.size() / 2; pn[2 * p + 1] = (int)b.size() / 2; lattice.insert(lattice.end(), b.begin(), b.end());
     }
     h->ped_shape = pshape;
-    std::vector<uint16_t> lut(256); ht::f16_lut(lut.data());
     std::vector<uint8_t> g(grid, grid + (size_t)H * W);
     std::vector<uint32_t> socc((size_t)H * c.Wb, 0u);
     for (int i = 0; i < H; i++) for (int j = 0; j < W; j++) if (grid[(size_t)i * W + j] < 250) socc[(size_t)i * c.Wb + (j >> 5)] |= 1u << (j & 31);
 
+    std::vector<uint32_t> scand, scrow, sorow;
+    ht::static_planes(socc, H, c.Wb, scand, scrow, sorow);
+    // footprint records: capacity of every part's bitmap and its offset inside a scene's slice (foot.cuh)
+    c.NPA = c.R + 2 * c.P; c.NP = c.NPA + c.max_obs;
+    if (c.NP > 32767) return fail("imgenv_create: more than 32767 footprint parts per scene (R + 2 P + max_obstacles)");
+    std::vector<int> part_off(c.NP + 1, 0);
+    c.ag_cap = 1;
+    for (int q = 0; q < c.NP; q++) {
+        int cap;
+        if (q < c.R) cap = stamp_bitmap_words(rts[type_of[q]].stamp_rad);
+        else if (q < c.NPA) cap = stamp_bitmap_words((int)ppart[3 * (q - c.R) + 2]);
+        else cap = c.obj_cap;
+        if (q < c.NPA) c.ag_cap = std::max(c.ag_cap, cap);
+        part_off[q + 1] = part_off[q] + 2 * cap;
+    }
+    c.scene_words = part_off[c.NP];
     Dev& d = h->d;
 #define UP(field, vec) if (dupload(h, &d.field, vec)) return -1;
     std::vector<uint32_t> kpack(khi.size());
@@ -310,14 +338,14 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     UP(kpack, kpack) UP(grid, g) UP(static_occ, socc) UP(types, rts) UP(type_of, type_of) UP(lattice_xy, lattice) UP(ray_end, ray_end)
     UP(fov_spans, spans) UP(own_mask, own_mask) UP(need_idx, need_idx) UP(cubic_tap, tap)
     UP(cubic_coef, coef) UP(f16_lut, lut) UP(lim_v, lv) UP(lim_w, lw) UP(ped_shape, pshape) UP(ped_size, psize)
-    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(dtab, dtab) UP(hstat, hstat) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_pts_off, poff)
+    UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(edge_tiles, edge_tiles) UP(dtab, dtab) UP(ostat, ostat) UP(static_cand, scand) UP(static_crow, scrow)
+    UP(static_orow, sorow) UP(part_off, part_off) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_pts_off, poff)
     UP(ped_pts_n, pn) UP(ped_ext, pext) UP(ped_part, ppart)
 #undef UP
     size_t S = c.S;
-    size_t pc = ((size_t)H * W + 3) & ~(size_t)3;
     d.max_verts = 16 * c.max_obs + 16;
 #define AL(field, n) if (dalloc(h, &d.field, (size_t)(n))) return -1;
-    AL(occ_all, S * H * c.Wb) AL(base_occ, S * H * c.Wb) AL(flags, S * pc) AL(rmin, S * pc) AL(coarse, S * c.Hc * c.Wb)
+    AL(foot_hdr, S * c.NP) AL(foot_words, S * (size_t)c.scene_words)
     AL(rb, (size_t)RB_FIELDS * S * c.R) AL(pd, (size_t)PD_FIELDS * S * c.P)
     AL(traj, S * c.P * c.max_traj * 3) AL(traj_v, c.scene_type == 4 ? S * c.P * c.max_traj * 3 : 1) AL(traj_len, S * c.P) AL(obs, S * c.max_obs * 8) AL(n_obs, S) AL(step_no, S)
     AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_nvel, S * c.NA * 2) AL(sfm_force, c.scene_type == 1 ? S * c.NA * 12 : 1)
@@ -387,14 +415,10 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     h->ped_smem = ped_smem_bytes(c);
     if (h->ped_smem > 200 * 1024) return fail("imgenv_create: too many pedestrians for the pedestrian observation kernel's shared memory");
     CK(cudaFuncSetAttribute(k_ped_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ped_smem));
-    {   // shared-memory cell bitmap of k_stamp_agents: sized for the largest footprint box
-        int words = 1;
-        for (const auto& t : rts) words = std::max(words, stamp_bitmap_words(t.stamp_rad));
-        for (int p = 0; p < 2 * c.P; p++) words = std::max(words, stamp_bitmap_words((int)ppart[3 * p + 2]));
-        h->stamp_smem = (size_t)words * 4;
-        if (h->stamp_smem > 200 * 1024) return fail("imgenv_create: an agent footprint is too large for the stamping kernel");
-        CK(cudaFuncSetAttribute(k_stamp_agents, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stamp_smem));
-    }
+    h->foot_smem = (size_t)FOOT_WARPS * c.ag_cap * 4; h->obj_smem = (size_t)c.obj_cap * 4;
+    if (h->foot_smem > 200 * 1024 || h->obj_smem > 200 * 1024) return fail("imgenv_create: an agent / object footprint is too large for the footprint kernels");
+    CK(cudaFuncSetAttribute(k_footprints, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->foot_smem));
+    CK(cudaFuncSetAttribute(k_object_footprints, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->obj_smem));
     h->view_smem = view_smem_bytes(c);
     h->dyn_smem = dyn_smem_bytes(c);
     if (h->view_smem > 227 * 1024) return fail("imgenv_create: view kernel needs too much shared memory for this configuration");
@@ -510,12 +534,10 @@ static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int i
         CK(cudaEventRecord(h->ev_tree, h->side));
         h->tree_pending = true;
     }
-    k_stamp_agents<<<n_scenes * (c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(d, d_scene_ids, 0);
+    k_footprints<<<(n_scenes * c.NPA + FOOT_WARPS - 1) / FOOT_WARPS, FOOT_WARPS * 32, h->foot_smem, st>>>(d, d_scene_ids, n_scenes, is_reset ? 0 : 1);
     if (ev) cudaEventRecord(ev[2], st);
     k_view<false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
     if (ev) cudaEventRecord(ev[3], st);
-    k_stamp_agents<<<n_scenes * (c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(d, d_scene_ids, is_reset ? 1 : 2);    // 2: also step_++
-    if (ev) cudaEventRecord(ev[4], st);
     CK(cudaStreamWaitEvent(st, h->ev_ped, 0));      // join: every output of the call is ordered on the caller's stream
     CK(cudaGetLastError());
     return 0;
@@ -568,6 +590,8 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
             int shape = (int)q[0];
             o[0] = shape; for (int m = 0; m < 4; m++) o[1 + m] = f32(q[1 + m]);
             o[5] = q[5]; o[6] = q[6]; o[7] = ht::yaw_from_quaternion(q[7], q[8], q[9], q[10]);   // img_env.cpp:180-185
+            { double ccx, ccy, rmax; object_bounds(o, ccx, ccy, rmax);
+              if (shape < 0 || shape > 1 || object_rad_cells(rmax, c.res) > c.obj_rad) return "imgenv_reset: reset object larger than max_object_radius (imgenv_config) or of unknown shape"; }
             // get_corners (agent.cpp:626-651) -> pedscene->addObs (img_env.cpp:188-192)
             Tf2 t = tf_from_pose(o[5], o[6], o[7]);
             double pax, pay, pbx, pby;
@@ -623,15 +647,15 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     for (int sl = 0; sl < n; sl++) ids_h[sl] = h->sti_h[iper * sl];
     int* ids_d = h->sti_d + iper * n;
     CK(cudaMemcpyAsync(ids_d, ids_h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    k_stamp_objects<<<n * c.max_obs, 128, 0, st>>>(d, ids_d, 1);     // remove the previous episode's objects
     k_apply_reset<<<n, 128, 0, st>>>(d, n, h->st_d, h->sti_d, h->stf_d, dper, iper, fper);
-    k_stamp_objects<<<n * c.max_obs, 128, 0, st>>>(d, ids_d, 0);     // obs.draw(obs_map_, 0, ...) img_env.cpp:187
+    k_object_footprints<<<n * c.max_obs, OBJ_THREADS, h->obj_smem, st>>>(d, ids_d);     // obs.draw(obs_map_, 0, ...) img_env.cpp:187
     if (launch_observe(h, ids_d, n, 1, st)) return -1;                 // view_agent(); get_states() img_env.cpp:285-286
     CK(cudaEventRecord(h->stage[h->stage_i].ev, st));                   // stream-ordered like imgenv_step: no host sync
     return 0;
 }
 
-extern "C" int imgenv_launches_per_step(const imgenv_t* h) { return !h ? 5 : (h->d.c.scene_type == 1 ? 7 : (h->d.c.NA > 0 ? 6 : 5)); }
+// k_dyn_solve (if a solver runs), k_dyn_apply, k_footprints, k_view, k_ped_obs (+ k_sfm_tree)
+extern "C" int imgenv_launches_per_step(const imgenv_t* h) { return !h ? 4 : (h->d.c.scene_type == 1 ? 6 : (h->d.c.NA > 0 ? 5 : 4)); }
 
 extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d_alive, void* stream) {
     if (!h) return fail("imgenv_step: null handle");
@@ -640,7 +664,7 @@ extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d
     Dev& d = h->d; const Cfg& c = d.c;
     cudaStream_t st = (cudaStream_t)stream;
     cudaEvent_t* ev = nullptr;
-    if (h->prof_n < h->prof_max) { ev = h->evs.data() + 5 * (size_t)h->prof_n; h->prof_n++; }
+    if (h->prof_n < h->prof_max) { ev = h->evs.data() + 4 * (size_t)h->prof_n; h->prof_n++; }
     if (ev) cudaEventRecord(ev[0], st);
     {
         const int nblk = dyn_nblk(c);
@@ -658,20 +682,20 @@ extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d
 extern "C" int imgenv_profile_begin(imgenv_t* h, int max_steps) {
     if (!h) return fail("null handle");
     for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
-    h->evs.assign(5 * (size_t)max_steps, nullptr);
+    h->evs.assign(4 * (size_t)max_steps, nullptr);
     for (auto& e : h->evs) CK(cudaEventCreate(&e));
     h->prof_max = max_steps; h->prof_n = 0;
     return 0;
 }
-// ms[4] = mean duration of k_dynamics, k_stamp_agents(stamp), k_view, k_stamp_agents(unstamp); returns #steps
+// ms[3] = mean duration of the dynamics kernels, k_footprints, k_view (k_ped_obs runs beside them on the side stream); returns #steps
 extern "C" int imgenv_profile_end(imgenv_t* h, float* ms) {
     if (!h) return fail("null handle");
     CK(cudaDeviceSynchronize());
-    for (int k = 0; k < 4; k++) ms[k] = 0.f;
+    for (int k = 0; k < 3; k++) ms[k] = 0.f;
     for (int i = 0; i < h->prof_n; i++)
-        for (int k = 0; k < 4; k++) { float t = 0; CK(cudaEventElapsedTime(&t, h->evs[5 * i + k], h->evs[5 * i + k + 1])); ms[k] += t; }
+        for (int k = 0; k < 3; k++) { float t = 0; CK(cudaEventElapsedTime(&t, h->evs[4 * i + k], h->evs[4 * i + k + 1])); ms[k] += t; }
     int n = h->prof_n;
-    for (int k = 0; k < 4 && n; k++) ms[k] /= n;
+    for (int k = 0; k < 3 && n; k++) ms[k] /= n;
     for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
     h->evs.clear(); h->prof_max = 0; h->prof_n = 0;
     return n;
@@ -895,9 +919,8 @@ extern "C" int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* 
     if (host_out) CK(cudaMalloc((void**)&buf, n));
     if (stats_out) { CK(cudaMalloc((void**)&sbuf, (size_t)c.S * c.R * 16)); CK(cudaMemsetAsync(sbuf, 0, (size_t)c.S * c.R * 16, st)); }
     d.dbg_view = buf; d.dbg_stats = sbuf;
-    k_stamp_agents<<<c.S * (c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(d, nullptr, 0);
+    k_footprints<<<(c.S * c.NPA + FOOT_WARPS - 1) / FOOT_WARPS, FOOT_WARPS * 32, h->foot_smem, st>>>(d, nullptr, c.S, 0);
     k_view<true><<<c.S * c.R, VIEW_THREADS, h->view_smem, st>>>(d, nullptr, 0);
-    k_stamp_agents<<<c.S * (c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(d, nullptr, 1);
     cudaError_t e = cudaSuccess;
     if (host_out) e = cudaMemcpyAsync(host_out, buf, n, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && stats_out) e = cudaMemcpyAsync(stats_out, sbuf, (size_t)c.S * c.R * 16, cudaMemcpyDeviceToHost, st);
@@ -943,83 +966,92 @@ extern "C" int imgenv_sfm_tree_set(imgenv_t* h, int32_t scene, int32_t n_nodes, 
 
 // The byte map robot `self` would see as its global_map_ (static + reset objects + pedestrians + other robots;
 // self < 0: peds_map_, i.e. no robots; self == -2: obs_map_, i.e. no pedestrians either) for one scene,
-// u8 [H][W] to host. Test / debugging aid: the node never materialises this on the GPU path.
-__global__ void k_debug_global_map(Dev d, int s, int self, uint8_t* out) {
-    const size_t n = (size_t)d.c.H * d.c.W;
-    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
-        const int cx = (int)(q / d.c.W), cy = (int)(q % d.c.W);
-        int v;
-        if (self >= 0) v = global_value(d, s, self, cx, cy);
-        else {
-            const size_t po = (size_t)s * plane_cells(d.c);
-            int sv = d.grid[q];
-            const unsigned f = d.flags[po + q];
-            if ((f & F_OBJ) && sv > 2) sv = 0;
-            if (self == -2) v = sv;
-            else if (f & F_RIGHT) v = 1;
-            else if (f & F_LEFT) v = (sv == 0) ? 0 : 1;
-            else if (f & F_CIRC) v = (sv <= 2) ? sv : 1;
-            else v = sv;
-        }
-        out[q] = (uint8_t)v;
+// u8 [H][W] to host. Test / debugging aid: the product path never materialises a map; here the footprint
+// records of the scene are painted into a scratch "who covers this cell" plane and composed with the static grid.
+__global__ void k_debug_paint(Dev d, int s, int self, uint8_t* cover) {
+    const int q = blockIdx.x;
+    const int4 h = d.foot_hdr[(size_t)s * d.c.NP + q];
+    const int nrow = foot_nrow(h), wpr = foot_wpr(h), kind = foot_kind(h);
+    if (!nrow) return;
+    if (kind == FK_ROBOT && (self < 0 || q == self)) return;
+    if (self == -2 && kind != FK_OBJ) return;
+    const uint32_t* occ = d.foot_words + (size_t)s * d.c.scene_words + d.part_off[q];
+    for (int k = threadIdx.x; k < nrow * wpr * 32; k += blockDim.x) {
+        const int w = k >> 5, b = k & 31;
+        if (!((occ[w] >> b) & 1u)) continue;
+        const int cx = h.x + w / wpr, cy = (foot_wj0(h) + w % wpr) * 32 + b;
+        const size_t ci = (size_t)cx * d.c.W + cy;
+        atomicOr(reinterpret_cast<unsigned*>(cover + (ci & ~(size_t)3)), foot_flag(kind) << (8 * (ci & 3)));
     }
+}
+__global__ void k_debug_compose(Dev d, const uint8_t* cover, uint8_t* out) {
+    const size_t n = (size_t)d.c.H * d.c.W;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x)
+        out[q] = (uint8_t)composed_value(d.grid[q], cover[q]);
 }
 extern "C" int imgenv_debug_global_map(imgenv_t* h, int32_t scene, int32_t self, uint8_t* host_out, void* stream) {
     if (!h || !host_out) return fail("imgenv_debug_global_map: null argument");
     Dev d = h->d; const Cfg& c = d.c;
     if (scene < 0 || scene >= c.S || self >= c.R) return fail("imgenv_debug_global_map: bad scene / robot");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)c.H * c.W;
-    uint8_t* buf = nullptr;
+    const size_t n = ((size_t)c.H * c.W + 3) & ~(size_t)3;
+    uint8_t* buf = nullptr; uint8_t* cover = nullptr;
     CK(cudaMalloc((void**)&buf, n));
-    // stamp EVERY agent of the scene (no culling is involved in a whole-map dump: stamp with an infinite reach)
+    CK(cudaMalloc((void**)&cover, n));
+    CK(cudaMemsetAsync(cover, 0, n, st));
+    // the record of EVERY agent of the scene (no culling in a whole-map dump: infinite reach)
     Dev dd = d; dd.c.cull_reach = 1e30;
     int* ids = nullptr;
     CK(cudaMalloc((void**)&ids, 4));
     CK(cudaMemcpyAsync(ids, &scene, 4, cudaMemcpyHostToDevice, st));
-    k_stamp_agents<<<(c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(dd, ids, 0);
-    k_debug_global_map<<<592, 256, 0, st>>>(dd, scene, self, buf);
-    k_stamp_agents<<<(c.R + c.P), STAMP_THREADS, h->stamp_smem, st>>>(dd, ids, 1);
-    cudaError_t e = cudaMemcpyAsync(host_out, buf, n, cudaMemcpyDeviceToHost, st);
+    k_footprints<<<(c.NPA + FOOT_WARPS - 1) / FOOT_WARPS, FOOT_WARPS * 32, h->foot_smem, st>>>(dd, ids, 1, 0);
+    k_debug_paint<<<c.NP, 128, 0, st>>>(dd, scene, self, cover);
+    k_debug_compose<<<592, 256, 0, st>>>(dd, cover, buf);
+    cudaError_t e = cudaMemcpyAsync(host_out, buf, (size_t)c.H * c.W, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(buf); cudaFree(ids);
+    cudaFree(buf); cudaFree(cover); cudaFree(ids);
     if (e != cudaSuccess) return fail(std::string("imgenv_debug_global_map: ") + cudaGetErrorString(e));
     return 0;
 }
 
-// Invariant check for the tests (SURVEY §8c "size-independent properties"): between calls no agent is stamped, so in
-// every scene occ_all == base_occ, no dynamic flag bit is set, no block carries the "stamped this step" mark and the
-// block counts equal the popcount of base_occ.  out[4] = number of violating occ words, flag bytes, block marks, block counts.
-__global__ void k_debug_check_planes(Dev d, unsigned long long* out) {
-    const size_t wpp = (size_t)d.c.H * d.c.Wb, pcs = plane_cells(d.c), nb = (size_t)d.c.Hc * d.c.Wb;
-    const size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    unsigned long long a = 0, b = 0, c2 = 0, e = 0;
-    for (size_t i = t0; i < wpp * d.c.S; i += stride) a += d.occ_all[i] != d.base_occ[i];
-    for (size_t i = t0; i < pcs * d.c.S; i += stride) b += (d.flags[i] & ~F_OBJ) != 0;
-    for (size_t i = t0; i < nb * d.c.S; i += stride) {
-        c2 += (d.coarse[i] >> 31) != 0;
-        const size_t s = i / nb, blk = i % nb; const int I = (int)(blk / d.c.Wb), J = (int)(blk % d.c.Wb);
-        unsigned cnt = 0;
-        for (int rr = 32 * I; rr < min(32 * I + 32, d.c.H); rr++) cnt += __popc(d.base_occ[s * wpp + (size_t)rr * d.c.Wb + J]);
-        e += (d.coarse[i] & 0x7FFFFFFFu) != cnt;
+// Footprint-record invariants for the tests: every record's candidate cells are a subset of its occupied cells, lie inside
+// the map and inside the record's box.  out[4] = non-empty records, occupied cells, candidate cells, violations.
+__global__ void k_debug_check_footprints(Dev d, unsigned long long* out) {
+    const size_t q = blockIdx.x;                                 // s * NP + part
+    const int part = (int)(q % d.c.NP);
+    const int4 h = d.foot_hdr[q];
+    const int nrow = foot_nrow(h), wpr = foot_wpr(h);
+    if (!nrow) return;
+    const int po = d.part_off[part], cap = (d.part_off[part + 1] - po) >> 1;
+    const uint32_t* occ = d.foot_words + (q / d.c.NP) * (size_t)d.c.scene_words + po;
+    unsigned long long no = 0, nc = 0, bad = 0;
+    for (int k = threadIdx.x; k < nrow * wpr; k += blockDim.x) {
+        const unsigned o = occ[k], cd = occ[cap + k];
+        no += __popc(o); nc += __popc(cd); bad += (cd & ~o) != 0;
+        const int cx = h.x + k / wpr, wj = foot_wj0(h) + k % wpr;
+        for (unsigned m = o; m; m &= m - 1) {
+            const int cy = wj * 32 + __ffs(m) - 1;
+            bad += (unsigned)cx >= (unsigned)d.c.H || (unsigned)cy >= (unsigned)d.c.W || cy < h.y || cy >= h.y + h.z;
+        }
     }
-    if (a) atomicAdd(out + 0, a);
-    if (b) atomicAdd(out + 1, b);
-    if (c2) atomicAdd(out + 2, c2);
-    if (e) atomicAdd(out + 3, e);
+    if (nrow * wpr > cap) bad++;
+    if (threadIdx.x == 0) atomicAdd(out + 0, 1ull);
+    if (no) atomicAdd(out + 1, no);
+    if (nc) atomicAdd(out + 2, nc);
+    if (bad) atomicAdd(out + 3, bad);
 }
-extern "C" int imgenv_debug_check_planes(imgenv_t* h, int64_t* out4, void* stream) {
-    if (!h || !out4) return fail("imgenv_debug_check_planes: null argument");
+extern "C" int imgenv_debug_check_footprints(imgenv_t* h, int64_t* out4, void* stream) {
+    if (!h || !out4) return fail("imgenv_debug_check_footprints: null argument");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* buf = nullptr;
     CK(cudaMalloc((void**)&buf, 32));
     CK(cudaMemsetAsync(buf, 0, 32, st));
-    k_debug_check_planes<<<1184, 256, 0, st>>>(h->d, buf);
+    k_debug_check_footprints<<<h->d.c.S * h->d.c.NP, 64, 0, st>>>(h->d, buf);
     unsigned long long r[4];
     cudaError_t e = cudaMemcpyAsync(r, buf, 32, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(buf);
-    if (e != cudaSuccess) return fail(std::string("imgenv_debug_check_planes: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(std::string("imgenv_debug_check_footprints: ") + cudaGetErrorString(e));
     for (int k = 0; k < 4; k++) out4[k] = (int64_t)r[k];
     return 0;
 }

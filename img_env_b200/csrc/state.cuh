@@ -1,24 +1,25 @@
 // Device-resident state of one handle (S scenes on one GPU) and the static per-config tables.
 // Layout notes (DESIGN.md "Data layout in HBM"):
-//   * one static occupancy grid (u8, H x W) + its 1-bit "value < 250" plane shared by all scenes
-//     (L2-resident: 0.5-54 MB), instead of the reference's R full-map clones per step
-//     (img_env.cpp:623);
-//   * per scene: a 1-bit plane occ_all = static | reset objects | pedestrians | robots, a u8 flag
-//     plane and a u16 "lowest robot id" plane; footprints are stamped/unstamped each step
-//     (O(footprint) work, never O(map));
+//   * one static occupancy grid (u8, H x W), its 1-bit "value < 250" plane and the 1-bit plane of its ray-hit
+//     candidates (occupied cells with a free cell in their 5x5 neighbourhood), shared by all scenes (L2-resident),
+//     instead of the reference's R full-map clones per step (img_env.cpp:623);
+//   * per scene NO map-sized state: every robot, pedestrian part and reset object keeps a FOOTPRINT RECORD -- the
+//     set of grid cells it covers as a small bitmap (box header + occupancy words + candidate words, foot.cuh).
+//     Robots' and pedestrians' records are rebuilt every step (O(footprint)), objects' at reset; the observation
+//     kernel composes the records near a robot on the fly;
 //   * robots / pedestrians as SoA of doubles ([S][R], [S][P]).
 #pragma once
 #include <stdint.h>
 #include "tfmath.cuh"
 
-// flag plane bits
+// who covers a cell (bit set), as the compositing rules of view_ped / view_robot / Agent::draw need it
 #define F_OBJ 1u      // reset object wrote 0 here   (img_env.cpp:187)
 #define F_RIGHT 2u    // right leg (overwrites 0)    (agent.cpp:757-772)
 #define F_LEFT 4u     // left leg                    (agent.cpp:742-756)
 #define F_CIRC 8u     // circle pedestrian           (img_env.cpp:599-601)
-#define F_ROBOT 16u   // some robot footprint
-#define F_MULTI 32u   // footprints of >= 2 different robots
-#define RMIN_EMPTY 0xFFFFu
+#define F_ROBOT 16u   // footprint of a robot other than the observer
+// footprint record kinds (foot.cuh)
+enum { FK_ROBOT = 0, FK_CIRC = 1, FK_LEFT = 2, FK_RIGHT = 3, FK_OBJ = 4 };
 
 #define MAX_SPANS 2
 #define RB_FIELDS 18   // doubles per robot
@@ -43,15 +44,17 @@ struct RobotType {
     int org_x, org_y;     // laser origin cell (agent.cpp:366-369)
     int ray_off;          // offset into ray_end (short2 units), range_total entries
     int span_off;         // offset into fov_spans (vh * MAX_SPANS * 2 shorts)
-    int zone_r0, zone_r1, zone_c0, zone_c1;  // view-raster box where the robot's own footprint may be the only stamp
+    int zone_r0, zone_r1, zone_c0, zone_c1;  // view-raster box that contains the robot's own footprint cells (own_mask)
     int khi_off;          // offset into kpack (vh*vw entries per type)
     int own_mask_off;     // offset into own_mask (vh*vw bits, u32 words)
     int tile_off;         // offset into tile_fov (u32 words): bit per 32x32 view tile that contains FOV pixels
     int edge_off, n_edge; // FOV pixels with an 8-neighbour outside the FOV (u32 row<<16|col), always evaluated forward
+    int etile_off;        // offset into edge_tiles (u32 words): bit per 16x16 view tile that holds (or touches) an edge pixel
     int fov_r0, fov_r1, fov_c0, fov_c1;   // bounding box (inclusive) of the FOV pixels in the view raster
     int dtab_off;         // offset into dtab (ns*img*4 u32)
+    int ostat_off;        // offset into ostat (img*img uint2)
     double stamp_cx, stamp_cy; int stamp_rad;   // footprint lattice: centre (base frame, m) and radius (cells, incl. margin) of its bounding circle
-    int zone_rad;         // world cells around the robot's position inside which a set occ_all bit may be its own stamp
+    int zone_rad;         // bound (world cells) on the distance from the robot's position to any cell of its footprint
     double size_last;     // python: robots[i].size[-1]
     double sensor_x, sensor_y;
 };
@@ -76,6 +79,11 @@ struct Cfg {
     int max_obs, max_traj;
     unsigned long long seed;
     int n_types;
+    // footprint records (foot.cuh): parts per scene = R robots, 2 per pedestrian (body or left leg, right leg), max_obs objects
+    int NPA, NP;                  // agent parts (R + 2P), all parts (NPA + max_obs)
+    int ag_cap, obj_cap;          // bitmap capacity (u32 words) of the largest agent part / of an object
+    int obj_rad;                  // largest object bounding radius in cells (incl. margin)
+    int scene_words;              // u32 words of record bitmaps per scene
 };
 
 struct Dev {
@@ -83,6 +91,9 @@ struct Dev {
     // static, shared
     const uint8_t* grid;          // [H][W]
     const uint32_t* static_occ;   // [H][Wb]  bit = grid < 250
+    const uint32_t* static_cand;  // [H][Wb]  static_occ cells that are within 2 cells of a free cell or of the map border
+    const uint32_t* static_crow;  // [Hc][Wb] per 32x32-cell block: bit r = row r of the block has a static_cand bit
+    const uint32_t* static_orow;  // [Hc][Wb] the same for static_occ
     const RobotType* types;       // [n_types]
     const int* type_of;           // [R]
     const double* lattice_xy;     // packed (x,y) pairs
@@ -92,8 +103,10 @@ struct Dev {
     const uint32_t* own_mask;     // per type: bit per view pixel = own footprint cell
     const uint32_t* tile_fov;     // per type: bit per 32x32 view tile (row-major, vwb per row) with any FOV pixel
     const uint32_t* edge_px;      // per type: FOV-edge pixels
+    const uint32_t* edge_tiles;   // per type: bit per 16x16 view tile near an edge pixel
     const uint32_t* dtab;         // per type [ns][img][4]: for tap k of output column oc on needed row rr: top ray (12b) | its step index there (10b) << 12 | own footprint << 31
-    const uint32_t* hstat;        // per type [ns][img][2]: (lowest | highest << 16) top ray over the output's taps, hit-free horizontal sum
+    const uint32_t* ostat;        // per type [img][img][2]: (lowest | highest << 16) top ray over the 16 source pixels of an output pixel,
+                                  //                         its float16 value when none of those rays hits anything
     const short* need_idx;        // [ns] source row/col index of the k-th needed row/col
     const short* cubic_tap;       // [img][4] index into need_idx space (0..ns-1) of the 4 taps
     const short* cubic_coef;      // [img][4] fixed-point weights (x2048)
@@ -108,13 +121,10 @@ struct Dev {
     const int* ped_pts_n;         // [P][2]
     const double* ped_part;       // [P][2][3] per stamped part (body / left leg, right leg): bounding circle centre x, y (m) and radius (cells)
     const double* ped_ext;        // [P] bound on the distance from the pedestrian position to any cell it stamps
-    // per scene planes
-    uint32_t* occ_all;            // [S][H][Wb] static | reset objects | this step's agent stamps
-    uint32_t* base_occ;           // [S][H][Wb] static | reset objects: what occ_all returns to when the agents are unstamped
-    uint8_t* flags;               // [S][H][W]
-    unsigned short* rmin;         // [S][H][W] id of the robot stamped on the cell; only meaningful while F_ROBOT is set without F_MULTI
-    uint32_t* coarse;             // [S][Hc][Wb] per 32x32-cell block: bits 0..30 = number of set base_occ bits, bit 31 = an agent is stamped
-                                  //              somewhere in the block this step (0 = block is free)
+    // per scene footprint records (foot.cuh)
+    int4* foot_hdr;               // [S][NP] first row (world cell x), first 32-cell word column, rows | words per row << 16, kind | id << 4
+    uint32_t* foot_words;         // [S][scene_words] per part: cap occupancy words, then cap candidate words
+    const int* part_off;          // [NP + 1] word offset of a part's bitmaps inside its scene's slice (cap = (off[q+1] - off[q]) / 2)
     // dynamic state
     double* rb;                   // [RB_FIELDS][S*R]
     double* pd;                   // [PD_FIELDS][S*P]

@@ -1,5 +1,5 @@
-// Observation stage: footprint stamping, collision codes, egocentric view raster, laser rays,
-// laser_map reconstruction, 400->48 cubic resize, pedestrian observation packing.
+// Observation stage: collision codes, egocentric view raster, laser rays, laser_map reconstruction, 400->48 cubic
+// resize, pedestrian observation packing.
 // Reference: ImgEnv::view_ped/view_robot (img_env.cpp:594-674), Agent::draw (agent.cpp:285-327),
 // PedAgent::draw_leg (agent.cpp:737-774), Agent::view (agent.cpp:356-509), Agent::bresenhamLine
 // (agent.cpp:511-624), ImgEnv::get_states (img_env.cpp:547-587) and the Python post-processing
@@ -8,246 +8,12 @@
 #pragma once
 #include "state.cuh"
 #include "kin.cuh"
+#include "foot.cuh"
 
 #define VIEW_THREADS 256
 #define FX_ONE 4294967296.0            // 2^32: fixed-point scale of cell coordinates
 #define FX_GUARD 8192u                 // |frac - 0.5| below 2^-19 cells -> exact fp64 fallback
 
-// ---------------------------------------------------------------------------------------------
-// per-scene planes
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ size_t plane_cells(const Cfg& c) { return ((size_t)c.H * c.W + 3) & ~(size_t)3; }
-
-__device__ __forceinline__ void flag_or(uint8_t* flags, size_t ci, unsigned bits) {
-    unsigned* w = reinterpret_cast<unsigned*>(flags + (ci & ~(size_t)3));
-    atomicOr(w, bits << (8 * (ci & 3)));
-}
-__device__ __forceinline__ void flag_clear(uint8_t* flags, size_t ci, unsigned bits) {
-    unsigned* w = reinterpret_cast<unsigned*>(flags + (ci & ~(size_t)3));
-    atomicAnd(w, ~(bits << (8 * (ci & 3))));
-}
-// The value Agent::draw / Agent::view would read from robot `self`'s global_map_ at a cell:
-// obs_map_ (static + reset objects) -> peds_map_ (pedestrians, value 1) -> other robots (value 2);
-// a writer never overwrites 0/1/2 except the right-leg quirk (agent.cpp:767-770).
-__device__ __forceinline__ int global_value(const Dev& d, int s, int self, int cx, int cy) {
-    size_t ci = (size_t)cx * d.c.W + cy;
-    size_t po = (size_t)s * plane_cells(d.c);
-    int sv = d.grid[ci];
-    unsigned f = d.flags[po + ci];
-    if ((f & F_OBJ) && sv > 2) sv = 0;
-    int v;
-    if (f & F_RIGHT) v = 1;
-    else if (f & F_LEFT) v = (sv == 0) ? 0 : 1;
-    else if (f & F_CIRC) v = (sv <= 2) ? sv : 1;
-    else v = sv;
-    if (v > 2 && (f & F_ROBOT)) {
-        if ((f & F_MULTI) || d.rmin[po + ci] != (unsigned short)self) v = 2;
-    }
-    return v;
-}
-
-// Reset objects (mode 4 stamp, 12 unstamp) are written point by point: they only change at reset. They live in
-// base_occ as well as occ_all, and the block counts in coarse's low bits count them (no agent is stamped then).
-__device__ __forceinline__ void stamp_object_cell(const Dev& d, int s, int cx, int cy, int mode) {
-    if ((unsigned)cx >= (unsigned)d.c.H || (unsigned)cy >= (unsigned)d.c.W) return;
-    const size_t ci = (size_t)cx * d.c.W + cy;
-    const size_t po = (size_t)s * plane_cells(d.c);
-    const size_t wi = (size_t)s * d.c.H * d.c.Wb + (size_t)cx * d.c.Wb + (cy >> 5);
-    uint32_t* cz = d.coarse + (size_t)s * d.c.Hc * d.c.Wb + (size_t)(cx >> 5) * d.c.Wb + (cy >> 5);
-    const uint32_t bit = 1u << (cy & 31);
-    if (mode == 4) {
-        flag_or(d.flags + po, ci, F_OBJ);
-        atomicOr(d.occ_all + wi, bit);
-        if (!(atomicOr(d.base_occ + wi, bit) & bit)) atomicAdd(cz, 1u);     // first setter of the bit maintains the block count
-    } else {
-        flag_clear(d.flags + po, ci, F_OBJ);
-        if (d.static_occ[(size_t)cx * d.c.Wb + (cy >> 5)] & bit) return;
-        atomicAnd(d.occ_all + wi, ~bit);
-        if (atomicAnd(d.base_occ + wi, ~bit) & bit) atomicSub(cz, 1u);
-    }
-}
-
-// Agent footprints.  The 0.01 m lattice puts 2-3 points into every 0.015 m cell, so a footprint is first reduced to
-// its set of cells in a shared-memory bitmap (rows x 32-cell words aligned with occ_all's words).  The planes are
-// then updated per group of 8 cells with fire-and-forget reductions only -- nothing waits for an L2 round trip
-// except the robots' flag words, whose previous value tells whether another robot already stamped the cell:
-//   stamp:   flags |= bits, rmin = id (plain store: with two robots on a cell F_MULTI makes rmin irrelevant),
-//            occ_all |= mask, coarse |= 1<<31
-//   unstamp: flags &= ~bits, occ_all = base_occ (every unstamping agent writes the same final word),
-//            coarse &= ~(1<<31)
-// mode: 0 robot(id), 1 ped body (circle), 2 left leg, 3 right leg; 8+ = unstamp of (mode-8)
-#define STAMP_THREADS 64
-struct StampBox { int cx0, wj0, nrow, wpr; };
-inline __host__ __device__ int stamp_rad_cells(double ext, double res) { return (int)ceil(ext / res) + 1; }
-inline __host__ __device__ int stamp_bitmap_words(int rad_cells) { return (2 * rad_cells + 1) * ((2 * rad_cells) / 32 + 2); }
-__device__ __forceinline__ StampBox stamp_box(const Dev& d, double x, double y, int rad_cells) {
-    const int ccx = world2cell(x, d.c.res), ccy = world2cell(y, d.c.res);
-    StampBox b;
-    b.cx0 = ccx - rad_cells; b.nrow = 2 * rad_cells + 1;
-    b.wj0 = (ccy - rad_cells) >> 5; b.wpr = ((ccy + rad_cells) >> 5) - b.wj0 + 1;
-    return b;
-}
-__device__ __forceinline__ void stamp_cells8(const Dev& d, int s, int cx, int cy0, unsigned m8, int mode, int id) {
-    // cells (cx, cy0 .. cy0+7) selected by m8; cy0 is a multiple of 8: one occ_all word, one coarse block, <= 3 flag words
-    if ((unsigned)cx >= (unsigned)d.c.H || cy0 < 0) return;
-    if (cy0 + 8 > d.c.W) m8 &= cy0 >= d.c.W ? 0u : (0xFFu >> (cy0 + 8 - d.c.W));
-    if (!m8) return;
-    const size_t po = (size_t)s * plane_cells(d.c);
-    const size_t ci0 = (size_t)cx * d.c.W + cy0;
-    const size_t wi = (size_t)s * d.c.H * d.c.Wb + (size_t)cx * d.c.Wb + (cy0 >> 5);
-    uint32_t* cz = d.coarse + (size_t)s * d.c.Hc * d.c.Wb + (size_t)(cx >> 5) * d.c.Wb + (cy0 >> 5);
-    const int m = mode & 7;
-    const unsigned fb = m == 0 ? F_ROBOT : m == 1 ? F_CIRC : m == 2 ? F_LEFT : F_RIGHT;
-    // spread the 8 cell bits over the (at most 3) aligned 32-bit words of the flags plane they fall into
-    const int a0 = (int)(ci0 & 3);
-    const unsigned long long sel = (unsigned long long)m8 << a0;              // bit k = byte k of the 12-byte window at ci0 - a0
-    unsigned wmask[3];
-#pragma unroll
-    for (int w = 0; w < 3; w++) {
-        const unsigned n4 = (unsigned)(sel >> (4 * w)) & 0xFu;
-        wmask[w] = ((n4 & 1u) | ((n4 & 2u) << 7) | ((n4 & 4u) << 14) | ((n4 & 8u) << 21)) * fb;
-    }
-    unsigned* fw = reinterpret_cast<unsigned*>(d.flags + po + (ci0 - a0));
-    if (mode < 8) {
-        if (m == 0) {
-            unsigned old[3];
-#pragma unroll
-            for (int w = 0; w < 3; w++) old[w] = wmask[w] ? atomicOr(fw + w, wmask[w]) : 0u;
-#pragma unroll
-            for (int b = 0; b < 8; b++) if ((m8 >> b) & 1u) d.rmin[po + ci0 + b] = (unsigned short)id;
-#pragma unroll
-            for (int w = 0; w < 3; w++) {
-                const unsigned again = old[w] & wmask[w];                        // another robot set F_ROBOT here before us
-                if (again) atomicOr(fw + w, again * (F_MULTI / F_ROBOT));
-            }
-        } else {
-#pragma unroll
-            for (int w = 0; w < 3; w++) if (wmask[w]) atomicOr(fw + w, wmask[w]);
-        }
-        atomicOr(d.occ_all + wi, m8 << (cy0 & 31));
-        atomicOr(cz, 0x80000000u);
-    } else {
-        const unsigned clr = m == 0 ? (F_MULTI / F_ROBOT + 1u) : 1u;            // robots also drop F_MULTI
-#pragma unroll
-        for (int w = 0; w < 3; w++) if (wmask[w]) atomicAnd(fw + w, ~(wmask[w] * clr));
-        d.occ_all[wi] = d.base_occ[wi];
-        atomicAnd(cz, 0x7FFFFFFFu);
-    }
-}
-__device__ __forceinline__ void stamp_part(const Dev& d, int s, const Tf2& t, const double* pts, int n, int mode, int id,
-                                           double offx, double offy, double ccx, double ccy, int rad_cells, uint32_t* bm) {
-    double bwx, bwy;
-    tf_apply(t, ccx + offx, ccy + offy, bwx, bwy);      // world position of the part's bounding-circle centre
-    const StampBox bx = stamp_box(d, bwx, bwy, rad_cells);
-    const int nw = bx.nrow * bx.wpr;
-    for (int k = threadIdx.x; k < nw; k += STAMP_THREADS) bm[k] = 0u;
-    __syncthreads();
-    const bool leg = (mode & 7) == 2 || (mode & 7) == 3;
-    for (int k = threadIdx.x; k < n; k += STAMP_THREADS) {
-        double px = pts[2 * k], py = pts[2 * k + 1];
-        if (leg) { px = px + offx; py = py + offy; }   // leg2base: identity rotation + leg origin (agent.cpp:815-837)
-        double wx, wy;
-        tf_apply(t, px, py, wx, wy);
-        const int cx = world2cell_fast(wx, d.c.res, d.c.inv_res), cy = world2cell_fast(wy, d.c.res, d.c.inv_res);
-        const int r = cx - bx.cx0, w = (cy >> 5) - bx.wj0;
-        if ((unsigned)r < (unsigned)bx.nrow && (unsigned)w < (unsigned)bx.wpr) atomicOr(&bm[r * bx.wpr + w], 1u << (cy & 31));
-        else stamp_cells8(d, s, cx, cy & ~7, 1u << (cy & 7), mode, id);   // cannot happen (the box bounds the footprint); still a valid write
-    }
-    __syncthreads();
-    const unsigned inv_wpr = (65536u + bx.wpr - 1) / bx.wpr;     // word / wpr == (word * inv_wpr) >> 16 for word < 8192, wpr <= 12 (checked exhaustively)
-    for (int it = threadIdx.x; it < 4 * nw; it += STAMP_THREADS) {
-        const int word = it >> 2, byte = it & 3;
-        const unsigned m8 = (bm[word] >> (8 * byte)) & 0xFFu;
-        if (!m8) continue;
-        const int r = bx.wpr <= 12 && nw < 8192 ? (int)(((unsigned)word * inv_wpr) >> 16) : word / bx.wpr, w = word - r * bx.wpr;
-        stamp_cells8(d, s, bx.cx0 + r, (bx.wj0 + w) * 32 + 8 * byte, m8, mode, id);
-    }
-    __syncthreads();
-}
-
-// grid = n_scenes * (R + P) CTAs; `unstamp` selects the inverse operation.
-__global__ void __launch_bounds__(STAMP_THREADS) k_stamp_agents(Dev d, const int* scene_ids, int unstamp) {
-    extern __shared__ uint32_t bm[];     // stamp_bitmap_words(largest agent) words
-    const int per = d.c.R + d.c.P;
-    const int sl = blockIdx.x / per, a = blockIdx.x % per;
-    const int s = scene_ids ? scene_ids[sl] : sl;
-    const int add = unstamp ? 8 : 0;
-    if (unstamp == 2 && a == 0 && threadIdx.x == 0) d.step_no[s] += 1;   // step_++ (img_env.cpp:518), after every reader of this step
-    const bool is_robot = a < d.c.R;
-    const int p = a - d.c.R;
-    // An agent's stamp can only be read by a robot whose collision lattice or view raster reaches it: skip agents
-    // farther than (view half-diagonal + own extent) from every (other) robot. The decision only depends on poses,
-    // so stamp and unstamp agree.
-    double x, y, yaw, ext;
-    if (is_robot) { const int idx = s * d.c.R + a; x = RBF(d, RB_X, idx); y = RBF(d, RB_Y, idx); yaw = RBF(d, RB_YAW, idx); ext = d.types[d.type_of[a]].zone_rad * d.c.res; }
-    else { const int idx = s * d.c.P + p; x = PDF(d, PD_X, idx); y = PDF(d, PD_Y, idx); yaw = PDF(d, PD_YAW, idx); ext = d.ped_ext[p]; }
-    const double reach = d.c.cull_reach + ext;
-    int rel = 0;
-    for (int j = threadIdx.x; j < d.c.R; j += STAMP_THREADS) {
-        if (is_robot && j == a) continue;
-        const int idx = s * d.c.R + j;
-        const double dx = RBF(d, RB_X, idx) - x, dy = RBF(d, RB_Y, idx) - y;
-        rel |= dx * dx + dy * dy <= reach * reach;
-    }
-    if (!__syncthreads_or(rel)) return;
-    const Tf2 t = tf_from_pose(x, y, yaw);
-    if (is_robot) {
-        const RobotType& ty = d.types[d.type_of[a]];
-        stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)ty.pts_off, ty.n_pts, 0 + add, a, 0, 0, ty.stamp_cx, ty.stamp_cy, ty.stamp_rad, bm);
-    } else {
-        const int idx = s * d.c.P + p;
-        const int shape = d.ped_shape[p];
-        const double* pc = d.ped_part + 6 * (size_t)p;
-        if (shape == 0) {
-            stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p], d.ped_pts_n[2 * p], 1 + add, p, 0, 0, pc[0], pc[1], (int)pc[2], bm);
-        } else if (shape == 2) {
-            stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p], d.ped_pts_n[2 * p], 2 + add, p,
-                       PDF(d, PD_LLX, idx), PDF(d, PD_LLY, idx), pc[0], pc[1], (int)pc[2], bm);
-            stamp_part(d, s, t, d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p + 1], d.ped_pts_n[2 * p + 1], 3 + add, p,
-                       PDF(d, PD_RLX, idx), PDF(d, PD_RLY, idx), pc[3], pc[4], (int)pc[5], bm);
-        }   // rectangle pedestrians are never drawn (img_env.cpp:599-616 has no branch for them)
-    }
-}
-
-// reset objects: grid = n_scenes * max_obs CTAs. Object lattices are generated on the fly
-// (agent.cpp:18-62) because their sizes change at every reset.
-__global__ void k_stamp_objects(Dev d, const int* scene_ids, int unstamp) {
-    int sl = blockIdx.x / d.c.max_obs, o = blockIdx.x % d.c.max_obs;
-    int s = scene_ids ? scene_ids[sl] : sl;
-    if (o >= d.n_obs[s]) return;
-    const double* ob = d.obs + ((size_t)s * d.c.max_obs + o) * 8;
-    int shape = (int)ob[0];
-    Tf2 t = tf_from_pose(ob[5], ob[6], ob[7]);
-    const double resolution = 0.01;
-    int mode = unstamp ? 12 : 4;
-    if (shape == 0) {
-        int bb = (int)ceil(ob[3] / resolution);
-        int side = 2 * bb + 1;
-        for (int k = threadIdx.x; k < side * side; k += blockDim.x) {
-            int m = k / side - bb, n = k % side - bb;
-            if (sqrt(m * resolution * m * resolution + n * resolution * n * resolution) <= ob[3]) {
-                double px = m * resolution + ob[1], py = n * resolution + ob[2];
-                double wx, wy;
-                tf_apply(t, px, py, wx, wy);
-                stamp_object_cell(d, s, world2cell(wx, d.c.res), world2cell(wy, d.c.res), mode);
-            }
-        }
-    } else if (shape == 1) {
-        int x_min = (int)floor(ob[1] / resolution), x_max = (int)ceil(ob[2] / resolution);
-        int y_min = (int)floor(ob[3] / resolution), y_max = (int)ceil(ob[4] / resolution);
-        int ny = y_max - y_min + 1, nx = x_max - x_min + 1;
-        for (int k = threadIdx.x; k < nx * ny; k += blockDim.x) {
-            int m = x_min + k / ny, n = y_min + k % ny;
-            double wx, wy;
-            tf_apply(t, m * resolution, n * resolution, wx, wy);
-            stamp_object_cell(d, s, world2cell(wx, d.c.res), world2cell(wy, d.c.res), mode);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// the per-robot observation kernel
-// ---------------------------------------------------------------------------------------------
 struct ViewShared {
     Tf2 base_world, view_world, world_base;
     long long ax, bx, cx, ay, by, cy;   // fixed-point (2^-32 cell) affine view pixel -> world cell
@@ -258,7 +24,8 @@ struct ViewShared {
     double inv[4], org[2];
     int blk[4];              // first block row / col, number of block rows / cols covering the FOV's world bounding box
     int wbb[4];              // world bounding box of the FOV in cells (x0, x1, y0, y1), clamped to the map
-    int zc[2];               // robot position in world cells
+    int n_near, n_cnear, n_dirty, n_hits;
+    int4 own_hdr;            // the observer's own footprint record header
 };
 
 // python float floor division (Objects/floatobject.c float_floor_div) used by yaml_env.py:414-415
@@ -333,35 +100,43 @@ __device__ __noinline__ void cell_rays_inline(unsigned* hitkey, const short* ren
     }
 }
 
-// Shared-memory plan of k_view (bytes for the canonical 400x400 view / 1000 rays / 48x48 outputs; 48 KB -> 4 CTAs per SM):
+// Shared-memory plan of k_view (bytes for the canonical 400x400 view / 1000 rays / 48x48 outputs; ~50 KB -> 4 CTAs per SM):
 //   region A  occupancy raster 400*13*4 = 20.8 KB (x2 with lasers off: + the "known" plane)            phases B-D
 //   region B  ray-hit candidate lists (BL_CAP + BL2_CAP)*4 = 13.3 KB                                     phases B-C
-//             later: horizontal resize buffer ns*HB_COLS*4 = 9.2 KB + hit prefix counts 2 KB            phases D-F
+//             later: list of output pixels that need the full evaluation img*img*2 = 4.6 KB + hit prefix counts 2 KB   phases D-F
 //   hitkey    range_total*4 (first hit per ray), ray end cells range_total*4, needed-line indices, FOV spans vh*8,
-//             list of occupied world blocks under the FOV INV_MAX_BLOCKS*4
-//   (no 400x400 pixel buffer: the laser_map values are evaluated inside the horizontal resize pass)
+//             list of world blocks under the FOV that hold static candidates INV_MAX_BLOCKS*4,
+//             footprint records near the robot: NP*2 (part ids) + (NP+1)*4 (running word counts) + colliding parts
+//   (no 400x400 pixel buffer: the laser_map values are evaluated per output pixel of the resize)
 #define BL_CAP 3072          // candidate cells kept in shared memory; further cells are resolved inline by their finder
 #define BL2_CAP 256          // cells touched by many rays (close to the origin): processed warp-cooperatively
 #define BL_HEAVY 24
 #define NOHIT 0xFFFFFFFFu
+#define CN_CAP 32            // footprint records that overlap the observer's own footprint box (collision candidates)
+#define NEAR_ALL 0x8000u     // near-list flag: read the part's occupancy words (it may touch the FOV edge), not its candidates
+#define ET_SHIFT 4           // edge tiles are 16x16 view pixels
 
-#define HB_COLS 16           // output columns per vertical-pass block (bounds the horizontal buffer)
 #define INV_EPS 0.004f       // band around a cell edge inside which the inverse rasterisation runs the exact forward map
 #define INV_MAX_BLOCKS 512   // 32x32-cell world blocks under the FOV; more -> forward (tile) rasterisation
-struct ViewLayout { size_t sh, regA, regB, hpre, hitkey, rays, need, spans, blocks, total; };
+struct ViewLayout { size_t sh, regA, regB, hpre, hitkey, rays, need, spans, blocks, near, npre, chdr, coff, total; };
 __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     ViewLayout L;
     size_t off = 0;
     L.sh = off; off += (sizeof(ViewShared) + 15) & ~(size_t)15;
     size_t occ = (size_t)c.vh * c.vwb * 4 * (c.use_laser ? 1 : 2);
     L.regA = off; off += (occ + 15) & ~(size_t)15;
-    size_t bl = (size_t)(BL_CAP + BL2_CAP) * 4, hb = (((size_t)c.ns * HB_COLS * 4 + 15) & ~(size_t)15) + ((size_t)c.range_total + 1) * 2;
-    L.regB = off; L.hpre = off + (((size_t)c.ns * HB_COLS * 4 + 15) & ~(size_t)15); off += ((bl > hb ? bl : hb) + 15) & ~(size_t)15;
+    const size_t dl = ((size_t)c.img * c.img * 2 + 15) & ~(size_t)15;
+    size_t bl = (size_t)(BL_CAP + BL2_CAP) * 4, hb = dl + ((size_t)c.range_total + 1) * 2;
+    L.regB = off; L.hpre = off + dl; off += ((bl > hb ? bl : hb) + 15) & ~(size_t)15;
     L.hitkey = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
     L.rays = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
     L.need = off; off += ((size_t)c.ns * 2 + 15) & ~(size_t)15;
     L.spans = off; off += ((size_t)c.vh * 8 + 15) & ~(size_t)15;
     L.blocks = off; off += (size_t)INV_MAX_BLOCKS * 4;
+    L.near = off; off += ((size_t)c.NP * 2 + 15) & ~(size_t)15;
+    L.npre = off; off += ((size_t)(c.NP + 1) * 4 + 15) & ~(size_t)15;
+    L.chdr = off; off += (size_t)CN_CAP * 16;
+    L.coff = off; off += (size_t)CN_CAP * 4;
     L.total = off + 16;
     return L;
 }
@@ -386,13 +161,20 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
     uint32_t* known = occ + (size_t)vh * vwb;                               // only when !use_laser
     uint32_t* blist = reinterpret_cast<uint32_t*>(smem_raw + L.regB);
     uint32_t* blist2 = blist + BL_CAP;
-    int* hbuf = reinterpret_cast<int*>(smem_raw + L.regB);
+    unsigned short* dirty = reinterpret_cast<unsigned short*>(smem_raw + L.regB);   // after phase C
     unsigned short* hpre = reinterpret_cast<unsigned short*>(smem_raw + L.hpre);   // after phase C: hpre[k] = #rays < k with a hit
     short* spans = reinterpret_cast<short*>(smem_raw + L.spans);
     uint32_t* blocks = reinterpret_cast<uint32_t*>(smem_raw + L.blocks);
     unsigned* hitkey = reinterpret_cast<unsigned*>(smem_raw + L.hitkey);
     short* rend = reinterpret_cast<short*>(smem_raw + L.rays);
     short* need = reinterpret_cast<short*>(smem_raw + L.need);
+    unsigned short* near = reinterpret_cast<unsigned short*>(smem_raw + L.near);
+    unsigned* npre = reinterpret_cast<unsigned*>(smem_raw + L.npre);
+    int4* chdr = reinterpret_cast<int4*>(smem_raw + L.chdr);
+    int* coff = reinterpret_cast<int*>(smem_raw + L.coff);
+
+    const int4* fhdr = d.foot_hdr + (size_t)s * c.NP;
+    const uint32_t* fwords = d.foot_words + (size_t)s * c.scene_words;
 
     if (tid == 0) {
         double x = RBF(d, RB_X, idx), y = RBF(d, RB_Y, idx), yaw = RBF(d, RB_YAW, idx);
@@ -406,8 +188,15 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         sh->cy = llrint((A.oy / c.res) * FX_ONE) + (1ll << 31);
         // Agent::view early-out (agent.cpp:358-360): stale view_map_/hits_/is_collision_ are re-sent
         sh->frozen = (RBF(d, RB_COLL, idx) != 0.0) || (RBF(d, RB_ARR, idx) != 0.0);
-        sh->coll_key = 0;      // reused as boundary-list counters below
+        sh->coll_key = 0;
         sh->red[0] = 0; sh->red[1] = 0; sh->red[2] = 0; sh->red[3] = 0; sh->red[4] = 0;
+        sh->n_near = 0; sh->n_cnear = 0; sh->n_dirty = 0; sh->n_hits = 0;
+        {   // the box of the robot's own footprint (the same box k_footprints gives its record; the record itself may be
+            // culled when no other robot is near, so it is not read here)
+            double bwx, bwy;
+            tf_apply(sh->base_world, ty.stamp_cx, ty.stamp_cy, bwx, bwy);
+            sh->own_hdr = foot_pack(foot_box(bwx, bwy, ty.stamp_rad, c.res), FK_ROBOT, r);
+        }
         {   // inverse map and the FOV's world bounding box (for the world->view rasterisation)
             const double det = A.m00 * A.m11 - A.m01 * A.m10;
             sh->inv[0] = A.m11 / det; sh->inv[1] = -A.m01 / det; sh->inv[2] = -A.m10 / det; sh->inv[3] = A.m00 / det;
@@ -424,7 +213,6 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             const bool empty = xmin > xmax || ymin > ymax || ty.fov_r1 < ty.fov_r0;
             sh->blk[0] = xmin >> 5; sh->blk[1] = ymin >> 5;
             sh->blk[2] = empty ? 0 : (xmax >> 5) - (xmin >> 5) + 1; sh->blk[3] = empty ? 0 : (ymax >> 5) - (ymin >> 5) + 1;
-            sh->zc[0] = world2cell(x, c.res); sh->zc[1] = world2cell(y, c.res);
         }
     }
     {   // static tables into shared memory
@@ -440,36 +228,123 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
     const bool frozen = DEBUG_FULL ? false : sh->frozen != 0;
 
     if (!frozen) {
+        const unsigned H = c.H, W = c.W, Wb = c.Wb;
+        const int ox = ty.org_x, oy = ty.org_y;
+        const uint32_t* kpack = d.kpack + (size_t)ty.khi_off;
+        const bool use_inverse = c.use_laser && sh->blk[2] * sh->blk[3] <= INV_MAX_BLOCKS;
+        const int X0 = sh->wbb[0], X1 = sh->wbb[1], Y0 = sh->wbb[2], Y1 = sh->wbb[3];
+        const float i00 = (float)sh->inv[0], i01 = (float)sh->inv[1], i10 = (float)sh->inv[2], i11 = (float)sh->inv[3];
+        const int orgi0 = (int)floor(sh->org[0]), orgi1 = (int)floor(sh->org[1]);
+        const float orgf0 = (float)(sh->org[0] - orgi0), orgf1 = (float)(sh->org[1] - orgi1);
+
+        // ---- Gather: footprint records of the scene whose box meets (a) the world bounding box of the field of view
+        //      -> `near` (raster / ray candidates), (b) the robot's own footprint box -> `chdr` (collision candidates).
+        //      A part that comes close to the FOV edge (or to the laser origin) contributes ALL of its cells, the others
+        //      only their candidate cells (see phase B).
+        {
+            const int4 own = sh->own_hdr;
+            const uint32_t* etiles = d.edge_tiles + ty.etile_off;
+            const int etw = (vw + (1 << ET_SHIFT) - 1) >> ET_SHIFT, eth = (vh + (1 << ET_SHIFT) - 1) >> ET_SHIFT;
+            for (int q = tid; q < c.NP; q += VIEW_THREADS) {
+                if (q == r) continue;                                   // the robot never sees itself (img_env.cpp:624-628)
+                const int4 h = __ldg(fhdr + q);
+                const int nrow = foot_nrow(h);
+                if (nrow == 0) continue;
+                const int bx0 = h.x, bx1 = h.x + nrow - 1, by0 = h.y, by1 = h.y + nrow - 1;
+                if (!DEBUG_FULL && bx0 <= own.x + own.z - 1 && bx1 >= own.x && by0 <= own.y + own.z - 1 && by1 >= own.y) {
+                    const int p = atomicAdd(&sh->n_cnear, 1);
+                    if (p < CN_CAP) { chdr[p] = h; coff[p] = d.part_off[q]; }
+                }
+                if (bx0 > X1 || bx1 < X0 || by0 > Y1 || by1 < Y0) continue;
+                unsigned all = (!use_inverse) ? NEAR_ALL : 0u;
+                if (!all) {   // view-space bounding box of the part's box (+3 px): does it touch a tile that holds FOV-edge pixels?
+                    float imin = 1e9f, imax = -1e9f, jmin = 1e9f, jmax = -1e9f;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float u = (float)(((k & 1) ? bx1 : bx0) - orgi0) - orgf0, v = (float)(((k & 2) ? by1 : by0) - orgi1) - orgf1;
+                        const float qi = i00 * u + i01 * v, qj = i10 * u + i11 * v;
+                        imin = fminf(imin, qi); imax = fmaxf(imax, qi); jmin = fminf(jmin, qj); jmax = fmaxf(jmax, qj);
+                    }
+                    const int ti0 = max((int)floorf(imin - 3.f) >> ET_SHIFT, 0), ti1 = min((int)floorf(imax + 3.f) >> ET_SHIFT, eth - 1);
+                    const int tj0 = max((int)floorf(jmin - 3.f) >> ET_SHIFT, 0), tj1 = min((int)floorf(jmax + 3.f) >> ET_SHIFT, etw - 1);
+                    if ((ti1 - ti0 + 1) * (tj1 - tj0 + 1) > 64) all = NEAR_ALL;        // huge part: do not bother
+                    else
+                        for (int ti = ti0; ti <= ti1 && !all; ti++)
+                            for (int tj = tj0; tj <= tj1; tj++) {
+                                const int t = ti * etw + tj;
+                                if ((__ldg(etiles + (t >> 5)) >> (t & 31)) & 1u) { all = NEAR_ALL; break; }
+                            }
+                }
+                near[atomicAdd(&sh->n_near, 1)] = (unsigned short)(q | all);
+            }
+        }
+        __syncthreads();
+        const int n_near = sh->n_near;
+        const int n_cnear = sh->n_cnear;
+        // running word counts of the near parts (work items of phase B), by warp 0
+        if (warp == 0) {
+            unsigned run = 0;
+            for (int k0 = 0; k0 < n_near; k0 += 32) {
+                const int k = k0 + lane;
+                unsigned cnt = 0;
+                if (k < n_near) { const int4 h = __ldg(fhdr + (near[k] & 0x7FFF)); cnt = (unsigned)(foot_nrow(h) * foot_wpr(h)); }
+                unsigned incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                if (k < n_near) npre[k] = run + incl - cnt;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) npre[n_near] = run;
+        }
+
         // ---- Phase A: collision code = code of the LAST colliding lattice point (agent.cpp:294-326)
         int best = 0;
         if (!DEBUG_FULL) {
             const double* pts = d.lattice_xy + 2 * (size_t)ty.pts_off;
+            const uint8_t* grid = d.grid;
             for (int k = tid; k < ty.n_pts; k += VIEW_THREADS) {
                 double wx, wy;
                 const double2 pt = __ldg(reinterpret_cast<const double2*>(pts) + k);
                 tf_apply(sh->base_world, pt.x, pt.y, wx, wy);
-                int cx = world2cell_fast(wx, c.res, c.inv_res), cy = world2cell_fast(wy, c.res, c.inv_res);
-                if ((unsigned)cx < (unsigned)c.H && (unsigned)cy < (unsigned)c.W) {
-                    int v = global_value(d, s, r, cx, cy);
+                const int cx = world2cell_fast(wx, c.res, c.inv_res), cy = world2cell_fast(wy, c.res, c.inv_res);
+                if ((unsigned)cx < H && (unsigned)cy < W) {
+                    unsigned f = 0;
+                    if (n_cnear <= CN_CAP) {
+                        for (int e = 0; e < n_cnear; e++) { const int4 h = chdr[e]; if (foot_covers(h, fwords + coff[e], cx, cy)) f |= foot_flag(foot_kind(h)); }
+                    } else {     // (more colliding parts than the list holds: scan every record of the scene)
+                        for (int q = 0; q < c.NP; q++) {
+                            if (q == r) continue;
+                            const int4 h = __ldg(fhdr + q);
+                            if (foot_nrow(h) && foot_covers(h, fwords + d.part_off[q], cx, cy)) f |= foot_flag(foot_kind(h));
+                        }
+                    }
+                    const int v = composed_value(__ldg(grid + (size_t)cx * W + cy), f);
                     if (v <= 2) best = max(best, ((k + 1) << 2) | (v + 1));
                 }
             }
             for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
         }
         // ---- Phase B: egocentric occupancy raster (agent.cpp:373-404), 1 bit per view cell:
-        // zero <=> in FOV && in map && global value < 250.  FOV = static column spans per row; the pixel ->
-        // world cell map is affine and evaluated in 2^-32-cell fixed point with an exact fp64 fallback inside
-        // a guard band around the rounding boundary.
-        // The raster is produced in 32x32-pixel tiles: a tile whose world footprint (bounding box of its four
-        // corner cells + 1 cell margin) only touches 32x32-cell blocks with a zero occupancy count
-        // (Dev::coarse, maintained by the stamp kernels) is all-free and is skipped.
-        const uint32_t* occ_all = d.occ_all + (size_t)s * c.H * c.Wb;
-        const uint32_t* coarse = d.coarse + (size_t)s * c.Hc * c.Wb;
-        const unsigned H = c.H, W = c.W, Wb = c.Wb;
-        const int ox = ty.org_x, oy = ty.org_y;
-        const uint32_t* kpack = d.kpack + (size_t)ty.khi_off;
+        // set <=> in FOV && in map && the robot's global_map_ value < 250.  FOV = static column spans per row; the pixel ->
+        // world cell map is affine and evaluated in 2^-32-cell fixed point with an exact fp64 fallback inside a guard
+        // band around the rounding boundary.
+        //
+        // (1) World -> view ("inverse") rasterisation, used when lasers are on: only raster cells that can be the first hit
+        //     of a ray matter, and every such cell has a free 8-neighbour in the view (its predecessor on the ray), hence
+        //     its world cell has a free cell within its 5x5 neighbourhood (a view step moves at most 2 world cells) or
+        //     lies within 2 cells of the map border -- it is a CANDIDATE cell of the static map (static_cand, computed
+        //     once at create) or of a footprint record (cand words) -- or the view cell sits on the FOV edge / is the laser
+        //     origin (no in-FOV predecessor).  So: walk the static candidate words under the FOV (32x32 blocks with a
+        //     non-zero row mask) and the words of the near footprint records, map every candidate cell back to its <= 4
+        //     candidate view pixels and keep those whose EXACT forward map returns that cell.  FOV-edge pixels (static
+        //     list) are evaluated forward against the static map, and parts close to FOV-edge pixels contribute all of
+        //     their cells instead of their candidates.  Every bit set is a truly occupied view cell and the first hit of
+        //     every ray is among them.
+        // (2) Otherwise (lasers off: the "known" plane needs every FOV pixel; or a huge FOV): forward rasterisation of the
+        //     static map in 32x32-pixel tiles (skipping tiles whose world footprint only touches empty blocks), then the
+        //     near footprint records (all of their cells) through the same inverse mapping.
+        const uint32_t* static_occ = d.static_occ;
         int* n_list = &sh->red[0]; int* n_list2 = &sh->red[1];
-        // a newly set raster cell goes straight to the ray-hit candidate lists (phase C)
         // every ray of [k0, k0+kstep, ...] within the cell's static ray interval that really passes through it
         // keeps the minimum step: hitkey[k] = min(step << 22 | cell)
         auto cell_rays = [&](unsigned cell, unsigned kp, int k0, int kstep) {      // cell = row << 16 | col
@@ -480,6 +355,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 if (i >= 0) atomicMin(&hitkey[k], hit_key(i, pr, pc));
             }
         };
+        // a newly set raster cell goes straight to the ray-hit candidate lists (phase C)
         auto push_cell = [&](int pr, int pc) {
             const unsigned kp = __ldg(kpack + pr * vw + pc);
             const int kh = kp & 0xFFFF;
@@ -490,28 +366,79 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             else cell_rays_inline(hitkey, rend, ox, oy, pr, pc, (int)(kp >> 16), kh);   // list full: resolve this cell right here
         };
         const int n_trow = (vh + 31) >> 5, n_tiles = n_trow * vwb;
-        // (1) World -> view ("inverse") rasterisation, used when lasers are on: only raster cells that can be the
-        //     first hit of a ray matter, and every such cell has a free 8-neighbour in the view, hence its world
-        //     cell has a free cell within its 5x5 neighbourhood (a view step moves at most 2 world cells), is
-        //     within 2 cells of the map border, lies next to the robot's own stamp, or the view cell sits on the
-        //     FOV edge.  So: walk the occupied world words under the FOV (32x32 blocks with a non-zero count),
-        //     drop 5x5-interior cells with word-parallel bit operations, map each remaining cell back to its
-        //     <= 4 candidate view pixels and keep those whose EXACT forward map returns that cell; FOV-edge
-        //     pixels (static list) are evaluated forward.  Every bit set is a truly occupied view cell and the
-        //     first hit of every ray is among them.
-        // (2) Otherwise (lasers off, or a huge FOV): forward rasterisation in 32x32-pixel tiles, skipping tiles
-        //     whose world footprint only touches blocks with a zero count.
-        const bool use_inverse = c.use_laser && sh->blk[2] * sh->blk[3] <= INV_MAX_BLOCKS;
         for (int q = tid; q < vh * vwb; q += VIEW_THREADS) { occ[q] = 0u; if (!c.use_laser) known[q] = 0u; }
         if (use_inverse) {
+            const uint32_t* crow = d.static_crow;
             const int nbj = sh->blk[3], nb = sh->blk[2] * nbj;
             for (int t = tid; t < nb; t += VIEW_THREADS) {
                 const int bi = sh->blk[0] + t / nbj, bj = sh->blk[1] + t % nbj;
-                if (__ldg(coarse + (unsigned)bi * Wb + bj)) blocks[atomicAdd(&sh->red[3], 1)] = ((unsigned)bi << 16) | (unsigned)bj;
+                if (__ldg(crow + (unsigned)bi * Wb + bj)) blocks[atomicAdd(&sh->red[3], 1)] = ((unsigned)bi << 16) | (unsigned)bj;
             }
-            if (!DEBUG_FULL && lane == 0) atomicMax(&sh->coll_key, best);
-            __syncthreads();
-            // FOV-edge pixels: forward
+        } else {
+            // forward rasterisation of the static map
+            const uint32_t* orow = d.static_orow;
+            int* n_active = &sh->red[2];
+            unsigned short* tile_list = reinterpret_cast<unsigned short*>(blist);     // region B is free until the candidate lists fill
+            for (int t = tid; t < n_tiles; t += VIEW_THREADS) {
+                if (!((d.tile_fov[ty.tile_off + (t >> 5)] >> (t & 31)) & 1u)) continue;
+                bool active = !c.use_laser;          // the "known" plane needs every FOV pixel
+                if (!active) {
+                    const int ti = t / vwb, tj = t - ti * vwb;
+                    const int i0 = ti * 32, i1 = min(i0 + 31, vh - 1), j0 = tj * 32, j1 = min(j0 + 31, vw - 1);
+                    int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int ii = (k & 1) ? i1 : i0, jj = (k & 2) ? j1 : j0;
+                        const int cx = (int)((sh->cx + (long long)ii * sh->ax + (long long)jj * sh->bx) >> 32);
+                        const int cy = (int)((sh->cy + (long long)ii * sh->ay + (long long)jj * sh->by) >> 32);
+                        xmin = min(xmin, cx); xmax = max(xmax, cx); ymin = min(ymin, cy); ymax = max(ymax, cy);
+                    }
+                    xmin = max(xmin - 1, 0); ymin = max(ymin - 1, 0); xmax = min(xmax + 1, (int)H - 1); ymax = min(ymax + 1, (int)W - 1);
+                    for (int bi = xmin >> 5; bi <= (xmax >> 5) && !active; bi++)
+                        for (int bj = ymin >> 5; bj <= (ymax >> 5); bj++)
+                            if (__ldg(orow + (unsigned)bi * Wb + bj)) { active = true; break; }
+                }
+                if (active) { const int ti = t / vwb; tile_list[atomicAdd(n_active, 1)] = (unsigned short)((ti << 8) | (t - ti * vwb)); }
+            }
+        }
+        if (!DEBUG_FULL && lane == 0) atomicMax(&sh->coll_key, best);
+        __syncthreads();
+        if (!use_inverse) {
+            const int n_items = sh->red[2] * 32;
+            const long long lbx = sh->cx + (long long)lane * sh->bx, lby = sh->cy + (long long)lane * sh->by;
+            const long long bx32 = sh->bx * 32, by32 = sh->by * 32;
+#pragma unroll 2
+            for (int item = warp; item < n_items; item += VIEW_THREADS / 32) {
+                const int t = reinterpret_cast<unsigned short*>(blist)[item >> 5];
+                const int wj = t & 255;
+                const int i = (t >> 8) * 32 + (item & 31);
+                if (i >= vh) continue;
+                const int a0 = spans[i * 4 + 0], a1 = spans[i * 4 + 1], b0 = spans[i * 4 + 2], b1 = spans[i * 4 + 3];
+                const int j = wj * 32 + lane;
+                const bool in_fov = (j >= a0 && j < a1) || (j >= b0 && j < b1);     // empty spans are (-1,-1)
+                bool o = false, kn = false;
+                if (in_fov) {
+                    const long long tx = lbx + (long long)i * sh->ax + (long long)wj * bx32;
+                    const long long tyy = lby + (long long)i * sh->ay + (long long)wj * by32;
+                    int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
+                    const unsigned lx = (unsigned)tx, ly = (unsigned)tyy;
+                    if (lx + FX_GUARD < 2 * FX_GUARD || ly + FX_GUARD < 2 * FX_GUARD) {
+                        double wx, wy;   // exact path: map2world, tf multiply, world2map
+                        tf_apply(sh->view_world, i * c.res, j * c.res, wx, wy);
+                        cx = world2cell(wx, c.res); cy = world2cell(wy, c.res);
+                    }
+                    if ((unsigned)cx < H && (unsigned)cy < W) {
+                        kn = true;
+                        o = (__ldg(static_occ + (unsigned)cx * Wb + ((unsigned)cy >> 5)) >> (cy & 31)) & 1u;
+                    }
+                }
+                const unsigned wo = __ballot_sync(0xffffffffu, o);
+                if (!c.use_laser) { const unsigned wk = __ballot_sync(0xffffffffu, kn); if (lane == 0) known[i * vwb + wj] = wk; }
+                if (lane == 0) occ[i * vwb + wj] = wo;
+            }
+            __syncthreads();      // the footprint records below OR into the words written above
+        } else {
+            // FOV-edge pixels (and the laser origin): forward, static map only -- footprint records near them come in whole below
             const uint32_t* edge = d.edge_px + ty.edge_off;
             for (int e = tid; e < ty.n_edge; e += VIEW_THREADS) {
                 const unsigned ep = __ldg(edge + e);
@@ -525,21 +452,20 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     cx = world2cell(wx, c.res); cy = world2cell(wy, c.res);
                 }
                 if ((unsigned)cx < H && (unsigned)cy < W) {
-                    bool o = (__ldg(occ_all + (unsigned)cx * Wb + ((unsigned)cy >> 5)) >> (cy & 31)) & 1u;
-                    if (o && i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1) o = global_value(d, s, r, cx, cy) < 250;
+                    const bool o = (__ldg(static_occ + (unsigned)cx * Wb + ((unsigned)cy >> 5)) >> (cy & 31)) & 1u;
                     if (o && !(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31)))) push_cell(i, j);
                 }
             }
-            // occupied world words -> candidate cells -> view pixels
-            const int n_blocks = sh->red[3], n_items = n_blocks * 32;
-            const int X0 = sh->wbb[0], X1 = sh->wbb[1], Y0 = sh->wbb[2], Y1 = sh->wbb[3];
-            const int zx = sh->zc[0], zy = sh->zc[1], zr = ty.zone_rad;
-            const float i00 = (float)sh->inv[0], i01 = (float)sh->inv[1], i10 = (float)sh->inv[2], i11 = (float)sh->inv[3];
-            const int orgi0 = (int)floor(sh->org[0]), orgi1 = (int)floor(sh->org[1]);
-            const float orgf0 = (float)(sh->org[0] - orgi0), orgf1 = (float)(sh->org[1] - orgi1);
+        }
+        {
+            // candidate words -> candidate cells -> view pixels.  Work items: 32 rows per listed static block, then every
+            // word of every near footprint record.  Each warp takes 32 items (one word per lane) from a shared counter --
+            // dense words make the work per batch very uneven -- and expands their candidate bits over all lanes.
+            const uint32_t* static_cand = d.static_cand;
+            const int n_static = use_inverse ? sh->red[3] * 32 : 0;
+            const int n_items = n_static + (int)npre[n_near];
             const float f00 = (float)sh->view_world.m00, f01 = (float)sh->view_world.m01, f10 = (float)sh->view_world.m10, f11 = (float)sh->view_world.m11;
-            // each warp takes 32 words (one per lane), then expands their candidate bits over all lanes
-            // batches of 32 words are handed out dynamically: dense world blocks make the work per batch very uneven
+            const bool list_cells = use_inverse;          // the forward path scans the finished raster for boundary cells instead
             for (;;) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(&sh->red[4], 32);
@@ -547,28 +473,26 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 if (base >= n_items) break;
                 const int item = base + lane;
                 unsigned cand = 0; int X = 0, bj = 0;
-                if (item < n_items) {
+                if (item < n_static) {
                     const unsigned bb = blocks[item >> 5];
                     X = (int)(bb >> 16) * 32 + (item & 31); bj = (int)(bb & 0xFFFF);
-                    unsigned w = 0;
-                    if (X >= X0 && X <= X1) w = __ldg(occ_all + (unsigned)X * Wb + bj);
-                    if (w) {
-                        unsigned interior = 0xffffffffu;
-                        for (int dxr = -2; dxr <= 2 && interior; dxr++) {
-                            const int Xr = X + dxr;
-                            if (Xr < 0 || Xr >= (int)H) { interior = 0; break; }
-                            const uint32_t* rp = occ_all + (unsigned)Xr * Wb + bj;
-                            const unsigned wc = __ldg(rp), wl = bj > 0 ? __ldg(rp - 1) : 0u, wr = bj + 1 < (int)Wb ? __ldg(rp + 1) : 0u;
-                            interior &= wc & ((wc << 1) | (wl >> 31)) & ((wc << 2) | (wl >> 30)) & ((wc >> 1) | (wr << 31)) & ((wc >> 2) | (wr << 30));
-                        }
-                        cand = w & ~interior;
-                        if (abs(X - zx) <= zr) {      // next to the robot's own stamp: no interior filter
-                            const int lo = max(zy - zr - bj * 32, 0), hi = min(zy + zr - bj * 32, 31);
-                            if (lo <= hi) cand |= w & ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo));
-                        }
-                        const int lo = max(Y0 - bj * 32, 0), hi = min(Y1 - bj * 32, 31);    // only columns under the FOV's bounding box
-                        cand = lo <= hi ? cand & ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo)) : 0u;
-                    }
+                    if (X >= X0 && X <= X1) cand = __ldg(static_cand + (unsigned)X * Wb + bj);
+                } else if (item < n_items) {
+                    const unsigned di = (unsigned)(item - n_static);
+                    int lo = 0, hi = n_near - 1;                       // last k with npre[k] <= di
+                    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (npre[mid] <= di) lo = mid; else hi = mid - 1; }
+                    const unsigned e = near[lo];
+                    const int q = e & 0x7FFF;
+                    const int4 h = __ldg(fhdr + q);
+                    const int wpr = foot_wpr(h), wi = (int)(di - npre[lo]);
+                    const int rr = wi / wpr;
+                    X = h.x + rr; bj = foot_wj0(h) + (wi - rr * wpr);
+                    const int po = __ldg(d.part_off + q), cap = (__ldg(d.part_off + q + 1) - po) >> 1;
+                    if (X >= X0 && X <= X1) cand = __ldg(fwords + po + ((e & NEAR_ALL) ? 0 : cap) + wi);
+                }
+                if (cand) {     // only columns under the FOV's bounding box
+                    const int lo = max(Y0 - bj * 32, 0), hi = min(Y1 - bj * 32, 31);
+                    cand = lo <= hi ? cand & ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo)) : 0u;
                 }
                 const int cnt = __popc(cand);
                 int incl = cnt;
@@ -585,7 +509,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     }
                     const int n = k - __shfl_sync(0xffffffffu, excl, src);
                     const unsigned m = __shfl_sync(0xffffffffu, cand, src);
-                    const int cX = X - lane + src, cbj = bj;      // a batch is the 32 rows of one block: row = first row + lane, same word column
+                    const int cX = __shfl_sync(0xffffffffu, X, src), cbj = __shfl_sync(0xffffffffu, bj, src);
                     if (k >= total) continue;
                     const int cY = cbj * 32 + nth_set_bit(m, n);
                     const float u = (float)(cX - orgi0) - orgf0, v = (float)(cY - orgi1) - orgf1;      // cell - org, exact integer part
@@ -623,74 +547,11 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                             }
                             if (cx != cX || cy != cY) continue;
                         }
-                        if (i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1 && !(global_value(d, s, r, cX, cY) < 250)) continue;
-                        if (!(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31)))) push_cell(i, j);
+                        if (!(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31))) && list_cells) push_cell(i, j);
                     }
                 }
-            }
-        } else {
-        int* n_active = &sh->red[2];
-        unsigned short* tile_list = reinterpret_cast<unsigned short*>(blist);     // region B is free until phase C
-        for (int t = tid; t < n_tiles; t += VIEW_THREADS) {
-            if (!((d.tile_fov[ty.tile_off + (t >> 5)] >> (t & 31)) & 1u)) continue;
-            bool active = !c.use_laser;          // the "known" plane needs every FOV pixel
-            if (!active) {
-                const int ti = t / vwb, tj = t - ti * vwb;
-                const int i0 = ti * 32, i1 = min(i0 + 31, vh - 1), j0 = tj * 32, j1 = min(j0 + 31, vw - 1);
-                int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int ii = (k & 1) ? i1 : i0, jj = (k & 2) ? j1 : j0;
-                    const int cx = (int)((sh->cx + (long long)ii * sh->ax + (long long)jj * sh->bx) >> 32);
-                    const int cy = (int)((sh->cy + (long long)ii * sh->ay + (long long)jj * sh->by) >> 32);
-                    xmin = min(xmin, cx); xmax = max(xmax, cx); ymin = min(ymin, cy); ymax = max(ymax, cy);
-                }
-                xmin = max(xmin - 1, 0); ymin = max(ymin - 1, 0); xmax = min(xmax + 1, (int)H - 1); ymax = min(ymax + 1, (int)W - 1);
-                for (int bi = xmin >> 5; bi <= (xmax >> 5) && !active; bi++)
-                    for (int bj = ymin >> 5; bj <= (ymax >> 5); bj++)
-                        if (__ldg(coarse + (unsigned)bi * Wb + bj)) { active = true; break; }
-            }
-            if (active) { const int ti = t / vwb; tile_list[atomicAdd(n_active, 1)] = (unsigned short)((ti << 8) | (t - ti * vwb)); }
-        }
-        if (!DEBUG_FULL && lane == 0) atomicMax(&sh->coll_key, best);
-        __syncthreads();
-        {
-            const int n_items = sh->red[2] * 32;
-            const long long lbx = sh->cx + (long long)lane * sh->bx, lby = sh->cy + (long long)lane * sh->by;
-            const long long bx32 = sh->bx * 32, by32 = sh->by * 32;
-#pragma unroll 2
-            for (int item = warp; item < n_items; item += VIEW_THREADS / 32) {
-                const int t = tile_list[item >> 5];
-                const int wj = t & 255;
-                const int i = (t >> 8) * 32 + (item & 31);
-                if (i >= vh) continue;
-                const int a0 = spans[i * 4 + 0], a1 = spans[i * 4 + 1], b0 = spans[i * 4 + 2], b1 = spans[i * 4 + 3];
-                const int j = wj * 32 + lane;
-                const bool in_fov = (j >= a0 && j < a1) || (j >= b0 && j < b1);     // empty spans are (-1,-1)
-                bool o = false, kn = false;
-                if (in_fov) {
-                    const long long tx = lbx + (long long)i * sh->ax + (long long)wj * bx32;
-                    const long long tyy = lby + (long long)i * sh->ay + (long long)wj * by32;
-                    int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
-                    const unsigned lx = (unsigned)tx, ly = (unsigned)tyy;
-                    if (lx + FX_GUARD < 2 * FX_GUARD || ly + FX_GUARD < 2 * FX_GUARD) {
-                        double wx, wy;   // exact path: map2world, tf multiply, world2map
-                        tf_apply(sh->view_world, i * c.res, j * c.res, wx, wy);
-                        cx = world2cell(wx, c.res); cy = world2cell(wy, c.res);
-                    }
-                    if ((unsigned)cx < H && (unsigned)cy < W) {
-                        kn = true;
-                        o = (__ldg(occ_all + (unsigned)cx * Wb + ((unsigned)cy >> 5)) >> (cy & 31)) & 1u;
-                        if (o && i >= ty.zone_r0 && i <= ty.zone_r1 && j >= ty.zone_c0 && j <= ty.zone_c1)
-                            o = global_value(d, s, r, cx, cy) < 250;   // exclude the robot's own stamp
-                    }
-                }
-                const unsigned wo = __ballot_sync(0xffffffffu, o);
-                if (!c.use_laser) { const unsigned wk = __ballot_sync(0xffffffffu, kn); if (lane == 0) known[i * vwb + wj] = wk; }
-                if (lane == 0) occ[i * vwb + wj] = wo;
             }
         }
-        }   // forward tile path
         __syncthreads();
         if (!DEBUG_FULL && tid == 0) {
             int code = sh->coll_key & 3;
@@ -703,40 +564,41 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         // integer line walk passes through it is scanned with the closed-form touch test and the ray keeps
         // the minimum step (atomicMin on step<<22|cell).  Cells that do not fit the lists are resolved inline.
         if (c.use_laser) {
-            if (!use_inverse)
-            for (int q = tid; q < vh * 16 * ((vwb + 15) / 16); q += VIEW_THREADS) {
-                const int wpr = 16 * ((vwb + 15) / 16);                  // words per row rounded up to 16: shift/mask indexing
-                const int i = (wpr == 16) ? (q >> 4) : q / wpr, wj = (wpr == 16) ? (q & 15) : q - i * wpr;
-                if (wj >= vwb) continue;
-                const unsigned O = occ[i * vwb + wj];
-                if (!O) continue;
-                unsigned all8 = 0xffffffffu;
-                for (int di = -1; di <= 1; di++) {
-                    const int ii = i + di;
-                    unsigned m = 0, ml = 0, mr = 0;      // outside the raster counts as free (conservative superset)
-                    if (ii >= 0 && ii < vh) {
-                        m = occ[ii * vwb + wj];
-                        ml = wj > 0 ? occ[ii * vwb + wj - 1] : 0u;
-                        mr = wj + 1 < vwb ? occ[ii * vwb + wj + 1] : 0u;
+            if (!use_inverse) {
+                for (int q = tid; q < vh * 16 * ((vwb + 15) / 16); q += VIEW_THREADS) {
+                    const int wpr = 16 * ((vwb + 15) / 16);                  // words per row rounded up to 16: shift/mask indexing
+                    const int i = (wpr == 16) ? (q >> 4) : q / wpr, wj = (wpr == 16) ? (q & 15) : q - i * wpr;
+                    if (wj >= vwb) continue;
+                    const unsigned O = occ[i * vwb + wj];
+                    if (!O) continue;
+                    unsigned all8 = 0xffffffffu;
+                    for (int di = -1; di <= 1; di++) {
+                        const int ii = i + di;
+                        unsigned m = 0, ml = 0, mr = 0;      // outside the raster counts as free (conservative superset)
+                        if (ii >= 0 && ii < vh) {
+                            m = occ[ii * vwb + wj];
+                            ml = wj > 0 ? occ[ii * vwb + wj - 1] : 0u;
+                            mr = wj + 1 < vwb ? occ[ii * vwb + wj + 1] : 0u;
+                        }
+                        const unsigned left = (m << 1) | (ml >> 31), right = (m >> 1) | (mr << 31);
+                        all8 &= left & right;
+                        if (di != 0) all8 &= m;
                     }
-                    const unsigned left = (m << 1) | (ml >> 31), right = (m >> 1) | (mr << 31);
-                    all8 &= left & right;
-                    if (di != 0) all8 &= m;
+                    unsigned bnd = O & ~all8;
+                    if (i == ox && (oy >> 5) == wj) bnd |= O & (1u << (oy & 31));   // an occupied origin hits every ray at step 0
+                    while (bnd) {
+                        const int b = __ffs(bnd) - 1; bnd &= bnd - 1;
+                        const int col = wj * 32 + b;
+                        if (col >= vw) break;
+                        push_cell(i, col);
+                    }
                 }
-                unsigned bnd = O & ~all8;
-                if (i == ox && (oy >> 5) == wj) bnd |= O & (1u << (oy & 31));   // an occupied origin hits every ray at step 0
-                while (bnd) {
-                    const int b = __ffs(bnd) - 1; bnd &= bnd - 1;
-                    const int col = wj * 32 + b;
-                    if (col >= vw) break;
-                    push_cell(i, col);
-                }
+                __syncthreads();
             }
-            __syncthreads();
             const int nl = min(sh->red[0], BL_CAP), nl2 = min(sh->red[1], BL2_CAP);
             if (d.dbg_stats && tid == 0) {
                 int* st = d.dbg_stats + 4 * (size_t)idx;
-                st[0] = sh->red[2] + sh->red[3]; st[1] = sh->red[0]; st[2] = sh->red[1];
+                st[0] = sh->red[2] + sh->red[3] + n_near; st[1] = sh->red[0]; st[2] = sh->red[1];
                 st[3] = sh->red[0] > BL_CAP || sh->red[1] > BL2_CAP;
             }
             for (int q = tid; q < nl; q += VIEW_THREADS) { const unsigned cell = blist[q]; cell_rays(cell, __ldg(kpack + (cell >> 16) * vw + (cell & 0xFFFFu)), 0, 1); }
@@ -767,20 +629,22 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 int run = incl - cnt;
                 for (int w = 0; w < warp; w++) run += sh->red[w];
                 for (int k = k0; k < k1; k++) { hpre[k] = (unsigned short)run; run += hitkey[k] != NOHIT; }
-                if (k1 == c.range_total) hpre[k1] = (unsigned short)run;
+                if (k1 == c.range_total) { hpre[k1] = (unsigned short)run; sh->n_hits = run; }
                 __syncthreads();
             }
         }
 
-        // ---- Phase D/E/F: laser_map reconstruction fused into the cubic resize.
+        // ---- Phase D/E/F: laser_map reconstruction fused into the cubic resize, per OUTPUT pixel.
         // D/E: the final view_map_ value of a pixel = last-writer-wins over the rays in index order, evaluated from
         //      the highest touching ray downwards (static tables), then the robot's own footprint (100, agent.cpp:503).
         //      dtab packs, per pixel the resize reads, the top ray, its step index there and the own-footprint bit:
         //      the top ray touches by construction, so the closed-form touch test only runs on fall-through.
         // F:   cv2.resize(INTER_CUBIC) 400->48 (yaml_env.py:433-434), OpenCV's own path: horizontal pass in int32 with
         //      11-bit weights, vertical pass as an fp32 FMA chain with weights * 2^-22, round-half-even, saturate; then
-        //      float16(x)/255 via a host-built table.  Every source pixel with a non-zero weight belongs to exactly one
-        //      output column, so the horizontal pass evaluates its (<= 4) pixels on the fly: no pixel buffer.
+        //      float16(x)/255 via a host-built table.  The scale is 8.33 > 4 taps, so the <= 16 source pixels of an output
+        //      pixel belong to it alone: an output whose source pixels' top rays ALL missed (prefix counts over the static
+        //      ray interval okk, O(1)) keeps its hit-free value, a table entry (oval).  Only the other ("dirty") outputs are
+        //      evaluated: 4 threads per output, one per source row, combined with shuffles.
         const uint32_t* own_mask = d.own_mask + (size_t)ty.own_mask_off;
         const uint32_t* dtab = d.dtab + (size_t)ty.dtab_off;
         // value code of tap k of output column oc on needed row rr: 0 -> 0, 1 -> 100, 2 -> 200, 3 -> 255.
@@ -845,53 +709,52 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 }
             }
         } else {
+            const int npx = c.img * c.img;
+            uint16_t* o_img = d.o_sensor + (size_t)idx * npx;
+            const uint32_t* okk = d.ostat + (size_t)ty.ostat_off;                                   // [npx] kmin | kmax << 16
+            const uint16_t* oval = reinterpret_cast<const uint16_t*>(d.ostat + (size_t)ty.ostat_off + npx);   // [npx] hit-free float16
+            const bool any_hit = !c.use_laser || sh->n_hits > 0;
+            for (int q = tid; q < npx; q += VIEW_THREADS) {
+                bool is_dirty = !c.use_laser;
+                if (c.use_laser && any_hit) {
+                    const unsigned kk = __ldg(okk + q);
+                    const int kmin = kk & 0xFFFFu, kmax = kk >> 16;
+                    is_dirty = kmax >= kmin && hpre[kmax + 1] != hpre[kmin];
+                }
+                if (is_dirty) dirty[atomicAdd(&sh->n_dirty, 1)] = (unsigned short)q;
+                else o_img[q] = __ldg(oval + q);
+            }
+            __syncthreads();
+            const int n4 = sh->n_dirty * 4;
             const float scale = 1.f / (2048.f * 2048.f);
-            for (int cb = 0; cb < c.img; cb += HB_COLS) {
-                const int nc = min(HB_COLS, c.img - cb);
-                // A warp covers a compact patch of 8 needed rows x 4 output columns (few rays cross it, so the whole warp often
-                // takes the hit-free shortcut below); with 8 warps and 16 columns per block a thread keeps its output column
-                // and walks down the needed rows in steps of 16.
-                static_assert(VIEW_THREADS == 256 && HB_COLS == 16, "item mapping of the horizontal resize pass");
-                const int ocl = (warp & 3) * 4 + (lane & 3);
-                if (ocl < nc) {
-                    const int oc = cb + ocl;
+            for (int base = warp * 32; base < n4; base += VIEW_THREADS) {
+                const int it = base + lane;
+                const bool act = it < n4;
+                const int q = act ? dirty[it >> 2] : 0, t = it & 3;
+                const int orow = q / c.img, oc = q - orow * c.img;
+                float sv = 0.f;
+                if (act) {
                     const short* tp = d.cubic_tap + 4 * oc;
                     const short4 cf = __ldg(reinterpret_cast<const short4*>(d.cubic_coef) + oc);
-                    const int rr0 = (warp >> 2) * 8 + (lane >> 2);
-                    const uint2* hsp = reinterpret_cast<const uint2*>(d.hstat) + (size_t)(ty.dtab_off >> 2) + oc;
-                    const uint4* dtp = reinterpret_cast<const uint4*>(dtab) + oc;
-                    for (int rr = rr0; rr < c.ns; rr += 16) {
-                        uint4 e4 = make_uint4(0u, 0u, 0u, 0u);
-                        if (c.use_laser) {
-                            // static shortcut: when none of the top rays of this output's taps hit anything, all of its source
-                            // pixels keep their hit-free value (free / own footprint / outside every ray) and the sum is a table entry
-                            const uint2 hs = __ldg(hsp + rr * c.img);
-                            const int kmin = hs.x & 0xFFFFu, kmax = hs.x >> 16;
-                            if (kmax < kmin || hpre[kmax + 1] == hpre[kmin]) { hbuf[rr * HB_COLS + ocl] = (int)hs.y; continue; }
-                            e4 = __ldg(dtp + rr * c.img);
-                        }
-                        int acc = 0;
-                        if (cf.x) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.x, rr, tp, 0))) & 0xFFu) * cf.x;
-                        if (cf.y) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.y, rr, tp, 1))) & 0xFFu) * cf.y;
-                        if (cf.z) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.z, rr, tp, 2))) & 0xFFu) * cf.z;
-                        if (cf.w) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.w, rr, tp, 3))) & 0xFFu) * cf.w;
-                        hbuf[rr * HB_COLS + ocl] = acc;
-                    }
+                    const int rr = d.cubic_tap[4 * orow + t];
+                    uint4 e4 = make_uint4(0u, 0u, 0u, 0u);
+                    if (c.use_laser) e4 = __ldg(reinterpret_cast<const uint4*>(dtab) + rr * c.img + oc);
+                    int acc = 0;
+                    if (cf.x) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.x, rr, tp, 0))) & 0xFFu) * cf.x;
+                    if (cf.y) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.y, rr, tp, 1))) & 0xFFu) * cf.y;
+                    if (cf.z) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.z, rr, tp, 2))) & 0xFFu) * cf.z;
+                    if (cf.w) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.w, rr, tp, 3))) & 0xFFu) * cf.w;
+                    sv = (float)acc;
                 }
-                __syncthreads();
-                for (int q = tid; q < c.img * HB_COLS; q += VIEW_THREADS) {
-                    const int orow = q / HB_COLS, ocl = q % HB_COLS;
-                    if (ocl >= nc) continue;
-                    const short4 tp = __ldg(reinterpret_cast<const short4*>(d.cubic_tap) + orow), cf = __ldg(reinterpret_cast<const short4*>(d.cubic_coef) + orow);
-                    const float b0 = cf.x * scale, b1 = cf.y * scale, b2 = cf.z * scale, b3 = cf.w * scale;
-                    const float s0 = (float)hbuf[tp.x * HB_COLS + ocl], s1 = (float)hbuf[tp.y * HB_COLS + ocl];
-                    const float s2 = (float)hbuf[tp.z * HB_COLS + ocl], s3 = (float)hbuf[tp.w * HB_COLS + ocl];
-                    const float v = fmaf(s0, b0, fmaf(s1, b1, fmaf(s2, b2, s3 * b3)));
+                const float s1 = __shfl_down_sync(0xffffffffu, sv, 1), s2 = __shfl_down_sync(0xffffffffu, sv, 2), s3 = __shfl_down_sync(0xffffffffu, sv, 3);
+                if (act && t == 0) {
+                    const short4 cv = __ldg(reinterpret_cast<const short4*>(d.cubic_coef) + orow);
+                    const float b0 = cv.x * scale, b1 = cv.y * scale, b2 = cv.z * scale, b3 = cv.w * scale;
+                    const float v = fmaf(sv, b0, fmaf(s1, b1, fmaf(s2, b2, s3 * b3)));
                     int iv = __float2int_rn(v);
                     iv = min(255, max(0, iv));
-                    d.o_sensor[(size_t)idx * c.img * c.img + orow * c.img + cb + ocl] = d.f16_lut[iv];
+                    o_img[q] = d.f16_lut[iv];
                 }
-                __syncthreads();
             }
         }
     }

@@ -210,6 +210,8 @@ class MultiRobotCleanWrapper(Wrapper):
                 c = clean.cpu().numpy() if _is_torch(clean) else clean
                 info["speeds"] = np.where(c[:, None], sp, 0.0)
             else:
+                if _is_torch(sp) and sp.device != clean.device:
+                    sp = sp.to(clean.device)
                 info["speeds"] = _where(clean[:, None], sp, _zeros_like(sp))
         self.is_clean = _where(done > 0, _zeros_like(clean), clean)
         return state, reward, done, info

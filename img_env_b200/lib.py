@@ -26,7 +26,7 @@ class ImgenvConfig(C.Structure):
                 ("max_ped", C.c_int32), ("ped_vec_dim", C.c_int32), ("ped_image_r", C.c_double), ("laser_max", C.c_double),
                 ("laser_norm", C.c_int32), ("num_scenes", C.c_int32), ("num_robots", C.c_int32), ("num_peds", C.c_int32),
                 ("scene_type", C.c_int32), ("robot_ktype", C.c_int32), ("max_obstacles", C.c_int32), ("max_traj", C.c_int32),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("max_object_radius", C.c_double)]
 
 
 class ImgenvOutputs(C.Structure):
@@ -39,7 +39,7 @@ EXPORTS = ["imgenv_create", "imgenv_destroy", "imgenv_bind_outputs", "imgenv_res
            "imgenv_solver_agents", "imgenv_view_dims", "imgenv_launches_per_step",
            "imgenv_algorithmic_bytes_per_robot_step", "imgenv_last_error", "imgenv_version",
            "imgenv_sampler_create", "imgenv_sampler_destroy", "imgenv_sampler_seed", "imgenv_sampler_sample", "imgenv_sampler_draw",
-           "imgenv_reset_sampled", "imgenv_debug_check_planes",
+           "imgenv_reset_sampled", "imgenv_debug_check_footprints",
            "imgenv_record_enable", "imgenv_record_fetch", "imgenv_debug_set_min_jerk", "imgenv_set_ped_yaw_mode"]
 
 
@@ -141,7 +141,7 @@ class BatchedSim:
                            ped_image_r=spec["ped_image_r"], laser_max=spec["laser_max"], laser_norm=int(spec["laser_norm"]),
                            num_scenes=self.S, num_robots=self.R, num_peds=self.P, scene_type=SCENES[spec["scene_type"]],
                            robot_ktype=KTYPES[spec["robot_ktype"]], max_obstacles=spec["max_obstacles"],
-                           max_traj=spec["max_traj"], seed=seed)
+                           max_traj=spec["max_traj"], seed=seed, max_object_radius=float(spec.get("max_object_radius", 0.0)))
         self.cfg = cfg
         grid = np.ascontiguousarray(spec["grid"], dtype=np.uint8)
         rd = np.ascontiguousarray(spec["robot_desc"], dtype=np.float64)
@@ -239,10 +239,10 @@ class BatchedSim:
         self._check(self.lib.imgenv_record_fetch(self.h, int(scene), C.byref(n), _ptr(rb), _ptr(pd), self._stream()))
         return dict(robots=rb[: n.value], peds=pd[: n.value, : self.P])
 
-    def debug_check_planes(self):
-        """-> (occ words, flag bytes, block marks, block counts) violating 'no agent is stamped between calls'."""
+    def debug_check_footprints(self):
+        """-> (non-empty footprint records, occupied cells, candidate cells, violations of the record invariants)."""
         out = np.zeros(4, np.int64)
-        self._check(self.lib.imgenv_debug_check_planes(self.h, _ptr(out, C.c_int64), self._stream()))
+        self._check(self.lib.imgenv_debug_check_footprints(self.h, _ptr(out, C.c_int64), self._stream()))
         return tuple(int(x) for x in out)
 
     def step(self, actions, alive=None):
@@ -284,7 +284,7 @@ class BatchedSim:
     def profile_end(self):
         ms = (C.c_float * 4)()
         n = self.lib.imgenv_profile_end(self.h, ms)
-        return n, dict(k_dynamics=ms[0], k_stamp=ms[1], k_view=ms[2], k_unstamp=ms[3])
+        return n, dict(k_dynamics=ms[0], k_footprints=ms[1], k_view=ms[2])
 
     def get_internal(self):
         rb = np.zeros((self.S, self.R, 16)); pd = np.zeros((self.S, max(self.P, 1), 20))

@@ -56,6 +56,7 @@ typedef struct imgenv_config {
     int32_t max_obstacles;                              /* reset objects per scene (cfg object.total) */
     int32_t max_traj;                                   /* waypoints per pedestrian (1 or 2 from reset_helper.py:337-342) */
     uint64_t seed;                                      /* beep Bernoulli draws (img_env.cpp:327 uses glibc rand()) */
+    double max_object_radius;                           /* bound (m) on a reset object's bounding radius; 0 = 0.75 */
 } imgenv_config;
 
 /* Device pointers the library WRITES every reset/step (caller-owned, e.g. torch tensors; bound
@@ -148,9 +149,9 @@ int imgenv_debug_global_map(imgenv_t* h, int32_t scene, int32_t self, uint8_t* h
  * max_steps = 0 disables and frees.  fetch copies the steps recorded since the last reset of `scene` to host arrays. */
 int imgenv_record_enable(imgenv_t* h, int32_t max_steps);
 int imgenv_record_fetch(imgenv_t* h, int32_t scene, int32_t* n_steps, double* robots, double* peds, void* stream);
-/* Invariant check (tests): between calls no agent is stamped in the per-scene planes. out4 = number of occupancy words,
- * flag bytes, block marks and block counts that violate it (all 0 when healthy). */
-int imgenv_debug_check_planes(imgenv_t* h, int64_t* out4, void* stream);
+/* Invariant check (tests) of the per-part footprint records the observation composes: out4 = non-empty records, occupied cells,
+ * candidate cells, violations (a candidate cell that is not occupied, a cell outside the map or outside its record's box). */
+int imgenv_debug_check_footprints(imgenv_t* h, int64_t* out4, void* stream);
 /* Test hook: the node's SpeedLimiter(msg) leaves min_jerk unassigned (speed_limit.cpp:56-65) and clamps with whatever its
  * stack held; the library defaults to min_jerk = max_jerk = msg.min_jerk.  min_jerk[R][2] (linear, angular) overrides it. */
 int imgenv_debug_set_min_jerk(imgenv_t* h, const double* min_jerk);

@@ -4,8 +4,8 @@ slow (C4: ~3 s per scene-step) or cannot run at all (C5) to serve as a lock-step
 * batch invariance — a scene gives bit-identical State whether it is simulated alone or inside a batch, and whatever
   its scene index (scenes are independent in the reference: one node per scene);
 * determinism — the same inputs give the same bits twice (all reductions are order independent);
-* plane restoration — after every call no agent is left stamped in the per-scene planes (occ_all == base_occ,
-  no dynamic flag, block counts == popcount), i.e. stamp -> observe -> unstamp is the identity on the map state;
+* footprint records — after every call the per-part cell bitmaps the observation composed are well formed (candidate
+  cells are occupied cells, every cell lies inside the map and inside its record's box, no bitmap exceeds its slot);
 * range/format checks of the nine State fields.
 """
 import numpy as np
@@ -28,7 +28,7 @@ def _run(spec, resets, actions, steps, scene_ids=None, num_scenes=None):
         other = [i for i in range(S) if i not in ids]
         sim.reset([resets[(k + 1) % n] for k in range(len(other))], scene_ids=other)
     sim.reset(resets, scene_ids=ids)
-    assert sim.debug_check_planes() == (0, 0, 0, 0)
+    assert sim.debug_check_footprints()[3] == 0
     outs = []
     for t in range(steps):
         a = np.zeros((S, spec["R"], 3), np.float32)
@@ -40,7 +40,8 @@ def _run(spec, resets, actions, steps, scene_ids=None, num_scenes=None):
         sim.step(torch.from_numpy(a).cuda())
         torch.cuda.synchronize()
         outs.append({k: v[ids].cpu().numpy().copy() for k, v in sim.out.items()})
-        assert sim.debug_check_planes() == (0, 0, 0, 0), "agents left stamped after step %d" % t
+        nrec, nocc, ncand, bad = sim.debug_check_footprints()
+        assert bad == 0 and ncand <= nocc, "footprint records broken after step %d: %s" % (t, (nrec, nocc, ncand, bad))
     sim.close()
     return outs
 
@@ -52,7 +53,7 @@ def _same(a, b):
 
 
 @pytest.mark.parametrize("wname,steps", [("c4", 3), ("c5", 3), ("c3", 4)])
-def test_batch_invariance_determinism_and_plane_restoration(wname, steps):
+def test_batch_invariance_determinism_and_footprint_records(wname, steps):
     w = bench.WORKLOADS[wname]
     spec = build_spec(bench.make_cfg(w))
     resets = bench.make_resets(spec, w, 2, seed=11)
