@@ -198,7 +198,7 @@ def run_b200(args):
         dist.barrier()
     w = WORKLOADS[args.workload]
     S = args.scenes or w["scenes"]
-    spec = build_spec(make_cfg(w))
+    spec = build_spec(make_cfg(w, args.synthetic_map))
     R = spec["R"]
     sim = BatchedSim(spec, num_scenes=S, device=local_rank, seed=1234 + rank, ped_yaw_mode=1)
     sim.reset(make_resets(spec, w, S, 1234 + rank * 100003))
@@ -403,6 +403,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=0, help="scenes per GPU (default: workload-specific)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", action="store_true", help="N > 1: also time sim + delivery of the State to rank 0")
+    ap.add_argument("--synthetic-map", action="store_true", help="round-1 synthetic room with random blocks instead of the reference's PNG")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -189,6 +189,7 @@ inline std::string build_type(const Cfg& c, const double* desc, double view_angl
     }
     // per-pixel highest / lowest touching ray: walk every ray over its full static cell sequence
     T.khi.assign(npx, 0xFFFF); T.klo.assign(npx, 0xFFFF);
+    std::vector<unsigned short> kcnt(npx, 0);
     for (int k = 0; k < c.range_total; k++) {
         int x1 = T.t.org_x, y1 = T.t.org_y, x2 = T.ray_end[2 * k], y2 = T.ray_end[2 * k + 1];
         int w = x2 - x1, h = y2 - y1;
@@ -199,6 +200,7 @@ inline std::string build_type(const Cfg& c, const double* desc, double view_angl
             size_t q = (size_t)cx * c.vw + cy;
             T.khi[q] = (unsigned short)k;                     // k ascending -> last write is the max
             if (T.klo[q] == 0xFFFF) T.klo[q] = (unsigned short)k;
+            kcnt[q]++;
         };
         if (w > h) {
             f = 2 * h - w;
@@ -216,6 +218,11 @@ inline std::string build_type(const Cfg& c, const double* desc, double view_angl
             }
         }
     }
+    // The rays through a cell form a contiguous index interval in practice (monotone fan of digital lines); where that holds
+    // (count == khi - klo + 1) bit 15 of klo is set and the kernel skips the per-ray touch test: on every ray through the cell
+    // the step index is the Chebyshev distance to the origin (x-major rays visit one cell per x, y-major one per y).
+    for (size_t q = 0; q < npx; q++)
+        if (T.khi[q] != 0xFFFF && kcnt[q] == T.khi[q] - T.klo[q] + 1) T.klo[q] |= 0x8000;
     return "";
 }
 

@@ -161,7 +161,11 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     c.view_base = tf_from_pose(vhei / 2, vwid / 2, 3.14159);      // agent.cpp:84-87
     c.base_view = tf_inv(c.view_base);
     c.cull_reach = hypot(vhei / 2, vwid / 2) + 4 * c.res;          // view pixels lie within [-h/2, h/2] x [-w/2, w/2] of the base frame
-    c.img = cfg->image_size; c.max_ped = cfg->max_ped; c.ped_vec_dim = cfg->ped_vec_dim;
+    c.img = cfg->image_size;
+    if (c.img < 1 || c.img > 255) return fail("imgenv_create: image_size must be in [1, 255]");
+    c.img_inv = (unsigned)(((1ull << 32) + c.img - 1) / c.img);
+    c.hb_shift = 0; while ((c.range_total >> c.hb_shift) >= 64) c.hb_shift++;
+    c.max_ped = cfg->max_ped; c.ped_vec_dim = cfg->ped_vec_dim;
     c.pvs_len = 1 + c.max_ped * c.ped_vec_dim;
     c.ped_image_r = cfg->ped_image_r; c.ped_res = 6.0 / cfg->ped_image_size; c.laser_max = cfg->laser_max;
     c.laser_norm = cfg->laser_norm;
@@ -177,6 +181,11 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     if (c.state_dim < 3 || c.state_dim > 5) return fail("imgenv_create: state_dim must be 3, 4 or 5");
     if (c.R < 1 || c.R > 4096 || c.P < 0 || c.P > 4096 || c.S < 1) return fail("imgenv_create: bad S/R/P");
     if (c.range_total > 4000 || c.range_total < 1) return fail("imgenv_create: range_total out of range");   // 12-bit ray ids, 0xFFF = none
+    {   // world blocks (32x32 cells) the field of view can span at worst (its diagonal, any rotation): the world->view
+        // rasterisation keeps their list in shared memory; larger views use the forward rasteriser
+        const int span = (int)ceil(hypot((double)c.vh, (double)c.vw)) / 32 + 2;
+        c.inverse_ok = c.use_laser && span * span <= INV_MAX_BLOCKS;
+    }
     if (c.scene_type < 0 || c.scene_type > 4) return fail("imgenv_create: unknown scene type");
 
     // ---- static tables ----
@@ -238,7 +247,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
                     for (int k = 0; k < 4; k++) {
                         const int pr = need_idx[rr], pc = need_idx[tap[4 * oc + k]];
                         const size_t full = (size_t)pr * c.vw + pc;
-                        uint32_t kh = T.khi[full], e;
+                        uint32_t kh = T.khi[full], e;   // (klo carries the "exact interval" flag in bit 15; khi does not)
                         if (kh == 0xFFFF) e = 0xFFFu;
                         else {
                             const int w0 = abs((int)T.ray_end[2 * kh] - T.t.org_x), h0 = abs((int)T.ray_end[2 * kh + 1] - T.t.org_y);
@@ -257,7 +266,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
             const float scale = 1.f / (2048.f * 2048.f);
             for (int orow = 0; orow < c.img; orow++)
                 for (int oc = 0; oc < c.img; oc++) {
-                    uint32_t kmin = 0xFFFFu, kmax = 0; bool any = false; float sv[4];
+                    uint32_t kmin = 0xFFFu, kmax = 0, imax = 0; bool any = false; float sv[4];
                     for (int t = 0; t < 4; t++) {
                         const int rr = tap[4 * orow + t];
                         int sum = 0;
@@ -266,7 +275,14 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
                             if (w == 0) continue;
                             const uint32_t e = T.dtab[((size_t)rr * c.img + oc) * 4 + k], kh = e & 0xFFFu;
                             int val = 200;                                   // no ray passes: unknown
-                            if (kh != 0xFFFu) { val = 255; if (coef[4 * orow + t] != 0) { kmin = std::min(kmin, kh); kmax = std::max(kmax, kh); any = true; } }
+                            if (kh != 0xFFFu) {
+                                val = 255;
+                                if (coef[4 * orow + t] != 0) {
+                                    kmin = std::min(kmin, kh); kmax = std::max(kmax, kh); any = true;
+                                    const int pr = need_idx[rr], pc = need_idx[tap[4 * oc + k]];
+                                    imax = std::max(imax, (uint32_t)std::max(abs(pr - T.t.org_x), abs(pc - T.t.org_y)));
+                                }
+                            }
                             if (e >> 31) val = 100;                          // own footprint
                             sum += val * w;
                         }
@@ -277,7 +293,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
                     const float v = fmaf(sv[0], b0, fmaf(sv[1], b1, fmaf(sv[2], b2, sv[3] * b3)));
                     int iv = (int)lrintf(v);
                     iv = std::min(255, std::max(0, iv));
-                    T.ostat[(size_t)orow * c.img + oc] = kmin | (kmax << 16);
+                    T.ostat[(size_t)orow * c.img + oc] = kmin | (kmax << 12) | (((imax + 3) / 4) << 24);
                     oval[(size_t)orow * c.img + oc] = lut[iv];
                 }
         }

@@ -68,11 +68,14 @@ struct Cfg {
     double cull_reach;       // farthest world distance from a robot's position to anything its observation can read
     double step_hz, control_hz;   // period (float32 widened), 0.05
     int state_dim, use_laser, range_total, ktype, scene_type, relation;
+    int inverse_ok;               // lasers on and the FOV spans few enough world blocks: world->view rasterisation, no raster in shared memory
     double beep_r, ped_ca_p;
     double view_max_dist;
     Tf2 view_base, base_view;     // tf_view_base_, tf_base_view_
     // python side
     int img, ns;                  // output image side (48), needed source rows/cols (144)
+    unsigned img_inv;             // ceil(2^32 / img): q / img == __umulhi(q, img_inv) for q < 2^16
+    int hb_shift;                 // rays are grouped in blocks of 2^hb_shift (< 64 blocks) for the nearest-hit table
     int max_ped, ped_vec_dim, pvs_len;
     double ped_image_r, ped_res, laser_max;
     int laser_norm;
@@ -99,14 +102,15 @@ struct Dev {
     const double* lattice_xy;     // packed (x,y) pairs
     const short* ray_end;         // (x2,y2) pairs
     const short* fov_spans;       // per type: [vh][MAX_SPANS][2] (c0,c1 exclusive), -1 = none
-    const uint32_t* kpack;        // khi | klo << 16 (one load per pixel)
+    const uint32_t* kpack;        // per view pixel: highest ray through it | lowest << 16 | (rays form exactly that interval) << 31; 0xFFFF = none
     const uint32_t* own_mask;     // per type: bit per view pixel = own footprint cell
     const uint32_t* tile_fov;     // per type: bit per 32x32 view tile (row-major, vwb per row) with any FOV pixel
     const uint32_t* edge_px;      // per type: FOV-edge pixels
     const uint32_t* edge_tiles;   // per type: bit per 16x16 view tile near an edge pixel
     const uint32_t* dtab;         // per type [ns][img][4]: for tap k of output column oc on needed row rr: top ray (12b) | its step index there (10b) << 12 | own footprint << 31
-    const uint32_t* ostat;        // per type [img][img][2]: (lowest | highest << 16) top ray over the 16 source pixels of an output pixel,
-                                  //                         its float16 value when none of those rays hits anything
+    const uint32_t* ostat;        // per type: [img*img] u32 lowest (12 b) | highest (12 b) top ray over the source pixels of an output pixel |
+                                  //           ceil(their largest Chebyshev distance to the laser origin / 4) << 24, then [img*img] u16: the
+                                  //           output's float16 value when none of those rays hits anything in front of / on a source pixel
     const short* need_idx;        // [ns] source row/col index of the k-th needed row/col
     const short* cubic_tap;       // [img][4] index into need_idx space (0..ns-1) of the 4 taps
     const short* cubic_coef;      // [img][4] fixed-point weights (x2048)

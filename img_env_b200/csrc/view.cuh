@@ -11,6 +11,7 @@
 #include "foot.cuh"
 
 #define VIEW_THREADS 256
+#define VIEW_MIN_CTAS 4                 // 64 registers per thread: the register file holds 32 warps per SM either way
 #define FX_ONE 4294967296.0            // 2^32: fixed-point scale of cell coordinates
 #define FX_GUARD 8192u                 // |frac - 0.5| below 2^-19 cells -> exact fp64 fallback
 
@@ -18,13 +19,14 @@ struct ViewShared {
     Tf2 base_world, view_world, world_base;
     long long ax, bx, cx, ay, by, cy;   // fixed-point (2^-32 cell) affine view pixel -> world cell
     int frozen;
-    int red[VIEW_THREADS / 32];
+    int red[8];              // counters / per-warp partial sums
     int coll_key;
     // inverse (world cell -> view pixel) search: pixel = inv * (cell - org), in double; world block range of the FOV
     double inv[4], org[2];
     int blk[4];              // first block row / col, number of block rows / cols covering the FOV's world bounding box
     int wbb[4];              // world bounding box of the FOV in cells (x0, x1, y0, y1), clamped to the map
     int n_near, n_cnear, n_dirty, n_hits;
+    int hmin[64];            // per block of rays: smallest hit step (Chebyshev distance of the hit cell), NOHIT >> 22 if none
     int4 own_hdr;            // the observer's own footprint record header
 };
 
@@ -123,7 +125,7 @@ __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     ViewLayout L;
     size_t off = 0;
     L.sh = off; off += (sizeof(ViewShared) + 15) & ~(size_t)15;
-    size_t occ = (size_t)c.vh * c.vwb * 4 * (c.use_laser ? 1 : 2);
+    size_t occ = c.inverse_ok ? 0 : (size_t)c.vh * c.vwb * 4 * (c.use_laser ? 1 : 2);   // no raster at all in the world->view mode
     L.regA = off; off += (occ + 15) & ~(size_t)15;
     const size_t dl = ((size_t)c.img * c.img * 2 + 15) & ~(size_t)15;
     size_t bl = (size_t)(BL_CAP + BL2_CAP) * 4, hb = dl + ((size_t)c.range_total + 1) * 2;
@@ -145,7 +147,7 @@ inline size_t view_smem_bytes(const Cfg& c) { return view_layout(c).total; }
 __device__ __forceinline__ unsigned hit_key(int i, int x, int y) { return ((unsigned)i << 22) | ((unsigned)x << 11) | (unsigned)y; }
 
 template <bool DEBUG_FULL>
-__global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_ids, int is_reset) {
+__global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, const int* scene_ids, int is_reset) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Cfg& c = d.c;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -223,6 +225,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         const int2* g_spans = reinterpret_cast<const int2*>(d.fov_spans + (size_t)ty.span_off);
         for (int k = tid; k < vh; k += VIEW_THREADS) reinterpret_cast<int2*>(spans)[k] = __ldg(g_spans + k);
         for (int k = tid; k < c.range_total; k += VIEW_THREADS) hitkey[k] = NOHIT;
+        if (tid < 64) sh->hmin[tid] = 1023;
     }
     __syncthreads();
     const bool frozen = DEBUG_FULL ? false : sh->frozen != 0;
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         const unsigned H = c.H, W = c.W, Wb = c.Wb;
         const int ox = ty.org_x, oy = ty.org_y;
         const uint32_t* kpack = d.kpack + (size_t)ty.khi_off;
-        const bool use_inverse = c.use_laser && sh->blk[2] * sh->blk[3] <= INV_MAX_BLOCKS;
+        const bool use_inverse = c.inverse_ok;
         const int X0 = sh->wbb[0], X1 = sh->wbb[1], Y0 = sh->wbb[2], Y1 = sh->wbb[3];
         const float i00 = (float)sh->inv[0], i01 = (float)sh->inv[1], i10 = (float)sh->inv[2], i11 = (float)sh->inv[3];
         const int orgi0 = (int)floor(sh->org[0]), orgi1 = (int)floor(sh->org[1]);
@@ -257,7 +260,8 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 }
                 if (bx0 > X1 || bx1 < X0 || by0 > Y1 || by1 < Y0) continue;
                 unsigned all = (!use_inverse) ? NEAR_ALL : 0u;
-                if (!all) {   // view-space bounding box of the part's box (+3 px): does it touch a tile that holds FOV-edge pixels?
+                {   // view-space bounding box of the part's box (+3 px): outside the FOV's pixel box -> the part cannot be seen;
+                    // does it touch a tile that holds FOV-edge pixels?
                     float imin = 1e9f, imax = -1e9f, jmin = 1e9f, jmax = -1e9f;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
@@ -265,6 +269,8 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                         const float qi = i00 * u + i01 * v, qj = i10 * u + i11 * v;
                         imin = fminf(imin, qi); imax = fmaxf(imax, qi); jmin = fminf(jmin, qj); jmax = fmaxf(jmax, qj);
                     }
+                    if (imax + 3.f < (float)ty.fov_r0 || imin - 3.f > (float)ty.fov_r1 || jmax + 3.f < (float)ty.fov_c0 || jmin - 3.f > (float)ty.fov_c1) continue;
+                  if (!all) {
                     const int ti0 = max((int)floorf(imin - 3.f) >> ET_SHIFT, 0), ti1 = min((int)floorf(imax + 3.f) >> ET_SHIFT, eth - 1);
                     const int tj0 = max((int)floorf(jmin - 3.f) >> ET_SHIFT, 0), tj1 = min((int)floorf(jmax + 3.f) >> ET_SHIFT, etw - 1);
                     if ((ti1 - ti0 + 1) * (tj1 - tj0 + 1) > 64) all = NEAR_ALL;        // huge part: do not bother
@@ -274,6 +280,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                                 const int t = ti * etw + tj;
                                 if ((__ldg(etiles + (t >> 5)) >> (t & 31)) & 1u) { all = NEAR_ALL; break; }
                             }
+                  }
                 }
                 near[atomicAdd(&sh->n_near, 1)] = (unsigned short)(q | all);
             }
@@ -347,9 +354,16 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
         int* n_list = &sh->red[0]; int* n_list2 = &sh->red[1];
         // every ray of [k0, k0+kstep, ...] within the cell's static ray interval that really passes through it
         // keeps the minimum step: hitkey[k] = min(step << 22 | cell)
+        // When the rays through the cell are exactly the interval [kl, kh] (static flag, true for virtually every cell) no
+        // touch test is needed and the step index is the cell's Chebyshev distance to the origin on every one of them.
         auto cell_rays = [&](unsigned cell, unsigned kp, int k0, int kstep) {      // cell = row << 16 | col
             const int pr = (int)(cell >> 16), pc = (int)(cell & 0xFFFFu);
-            const int kh = kp & 0xFFFF, kl = kp >> 16;
+            const int kh = kp & 0xFFFF, kl = (kp >> 16) & 0x7FFF;
+            if (kp >> 31) {
+                const unsigned key = hit_key(max(abs(pr - ox), abs(pc - oy)), pr, pc);
+                for (int k = kl + k0; k <= kh; k += kstep) atomicMin(&hitkey[k], key);
+                return;
+            }
             for (int k = kl + k0; k <= kh; k += kstep) {
                 const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
                 if (i >= 0) atomicMin(&hitkey[k], hit_key(i, pr, pc));
@@ -360,13 +374,13 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             const unsigned kp = __ldg(kpack + pr * vw + pc);
             const int kh = kp & 0xFFFF;
             if (kh == 0xFFFF) return;                                      // no ray passes through this cell
-            const bool heavy = kh - (int)(kp >> 16) + 1 > BL_HEAVY;
+            const bool heavy = kh - (int)((kp >> 16) & 0x7FFF) + 1 > BL_HEAVY;
             const int p = atomicAdd(heavy ? n_list2 : n_list, 1);
             if (p < (heavy ? BL2_CAP : BL_CAP)) (heavy ? blist2 : blist)[p] = ((unsigned)pr << 16) | (unsigned)pc;
-            else cell_rays_inline(hitkey, rend, ox, oy, pr, pc, (int)(kp >> 16), kh);   // list full: resolve this cell right here
+            else cell_rays_inline(hitkey, rend, ox, oy, pr, pc, (int)((kp >> 16) & 0x7FFF), kh);   // list full: resolve this cell right here
         };
         const int n_trow = (vh + 31) >> 5, n_tiles = n_trow * vwb;
-        for (int q = tid; q < vh * vwb; q += VIEW_THREADS) { occ[q] = 0u; if (!c.use_laser) known[q] = 0u; }
+        if (!use_inverse) for (int q = tid; q < vh * vwb; q += VIEW_THREADS) { occ[q] = 0u; if (!c.use_laser) known[q] = 0u; }
         if (use_inverse) {
             const uint32_t* crow = d.static_crow;
             const int nbj = sh->blk[3], nb = sh->blk[2] * nbj;
@@ -453,7 +467,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 }
                 if ((unsigned)cx < H && (unsigned)cy < W) {
                     const bool o = (__ldg(static_occ + (unsigned)cx * Wb + ((unsigned)cy >> 5)) >> (cy & 31)) & 1u;
-                    if (o && !(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31)))) push_cell(i, j);
+                    if (o) push_cell(i, j);
                 }
             }
         }
@@ -465,7 +479,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
             const int n_static = use_inverse ? sh->red[3] * 32 : 0;
             const int n_items = n_static + (int)npre[n_near];
             const float f00 = (float)sh->view_world.m00, f01 = (float)sh->view_world.m01, f10 = (float)sh->view_world.m10, f11 = (float)sh->view_world.m11;
-            const bool list_cells = use_inverse;          // the forward path scans the finished raster for boundary cells instead
+            const float fr0 = (float)ty.fov_r0 - 1.5f, fr1 = (float)ty.fov_r1 + 1.5f, fc0 = (float)ty.fov_c0 - 1.5f, fc1 = (float)ty.fov_c1 + 1.5f;
             for (;;) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(&sh->red[4], 32);
@@ -517,6 +531,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                     // Pixel (i,j) maps to this cell iff M*((i,j) - q) lies in the unit square around the cell centre (M =
                     // rotation of view_world).  The float test decides all pixels farther than INV_EPS from the square's
                     // edge; only the others run the exact forward map.  |q| < 2^10 so the float error is < 1e-3 cell.
+                    if (qi < fr0 || qi > fr1 || qj < fc0 || qj > fc1) continue;       // (pixel box of the FOV, 1.5 px margin)
                     const int ia = (int)ceilf(qi - 0.72f), ja = (int)ceilf(qj - 0.72f);
                     // cheap part for the 2 x 2 window at once (M*d is linear: the four offsets share two products), ...
                     const float du0 = (float)ia - qi, dv0 = (float)ja - qj;
@@ -547,7 +562,11 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                             }
                             if (cx != cX || cy != cY) continue;
                         }
-                        if (!(atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31)) & (1u << (j & 31))) && list_cells) push_cell(i, j);
+                        // World->view mode: no raster is kept -- a view pixel has ONE world cell, so it can only be found twice when
+                        // two records (or a record and the static map) cover that cell; it is then listed twice, which is harmless.
+                        // Forward mode: into the raster; its boundary cells are listed by the scan below.
+                        if (use_inverse) push_cell(i, j);
+                        else atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31));
                     }
                 }
             }
@@ -628,7 +647,11 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 __syncthreads();
                 int run = incl - cnt;
                 for (int w = 0; w < warp; w++) run += sh->red[w];
-                for (int k = k0; k < k1; k++) { hpre[k] = (unsigned short)run; run += hitkey[k] != NOHIT; }
+                for (int k = k0; k < k1; k++) {
+                    const unsigned key = hitkey[k];
+                    hpre[k] = (unsigned short)run; run += key != NOHIT;
+                    if (key != NOHIT) atomicMin(&sh->hmin[k >> c.hb_shift], (int)(key >> 22));      // nearest hit per block of rays
+                }
                 if (k1 == c.range_total) { hpre[k1] = (unsigned short)run; sh->n_hits = run; }
                 __syncthreads();
             }
@@ -663,7 +686,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                         const int pr = need[rr], pc = need[tp[k]];
                         if (!(pr != (int)((key >> 11) & 2047) && pc != (int)(key & 2047))) {     // no shadow write: fall through to lower rays
                             const unsigned kp = __ldg(kpack + pr * vw + pc);
-                            code = pixel_code_below(hitkey, rend, ox, oy, pr, pc, kh, (int)(kp >> 16));
+                            code = pixel_code_below(hitkey, rend, ox, oy, pr, pc, kh, (int)((kp >> 16) & 0x7FFF));
                         }
                     }
                 }
@@ -687,7 +710,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                         const unsigned kp = __ldg(kpack + full);
                         const int kh = kp & 0xFFFF;
                         if (kh != 0xFFFF) {
-                            const int kl = kp >> 16;
+                            const int kl = (kp >> 16) & 0x7FFF;
                             for (int k = kh; k >= kl; k--) {
                                 const int i = ray_touch(ox, oy, rend[2 * k], rend[2 * k + 1], pr, pc);
                                 if (i < 0) continue;
@@ -718,8 +741,14 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 bool is_dirty = !c.use_laser;
                 if (c.use_laser && any_hit) {
                     const unsigned kk = __ldg(okk + q);
-                    const int kmin = kk & 0xFFFFu, kmax = kk >> 16;
-                    is_dirty = kmax >= kmin && hpre[kmax + 1] != hpre[kmin];
+                    const int kmin = kk & 0xFFFu, kmax = (kk >> 12) & 0xFFFu;
+                    if (kmax >= kmin && hpre[kmax + 1] != hpre[kmin]) {
+                        // some of the rays hit something: still clean if every hit lies beyond all of the output's source pixels
+                        // (they are then all "free", as in the hit-free value) -- nearest hit over the covering ray blocks
+                        int hm = 1023;
+                        for (int b = kmin >> c.hb_shift; b <= (kmax >> c.hb_shift); b++) hm = min(hm, sh->hmin[b]);
+                        is_dirty = hm <= (int)(kk >> 24) * 4;
+                    }
                 }
                 if (is_dirty) dirty[atomicAdd(&sh->n_dirty, 1)] = (unsigned short)q;
                 else o_img[q] = __ldg(oval + q);
@@ -731,7 +760,7 @@ __global__ void __launch_bounds__(VIEW_THREADS) k_view(Dev d, const int* scene_i
                 const int it = base + lane;
                 const bool act = it < n4;
                 const int q = act ? dirty[it >> 2] : 0, t = it & 3;
-                const int orow = q / c.img, oc = q - orow * c.img;
+                const int orow = (int)__umulhi((unsigned)q, c.img_inv), oc = q - orow * c.img;
                 float sv = 0.f;
                 if (act) {
                     const short* tp = d.cubic_tap + 4 * oc;
