@@ -28,7 +28,19 @@ def needs_build():
     return any(os.path.getmtime(f) > t for f in deps)
 
 
+def build_variant(out, defs):
+    """Experiment helper: the same sources with extra -D macros into another .so (selected with IMGENV_LIB_PATH)."""
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false",
+           "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-o", out] + ["-D" + d for d in defs] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 def build(force=False, verbose=False):
+    if os.environ.get("IMGENV_LIB_PATH"):
+        return os.environ["IMGENV_LIB_PATH"]
     if not force and not needs_build():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false",

@@ -438,8 +438,10 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     h->view_smem = view_smem_bytes(c);
     h->dyn_smem = dyn_smem_bytes(c);
     if (h->view_smem > 227 * 1024) return fail("imgenv_create: view kernel needs too much shared memory for this configuration");
-    CK(cudaFuncSetAttribute(k_view<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
-    CK(cudaFuncSetAttribute(k_view<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
+    CK(cudaFuncSetAttribute(k_view<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
+    CK(cudaFuncSetAttribute(k_view<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
+    CK(cudaFuncSetAttribute(k_view<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
+    CK(cudaFuncSetAttribute(k_view<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
     if (h->dyn_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_dyn_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
     k_init_state<<<1184, 256>>>(d);
     CK(cudaGetLastError());
@@ -552,7 +554,8 @@ static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int i
     }
     k_footprints<<<(n_scenes * c.NPA + FOOT_WARPS - 1) / FOOT_WARPS, FOOT_WARPS * 32, h->foot_smem, st>>>(d, d_scene_ids, n_scenes, is_reset ? 0 : 1);
     if (ev) cudaEventRecord(ev[2], st);
-    k_view<false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
+    if (c.inverse_ok) k_view<false, false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
+    else k_view<false, true><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
     if (ev) cudaEventRecord(ev[3], st);
     CK(cudaStreamWaitEvent(st, h->ev_ped, 0));      // join: every output of the call is ordered on the caller's stream
     CK(cudaGetLastError());
@@ -936,7 +939,8 @@ extern "C" int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* 
     if (stats_out) { CK(cudaMalloc((void**)&sbuf, (size_t)c.S * c.R * 16)); CK(cudaMemsetAsync(sbuf, 0, (size_t)c.S * c.R * 16, st)); }
     d.dbg_view = buf; d.dbg_stats = sbuf;
     k_footprints<<<(c.S * c.NPA + FOOT_WARPS - 1) / FOOT_WARPS, FOOT_WARPS * 32, h->foot_smem, st>>>(d, nullptr, c.S, 0);
-    k_view<true><<<c.S * c.R, VIEW_THREADS, h->view_smem, st>>>(d, nullptr, 0);
+    if (c.inverse_ok) k_view<true, false><<<c.S * c.R, VIEW_THREADS, h->view_smem, st>>>(d, nullptr, 0);
+    else k_view<true, true><<<c.S * c.R, VIEW_THREADS, h->view_smem, st>>>(d, nullptr, 0);
     cudaError_t e = cudaSuccess;
     if (host_out) e = cudaMemcpyAsync(host_out, buf, n, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && stats_out) e = cudaMemcpyAsync(stats_out, sbuf, (size_t)c.S * c.R * 16, cudaMemcpyDeviceToHost, st);

@@ -11,7 +11,7 @@
 #include "foot.cuh"
 
 #define VIEW_THREADS 256
-#define VIEW_MIN_CTAS 4                 // 64 registers per thread: the register file holds 32 warps per SM either way
+#define VIEW_MIN_CTAS 4                // 64 registers per thread: the register file holds 32 warps per SM either way
 #define FX_ONE 4294967296.0            // 2^32: fixed-point scale of cell coordinates
 #define FX_GUARD 8192u                 // |frac - 0.5| below 2^-19 cells -> exact fp64 fallback
 
@@ -104,14 +104,13 @@ __device__ __noinline__ void cell_rays_inline(unsigned* hitkey, const short* ren
 
 // Shared-memory plan of k_view (bytes for the canonical 400x400 view / 1000 rays / 48x48 outputs; ~50 KB -> 4 CTAs per SM):
 //   region A  occupancy raster 400*13*4 = 20.8 KB (x2 with lasers off: + the "known" plane)            phases B-D
-//   region B  ray-hit candidate lists (BL_CAP + BL2_CAP)*4 = 13.3 KB                                     phases B-C
+//   region B  raster cells crossed by many rays BL2_CAP*4 = 2 KB (the others update their rays on the spot)  phases B-C
 //             later: list of output pixels that need the full evaluation img*img*2 = 4.6 KB + hit prefix counts 2 KB   phases D-F
 //   hitkey    range_total*4 (first hit per ray), ray end cells range_total*4, needed-line indices, FOV spans vh*8,
 //             list of world blocks under the FOV that hold static candidates INV_MAX_BLOCKS*4,
 //             footprint records near the robot: NP*2 (part ids) + (NP+1)*4 (running word counts) + colliding parts
 //   (no 400x400 pixel buffer: the laser_map values are evaluated per output pixel of the resize)
-#define BL_CAP 3072          // candidate cells kept in shared memory; further cells are resolved inline by their finder
-#define BL2_CAP 256          // cells touched by many rays (close to the origin): processed warp-cooperatively
+#define BL2_CAP 512          // cells touched by many rays (close to the origin): listed, then processed warp-cooperatively
 #define BL_HEAVY 24
 #define NOHIT 0xFFFFFFFFu
 #define CN_CAP 32            // footprint records that overlap the observer's own footprint box (collision candidates)
@@ -128,7 +127,8 @@ __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     size_t occ = c.inverse_ok ? 0 : (size_t)c.vh * c.vwb * 4 * (c.use_laser ? 1 : 2);   // no raster at all in the world->view mode
     L.regA = off; off += (occ + 15) & ~(size_t)15;
     const size_t dl = ((size_t)c.img * c.img * 2 + 15) & ~(size_t)15;
-    size_t bl = (size_t)(BL_CAP + BL2_CAP) * 4, hb = dl + ((size_t)c.range_total + 1) * 2;
+    size_t bl = (size_t)BL2_CAP * 4, hb = dl + ((size_t)c.range_total + 1) * 2;
+    if (!c.inverse_ok) bl = bl > (size_t)((c.vh + 31) / 32) * c.vwb * 2 ? bl : (size_t)((c.vh + 31) / 32) * c.vwb * 2;   // forward mode: tile list
     L.regB = off; L.hpre = off + dl; off += ((bl > hb ? bl : hb) + 15) & ~(size_t)15;
     L.hitkey = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
     L.rays = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
@@ -146,7 +146,76 @@ inline size_t view_smem_bytes(const Cfg& c) { return view_layout(c).total; }
 
 __device__ __forceinline__ unsigned hit_key(int i, int x, int y) { return ((unsigned)i << 22) | ((unsigned)x << 11) | (unsigned)y; }
 
-template <bool DEBUG_FULL>
+// exact reference operation sequence for a view pixel's world cell (map2world, tf multiply, world2map): only inside the
+// fixed-point form's guard band, hence out of line
+__device__ __noinline__ void exact_cell(const Tf2& view_world, double res, int i, int j, int& cx, int& cy) {
+    double wx, wy;
+    tf_apply(view_world, i * res, j * res, wx, wy);
+    cx = world2cell(wx, res); cy = world2cell(wy, res);
+}
+// pose-dependent constants of one robot's observation (one thread per CTA)
+__device__ __forceinline__ void view_prologue(const Dev& d, ViewShared* sh, int idx, int r) {
+    const Cfg& c = d.c;
+    const RobotType& ty = d.types[d.type_of[r]];
+    double x = RBF(d, RB_X, idx), y = RBF(d, RB_Y, idx), yaw = RBF(d, RB_YAW, idx);
+    sh->base_world = tf_from_pose(x, y, yaw);
+    sh->view_world = tf_mul(sh->base_world, c.view_base);       // get_view_world(), agent.cpp:128-131
+    sh->world_base = tf_inv(sh->base_world);
+    const Tf2& A = sh->view_world;
+    sh->ax = llrint(A.m00 * FX_ONE); sh->bx = llrint(A.m01 * FX_ONE);
+    sh->cx = llrint((A.ox / c.res) * FX_ONE) + (1ll << 31);
+    sh->ay = llrint(A.m10 * FX_ONE); sh->by = llrint(A.m11 * FX_ONE);
+    sh->cy = llrint((A.oy / c.res) * FX_ONE) + (1ll << 31);
+    // Agent::view early-out (agent.cpp:358-360): stale view_map_/hits_/is_collision_ are re-sent
+    sh->frozen = (RBF(d, RB_COLL, idx) != 0.0) || (RBF(d, RB_ARR, idx) != 0.0);
+    sh->coll_key = 0;
+    sh->red[0] = 0; sh->red[1] = 0; sh->red[2] = 0; sh->red[3] = 0; sh->red[4] = 0;
+    sh->n_near = 0; sh->n_cnear = 0; sh->n_dirty = 0; sh->n_hits = 0;
+    {   // the box of the robot's own footprint (the same box k_footprints gives its record; the record itself may be
+        // culled when no other robot is near, so it is not read here)
+        double bwx, bwy;
+        tf_apply(sh->base_world, ty.stamp_cx, ty.stamp_cy, bwx, bwy);
+        sh->own_hdr = foot_pack(foot_box(bwx, bwy, ty.stamp_rad, c.res), FK_ROBOT, r);
+    }
+    {   // inverse map and the FOV's world bounding box (for the world->view rasterisation)
+        const double det = A.m00 * A.m11 - A.m01 * A.m10;
+        sh->inv[0] = A.m11 / det; sh->inv[1] = -A.m01 / det; sh->inv[2] = -A.m10 / det; sh->inv[3] = A.m00 / det;
+        sh->org[0] = A.ox / c.res; sh->org[1] = A.oy / c.res;
+        int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
+        for (int k = 0; k < 4; k++) {
+            const int ii = (k & 1) ? ty.fov_r1 : ty.fov_r0, jj = (k & 2) ? ty.fov_c1 : ty.fov_c0;
+            const int cx = (int)((sh->cx + (long long)ii * sh->ax + (long long)jj * sh->bx) >> 32);
+            const int cy = (int)((sh->cy + (long long)ii * sh->ay + (long long)jj * sh->by) >> 32);
+            xmin = min(xmin, cx); xmax = max(xmax, cx); ymin = min(ymin, cy); ymax = max(ymax, cy);
+        }
+        xmin = max(xmin - 1, 0); ymin = max(ymin - 1, 0); xmax = min(xmax + 1, c.H - 1); ymax = min(ymax + 1, c.W - 1);
+        sh->wbb[0] = xmin; sh->wbb[1] = xmax; sh->wbb[2] = ymin; sh->wbb[3] = ymax;
+        const bool empty = xmin > xmax || ymin > ymax || ty.fov_r1 < ty.fov_r0;
+        sh->blk[0] = xmin >> 5; sh->blk[1] = ymin >> 5;
+        sh->blk[2] = empty ? 0 : (xmax >> 5) - (xmin >> 5) + 1; sh->blk[3] = empty ? 0 : (ymax >> 5) - (ymin >> 5) + 1;
+    }
+}
+// Phase G: state vector and the episode bookkeeping (img_env.cpp:547-587, yaml_env.py:316, 374-376, 467-471)
+__device__ __forceinline__ void view_state_vector(const Dev& d, int idx, int is_reset) {
+    const Cfg& c = d.c;
+    double st[5];
+    robot_state_vec(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx), RBF(d, RB_GX, idx), RBF(d, RB_GY, idx),
+                    RBF(d, RB_GYAW, idx), RBF(d, RB_L0V, idx), RBF(d, RB_L0W, idx), c.state_dim, st);
+    float s0 = (float)st[0], s1 = (float)st[1];
+    for (int k = 0; k < c.state_dim; k++) d.o_vec[(size_t)idx * c.state_dim + k] = (float)st[k];
+    double dist = sqrt((double)s0 * (double)s0 + (double)s1 * (double)s1);   // yaml_env.py:467
+    double prev = RBF(d, RB_PREVD, idx);
+    d.o_stepd[idx] = isnan(prev) ? 0.f : (float)(prev - dist);
+    RBF(d, RB_PREVD, idx) = dist;
+    int coll = (int)RBF(d, RB_COLL, idx), arr = RBF(d, RB_ARR, idx) != 0.0;
+    d.o_coll[idx] = (int8_t)coll;
+    d.o_arr[idx] = (uint8_t)arr;
+    RBF(d, RB_DONE, idx) = is_reset ? 0.0 : (double)min(1, min(coll, 1) + arr);   // yaml_env.py:316, 374-376
+}
+
+// FWD = false: lasers on and a FOV of ordinary size -> world->view rasterisation, no raster in shared memory (the hot variant);
+// FWD = true: lasers off (the "known" plane needs every FOV pixel) or a huge FOV -> forward rasterisation into a raster.
+template <bool DEBUG_FULL, bool FWD>
 __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, const int* scene_ids, int is_reset) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Cfg& c = d.c;
@@ -161,8 +230,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
     ViewShared* sh = reinterpret_cast<ViewShared*>(smem_raw + L.sh);
     uint32_t* occ = reinterpret_cast<uint32_t*>(smem_raw + L.regA);
     uint32_t* known = occ + (size_t)vh * vwb;                               // only when !use_laser
-    uint32_t* blist = reinterpret_cast<uint32_t*>(smem_raw + L.regB);
-    uint32_t* blist2 = blist + BL_CAP;
+    uint32_t* blist2 = reinterpret_cast<uint32_t*>(smem_raw + L.regB);
     unsigned short* dirty = reinterpret_cast<unsigned short*>(smem_raw + L.regB);   // after phase C
     unsigned short* hpre = reinterpret_cast<unsigned short*>(smem_raw + L.hpre);   // after phase C: hpre[k] = #rays < k with a hit
     short* spans = reinterpret_cast<short*>(smem_raw + L.spans);
@@ -178,45 +246,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
     const int4* fhdr = d.foot_hdr + (size_t)s * c.NP;
     const uint32_t* fwords = d.foot_words + (size_t)s * c.scene_words;
 
-    if (tid == 0) {
-        double x = RBF(d, RB_X, idx), y = RBF(d, RB_Y, idx), yaw = RBF(d, RB_YAW, idx);
-        sh->base_world = tf_from_pose(x, y, yaw);
-        sh->view_world = tf_mul(sh->base_world, c.view_base);       // get_view_world(), agent.cpp:128-131
-        sh->world_base = tf_inv(sh->base_world);
-        const Tf2& A = sh->view_world;
-        sh->ax = llrint(A.m00 * FX_ONE); sh->bx = llrint(A.m01 * FX_ONE);
-        sh->cx = llrint((A.ox / c.res) * FX_ONE) + (1ll << 31);
-        sh->ay = llrint(A.m10 * FX_ONE); sh->by = llrint(A.m11 * FX_ONE);
-        sh->cy = llrint((A.oy / c.res) * FX_ONE) + (1ll << 31);
-        // Agent::view early-out (agent.cpp:358-360): stale view_map_/hits_/is_collision_ are re-sent
-        sh->frozen = (RBF(d, RB_COLL, idx) != 0.0) || (RBF(d, RB_ARR, idx) != 0.0);
-        sh->coll_key = 0;
-        sh->red[0] = 0; sh->red[1] = 0; sh->red[2] = 0; sh->red[3] = 0; sh->red[4] = 0;
-        sh->n_near = 0; sh->n_cnear = 0; sh->n_dirty = 0; sh->n_hits = 0;
-        {   // the box of the robot's own footprint (the same box k_footprints gives its record; the record itself may be
-            // culled when no other robot is near, so it is not read here)
-            double bwx, bwy;
-            tf_apply(sh->base_world, ty.stamp_cx, ty.stamp_cy, bwx, bwy);
-            sh->own_hdr = foot_pack(foot_box(bwx, bwy, ty.stamp_rad, c.res), FK_ROBOT, r);
-        }
-        {   // inverse map and the FOV's world bounding box (for the world->view rasterisation)
-            const double det = A.m00 * A.m11 - A.m01 * A.m10;
-            sh->inv[0] = A.m11 / det; sh->inv[1] = -A.m01 / det; sh->inv[2] = -A.m10 / det; sh->inv[3] = A.m00 / det;
-            sh->org[0] = A.ox / c.res; sh->org[1] = A.oy / c.res;
-            int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
-            for (int k = 0; k < 4; k++) {
-                const int ii = (k & 1) ? ty.fov_r1 : ty.fov_r0, jj = (k & 2) ? ty.fov_c1 : ty.fov_c0;
-                const int cx = (int)((sh->cx + (long long)ii * sh->ax + (long long)jj * sh->bx) >> 32);
-                const int cy = (int)((sh->cy + (long long)ii * sh->ay + (long long)jj * sh->by) >> 32);
-                xmin = min(xmin, cx); xmax = max(xmax, cx); ymin = min(ymin, cy); ymax = max(ymax, cy);
-            }
-            xmin = max(xmin - 1, 0); ymin = max(ymin - 1, 0); xmax = min(xmax + 1, c.H - 1); ymax = min(ymax + 1, c.W - 1);
-            sh->wbb[0] = xmin; sh->wbb[1] = xmax; sh->wbb[2] = ymin; sh->wbb[3] = ymax;
-            const bool empty = xmin > xmax || ymin > ymax || ty.fov_r1 < ty.fov_r0;
-            sh->blk[0] = xmin >> 5; sh->blk[1] = ymin >> 5;
-            sh->blk[2] = empty ? 0 : (xmax >> 5) - (xmin >> 5) + 1; sh->blk[3] = empty ? 0 : (ymax >> 5) - (ymin >> 5) + 1;
-        }
-    }
+    if (tid == 0) view_prologue(d, sh, idx, r);
     {   // static tables into shared memory
         // one ray end = 2 shorts, one row of FOV spans = 4 shorts: copied as 4- and 8-byte words
         const int* g_rend = reinterpret_cast<const int*>(d.ray_end + 2 * (size_t)ty.ray_off);
@@ -234,7 +264,8 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
         const unsigned H = c.H, W = c.W, Wb = c.Wb;
         const int ox = ty.org_x, oy = ty.org_y;
         const uint32_t* kpack = d.kpack + (size_t)ty.khi_off;
-        const bool use_inverse = c.inverse_ok;
+        const bool use_inverse = !FWD;
+        const bool use_laser = FWD ? c.use_laser != 0 : true;
         const int X0 = sh->wbb[0], X1 = sh->wbb[1], Y0 = sh->wbb[2], Y1 = sh->wbb[3];
         const float i00 = (float)sh->inv[0], i01 = (float)sh->inv[1], i10 = (float)sh->inv[2], i11 = (float)sh->inv[3];
         const int orgi0 = (int)floor(sh->org[0]), orgi1 = (int)floor(sh->org[1]);
@@ -351,7 +382,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
         //     static map in 32x32-pixel tiles (skipping tiles whose world footprint only touches empty blocks), then the
         //     near footprint records (all of their cells) through the same inverse mapping.
         const uint32_t* static_occ = d.static_occ;
-        int* n_list = &sh->red[0]; int* n_list2 = &sh->red[1];
+        int* n_list2 = &sh->red[1];
         // every ray of [k0, k0+kstep, ...] within the cell's static ray interval that really passes through it
         // keeps the minimum step: hitkey[k] = min(step << 22 | cell)
         // When the rays through the cell are exactly the interval [kl, kh] (static flag, true for virtually every cell) no
@@ -369,18 +400,23 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 if (i >= 0) atomicMin(&hitkey[k], hit_key(i, pr, pc));
             }
         };
-        // a newly set raster cell goes straight to the ray-hit candidate lists (phase C)
+        // An occupied raster cell updates the rays through it on the spot (phase C); only cells crossed by many rays (close
+        // to the origin) are listed and shared out over a warp after the barrier.
         auto push_cell = [&](int pr, int pc) {
             const unsigned kp = __ldg(kpack + pr * vw + pc);
-            const int kh = kp & 0xFFFF;
+            const int kh = kp & 0xFFFF, kl = (kp >> 16) & 0x7FFF;
             if (kh == 0xFFFF) return;                                      // no ray passes through this cell
-            const bool heavy = kh - (int)((kp >> 16) & 0x7FFF) + 1 > BL_HEAVY;
-            const int p = atomicAdd(heavy ? n_list2 : n_list, 1);
-            if (p < (heavy ? BL2_CAP : BL_CAP)) (heavy ? blist2 : blist)[p] = ((unsigned)pr << 16) | (unsigned)pc;
-            else cell_rays_inline(hitkey, rend, ox, oy, pr, pc, (int)((kp >> 16) & 0x7FFF), kh);   // list full: resolve this cell right here
+            if (kh - kl + 1 > BL_HEAVY) {
+                const int p = atomicAdd(n_list2, 1);
+                if (p < BL2_CAP) { blist2[p] = ((unsigned)pr << 16) | (unsigned)pc; return; }
+            }
+            if (kp >> 31) {
+                const unsigned key = hit_key(max(abs(pr - ox), abs(pc - oy)), pr, pc);
+                for (int k = kl; k <= kh; k++) atomicMin(&hitkey[k], key);
+            } else cell_rays_inline(hitkey, rend, ox, oy, pr, pc, kl, kh);
         };
         const int n_trow = (vh + 31) >> 5, n_tiles = n_trow * vwb;
-        if (!use_inverse) for (int q = tid; q < vh * vwb; q += VIEW_THREADS) { occ[q] = 0u; if (!c.use_laser) known[q] = 0u; }
+        if (!use_inverse) for (int q = tid; q < vh * vwb; q += VIEW_THREADS) { occ[q] = 0u; if (!use_laser) known[q] = 0u; }
         if (use_inverse) {
             const uint32_t* crow = d.static_crow;
             const int nbj = sh->blk[3], nb = sh->blk[2] * nbj;
@@ -392,10 +428,10 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
             // forward rasterisation of the static map
             const uint32_t* orow = d.static_orow;
             int* n_active = &sh->red[2];
-            unsigned short* tile_list = reinterpret_cast<unsigned short*>(blist);     // region B is free until the candidate lists fill
+            unsigned short* tile_list = reinterpret_cast<unsigned short*>(blist2);     // region B is free until the heavy-cell list fills
             for (int t = tid; t < n_tiles; t += VIEW_THREADS) {
                 if (!((d.tile_fov[ty.tile_off + (t >> 5)] >> (t & 31)) & 1u)) continue;
-                bool active = !c.use_laser;          // the "known" plane needs every FOV pixel
+                bool active = !use_laser;          // the "known" plane needs every FOV pixel
                 if (!active) {
                     const int ti = t / vwb, tj = t - ti * vwb;
                     const int i0 = ti * 32, i1 = min(i0 + 31, vh - 1), j0 = tj * 32, j1 = min(j0 + 31, vw - 1);
@@ -423,7 +459,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
             const long long bx32 = sh->bx * 32, by32 = sh->by * 32;
 #pragma unroll 2
             for (int item = warp; item < n_items; item += VIEW_THREADS / 32) {
-                const int t = reinterpret_cast<unsigned short*>(blist)[item >> 5];
+                const int t = reinterpret_cast<unsigned short*>(blist2)[item >> 5];
                 const int wj = t & 255;
                 const int i = (t >> 8) * 32 + (item & 31);
                 if (i >= vh) continue;
@@ -437,9 +473,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                     int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
                     const unsigned lx = (unsigned)tx, ly = (unsigned)tyy;
                     if (lx + FX_GUARD < 2 * FX_GUARD || ly + FX_GUARD < 2 * FX_GUARD) {
-                        double wx, wy;   // exact path: map2world, tf multiply, world2map
-                        tf_apply(sh->view_world, i * c.res, j * c.res, wx, wy);
-                        cx = world2cell(wx, c.res); cy = world2cell(wy, c.res);
+                        exact_cell(sh->view_world, c.res, i, j, cx, cy);
                     }
                     if ((unsigned)cx < H && (unsigned)cy < W) {
                         kn = true;
@@ -447,7 +481,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                     }
                 }
                 const unsigned wo = __ballot_sync(0xffffffffu, o);
-                if (!c.use_laser) { const unsigned wk = __ballot_sync(0xffffffffu, kn); if (lane == 0) known[i * vwb + wj] = wk; }
+                if (!use_laser) { const unsigned wk = __ballot_sync(0xffffffffu, kn); if (lane == 0) known[i * vwb + wj] = wk; }
                 if (lane == 0) occ[i * vwb + wj] = wo;
             }
             __syncthreads();      // the footprint records below OR into the words written above
@@ -461,9 +495,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 const long long tyy = sh->cy + (long long)i * sh->ay + (long long)j * sh->by;
                 int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
                 if ((unsigned)tx + FX_GUARD < 2 * FX_GUARD || (unsigned)tyy + FX_GUARD < 2 * FX_GUARD) {
-                    double wx, wy;
-                    tf_apply(sh->view_world, i * c.res, j * c.res, wx, wy);
-                    cx = world2cell(wx, c.res); cy = world2cell(wy, c.res);
+                    exact_cell(sh->view_world, c.res, i, j, cx, cy);
                 }
                 if ((unsigned)cx < H && (unsigned)cy < W) {
                     const bool o = (__ldg(static_occ + (unsigned)cx * Wb + ((unsigned)cy >> 5)) >> (cy & 31)) & 1u;
@@ -556,9 +588,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                             const long long tyy = sh->cy + (long long)i * sh->ay + (long long)j * sh->by;
                             int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
                             if ((unsigned)tx + FX_GUARD < 2 * FX_GUARD || (unsigned)tyy + FX_GUARD < 2 * FX_GUARD) {
-                                double wx, wy;
-                                tf_apply(sh->view_world, i * c.res, j * c.res, wx, wy);
-                                cx = world2cell(wx, c.res); cy = world2cell(wy, c.res);
+                                exact_cell(sh->view_world, c.res, i, j, cx, cy);
                             }
                             if (cx != cX || cy != cY) continue;
                         }
@@ -582,7 +612,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
         // cells of the raster can be hits.  For each boundary cell the (static) interval of ray indices whose
         // integer line walk passes through it is scanned with the closed-form touch test and the ray keeps
         // the minimum step (atomicMin on step<<22|cell).  Cells that do not fit the lists are resolved inline.
-        if (c.use_laser) {
+        if (use_laser) {
             if (!use_inverse) {
                 for (int q = tid; q < vh * 16 * ((vwb + 15) / 16); q += VIEW_THREADS) {
                     const int wpr = 16 * ((vwb + 15) / 16);                  // words per row rounded up to 16: shift/mask indexing
@@ -614,13 +644,12 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 }
                 __syncthreads();
             }
-            const int nl = min(sh->red[0], BL_CAP), nl2 = min(sh->red[1], BL2_CAP);
+            const int nl2 = min(sh->red[1], BL2_CAP);
             if (d.dbg_stats && tid == 0) {
                 int* st = d.dbg_stats + 4 * (size_t)idx;
                 st[0] = sh->red[2] + sh->red[3] + n_near; st[1] = sh->red[0]; st[2] = sh->red[1];
-                st[3] = sh->red[0] > BL_CAP || sh->red[1] > BL2_CAP;
+                st[3] = sh->red[1] > BL2_CAP;
             }
-            for (int q = tid; q < nl; q += VIEW_THREADS) { const unsigned cell = blist[q]; cell_rays(cell, __ldg(kpack + (cell >> 16) * vw + (cell & 0xFFFFu)), 0, 1); }
             for (int q = warp; q < nl2; q += VIEW_THREADS / 32) { const unsigned cell = blist2[q]; cell_rays(cell, __ldg(kpack + (cell >> 16) * vw + (cell & 0xFFFFu)), lane, 32); }
             __syncthreads();
             if (!DEBUG_FULL) {
@@ -674,7 +703,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
         // e is the tap's dtab entry; the source column is only looked up on the rare fall-through path.
         auto pixel_code = [&](unsigned e, int rr, const short* tp, int k) -> unsigned {
             unsigned code = 2u; bool own;
-            if (c.use_laser) {
+            if (use_laser) {
                 own = e >> 31;
                 const int kh = e & 0xFFF;
                 if (kh != 0xFFF) {
@@ -706,7 +735,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 for (int cc = lane; cc < vw; cc += 32) {
                     const int pr = rr, pc = cc, full = pr * vw + pc;
                     int val = 200;
-                    if (c.use_laser) {
+                    if (use_laser) {
                         const unsigned kp = __ldg(kpack + full);
                         const int kh = kp & 0xFFFF;
                         if (kh != 0xFFFF) {
@@ -736,10 +765,10 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
             uint16_t* o_img = d.o_sensor + (size_t)idx * npx;
             const uint32_t* okk = d.ostat + (size_t)ty.ostat_off;                                   // [npx] kmin | kmax << 16
             const uint16_t* oval = reinterpret_cast<const uint16_t*>(d.ostat + (size_t)ty.ostat_off + npx);   // [npx] hit-free float16
-            const bool any_hit = !c.use_laser || sh->n_hits > 0;
+            const bool any_hit = !use_laser || sh->n_hits > 0;
             for (int q = tid; q < npx; q += VIEW_THREADS) {
-                bool is_dirty = !c.use_laser;
-                if (c.use_laser && any_hit) {
+                bool is_dirty = !use_laser;
+                if (use_laser && any_hit) {
                     const unsigned kk = __ldg(okk + q);
                     const int kmin = kk & 0xFFFu, kmax = (kk >> 12) & 0xFFFu;
                     if (kmax >= kmin && hpre[kmax + 1] != hpre[kmin]) {
@@ -767,7 +796,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                     const short4 cf = __ldg(reinterpret_cast<const short4*>(d.cubic_coef) + oc);
                     const int rr = d.cubic_tap[4 * orow + t];
                     uint4 e4 = make_uint4(0u, 0u, 0u, 0u);
-                    if (c.use_laser) e4 = __ldg(reinterpret_cast<const uint4*>(dtab) + rr * c.img + oc);
+                    if (use_laser) e4 = __ldg(reinterpret_cast<const uint4*>(dtab) + rr * c.img + oc);
                     int acc = 0;
                     if (cf.x) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.x, rr, tp, 0))) & 0xFFu) * cf.x;
                     if (cf.y) acc += (int)((0xFFC86400u >> (8 * pixel_code(e4.y, rr, tp, 1))) & 0xFFu) * cf.y;
@@ -789,23 +818,9 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
     }
     if (DEBUG_FULL) return;
 
-    // ---- Phase G: state vector and the episode bookkeeping (img_env.cpp:547-587, yaml_env.py:316, 374-376, 467-471).
-    //      The pedestrian observation does not depend on the raster: k_ped_obs below, on its own stream.
-    if (tid == 0) {
-        double st[5];
-        robot_state_vec(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx), RBF(d, RB_GX, idx), RBF(d, RB_GY, idx),
-                        RBF(d, RB_GYAW, idx), RBF(d, RB_L0V, idx), RBF(d, RB_L0W, idx), c.state_dim, st);
-        float s0 = (float)st[0], s1 = (float)st[1];
-        for (int k = 0; k < c.state_dim; k++) d.o_vec[(size_t)idx * c.state_dim + k] = (float)st[k];
-        double dist = sqrt((double)s0 * (double)s0 + (double)s1 * (double)s1);   // yaml_env.py:467
-        double prev = RBF(d, RB_PREVD, idx);
-        d.o_stepd[idx] = isnan(prev) ? 0.f : (float)(prev - dist);
-        RBF(d, RB_PREVD, idx) = dist;
-        int coll = (int)RBF(d, RB_COLL, idx), arr = RBF(d, RB_ARR, idx) != 0.0;
-        d.o_coll[idx] = (int8_t)coll;
-        d.o_arr[idx] = (uint8_t)arr;
-        RBF(d, RB_DONE, idx) = is_reset ? 0.0 : (double)min(1, min(coll, 1) + arr);   // yaml_env.py:316, 374-376
-    }
+    // ---- Phase G: state vector and the episode bookkeeping.  The pedestrian observation does not depend on the raster:
+    //      k_ped_obs below, on its own stream.
+    if (tid == 0) view_state_vector(d, idx, is_reset);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ import numpy as np
 from .spec import SCENES, KTYPES
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libimgenv_b200.so")
+LIB_PATH = os.environ.get("IMGENV_LIB_PATH") or os.path.join(_HERE, "libimgenv_b200.so")    # (override: kernel-variant experiments)
 _LIB = None
 
 
