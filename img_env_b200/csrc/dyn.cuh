@@ -9,10 +9,10 @@
 #pragma once
 #include "state.cuh"
 #include "kin.cuh"
+#define DYN_THREADS 64
 #include "orca.cuh"
 #include "sfmtree.cuh"
 
-#define DYN_THREADS 64
 
 struct V3 { double x, y, z; };
 __device__ __forceinline__ V3 v3(double x, double y, double z = 0) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -217,16 +217,31 @@ __host__ __device__ __forceinline__ int dyn_nblk(const Cfg& c) {
     return (n + DYN_THREADS - 1) / DYN_THREADS;
 }
 
-__global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* actions, const uint8_t* alive) {
+// shared memory of k_dyn_solve: agents' pos + vel, beeps, spatial hash (head table + chain), per-thread ORCA tables
+__host__ __device__ inline size_t dyn_scratch_offset(const Cfg& c) {
+    size_t off = (size_t)c.NA * 16 + (size_t)c.R * 8 + ((size_t)c.R + (c.R & 1)) * 4 + ((size_t)agent_hash_size(c.NA) + c.NA) * 2;
+    return (off + 15) & ~(size_t)15;
+}
+inline size_t dyn_smem_bytes(const Cfg& c) {
+    return dyn_scratch_offset(c) + ((c.scene_type == 2 || c.scene_type == 3) ? orca_scratch_bytes() : 0) + 16;
+}
+
+__global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* actions, const uint8_t* alive, int parity) {
     extern __shared__ __align__(16) unsigned char dsm[];
     const Cfg& c = d.c;
     const int nblk = dyn_nblk(c);
     const int s = blockIdx.x / nblk, blk = blockIdx.x % nblk, tid = threadIdx.x;
     if (!(c.P > 0 && c.scene_type != 0 && c.scene_type != 4)) return;
+    // shared memory: the scene's agents (position, velocity), beeps, spatial hash, then the per-thread ORCA tables
     V2* pos = reinterpret_cast<V2*>(dsm);
     V2* vel = pos + c.NA;
     V2* beep_p = vel + c.NA;
     float* beep_r = reinterpret_cast<float*>(beep_p + c.R);
+    AgentHash hash;
+    hash.mask = agent_hash_size(c.NA) - 1;
+    hash.head = reinterpret_cast<unsigned short*>(beep_r + c.R + (c.R & 1));
+    hash.next = hash.head + hash.mask + 1;
+    unsigned char* scratch = dsm + dyn_scratch_offset(c);
     const unsigned long long step = d.step_no[s];
     // beeps (img_env.cpp:323-342): robots' PRE-step poses; recomputed identically by every CTA of the scene
     for (int j = tid; j < c.R; j += DYN_THREADS) {
@@ -248,11 +263,14 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* a
             vel[k] = v2(d.rvo_vel[((size_t)s * c.NA + k) * 2], d.rvo_vel[((size_t)s * c.NA + k) * 2 + 1]);
         }
         __syncthreads();
+        agent_hash_build(hash, pos, c.NA, tid, DYN_THREADS);
         if (a >= c.NA) return;
-        ObstView ob;
+        ObstacleSet ob;
         ob.verts = d.rvo_verts + (size_t)s * d.max_verts * 8;
-        ob.nodes = d.rvo_nodes + (size_t)s * d.max_verts * 3;
+        ob.nodes = d.rvo_nodes + (size_t)s * d.max_verts * 4;
+        ob.node_seg = d.rvo_nodeseg + (size_t)s * d.max_verts * 4;
         ob.root = d.rvo_counts[2 * s + 1];
+        if (blockIdx.x == 0 && tid == 0) d.orca_cursor[parity ^ 1] = 0u;       // the next call's slab cursor
         V2 pref = v2(0.f, 0.f);
         float maxSpeed = 0.6f;
         if (a < c.P) {
@@ -269,11 +287,14 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* a
             PDF(d, PD_TIDX, pi) = ti;
             const double* g = tr + 3 * (ti % tl);
             V2 goalVector = v2((float)g[0], (float)g[1]) - pos[a];     // rvoscene.h:37-44
-            if (absSq(goalVector) > 1.0f) goalVector = normalize(goalVector);
+            if (norm2(goalVector) > 1.0f) goalVector = unit(goalVector);
             pref = goalVector;
             maxSpeed = (float)d.ped_maxspeed[a];
         }
-        V2 nv = orca_new_velocity(a, c.NA, pos, vel, pref, maxSpeed, (float)c.step_hz, ob, c.scene_type == 3, c.R, beep_p, beep_r);
+        OrcaScratch sc = orca_scratch(scratch, tid);
+        OrcaPool pool;
+        pool.slabs = d.orca_pool; pool.n_slabs = d.orca_nslabs; pool.cursor = d.orca_cursor + parity; pool.overflow = d.counters;
+        V2 nv = orca_new_velocity(a, pos, vel, hash, pref, maxSpeed, (float)c.step_hz, ob, sc, pool, c.scene_type == 3, c.R, beep_p, beep_r);
         d.rvo_nvel[((size_t)s * c.NA + a) * 2] = nv.x; d.rvo_nvel[((size_t)s * c.NA + a) * 2 + 1] = nv.y;
     } else if (c.scene_type == 1) {
         if (a >= c.NA) return;
@@ -411,4 +432,4 @@ __global__ void __launch_bounds__(32) k_sfm_tree(Dev d) {
     for (int a = threadIdx.x; a < d.c.NA; a += 32) d.sfm[((size_t)s * d.c.NA + a) * SFM_REC + 10] = qt_in_tree(t, a) ? 1.0 : 0.0;
 }
 
-inline size_t dyn_smem_bytes(const Cfg& c) { return (size_t)c.NA * 2 * 8 + (size_t)c.R * 12 + 64; }
+

@@ -315,7 +315,7 @@ inline void f16_lut(uint16_t* out) { for (int i = 0; i < 256; i++) out[i] = f32_
 
 // ---------------- RVO2 obstacles ----------------
 struct RvoObst { float px, py, dx, dy; int convex, next, prev; };
-struct RvoNode { int obstacle, left, right; };
+struct RvoNode { int obstacle, left, right, parent; };
 struct F2 { float x, y; };
 inline F2 f2(float x, float y) { F2 r; r.x = x; r.y = y; return r; }
 inline F2 sub(F2 a, F2 b) { return f2(a.x - b.x, a.y - b.y); }
@@ -388,11 +388,13 @@ inline int rvo_build_tree(std::vector<RvoObst>& obs, std::vector<RvoNode>& nodes
     }
     int me = (int)nodes.size();
     nodes.push_back(RvoNode());
-    nodes[me].obstacle = I1;
+    nodes[me].obstacle = I1; nodes[me].parent = -1;
     int l = rvo_build_tree(obs, nodes, leftObstacles);
     nodes[me].left = l;
+    if (l >= 0) nodes[l].parent = me;
     int r = rvo_build_tree(obs, nodes, rightObstacles);
     nodes[me].right = r;
+    if (r >= 0) nodes[r].parent = me;
     return me;
 }
 

@@ -30,6 +30,7 @@ struct imgenv {
     std::vector<int> ped_shape;
     bool outputs_bound = false;
     int ped_yaw_mode = 0;
+    unsigned solve_calls = 0;
     // reset staging (pinned host + device)
     // two sets used alternately: a reset only waits (on the set's event) for the reset before the previous one
     struct Stage { double* h = nullptr; double* d = nullptr; int* ih = nullptr; int* id = nullptr; float* fh = nullptr; float* fd = nullptr; cudaEvent_t ev = nullptr; };
@@ -365,7 +366,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     AL(rb, (size_t)RB_FIELDS * S * c.R) AL(pd, (size_t)PD_FIELDS * S * c.P)
     AL(traj, S * c.P * c.max_traj * 3) AL(traj_v, c.scene_type == 4 ? S * c.P * c.max_traj * 3 : 1) AL(traj_len, S * c.P) AL(obs, S * c.max_obs * 8) AL(n_obs, S) AL(step_no, S)
     AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_nvel, S * c.NA * 2) AL(sfm_force, c.scene_type == 1 ? S * c.NA * 12 : 1)
-    AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 3)
+    AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 4) AL(rvo_nodeseg, S * d.max_verts * 4) AL(counters, 4) AL(orca_cursor, 2)
     AL(rvo_counts, S * 2) AL(sfm, S * c.NA * SFM_REC) AL(sfm_obs, S * c.max_obs * 4) AL(sfm_nobs, S)
     AL(sfm_wp, S * c.P * (1 + c.max_traj) * 3)
     {
@@ -406,6 +407,8 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         }
         if (dupload(h, &d.sfm_vmax0, vmax0)) return -1;
     }
+    d.orca_nslabs = (c.scene_type == 2 || c.scene_type == 3) ? 4096 : 0;
+    if (dalloc(h, &d.orca_pool, (size_t)std::max(d.orca_nslabs, 1) * ORCA_SLAB_BYTES)) return -1;
     if (dalloc(h, &h->act_d, S * c.R * 3)) return -1;
     if (dalloc(h, &h->alive_d, S * c.R)) return -1;
     {   // rvo root = -1 (no obstacle tree) until the first reset
@@ -415,8 +418,8 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     }
     // reset staging: per scene doubles = obs 8*max_obs + robots 5*R + peds 5*P + traj 3*max_traj*P + sfm segs 4*max_obs
     h->st_doubles = S * ((size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 6 * (size_t)c.max_traj * c.P + 4 * c.max_obs) + 8;
-    h->st_ints = S * ((size_t)5 + c.P + 3 * (size_t)d.max_verts) + S + 8;
-    h->st_floats = S * ((size_t)8 * d.max_verts) + 8;
+    h->st_ints = S * ((size_t)5 + c.P + 4 * (size_t)d.max_verts) + S + 8;
+    h->st_floats = S * ((size_t)12 * d.max_verts) + 8;
     for (auto& g : h->stage) {
         CK(cudaMallocHost((void**)&g.h, h->st_doubles * 8)); if (dalloc(h, &g.d, h->st_doubles)) return -1;
         CK(cudaMallocHost((void**)&g.ih, h->st_ints * 4)); if (dalloc(h, &g.id, h->st_ints)) return -1;
@@ -442,6 +445,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     CK(cudaFuncSetAttribute(k_view<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
     CK(cudaFuncSetAttribute(k_view<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
     CK(cudaFuncSetAttribute(k_view<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
+    if (h->dyn_smem > 200 * 1024) return fail("imgenv_create: too many solver agents per scene for the dynamics kernel's shared memory");
     if (h->dyn_smem > 48 * 1024) CK(cudaFuncSetAttribute(k_dyn_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
     k_init_state<<<1184, 256>>>(d);
     CK(cudaGetLastError());
@@ -476,7 +480,7 @@ extern "C" int imgenv_bind_outputs(imgenv_t* h, const imgenv_outputs* o) {
 
 // staged reset record layout (per listed scene), doubles:
 //   obs[max_obs][8] | robots[R][5] x,y,yaw,gx,gy | peds[P][5] x,y,yaw,gx,gy | traj[P][max_traj][3] | segs[max_obs][4] | traj_v[P][max_traj][3]
-// ints: scene_id, n_obs, n_segs, n_verts, root | traj_len[P] | nodes[max_verts][3]   floats: verts[max_verts][8]
+// ints: scene_id, n_obs, n_segs, n_verts, root | traj_len[P] | nodes[max_verts][4]   floats: verts[max_verts][8]
 __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, const float* stf, size_t dper, size_t iper, size_t fper) {
     const Cfg& c = d.c;
     int sl = blockIdx.x;
@@ -493,7 +497,8 @@ __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, co
         d.n_obs[s] = I[1]; d.sfm_nobs[s] = I[2]; d.rvo_counts[2 * s] = I[3]; d.rvo_counts[2 * s + 1] = I[4]; d.step_no[s] = 0;
     }
     for (int k = threadIdx.x; k < 8 * d.max_verts; k += blockDim.x) d.rvo_verts[(size_t)s * d.max_verts * 8 + k] = Fp[k];
-    for (int k = threadIdx.x; k < 3 * d.max_verts; k += blockDim.x) d.rvo_nodes[(size_t)s * d.max_verts * 3 + k] = nodes[k];
+    for (int k = threadIdx.x; k < 4 * d.max_verts; k += blockDim.x) d.rvo_nodeseg[(size_t)s * d.max_verts * 4 + k] = Fp[8 * d.max_verts + k];
+    for (int k = threadIdx.x; k < 4 * d.max_verts; k += blockDim.x) d.rvo_nodes[(size_t)s * d.max_verts * 4 + k] = nodes[k];
     for (int j = threadIdx.x; j < c.R; j += blockDim.x) {
         int idx = s * c.R + j;
         const double* q = rob + 5 * j;
@@ -589,8 +594,8 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
         }
     }
     size_t dper = (size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 6 * (size_t)c.max_traj * c.P + 4 * c.max_obs;
-    size_t iper = (size_t)5 + c.P + 3 * (size_t)d.max_verts;
-    size_t fper = (size_t)8 * d.max_verts;
+    size_t iper = (size_t)5 + c.P + 4 * (size_t)d.max_verts;
+    size_t fper = (size_t)12 * d.max_verts;
     memset(h->st_h, 0, dper * n * 8); memset(h->sti_h, 0, iper * n * 4); memset(h->stf_h, 0, fper * n * 4);
     auto pack_scene = [&](int sl) -> const char* {
         int s = scene_ids ? scene_ids[sl] : sl;
@@ -636,7 +641,10 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
                 v[5] = (float)robst[k].next; v[6] = (float)robst[k].prev; v[7] = 0;
             }
             int* nd = I + 5 + c.P;
-            for (size_t k = 0; k < nodes.size(); k++) { nd[3 * k] = nodes[k].obstacle; nd[3 * k + 1] = nodes[k].left; nd[3 * k + 2] = nodes[k].right; }
+            for (size_t k = 0; k < nodes.size(); k++) { nd[4 * k] = nodes[k].obstacle; nd[4 * k + 1] = nodes[k].left; nd[4 * k + 2] = nodes[k].right; nd[4 * k + 3] = nodes[k].parent;
+                float* sg = Fp + 8 * (size_t)d.max_verts + 4 * k;           // the node's edge: its vertex and that vertex's successor
+                const ht::RvoObst& a = robst[nodes[k].obstacle]; const ht::RvoObst& b = robst[a.next];
+                sg[0] = a.px; sg[1] = a.py; sg[2] = b.px; sg[3] = b.py; }
         }
         I[3] = (int)robst.size(); I[4] = root;
         for (int j = 0; j < c.R; j++) {
@@ -688,7 +696,7 @@ extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d
     {
         const int nblk = dyn_nblk(c);
         if (h->tree_pending) { CK(cudaStreamWaitEvent(st, h->ev_tree, 0)); h->tree_pending = false; }
-        if (c.NA > 0) k_dyn_solve<<<c.S * nblk, DYN_THREADS, h->dyn_smem, st>>>(d, d_actions, d_alive);
+        if (c.NA > 0) k_dyn_solve<<<c.S * nblk, DYN_THREADS, h->dyn_smem, st>>>(d, d_actions, d_alive, (int)(h->solve_calls++ & 1));
         k_dyn_apply<<<c.S * nblk, DYN_THREADS, 0, st>>>(d, d_actions, d_alive, h->ped_yaw_mode);
 
     }
@@ -847,6 +855,16 @@ extern "C" int imgenv_reset_sampled(imgenv_t* h, imgenv_sampler_t* w, int32_t n,
     return imgenv_reset(h, n, scene_ids, w->n_obs.data(), w->obs.data(), w->robots.data(), w->peds.data(), w->traj_len.data(), w->traj.data(), nullptr, ignore_obstacle, stream);
 }
 
+// Diagnostic counters since creation: out4[0] = ORCA obstacle-neighbour table overflows (an agent had more than ORCA_OBST_CAP
+// facing obstacle edges in range and kept the nearest; the reference keeps all of them), out4[1..3] reserved.
+extern "C" int imgenv_debug_counters(imgenv_t* h, int64_t* out4, void* stream) {
+    if (!h || !out4) return fail("imgenv_debug_counters: null argument");
+    unsigned long long r[4];
+    CK(cudaMemcpyAsync(r, h->d.counters, 32, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int k = 0; k < 4; k++) out4[k] = (int64_t)r[k];
+    return 0;
+}
 extern "C" int imgenv_end_episode(imgenv_t* h, int32_t) { return h ? 0 : fail("imgenv_end_episode: null handle"); }
 extern "C" int imgenv_solver_agents(const imgenv_t* h) { return h ? h->d.c.NA : 0; }
 extern "C" int imgenv_view_dims(const imgenv_t* h, int32_t* vh, int32_t* vw) {

@@ -40,7 +40,7 @@ EXPORTS = ["imgenv_create", "imgenv_destroy", "imgenv_bind_outputs", "imgenv_res
            "imgenv_algorithmic_bytes_per_robot_step", "imgenv_last_error", "imgenv_version",
            "imgenv_sampler_create", "imgenv_sampler_destroy", "imgenv_sampler_seed", "imgenv_sampler_sample", "imgenv_sampler_draw",
            "imgenv_reset_sampled", "imgenv_debug_check_footprints",
-           "imgenv_record_enable", "imgenv_record_fetch", "imgenv_debug_set_min_jerk", "imgenv_set_ped_yaw_mode"]
+           "imgenv_record_enable", "imgenv_record_fetch", "imgenv_debug_set_min_jerk", "imgenv_set_ped_yaw_mode", "imgenv_debug_counters"]
 
 
 def load_library(path=None):
@@ -269,6 +269,12 @@ class BatchedSim:
         self._check(self.lib.imgenv_step_host(self.h, C.c_void_p(actions_ptr), C.c_void_p(alive_ptr) if alive_ptr else None,
                                               self._stream()))
         return self.out
+
+    def debug_counters(self):
+        """-> (ORCA obstacle-neighbour table overflows, 0, 0, 0) since creation."""
+        out = np.zeros(4, np.int64)
+        self._check(self.lib.imgenv_debug_counters(self.h, _ptr(out, C.c_int64), self._stream()))
+        return tuple(int(x) for x in out)
 
     def debug_set_min_jerk(self, min_jerk):
         """min_jerk[R,2] (linear, angular): the value the node's unassigned SpeedLimiter::min_jerk holds (tests)."""

@@ -157,6 +157,9 @@ int imgenv_debug_check_footprints(imgenv_t* h, int64_t* out4, void* stream);
 int imgenv_debug_set_min_jerk(imgenv_t* h, const double* min_jerk);
 /* Pedestrian yaw the node reads from an unassigned local (img_env.cpp:346-349): 0 keep, 1 zero (this build of the node), 2 heading. */
 int imgenv_set_ped_yaw_mode(imgenv_t* h, int mode);
+/* Diagnostic counters since creation: out4[0] = times an ORCA agent had more facing obstacle edges in range than the solver's
+ * per-agent table holds (it then keeps the nearest; the reference keeps all).  Tests assert 0. */
+int imgenv_debug_counters(imgenv_t* h, int64_t* out4, void* stream);
 /* ped_min_dists persistence (NearbyPed, reset_helper.py:85-99) and dones are library state. */
 int imgenv_solver_agents(const imgenv_t* h);   /* P + R' */
 int imgenv_view_dims(const imgenv_t* h, int32_t* vh, int32_t* vw);

@@ -106,6 +106,7 @@ def run_lockstep(cfg, seed, steps, S=1, beep=False, sync=True, opt_in_beep=False
                 del now_frozen
             dones[s] = np.clip(np.clip(want["is_collisions"], -1, 1) + want["is_arrives"], 0, 1)
         assert not errs, "\n".join(errs[:20])
+    assert sim.debug_counters()[0] == 0, "an ORCA agent saw more obstacle edges than its table holds (the reference keeps all)"
     sim.close()
 
 
