@@ -222,8 +222,10 @@ __host__ __device__ inline size_t dyn_scratch_offset(const Cfg& c) {
     size_t off = (size_t)c.NA * 16 + (size_t)c.R * 8 + ((size_t)c.R + (c.R & 1)) * 4 + ((size_t)agent_hash_size(c.NA) + c.NA) * 2;
     return (off + 15) & ~(size_t)15;
 }
-inline size_t dyn_smem_bytes(const Cfg& c) {
-    return dyn_scratch_offset(c) + ((c.scene_type == 2 || c.scene_type == 3) ? orca_scratch_bytes() : 0) + 16;
+__host__ __device__ inline int dyn_node_cache(const Dev& d) { return d.max_verts < ORCA_NODE_CACHE ? d.max_verts : ORCA_NODE_CACHE; }
+inline size_t dyn_smem_bytes(const Dev& d) {
+    const Cfg& c = d.c;
+    return dyn_scratch_offset(c) + ((c.scene_type == 2 || c.scene_type == 3) ? orca_scratch_bytes() + (size_t)dyn_node_cache(d) * 32 : 0) + 16;
 }
 
 __global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* actions, const uint8_t* alive, int parity) {
@@ -242,6 +244,8 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* a
     hash.head = reinterpret_cast<unsigned short*>(beep_r + c.R + (c.R & 1));
     hash.next = hash.head + hash.mask + 1;
     unsigned char* scratch = dsm + dyn_scratch_offset(c);
+    int4* node_cache = reinterpret_cast<int4*>(scratch + orca_scratch_bytes());
+    float4* seg_cache = reinterpret_cast<float4*>(node_cache + dyn_node_cache(d));
     const unsigned long long step = d.step_no[s];
     // beeps (img_env.cpp:323-342): robots' PRE-step poses; recomputed identically by every CTA of the scene
     for (int j = tid; j < c.R; j += DYN_THREADS) {
@@ -256,20 +260,46 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* a
         if (!is_beep) { beep_p[j] = v2(0.f, 0.f); beep_r[j] = 0.f; }
         if (blk == 0) RBF(d, RB_BEEP, idx) = is_beep ? 1.0 : 0.0;
     }
+    // ERVO only looks at robots that beep: keep those, in robot order (the evacuation velocities are summed in that order)
+    __shared__ int s_nbeep;
+    __syncthreads();
+    if (tid < 32) {
+        int base = 0;
+        for (int j0 = 0; j0 < c.R; j0 += 32) {
+            const int j = j0 + tid;
+            const bool on = j < c.R && beep_r[j] > 0.f;
+            const V2 bp = j < c.R ? beep_p[j] : v2(0.f, 0.f);
+            const float br = j < c.R ? beep_r[j] : 0.f;
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            __syncwarp();
+            if (on) { const int k = base + __popc(m & ((1u << tid) - 1u)); beep_p[k] = bp; beep_r[k] = br; }
+            base += __popc(m);
+            __syncwarp();
+        }
+        if (tid == 0) s_nbeep = base;
+    }
+    __syncthreads();
     const int a = blk * DYN_THREADS + tid;
     if (c.scene_type == 2 || c.scene_type == 3) {
         for (int k = tid; k < c.NA; k += DYN_THREADS) {
             pos[k] = v2(d.rvo_pos[((size_t)s * c.NA + k) * 2], d.rvo_pos[((size_t)s * c.NA + k) * 2 + 1]);
             vel[k] = v2(d.rvo_vel[((size_t)s * c.NA + k) * 2], d.rvo_vel[((size_t)s * c.NA + k) * 2 + 1]);
         }
-        __syncthreads();
-        agent_hash_build(hash, pos, c.NA, tid, DYN_THREADS);
-        if (a >= c.NA) return;
         ObstacleSet ob;
         ob.verts = d.rvo_verts + (size_t)s * d.max_verts * 8;
         ob.nodes = d.rvo_nodes + (size_t)s * d.max_verts * 4;
         ob.node_seg = d.rvo_nodeseg + (size_t)s * d.max_verts * 4;
         ob.root = d.rvo_counts[2 * s + 1];
+        ob.n_cached = min(d.rvo_counts[2 * s], dyn_node_cache(d));
+        ob.cache_nodes = node_cache; ob.cache_seg = seg_cache;
+        for (int k = tid; k < ob.n_cached; k += DYN_THREADS) {     // the obstacle BSP is walked by every agent: stage it
+            node_cache[k] = __ldg(reinterpret_cast<const int4*>(ob.nodes) + k);
+            seg_cache[k] = __ldg(reinterpret_cast<const float4*>(ob.node_seg) + k);
+        }
+        __syncthreads();
+        agent_hash_build(hash, pos, c.NA, tid, DYN_THREADS);
+        const unsigned warp_mask = __ballot_sync(0xffffffffu, a < c.NA);
+        if (a >= c.NA) return;
         if (blockIdx.x == 0 && tid == 0) d.orca_cursor[parity ^ 1] = 0u;       // the next call's slab cursor
         V2 pref = v2(0.f, 0.f);
         float maxSpeed = 0.6f;
@@ -294,7 +324,7 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* a
         OrcaScratch sc = orca_scratch(scratch, tid);
         OrcaPool pool;
         pool.slabs = d.orca_pool; pool.n_slabs = d.orca_nslabs; pool.cursor = d.orca_cursor + parity; pool.overflow = d.counters;
-        V2 nv = orca_new_velocity(a, pos, vel, hash, pref, maxSpeed, (float)c.step_hz, ob, sc, pool, c.scene_type == 3, c.R, beep_p, beep_r);
+        V2 nv = orca_new_velocity(a, pos, vel, hash, pref, maxSpeed, (float)c.step_hz, ob, sc, pool, warp_mask, c.scene_type == 3, s_nbeep, beep_p, beep_r);
         d.rvo_nvel[((size_t)s * c.NA + a) * 2] = nv.x; d.rvo_nvel[((size_t)s * c.NA + a) * 2 + 1] = nv.y;
     } else if (c.scene_type == 1) {
         if (a >= c.NA) return;

@@ -439,7 +439,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     CK(cudaFuncSetAttribute(k_footprints, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->foot_smem));
     CK(cudaFuncSetAttribute(k_object_footprints, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->obj_smem));
     h->view_smem = view_smem_bytes(c);
-    h->dyn_smem = dyn_smem_bytes(c);
+    h->dyn_smem = dyn_smem_bytes(d);
     if (h->view_smem > 227 * 1024) return fail("imgenv_create: view kernel needs too much shared memory for this configuration");
     CK(cudaFuncSetAttribute(k_view<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
     CK(cudaFuncSetAttribute(k_view<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));

@@ -30,6 +30,7 @@
 #define ORCA_FAST 16                    // obstacle neighbours / lines per agent kept in shared memory
 #define ORCA_OBST_CAP 256               // obstacle neighbours per agent in total (beyond ORCA_FAST: in a pool slab)
 #define ORCA_LINE_CAP (ORCA_NEIGH_CAP + ORCA_OBST_CAP)
+#define ORCA_NODE_CACHE 1024             // BSP nodes (32 bytes each) staged in shared memory per CTA
 #define ORCA_SLAB_BYTES ((ORCA_LINE_CAP - ORCA_FAST) * 16 + (ORCA_OBST_CAP - ORCA_FAST) * 8)
 #ifndef DYN_THREADS
 #define DYN_THREADS 64
@@ -65,6 +66,7 @@ struct ObstacleSet {
     const float* verts;   // [n][8] px, py, edge direction x, y, convex, next, prev, 0
     const int* nodes;     // [n][4] edge (= its first vertex), left child, right child, parent
     const float* node_seg;// [n][4] the end points of the node's edge
+    const int4* cache_nodes; const float4* cache_seg; int n_cached;   // the first nodes of both arrays, staged in shared memory
     int root;
     __device__ __forceinline__ V2 point(int i) const { return v2(verts[8 * i], verts[8 * i + 1]); }
     __device__ __forceinline__ V2 dir(int i) const { return v2(verts[8 * i + 2], verts[8 * i + 3]); }
@@ -185,8 +187,9 @@ __device__ __forceinline__ int gather_obstacle_neighbours(OrcaScratch& sc, const
     int n = 0;
     int node = ob.root, came_from = -2;        // -2: arrived from the parent; otherwise the child we return from
     while (node >= 0) {
-        const int4 nd = __ldg(reinterpret_cast<const int4*>(ob.nodes) + node);         // edge, left, right, parent
-        const float4 sg = __ldg(reinterpret_cast<const float4*>(ob.node_seg) + node);   // the edge's end points
+        int4 nd; float4 sg;                      // (edge, left, right, parent), the edge's end points
+        if (node < ob.n_cached) { nd = ob.cache_nodes[node]; sg = ob.cache_seg[node]; }
+        else { nd = __ldg(reinterpret_cast<const int4*>(ob.nodes) + node); sg = __ldg(reinterpret_cast<const float4*>(ob.node_seg) + node); }
         const V2 a = v2(sg.x, sg.y), b = v2(sg.z, sg.w);
         const float side = side_of(a, b, p);
         const int near_child = side >= 0.0f ? nd.y : nd.z;
@@ -422,12 +425,16 @@ __device__ __forceinline__ Line agent_line(V2 pos, V2 vel, V2 opos, V2 ovel, flo
 // New velocity of agent `self` (RVOSimulator::doStep / ERVOSimulator::doStep for one agent; the caller applies
 // Agent::update after every agent of the scene is done).  pos / vel: the scene's agents in shared memory.
 __device__ __forceinline__ V2 orca_new_velocity(int self, const V2* pos, const V2* vel, const AgentHash& hash, V2 pref_velocity, float max_speed,
-                                                float time_step, const ObstacleSet& ob, OrcaScratch& sc, const OrcaPool& pool,
+                                                float time_step, const ObstacleSet& ob, OrcaScratch& sc, const OrcaPool& pool, unsigned warp_mask,
                                                 bool ervo, int n_beeps, const V2* beep_p, const float* beep_r) {
     const float radius = 0.5f, neighbour_dist = 0.5f, horizon = 5.f, horizon_obst = 5.f;   // rvoscene.h:53-66
     const V2 p = pos[self], v = vel[self];
+    // Every stage below is a data-dependent loop; the lanes of the warp (warp_mask = those that own an agent) are brought
+    // back together after each one, otherwise they drift apart for the rest of the kernel and execute one by one.
     const int n_obst_nb = gather_obstacle_neighbours(sc, pool, ob, p, sq(horizon_obst * max_speed + radius));
+    __syncwarp(warp_mask);
     const int n_nb = gather_agent_neighbours(sc, hash, pos, self, neighbour_dist);
+    __syncwarp(warp_mask);
     int n_lines = 0;
     const float inv_horizon_obst = 1.0f / horizon_obst;
     for (int i = 0; i < n_obst_nb; ++i) {
@@ -437,6 +444,7 @@ __device__ __forceinline__ V2 orca_new_velocity(int self, const V2* pos, const V
             else atomicAdd(pool.overflow, 1ull);
         }
     }
+    __syncwarp(warp_mask);
     const int n_obst_lines = n_lines;
     const float inv_horizon = 1.0f / horizon;
     for (int i = 0; i < n_nb; ++i) {
@@ -445,9 +453,12 @@ __device__ __forceinline__ V2 orca_new_velocity(int self, const V2* pos, const V
         if (sc.put_line(n_lines, make_float4(l.p.x, l.p.y, l.d.x, l.d.y), pool)) n_lines++;
         else atomicAdd(pool.overflow, 1ull);
     }
+    __syncwarp(warp_mask);
     V2 result;
     const int bad = solve_plane(TableLines{&sc}, n_lines, max_speed, pref_velocity, false, result);
+    __syncwarp(warp_mask);
     if (bad < n_lines) solve_relaxed(&sc, n_lines, n_obst_lines, bad, max_speed, result);
+    __syncwarp(warp_mask);
     if (ervo) {   // evacuation velocity: away from every beeping robot within its beep radius
         for (int b = 0; b < n_beeps; b++) {
             const V2 away = p - beep_p[b];
