@@ -830,9 +830,22 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
 // It only reads poses, so it runs beside the stamp / view kernels on the library's side stream.
 // ---------------------------------------------------------------------------------------------
 #define PED_THREADS 128
-inline size_t ped_smem_bytes(const Cfg& c) {
-    return (((size_t)c.img * c.img * 4 + 15) & ~(size_t)15) + (size_t)((c.P + 1) & ~1) * 8 + (size_t)c.P * 16 + (size_t)c.P * 4 + 16;
+struct PedLayout { size_t winner, keys, idx, pobs, row, total; int n_sort; };
+__host__ __device__ inline PedLayout ped_layout(const Cfg& c) {
+    PedLayout L;
+    int n = 1; while (n < c.P) n <<= 1;
+    L.n_sort = n;
+    size_t off = 0;
+    L.winner = off; off += ((size_t)c.img * c.img * 4 + 15) & ~(size_t)15;
+    L.keys = off; off += ((size_t)n * 8 + 15) & ~(size_t)15;
+    L.pobs = off; off += (size_t)(c.P > 0 ? c.P : 1) * 16;
+    L.row = off; off += ((size_t)c.pvs_len * 4 + 15) & ~(size_t)15;
+    L.idx = off; off += ((size_t)n * 2 + 15) & ~(size_t)15;
+    L.total = off + 16;
+    return L;
 }
+inline size_t ped_smem_bytes(const Cfg& c) { return ped_layout(c).total; }
+
 __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene_ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Cfg& c = d.c;
@@ -841,68 +854,83 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
     const int s = scene_ids ? scene_ids[sl] : sl;
     const int idx = s * c.R + r;
     const RobotType& ty = d.types[d.type_of[r]];
-    int* winner = reinterpret_cast<int*>(smem_raw);
-    double* pkey = reinterpret_cast<double*>(smem_raw + (((size_t)c.img * c.img * 4 + 15) & ~(size_t)15));
-    float* pobs = reinterpret_cast<float*>(pkey + ((c.P + 1) & ~1));
-    int* prank = reinterpret_cast<int*>(pobs + 4 * (size_t)c.P);
+    const PedLayout L = ped_layout(c);
+    int* winner = reinterpret_cast<int*>(smem_raw + L.winner);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + L.keys);     // bit pattern of the (non-negative) double key
+    unsigned short* order = reinterpret_cast<unsigned short*>(smem_raw + L.idx);            // pedestrian index, sorted along with the keys
+    float4* pobs = reinterpret_cast<float4*>(smem_raw + L.pobs);                             // px, py, vx, vy in the robot frame (float32 like PedInfo)
+    float* row = reinterpret_cast<float*>(smem_raw + L.row);                                 // this robot's ped_vector_states row
     const Tf2 world_base = tf_inv(tf_from_pose(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx)));
-    for (int k = tid; k < c.img * c.img; k += PED_THREADS) winner[k] = -1;
-    float* pvs = d.o_pvs + (size_t)idx * c.pvs_len;
-    for (int k = tid; k < c.pvs_len; k += PED_THREADS) pvs[k] = k == 0 ? (float)c.P : 0.f;
-    for (int j = tid; j < c.P; j += PED_THREADS) {
-        int pi = s * c.P + j;
-        double bx, by, bvx, bvy;
-        tf_apply(world_base, PDF(d, PD_X, pi), PDF(d, PD_Y, pi), bx, by);
-        tf_rotate(world_base, PDF(d, PD_VX, pi), PDF(d, PD_VY, pi), bvx, bvy);
-        float px = (float)bx, py = (float)by;
-        pobs[4 * j] = px; pobs[4 * j + 1] = py; pobs[4 * j + 2] = (float)bvx; pobs[4 * j + 3] = (float)bvy;
-        pkey[j] = (double)px * (double)px + (double)py * (double)py;
+    const int npm = c.img * c.img;
+    for (int k = tid; k < npm; k += PED_THREADS) winner[k] = -1;
+    for (int k = tid; k < c.pvs_len; k += PED_THREADS) row[k] = k == 0 ? (float)c.P : 0.f;
+    for (int j = tid; j < L.n_sort; j += PED_THREADS) {
+        unsigned long long key = 0x7FF0000000000000ull;        // +inf: padding sorts last
+        if (j < c.P) {
+            const int pi = s * c.P + j;
+            double bx, by, bvx, bvy;
+            tf_apply(world_base, PDF(d, PD_X, pi), PDF(d, PD_Y, pi), bx, by);
+            tf_rotate(world_base, PDF(d, PD_VX, pi), PDF(d, PD_VY, pi), bvx, bvy);
+            const float px = (float)bx, py = (float)by;
+            pobs[j] = make_float4(px, py, (float)bvx, (float)bvy);
+            key = (unsigned long long)__double_as_longlong((double)px * (double)px + (double)py * (double)py);   // python: float(x)**2 + float(y)**2
+        }
+        keys[j] = key; order[j] = (unsigned short)j;
     }
     __syncthreads();
-    for (int j = tid; j < c.P; j += PED_THREADS) {   // stable rank == python's list.sort(key=...)
-        const double kj = pkey[j];
-        const int jb = j - (tid & 31);       // a warp ranks 32 consecutive pedestrians: ties only need care inside that group
-        int rk = 0;
-        for (int i = 0; i < jb; i++) rk += pkey[i] <= kj;
-        for (int i = jb; i < min(jb + 32, c.P); i++) rk += (pkey[i] < kj) || (pkey[i] == kj && i < j);
-        for (int i = jb + 32; i < c.P; i++) rk += pkey[i] < kj;
-        prank[j] = rk;
-    }
-    __syncthreads();
-    for (int j = tid; j < c.P; j += PED_THREADS) {
-        int q = prank[j];
-        double px = pobs[4 * j], py = pobs[4 * j + 1];
-        double ped_r = d.ped_r_round[j];
-        float f5 = (float)ped_r, f6 = (float)(ped_r + ty.size_last), f7 = (float)sqrt(px * px + py * py);
+    // stable nearest-first order == python's list.sort(key=...): bitonic network on (key, index) pairs
+    for (int k = 2; k <= L.n_sort; k <<= 1)
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int t = tid; t < (L.n_sort >> 1); t += PED_THREADS) {
+                const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1)), p = i | jj;      // the pair (i, i + jj) of this stage
+                const unsigned long long ka = keys[i], kb = keys[p];
+                const unsigned short ia = order[i], ib = order[p];
+                const bool up = (i & k) == 0;
+                const bool a_after_b = ka > kb || (ka == kb && ia > ib);
+                if (a_after_b == up) { keys[i] = kb; keys[p] = ka; order[i] = ib; order[p] = ia; }
+            }
+            __syncthreads();
+        }
+    for (int q = tid; q < c.P; q += PED_THREADS) {       // q = rank (0 = nearest), j = pedestrian
+        const int j = order[q];
+        const float4 o = pobs[j];
+        const double px = o.x, py = o.y;
+        const double ped_r = d.ped_r_round[j];
+        const float f5 = (float)ped_r, f6 = (float)(ped_r + ty.size_last), f7 = (float)sqrt(px * px + py * py);
         if (q < c.max_ped) {
-            float* o = pvs + 1 + (size_t)q * c.ped_vec_dim;
-            o[0] = pobs[4 * j]; o[1] = pobs[4 * j + 1]; o[2] = pobs[4 * j + 2]; o[3] = pobs[4 * j + 3];
-            o[4] = f5; o[5] = f6; o[6] = f7;
+            float* w = row + 1 + (size_t)q * c.ped_vec_dim;
+            w[0] = o.x; w[1] = o.y; w[2] = o.z; w[3] = o.w; w[4] = f5; w[5] = f6; w[6] = f7;
         }
-        if (q == 0) {   // NearbyPed.set(i, ped_tmp[7] - ped_tmp[6]) in float32 (yaml_env.py:455-456)
-            float md = f7 - f6;
-            RBF(d, RB_MIND, idx) = (double)md;
-        }
+        if (q == 0) RBF(d, RB_MIND, idx) = (double)(f7 - f6);      // NearbyPed.set(i, ped_tmp[7] - ped_tmp[6]) in float32 (yaml_env.py:455-456)
         if (px > 3 || px < -3 || py > 3 || py < -3) continue;
-        double tmx = -px + 3, tmy = -py + 3;
-        int x0 = (int)py_floordiv(tmx - c.ped_image_r, c.ped_res), x1 = (int)py_floordiv(tmx + c.ped_image_r, c.ped_res);
-        int y0 = (int)py_floordiv(tmy - c.ped_image_r, c.ped_res), y1 = (int)py_floordiv(tmy + c.ped_image_r, c.ped_res);
+        const double tmx = -px + 3, tmy = -py + 3;
+        const int x0 = (int)py_floordiv(tmx - c.ped_image_r, c.ped_res), x1 = (int)py_floordiv(tmx + c.ped_image_r, c.ped_res);
+        const int y0 = (int)py_floordiv(tmy - c.ped_image_r, c.ped_res), y1 = (int)py_floordiv(tmy + c.ped_image_r, c.ped_res);
         for (int jj = x0; jj < x1; jj++)
             for (int kk = y0; kk < y1; kk++) {
                 if (jj < 0 || jj >= c.img || kk < 0 || kk >= c.img) continue;
-                double ddx = (jj + 0.5) * c.ped_res - tmx, ddy = (kk + 0.5) * c.ped_res - tmy;
-                if (ddx * ddx + ddy * ddy < c.ped_image_r * c.ped_image_r) atomicMax(&winner[jj * c.img + kk], (q << 16) | j);
+                const double ddx = (jj + 0.5) * c.ped_res - tmx, ddy = (kk + 0.5) * c.ped_res - tmy;
+                if (ddx * ddx + ddy * ddy < c.ped_image_r * c.ped_image_r) atomicMax(&winner[jj * c.img + kk], (q << 16) | j);   // farther pedestrians overwrite
             }
     }
     __syncthreads();
     if (tid == 0) d.o_mind[idx] = (float)RBF(d, RB_MIND, idx);
-    float* pm = d.o_pmap + (size_t)idx * 3 * c.img * c.img;
-    const int npm = c.img * c.img;
-    for (int ch = 0; ch < 3; ch++)
-        for (int cell = tid; cell < npm; cell += PED_THREADS) {
-            int wv = winner[cell];
-            float v = 0.f;
-            if (wv >= 0) { int j = wv & 0xFFFF; v = ch == 0 ? 1.0f : pobs[4 * j + 1 + ch]; }
-            pm[ch * npm + cell] = v;
+    float* pvs = d.o_pvs + (size_t)idx * c.pvs_len;
+    for (int k = tid; k < c.pvs_len; k += PED_THREADS) pvs[k] = row[k];
+    // 3 x img x img float32, mostly zeros: 16-byte stores (each robot's block starts on a 16-byte boundary when img*img*3 % 4 == 0)
+    float* pm = d.o_pmap + (size_t)idx * 3 * npm;
+    auto value = [&](int ch, int cell) -> float {
+        const int wv = winner[cell];
+        if (wv < 0) return 0.f;
+        const float4 o = pobs[wv & 0xFFFF];
+        return ch == 0 ? 1.0f : (ch == 1 ? o.z : o.w);
+    };
+    if ((npm & 3) == 0) {
+        for (int v = tid; v < 3 * npm / 4; v += PED_THREADS) {
+            const int ch = (4 * v) / npm, cell = 4 * v - ch * npm;
+            reinterpret_cast<float4*>(pm)[v] = make_float4(value(ch, cell), value(ch, cell + 1), value(ch, cell + 2), value(ch, cell + 3));
         }
+    } else {
+        for (int v = tid; v < 3 * npm; v += PED_THREADS) { const int ch = v / npm; pm[v] = value(ch, v - ch * npm); }
+    }
 }
