@@ -860,9 +860,12 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
     unsigned short* order = reinterpret_cast<unsigned short*>(smem_raw + L.idx);            // pedestrian index, sorted along with the keys
     float4* pobs = reinterpret_cast<float4*>(smem_raw + L.pobs);                             // px, py, vx, vy in the robot frame (float32 like PedInfo)
     float* row = reinterpret_cast<float*>(smem_raw + L.row);                                 // this robot's ped_vector_states row
-    const Tf2 world_base = tf_inv(tf_from_pose(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx)));
+    __shared__ Tf2 s_world_base;
+    if (tid == 0) s_world_base = tf_inv(tf_from_pose(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx)));
     const int npm = c.img * c.img;
     for (int k = tid; k < npm; k += PED_THREADS) winner[k] = -1;
+    __syncthreads();
+    const Tf2 world_base = s_world_base;
     for (int k = tid; k < c.pvs_len; k += PED_THREADS) row[k] = k == 0 ? (float)c.P : 0.f;
     for (int j = tid; j < L.n_sort; j += PED_THREADS) {
         unsigned long long key = 0x7FF0000000000000ull;        // +inf: padding sorts last
@@ -878,7 +881,40 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
         keys[j] = key; order[j] = (unsigned short)j;
     }
     __syncthreads();
-    // stable nearest-first order == python's list.sort(key=...): bitonic network on (key, index) pairs
+    // stable nearest-first order == python's list.sort(key=...): bitonic network on (key, index) pairs.
+    if (L.n_sort == 2 * PED_THREADS) {
+        // 2 elements per thread in registers (2t, 2t+1): partners inside a warp are reached with shuffles, only the last
+        // stages (partner thread >= 32 lanes away) go through shared memory
+        unsigned long long k0 = keys[2 * tid], k1 = keys[2 * tid + 1];
+        unsigned i0 = order[2 * tid], i1 = order[2 * tid + 1];
+        auto after = [](unsigned long long ka, unsigned ia, unsigned long long kb, unsigned ib) { return ka > kb || (ka == kb && ia > ib); };
+        for (int k = 2; k <= 2 * PED_THREADS; k <<= 1)
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                const bool up = ((2 * tid) & k) == 0;
+                if (jj == 1) {
+                    if (after(k0, i0, k1, i1) == up) { const unsigned long long tk = k0; k0 = k1; k1 = tk; const unsigned ti = i0; i0 = i1; i1 = ti; }
+                    continue;
+                }
+                const int tj = jj >> 1;                       // partner thread = tid ^ tj holds the partners of both elements
+                unsigned long long p0, p1; unsigned q0, q1;
+                if (tj < 32) {
+                    p0 = __shfl_xor_sync(0xffffffffu, k0, tj); p1 = __shfl_xor_sync(0xffffffffu, k1, tj);
+                    q0 = __shfl_xor_sync(0xffffffffu, i0, tj); q1 = __shfl_xor_sync(0xffffffffu, i1, tj);
+                } else {
+                    __syncthreads();
+                    keys[2 * tid] = k0; keys[2 * tid + 1] = k1; order[2 * tid] = (unsigned short)i0; order[2 * tid + 1] = (unsigned short)i1;
+                    __syncthreads();
+                    const int pt = tid ^ tj;
+                    p0 = keys[2 * pt]; p1 = keys[2 * pt + 1]; q0 = order[2 * pt]; q1 = order[2 * pt + 1];
+                }
+                const bool take_min = (((2 * tid) & jj) == 0) == up;
+                if (after(k0, i0, p0, q0) == take_min) { k0 = p0; i0 = q0; }
+                if (after(k1, i1, p1, q1) == take_min) { k1 = p1; i1 = q1; }
+            }
+        __syncthreads();
+        order[2 * tid] = (unsigned short)i0; order[2 * tid + 1] = (unsigned short)i1;
+        __syncthreads();
+    } else
     for (int k = 2; k <= L.n_sort; k <<= 1)
         for (int jj = k >> 1; jj > 0; jj >>= 1) {
             for (int t = tid; t < (L.n_sort >> 1); t += PED_THREADS) {
@@ -926,10 +962,13 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
         return ch == 0 ? 1.0f : (ch == 1 ? o.z : o.w);
     };
     if ((npm & 3) == 0) {
-        for (int v = tid; v < 3 * npm / 4; v += PED_THREADS) {
-            const int ch = (4 * v) / npm, cell = 4 * v - ch * npm;
-            reinterpret_cast<float4*>(pm)[v] = make_float4(value(ch, cell), value(ch, cell + 1), value(ch, cell + 2), value(ch, cell + 3));
-        }
+        for (int ch = 0; ch < 3; ch++)
+            for (int v = tid; v < npm / 4; v += PED_THREADS) {
+                const int4 w4 = reinterpret_cast<const int4*>(winner)[v];
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((w4.x & w4.y & w4.z & w4.w) >= 0) o = make_float4(value(ch, 4 * v), value(ch, 4 * v + 1), value(ch, 4 * v + 2), value(ch, 4 * v + 3));   // some cell is painted
+                reinterpret_cast<float4*>(pm + (size_t)ch * npm)[v] = o;
+            }
     } else {
         for (int v = tid; v < 3 * npm; v += PED_THREADS) { const int ch = v / npm; pm[v] = value(ch, v - ch * npm); }
     }
