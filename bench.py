@@ -178,6 +178,71 @@ def run_reference(wname, steps, warmup, procs=None, budget_s=200.0, target_s=0.0
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+def measure_gather(sim, step, world, S, R, kg, dist, torch):
+    """sim + delivery of all nine State tensors of every rank to rank 0; device-timed, max over ranks."""
+    from img_env_b200.parallel import ObservationGatherer
+    gat = ObservationGatherer(sim.out, dst=0)
+    step(0); gat(sim.out)
+    torch.cuda.synchronize(); dist.barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for t in range(kg):
+        step(t); gat(sim.out)
+    g1.record()
+    torch.cuda.synchronize()
+    tg = torch.tensor([g0.elapsed_time(g1)], device="cuda"); dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+    out = {"value": world * S * R * kg / (float(tg.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(tg.item()) / kg,
+           "bytes_to_learner_per_step": int(gat.bytes_to_learner),
+           "note": "sim + point-to-point delivery of all nine State tensors of every rank to rank 0 (NCCL isend/irecv "
+                   "over NVLink); not part of the headline metric"}
+    del gat
+    return out
+
+
+def measure_c5(args, world, rank, local_rank, dist, torch):
+    """BASELINE config 5 beside the headline line: device-timed sim-only rate and sim + gather to the learner GPU."""
+    from img_env_b200.spec import build_spec
+    from img_env_b200.lib import BatchedSim
+    w = WORKLOADS["c5"]
+    S = w["scenes"]
+    spec = build_spec(make_cfg(w, args.synthetic_map))
+    R = spec["R"]
+    sim = BatchedSim(spec, num_scenes=S, device=local_rank, seed=99 + rank, ped_yaw_mode=1)
+    sim.reset(make_resets(spec, w, S, 4321 + rank * 100003))
+    rng = np.random.default_rng(77 + rank)
+    acts = torch.from_numpy(np.stack([np.stack([random_actions(R, rng) for _ in range(S)]) for _ in range(4)])).cuda()
+    alive = torch.ones(S, R, dtype=torch.uint8, device="cuda")
+
+    def step(t):
+        sim.revive(); sim.step(acts[t % 4], alive)
+    for t in range(3):
+        step(t)
+    torch.cuda.synchronize(); dist.barrier()
+    k5 = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(k5):
+        step(t)
+    e1.record()
+    torch.cuda.synchronize()
+    tm = torch.tensor([e0.elapsed_time(e1)], device="cuda"); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    out = {"workload": "c5: " + w["desc"], "scenes_per_gpu": S, "scenes_total": S * world, "value": world * S * R * k5 / (float(tm.item()) * 1e-3),
+           "unit": UNIT, "ms_per_step": float(tm.item()) / k5, "steps": k5,
+           "gather_to_learner": measure_gather(sim, step, world, S, R, 5, dist, torch)}
+    sim.close()
+    return out
+
+
+def source_sha():
+    """Hash of the CUDA sources the library is built from: keys measured-traffic records to the code they were taken on."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "img_env_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def run_b200(args):
     import torch
     from img_env_b200.build import build
@@ -280,32 +345,23 @@ def run_b200(args):
     if dist:
         tt = torch.tensor([full_s], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); full_s = float(tt.item())
 
-    # ---- N > 1: the same steps with the State of every rank delivered to the learner GPU (rank 0) over NVLink
+    # ---- N > 1: the same steps with the State of every rank delivered to the learner GPU (rank 0) over NVLink,
+    #      on this workload and on BASELINE config 5 (4096 SFM scenes x (64 + 64) sharded over 8 GPUs = 512 per GPU)
     gather = None
-    if dist and args.gather:
-        from img_env_b200.parallel import ObservationGatherer
-        gat = ObservationGatherer(sim.out, dst=0)
-        kg = max(2, min(K, 10))
-        step(0); gat(sim.out)
-        torch.cuda.synchronize(); dist.barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for t in range(kg):
-            step(t); gat(sim.out)
-        g1.record()
-        torch.cuda.synchronize()
-        tg = torch.tensor([g0.elapsed_time(g1)], device="cuda"); dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gather = {"value": world * S * R * kg / (float(tg.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(tg.item()) / kg,
-                  "bytes_to_learner_per_step": int(gat.bytes_to_learner),
-                  "note": "sim + point-to-point delivery of all nine State tensors of every rank to rank 0 (NCCL isend/irecv "
-                          "over NVLink); not part of the headline metric"}
+    c5 = None
+    B, range_total, pvs_len, ped_img = sim.bytes_per_robot_step, sim.range_total, sim.pvs_len, sim.spec["ped_image_size"][0]
+    if dist:
+        gather = measure_gather(sim, step, world, S, R, max(2, min(K, 10)), dist, torch)
+        if args.workload != "c5" and not args.no_c5:
+            sim.close(); del sim
+            torch.cuda.empty_cache()
+            c5 = measure_c5(args, world, rank, local_rank, dist, torch)
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
     total_robot_steps = world * S * R * K
     value = total_robot_steps / (ms * 1e-3)
-    B = sim.bytes_per_robot_step
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -315,25 +371,28 @@ def run_b200(args):
     view_ms = kms["k_view"]
     achieved = (B * S * R) / (view_ms * 1e-3) / 1e9 if view_ms > 0 else None
     # bytes k_view itself moves: everything except the pedestrian observation, which k_ped_obs writes concurrently
-    B_ped = 3 * sim.spec["ped_image_size"][0] ** 2 * 4 + 4 * sim.pvs_len + 4
+    B_ped = 3 * ped_img ** 2 * 4 + 4 * pvs_len + 4
     traffic = None
-    try:   # measured per robot-step by ncu (profiles/): scaled to this launch's robot count
+    try:   # measured per robot-step by ncu (tools/profile_summary.py --traffic): only valid for the sources it was taken on
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        traffic = float(tj["bytes_per_robot_step"]) * S * R
+        if tj and tj.get("source_sha") == source_sha() and not args.synthetic_map:
+            traffic = float(tj["bytes_per_robot_step"]) * S * R
     except Exception:
         pass
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload + ": " + w["desc"], "scenes_per_gpu": S, "robots_per_scene": R, "peds_per_scene": spec["P"],
-                   "grid": list(spec["grid"].shape), "view": "400x400@0.015", "range_total": sim.range_total,
-                   "l2_policy": "working set (per-scene planes + outputs, %.1f GB) larger than the 126 MB L2" %
-                                ((S * (spec["grid"].size * (1 / 8 + 1 + 2)) + S * R * B) / 1e9),
+                   "grid": list(spec["grid"].shape), "view": "400x400@0.015", "range_total": range_total,
+                   "map": workload_map(w, args.synthetic_map)[1],
+                   "l2_policy": "working set (State outputs + footprint records, %.2f GB) larger than the 126 MB L2" % (S * R * B / 1e9),
                    "all_robots_alive": True, "parallelism": "scenes sharded, %d per GPU, no collective in the step" % S},
         "e2e": {"value": world * S * R * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "note": "imgenv_step_host from pinned host actions; vector_states/codes/step_ds/ped_min_dists read back and "
                         "synchronised every step; sensor_maps/ped_maps/lasers stay device-resident for the learner"},
-        "e2e_full_state_to_host": {"value": world * S * R * kf / full_s, "unit": UNIT, "d2h_bytes_per_step": int(d2h_full)},
+        "e2e_full_state_to_host": {"value": world * S * R * kf / full_s, "unit": UNIT, "d2h_bytes_per_step": int(d2h_full),
+                                   "note": "the same call with ALL nine State tensors copied to pinned host memory every step (what a "
+                                           "CPU-side learner would need); PCIe-bound"},
         "gpu_launches": int(K * launches_per_step),
         "kernel_ms": {k: round(v, 4) for k, v in kms.items()},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
@@ -348,6 +407,8 @@ def run_b200(args):
     }
     if gather:
         out["gather_to_learner"] = gather
+    if c5:
+        out["c5"] = c5
     if world == 1 and not args.no_cpu_baseline:
         try:
             ref = run_reference(args.workload, steps=2, warmup=1, budget_s=25.0 * 8, target_s=12.0, hard_timeout=240.0)
@@ -396,13 +457,14 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--scenes", type=int, default=0, help="scenes per GPU (default: workload-specific)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", action="store_true", help="N > 1: also time sim + delivery of the State to rank 0")
+    ap.add_argument("--gather", action="store_true", help="(kept for compatibility: N > 1 always reports sim + delivery of the State to rank 0)")
+    ap.add_argument("--no-c5", action="store_true", help="N > 1: skip the BASELINE config 5 sub-record")
     ap.add_argument("--synthetic-map", action="store_true", help="round-1 synthetic room with random blocks instead of the reference's PNG")
     args = ap.parse_args()
     if args.impl == "reference":
