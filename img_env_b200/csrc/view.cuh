@@ -25,7 +25,8 @@ struct ViewShared {
     double inv[4], org[2];
     int blk[4];              // first block row / col, number of block rows / cols covering the FOV's world bounding box
     int wbb[4];              // world bounding box of the FOV in cells (x0, x1, y0, y1), clamped to the map
-    int n_near, n_cnear, n_dirty, n_hits;
+    int n_cnear, n_dirty;
+    unsigned long long near_pack;   // number of near records << 32 | their words so far (one atomic hands out slot and word offset)
     int hmin[64];            // per block of rays: smallest hit step (Chebyshev distance of the hit cell), NOHIT >> 22 if none
     int4 own_hdr;            // the observer's own footprint record header
 };
@@ -170,7 +171,7 @@ __device__ __forceinline__ void view_prologue(const Dev& d, ViewShared* sh, int 
     sh->frozen = (RBF(d, RB_COLL, idx) != 0.0) || (RBF(d, RB_ARR, idx) != 0.0);
     sh->coll_key = 0;
     sh->red[0] = 0; sh->red[1] = 0; sh->red[2] = 0; sh->red[3] = 0; sh->red[4] = 0;
-    sh->n_near = 0; sh->n_cnear = 0; sh->n_dirty = 0; sh->n_hits = 0;
+    sh->near_pack = 0ull; sh->n_cnear = 0; sh->n_dirty = 0;
     {   // the box of the robot's own footprint (the same box k_footprints gives its record; the record itself may be
         // culled when no other robot is near, so it is not read here)
         double bwx, bwy;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
     uint32_t* known = occ + (size_t)vh * vwb;                               // only when !use_laser
     uint32_t* blist2 = reinterpret_cast<uint32_t*>(smem_raw + L.regB);
     unsigned short* dirty = reinterpret_cast<unsigned short*>(smem_raw + L.regB);   // after phase C
-    unsigned short* hpre = reinterpret_cast<unsigned short*>(smem_raw + L.hpre);   // after phase C: hpre[k] = #rays < k with a hit
+    unsigned* hbits = reinterpret_cast<unsigned*>(smem_raw + L.hpre);              // after phase C: bit k = ray k hit something
     short* spans = reinterpret_cast<short*>(smem_raw + L.spans);
     uint32_t* blocks = reinterpret_cast<uint32_t*>(smem_raw + L.blocks);
     unsigned* hitkey = reinterpret_cast<unsigned*>(smem_raw + L.hitkey);
@@ -313,28 +314,24 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                             }
                   }
                 }
-                near[atomicAdd(&sh->n_near, 1)] = (unsigned short)(q | all);
+                {   // slot in the near list and offset of the part's words among the work items of phase B, from one atomic
+                    const unsigned long long t = atomicAdd(&sh->near_pack, (1ull << 32) | (unsigned long long)(nrow * foot_wpr(h)));
+                    near[t >> 32] = (unsigned short)(q | all); npre[t >> 32] = (unsigned)t;
+                }
+            }
+            if (use_inverse) {      // 32x32-cell world blocks under the FOV that hold static candidates
+                const uint32_t* crow = d.static_crow;
+                const int nbj = sh->blk[3], nb = sh->blk[2] * nbj;
+                for (int t = tid; t < nb; t += VIEW_THREADS) {
+                    const int bi = sh->blk[0] + t / nbj, bj = sh->blk[1] + t % nbj;
+                    if (__ldg(crow + (unsigned)bi * c.Wb + bj)) blocks[atomicAdd(&sh->red[3], 1)] = ((unsigned)bi << 16) | (unsigned)bj;
+                }
             }
         }
         __syncthreads();
-        const int n_near = sh->n_near;
+        const int n_near = (int)(sh->near_pack >> 32);
+        const unsigned n_near_words = (unsigned)sh->near_pack;
         const int n_cnear = sh->n_cnear;
-        // running word counts of the near parts (work items of phase B), by warp 0
-        if (warp == 0) {
-            unsigned run = 0;
-            for (int k0 = 0; k0 < n_near; k0 += 32) {
-                const int k = k0 + lane;
-                unsigned cnt = 0;
-                if (k < n_near) { const int4 h = __ldg(fhdr + (near[k] & 0x7FFF)); cnt = (unsigned)(foot_nrow(h) * foot_wpr(h)); }
-                unsigned incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                if (k < n_near) npre[k] = run + incl - cnt;
-                run += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            if (lane == 0) npre[n_near] = run;
-        }
-
         // ---- Phase A: collision code = code of the LAST colliding lattice point (agent.cpp:294-326)
         int best = 0;
         if (!DEBUG_FULL) {
@@ -417,14 +414,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
         };
         const int n_trow = (vh + 31) >> 5, n_tiles = n_trow * vwb;
         if (!use_inverse) for (int q = tid; q < vh * vwb; q += VIEW_THREADS) { occ[q] = 0u; if (!use_laser) known[q] = 0u; }
-        if (use_inverse) {
-            const uint32_t* crow = d.static_crow;
-            const int nbj = sh->blk[3], nb = sh->blk[2] * nbj;
-            for (int t = tid; t < nb; t += VIEW_THREADS) {
-                const int bi = sh->blk[0] + t / nbj, bj = sh->blk[1] + t % nbj;
-                if (__ldg(crow + (unsigned)bi * Wb + bj)) blocks[atomicAdd(&sh->red[3], 1)] = ((unsigned)bi << 16) | (unsigned)bj;
-            }
-        } else {
+        if (!use_inverse) {
             // forward rasterisation of the static map
             const uint32_t* orow = d.static_orow;
             int* n_active = &sh->red[2];
@@ -452,7 +442,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
             }
         }
         if (!DEBUG_FULL && lane == 0) atomicMax(&sh->coll_key, best);
-        __syncthreads();
+        if (!use_inverse) __syncthreads();       // (world->view mode: block list and near list were finished before the last barrier)
         if (!use_inverse) {
             const int n_items = sh->red[2] * 32;
             const long long lbx = sh->cx + (long long)lane * sh->bx, lby = sh->cy + (long long)lane * sh->by;
@@ -509,7 +499,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
             // dense words make the work per batch very uneven -- and expands their candidate bits over all lanes.
             const uint32_t* static_cand = d.static_cand;
             const int n_static = use_inverse ? sh->red[3] * 32 : 0;
-            const int n_items = n_static + (int)npre[n_near];
+            const int n_items = n_static + (int)n_near_words;
             const float f00 = (float)sh->view_world.m00, f01 = (float)sh->view_world.m01, f10 = (float)sh->view_world.m10, f11 = (float)sh->view_world.m11;
             const float fr0 = (float)ty.fov_r0 - 1.5f, fr1 = (float)ty.fov_r1 + 1.5f, fc0 = (float)ty.fov_c0 - 1.5f, fc1 = (float)ty.fov_c1 + 1.5f;
             for (;;) {
@@ -612,6 +602,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
         // cells of the raster can be hits.  For each boundary cell the (static) interval of ray indices whose
         // integer line walk passes through it is scanned with the closed-form touch test and the ray keeps
         // the minimum step (atomicMin on step<<22|cell).  Cells that do not fit the lists are resolved inline.
+        int any_hit_all = 0;
         if (use_laser) {
             if (!use_inverse) {
                 for (int q = tid; q < vh * 16 * ((vwb + 15) / 16); q += VIEW_THREADS) {
@@ -653,36 +644,35 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
             for (int q = warp; q < nl2; q += VIEW_THREADS / 32) { const unsigned cell = blist2[q]; cell_rays(cell, __ldg(kpack + (cell >> 16) * vw + (cell & 0xFFFFu)), lane, 32); }
             __syncthreads();
             if (!DEBUG_FULL) {
-                for (int k = tid; k < c.range_total; k += VIEW_THREADS) {
-                    const unsigned key = hitkey[k];
-                    double hit = 6;   // agent.cpp:513
-                    if (key != NOHIT) {
-                        const int hx = (key >> 11) & 2047, hy = key & 2047;
-                        double x0 = ox * c.res, y0 = oy * c.res, xc = hx * c.res, yc = hy * c.res;
-                        hit = sqrt((x0 - xc) * (x0 - xc) + (y0 - yc) * (y0 - yc));
+                // laser ranges out; one bit per ray "hit something" (ballots: a warp's 32 rays are one word) and, per block of
+                // rays, the nearest hit -- the output classification below asks both about ray intervals
+                int any_local = 0;
+                for (int k0 = 0; k0 < c.range_total; k0 += VIEW_THREADS) {
+                    const int k = k0 + tid;
+                    const bool valid = k < c.range_total;
+                    const unsigned key = valid ? hitkey[k] : NOHIT;
+                    const bool hit_any = key != NOHIT;
+                    if (valid) {
+                        double hit = 6;   // agent.cpp:513
+                        if (hit_any) {
+                            const int hx = (key >> 11) & 2047, hy = key & 2047;
+                            double x0 = ox * c.res, y0 = oy * c.res, xc = hx * c.res, yc = hy * c.res;
+                            hit = sqrt((x0 - xc) * (x0 - xc) + (y0 - yc) * (y0 - yc));
+                        }
+                        const float wire = (float)hit;                         // AgentState.laser is float32[]
+                        d.o_laser[(size_t)idx * c.range_total + k] = c.laser_norm ? (float)((double)wire / c.laser_max) : wire;   // yaml_env.py:440-444
                     }
-                    const float wire = (float)hit;                         // AgentState.laser is float32[]
-                    d.o_laser[(size_t)idx * c.range_total + k] = c.laser_norm ? (float)((double)wire / c.laser_max) : wire;   // yaml_env.py:440-444
-                }
-                // prefix counts of the rays that hit something: phase D/F asks "any hit among rays [a, b]?" in O(1)
-                const int per = (c.range_total + VIEW_THREADS - 1) / VIEW_THREADS;
-                const int k0 = min(tid * per, c.range_total), k1 = min(k0 + per, c.range_total);
-                int cnt = 0;
-                for (int k = k0; k < k1; k++) cnt += hitkey[k] != NOHIT;
-                int incl = cnt;
+                    const unsigned word = __ballot_sync(0xffffffffu, hit_any);
+                    if (lane == 0 && (k >> 5) <= ((c.range_total - 1) >> 5)) hbits[k >> 5] = word;
+                    any_local |= word != 0u;
+                    if (c.hb_shift == 4) {      // blocks of 16 rays = half warps: shuffle minimum, no atomics
+                        int hp = (int)(key >> 22);
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                if (lane == 31) sh->red[warp] = incl;      // the list counters in red[] are dead after the barrier above
-                __syncthreads();
-                int run = incl - cnt;
-                for (int w = 0; w < warp; w++) run += sh->red[w];
-                for (int k = k0; k < k1; k++) {
-                    const unsigned key = hitkey[k];
-                    hpre[k] = (unsigned short)run; run += key != NOHIT;
-                    if (key != NOHIT) atomicMin(&sh->hmin[k >> c.hb_shift], (int)(key >> 22));      // nearest hit per block of rays
+                        for (int o = 8; o; o >>= 1) hp = min(hp, __shfl_xor_sync(0xffffffffu, hp, o));
+                        if ((lane & 15) == 0 && valid) sh->hmin[k >> 4] = hp;
+                    } else if (hit_any) atomicMin(&sh->hmin[k >> c.hb_shift], (int)(key >> 22));
                 }
-                if (k1 == c.range_total) { hpre[k1] = (unsigned short)run; sh->n_hits = run; }
-                __syncthreads();
+                any_hit_all = __syncthreads_or(any_local);
             }
         }
 
@@ -765,13 +755,22 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
             uint16_t* o_img = d.o_sensor + (size_t)idx * npx;
             const uint32_t* okk = d.ostat + (size_t)ty.ostat_off;                                   // [npx] kmin | kmax << 16
             const uint16_t* oval = reinterpret_cast<const uint16_t*>(d.ostat + (size_t)ty.ostat_off + npx);   // [npx] hit-free float16
-            const bool any_hit = !use_laser || sh->n_hits > 0;
+            const bool any_hit = !use_laser || any_hit_all != 0;
+            // any ray of [a, b] with a hit?  (a, b at most a few words apart)
+            auto range_hit = [&](int a, int b) -> bool {
+                const int wa = a >> 5, wb = b >> 5;
+                const unsigned ma = 0xffffffffu << (a & 31), mb = 0xffffffffu >> (31 - (b & 31));
+                if (wa == wb) return (hbits[wa] & ma & mb) != 0u;
+                unsigned acc = (hbits[wa] & ma) | (hbits[wb] & mb);
+                for (int w = wa + 1; w < wb; w++) acc |= hbits[w];
+                return acc != 0u;
+            };
             for (int q = tid; q < npx; q += VIEW_THREADS) {
                 bool is_dirty = !use_laser;
                 if (use_laser && any_hit) {
                     const unsigned kk = __ldg(okk + q);
                     const int kmin = kk & 0xFFFu, kmax = (kk >> 12) & 0xFFFu;
-                    if (kmax >= kmin && hpre[kmax + 1] != hpre[kmin]) {
+                    if (kmax >= kmin && range_hit(kmin, kmax)) {
                         // some of the rays hit something: still clean if every hit lies beyond all of the output's source pixels
                         // (they are then all "free", as in the hit-free value) -- nearest hit over the covering ray blocks
                         int hm = 1023;
