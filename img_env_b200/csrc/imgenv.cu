@@ -14,6 +14,7 @@
 #include "foot.cuh"
 #include "view.cuh"
 #include "dyn.cuh"
+#include "rvotree.cuh"
 #include "host_tables.h"
 #include "sampler.h"
 #include <random>
@@ -367,6 +368,8 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     AL(traj, S * c.P * c.max_traj * 3) AL(traj_v, c.scene_type == 4 ? S * c.P * c.max_traj * 3 : 1) AL(traj_len, S * c.P) AL(obs, S * c.max_obs * 8) AL(n_obs, S) AL(step_no, S)
     AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_nvel, S * c.NA * 2) AL(sfm_force, c.scene_type == 1 ? S * c.NA * 12 : 1)
     AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 4) AL(rvo_nodeseg, S * d.max_verts * 4) AL(counters, 4) AL(orca_cursor, 2)
+    d.rvo_arena_len = (c.scene_type == 2 || c.scene_type == 3) ? 32 * d.max_verts : 1;
+    AL(rvo_arena, S * (size_t)d.rvo_arena_len)
     AL(rvo_counts, S * 2) AL(sfm, S * c.NA * SFM_REC) AL(sfm_obs, S * c.max_obs * 4) AL(sfm_nobs, S)
     AL(sfm_wp, S * c.P * (1 + c.max_traj) * 3)
     {
@@ -418,8 +421,8 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     }
     // reset staging: per scene doubles = obs 8*max_obs + robots 5*R + peds 5*P + traj 3*max_traj*P + sfm segs 4*max_obs
     h->st_doubles = S * ((size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 6 * (size_t)c.max_traj * c.P + 4 * c.max_obs) + 8;
-    h->st_ints = S * ((size_t)5 + c.P + 4 * (size_t)d.max_verts) + S + 8;
-    h->st_floats = S * ((size_t)12 * d.max_verts) + 8;
+    h->st_ints = S * ((size_t)5 + c.P) + S + 8;
+    h->st_floats = 8;
     for (auto& g : h->stage) {
         CK(cudaMallocHost((void**)&g.h, h->st_doubles * 8)); if (dalloc(h, &g.d, h->st_doubles)) return -1;
         CK(cudaMallocHost((void**)&g.ih, h->st_ints * 4)); if (dalloc(h, &g.id, h->st_ints)) return -1;
@@ -480,25 +483,22 @@ extern "C" int imgenv_bind_outputs(imgenv_t* h, const imgenv_outputs* o) {
 
 // staged reset record layout (per listed scene), doubles:
 //   obs[max_obs][8] | robots[R][5] x,y,yaw,gx,gy | peds[P][5] x,y,yaw,gx,gy | traj[P][max_traj][3] | segs[max_obs][4] | traj_v[P][max_traj][3]
-// ints: scene_id, n_obs, n_segs, n_verts, root | traj_len[P] | nodes[max_verts][4]   floats: verts[max_verts][8]
+// ints: scene_id, n_obs, n_segs, 0, 0 | traj_len[P]      (the RVO obstacle ring + BSP are built on the device: rvotree.cuh)
 __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, const float* stf, size_t dper, size_t iper, size_t fper) {
     const Cfg& c = d.c;
     int sl = blockIdx.x;
     if (sl >= n) return;
-    const double* D = st + dper * sl; const int* I = sti + iper * sl; const float* Fp = stf + fper * sl;
+    const double* D = st + dper * sl; const int* I = sti + iper * sl;
     int s = I[0];
     const double* obs = D; const double* rob = obs + 8 * (size_t)c.max_obs; const double* ped = rob + 5 * (size_t)c.R;
     const double* traj = ped + 5 * (size_t)c.P; const double* segs = traj + 3 * (size_t)c.max_traj * c.P;
     const double* trajv = segs + 4 * (size_t)c.max_obs;
-    const int* tl = I + 5; const int* nodes = tl + c.P;
+    const int* tl = I + 5;
     for (int k = threadIdx.x; k < 8 * c.max_obs; k += blockDim.x) d.obs[(size_t)s * c.max_obs * 8 + k] = obs[k];
     for (int k = threadIdx.x; k < 4 * c.max_obs; k += blockDim.x) d.sfm_obs[(size_t)s * c.max_obs * 4 + k] = segs[k];
     if (threadIdx.x == 0) {
-        d.n_obs[s] = I[1]; d.sfm_nobs[s] = I[2]; d.rvo_counts[2 * s] = I[3]; d.rvo_counts[2 * s + 1] = I[4]; d.step_no[s] = 0;
+        d.n_obs[s] = I[1]; d.sfm_nobs[s] = I[2]; d.step_no[s] = 0;
     }
-    for (int k = threadIdx.x; k < 8 * d.max_verts; k += blockDim.x) d.rvo_verts[(size_t)s * d.max_verts * 8 + k] = Fp[k];
-    for (int k = threadIdx.x; k < 4 * d.max_verts; k += blockDim.x) d.rvo_nodeseg[(size_t)s * d.max_verts * 4 + k] = Fp[8 * d.max_verts + k];
-    for (int k = threadIdx.x; k < 4 * d.max_verts; k += blockDim.x) d.rvo_nodes[(size_t)s * d.max_verts * 4 + k] = nodes[k];
     for (int j = threadIdx.x; j < c.R; j += blockDim.x) {
         int idx = s * c.R + j;
         const double* q = rob + 5 * j;
@@ -594,20 +594,20 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
         }
     }
     size_t dper = (size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 6 * (size_t)c.max_traj * c.P + 4 * c.max_obs;
-    size_t iper = (size_t)5 + c.P + 4 * (size_t)d.max_verts;
-    size_t fper = (size_t)12 * d.max_verts;
-    memset(h->st_h, 0, dper * n * 8); memset(h->sti_h, 0, iper * n * 4); memset(h->stf_h, 0, fper * n * 4);
+    size_t iper = (size_t)5 + c.P;
+    size_t fper = 0;
+    memset(h->st_h, 0, dper * n * 8); memset(h->sti_h, 0, iper * n * 4);
     auto pack_scene = [&](int sl) -> const char* {
         int s = scene_ids ? scene_ids[sl] : sl;
         if (s < 0 || s >= c.S) return "imgenv_reset: scene id out of range";
-        double* D = h->st_h + dper * sl; int* I = h->sti_h + iper * sl; float* Fp = h->stf_h + fper * sl;
+        double* D = h->st_h + dper * sl; int* I = h->sti_h + iper * sl;
         double* o_obs = D; double* o_rob = o_obs + 8 * (size_t)c.max_obs; double* o_ped = o_rob + 5 * (size_t)c.R;
         double* o_traj = o_ped + 5 * (size_t)c.P; double* o_seg = o_traj + 3 * (size_t)c.max_traj * c.P;
         double* o_trajv = o_seg + 4 * (size_t)c.max_obs;
         int no = n_obs ? n_obs[sl] : 0;
         if (no < 0 || no > c.max_obs) return "imgenv_reset: too many obstacles for max_obstacles";
         I[0] = s; I[1] = no;
-        std::vector<ht::RvoObst> robst; int nseg = 0;
+        int nseg = 0;
         for (int k = 0; k < no; k++) {
             const double* q = obs + ((size_t)sl * c.max_obs + k) * 11;
             double* o = o_obs + 8 * k;
@@ -623,30 +623,10 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
             else { tf_apply(t, o[1], o[3], pax, pay); tf_apply(t, o[2], o[4], pbx, pby); }
             if (!ignore_obstacle) {
                 double* sg = o_seg + 4 * nseg; sg[0] = pax; sg[1] = pay; sg[2] = pbx; sg[3] = pby; nseg++;   // pedscene.h:23-27
-                ht::F2 v[4] = {ht::f2((float)pax, (float)pay), ht::f2((float)pax, (float)pby), ht::f2((float)pbx, (float)pby), ht::f2((float)pbx, (float)pay)};
-                ht::rvo_add_obstacle(robst, v, 4);                                                         // rvoscene.h:19-26
+                // (the same two corners span the RVO polygon (ax,ay),(ax,by),(bx,by),(bx,ay), rvoscene.h:19-26: built by k_rvo_build)
             }
         }
         I[2] = nseg;
-        std::vector<ht::RvoNode> nodes;
-        int root = -1;
-        if (c.scene_type == 2 || c.scene_type == 3) {   // processObstacles (KdTree.cpp:119-128)
-            std::vector<int> list(robst.size());
-            for (size_t k = 0; k < list.size(); k++) list[k] = (int)k;
-            root = ht::rvo_build_tree(robst, nodes, list);
-            if ((int)robst.size() > d.max_verts || (int)nodes.size() > d.max_verts) return "imgenv_reset: obstacle k-d tree exceeds max_verts";
-            for (size_t k = 0; k < robst.size(); k++) {
-                float* v = Fp + 8 * k;
-                v[0] = robst[k].px; v[1] = robst[k].py; v[2] = robst[k].dx; v[3] = robst[k].dy; v[4] = (float)robst[k].convex;
-                v[5] = (float)robst[k].next; v[6] = (float)robst[k].prev; v[7] = 0;
-            }
-            int* nd = I + 5 + c.P;
-            for (size_t k = 0; k < nodes.size(); k++) { nd[4 * k] = nodes[k].obstacle; nd[4 * k + 1] = nodes[k].left; nd[4 * k + 2] = nodes[k].right; nd[4 * k + 3] = nodes[k].parent;
-                float* sg = Fp + 8 * (size_t)d.max_verts + 4 * k;           // the node's edge: its vertex and that vertex's successor
-                const ht::RvoObst& a = robst[nodes[k].obstacle]; const ht::RvoObst& b = robst[a.next];
-                sg[0] = a.px; sg[1] = a.py; sg[2] = b.px; sg[3] = b.py; }
-        }
-        I[3] = (int)robst.size(); I[4] = root;
         for (int j = 0; j < c.R; j++) {
             const double* q = robots + ((size_t)sl * c.R + j) * 8;
             double* o = o_rob + 5 * j;
@@ -667,7 +647,6 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     if (const char* e = for_scenes(n, pack_scene)) return fail(e);
     CK(cudaMemcpyAsync(h->st_d, h->st_h, dper * n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->sti_d, h->sti_h, iper * n * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->stf_d, h->stf_h, fper * n * 4, cudaMemcpyHostToDevice, st));
     // the scene-id list lives at the head of each int record; build a compact list after the records
     int* ids_h = h->sti_h + iper * n;   // (st_ints has S*(...)+8 >= iper*n + n only if checked)
     if (iper * (size_t)n + n > h->st_ints) return fail("imgenv_reset: staging overflow");
@@ -676,6 +655,7 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     CK(cudaMemcpyAsync(ids_d, ids_h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     k_apply_reset<<<n, 128, 0, st>>>(d, n, h->st_d, h->sti_d, h->stf_d, dper, iper, fper);
     k_object_footprints<<<n * c.max_obs, OBJ_THREADS, h->obj_smem, st>>>(d, ids_d);     // obs.draw(obs_map_, 0, ...) img_env.cpp:187
+    if (c.scene_type == 2 || c.scene_type == 3) k_rvo_build<<<n, 32, 0, st>>>(d, ids_d, ignore_obstacle);   // processObstacles (KdTree.cpp:119-128)
     if (launch_observe(h, ids_d, n, 1, st)) return -1;                 // view_agent(); get_states() img_env.cpp:285-286
     CK(cudaEventRecord(h->stage[h->stage_i].ev, st));                   // stream-ordered like imgenv_step: no host sync
     return 0;
@@ -864,6 +844,44 @@ extern "C" int imgenv_debug_counters(imgenv_t* h, int64_t* out4, void* stream) {
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     for (int k = 0; k < 4; k++) out4[k] = (int64_t)r[k];
     return 0;
+}
+// The RVO obstacle set of one scene as built on the device (tests compare it with the host restatement of
+// RVOSimulator::addObstacle / KdTree::buildObstacleTreeRecursive in host_tables.h and with the reference node's obstacles_):
+// verts[max_verts][8], nodes[max_verts][4]; returns n_verts in *n and the root in *root.
+extern "C" int imgenv_debug_rvo_tree(imgenv_t* h, int32_t scene, int32_t* n, int32_t* root, float* verts, int32_t* nodes, double* corners, void* stream) {
+    if (!h || !n || !root || !verts || !nodes || !corners) return fail("imgenv_debug_rvo_tree: null argument");
+    Dev& d = h->d;
+    if (scene < 0 || scene >= d.c.S) return fail("imgenv_debug_rvo_tree: bad scene");
+    cudaStream_t st = (cudaStream_t)stream;
+    int cnt[2];
+    CK(cudaMemcpyAsync(cnt, d.rvo_counts + 2 * scene, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(verts, d.rvo_verts + (size_t)scene * d.max_verts * 8, (size_t)d.max_verts * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(nodes, d.rvo_nodes + (size_t)scene * d.max_verts * 4, (size_t)d.max_verts * 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(corners, d.sfm_obs + (size_t)scene * d.c.max_obs * 4, (size_t)d.c.max_obs * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n = cnt[0]; *root = cnt[1];
+    return 0;
+}
+// Host restatement of the same build (no CUDA): corners[n_obj][4] = ax, ay, bx, by.  Returns the vertex count or -1.
+extern "C" int imgenv_host_rvo_tree(const double* corners, int32_t n_obj, int32_t max_verts, int32_t* root, float* verts, int32_t* nodes) {
+    std::vector<ht::RvoObst> robst;
+    for (int k = 0; k < n_obj; k++) {
+        const double* q = corners + 4 * k;
+        ht::F2 v[4] = {ht::f2((float)q[0], (float)q[1]), ht::f2((float)q[0], (float)q[3]), ht::f2((float)q[2], (float)q[3]), ht::f2((float)q[2], (float)q[1])};
+        ht::rvo_add_obstacle(robst, v, 4);
+    }
+    std::vector<ht::RvoNode> nd;
+    std::vector<int> list(robst.size());
+    for (size_t k = 0; k < list.size(); k++) list[k] = (int)k;
+    *root = ht::rvo_build_tree(robst, nd, list);
+    if ((int)robst.size() > max_verts) return -1;
+    for (size_t k = 0; k < robst.size(); k++) {
+        float* v = verts + 8 * k;
+        v[0] = robst[k].px; v[1] = robst[k].py; v[2] = robst[k].dx; v[3] = robst[k].dy; v[4] = (float)robst[k].convex;
+        v[5] = (float)robst[k].next; v[6] = (float)robst[k].prev; v[7] = 0;
+    }
+    for (size_t k = 0; k < nd.size(); k++) { nodes[4 * k] = nd[k].obstacle; nodes[4 * k + 1] = nd[k].left; nodes[4 * k + 2] = nd[k].right; nodes[4 * k + 3] = nd[k].parent; }
+    return (int)robst.size();
 }
 extern "C" int imgenv_end_episode(imgenv_t* h, int32_t) { return h ? 0 : fail("imgenv_end_episode: null handle"); }
 extern "C" int imgenv_solver_agents(const imgenv_t* h) { return h ? h->d.c.NA : 0; }

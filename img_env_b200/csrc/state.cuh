@@ -149,7 +149,8 @@ struct Dev {
     float* rvo_verts;                       // [S][max_verts][8]: px,py,dx,dy,convex,next,prev,0
     int* rvo_nodes;                         // [S][max_verts][4]: obstacle edge, left child, right child, parent
     float* rvo_nodeseg;                     // [S][max_verts][4]: end points of every BSP node's edge
-    unsigned long long* counters;           // [4] diagnostics: [0] ORCA obstacle-neighbour / line table overflows
+    int* rvo_arena; int rvo_arena_len;      // [S][rvo_arena_len] edge lists of the device-side BSP build (rvotree.cuh)
+    unsigned long long* counters;           // [4] diagnostics: [0] ORCA obstacle-neighbour / line table overflows, [1] obstacle BSP build overflows
     unsigned char* orca_pool; int orca_nslabs; unsigned* orca_cursor;   // overflow slabs of the ORCA tables (orca.cuh), [2] cursors used alternately
     int* rvo_counts;                        // [S][2]: n_verts, root(-1 none)
     int max_verts;

@@ -11,7 +11,10 @@
 #include "foot.cuh"
 
 #define VIEW_THREADS 256
-#define VIEW_MIN_CTAS 4                // 64 registers per thread: the register file holds 32 warps per SM either way
+#ifndef VIEW_MIN_CTAS
+#define VIEW_MIN_CTAS 4
+#endif
+//               // 64 registers per thread: the register file holds 32 warps per SM either way
 #define FX_ONE 4294967296.0            // 2^32: fixed-point scale of cell coordinates
 #define FX_GUARD 8192u                 // |frac - 0.5| below 2^-19 cells -> exact fp64 fallback
 

@@ -40,7 +40,7 @@ EXPORTS = ["imgenv_create", "imgenv_destroy", "imgenv_bind_outputs", "imgenv_res
            "imgenv_algorithmic_bytes_per_robot_step", "imgenv_last_error", "imgenv_version",
            "imgenv_sampler_create", "imgenv_sampler_destroy", "imgenv_sampler_seed", "imgenv_sampler_sample", "imgenv_sampler_draw",
            "imgenv_reset_sampled", "imgenv_debug_check_footprints",
-           "imgenv_record_enable", "imgenv_record_fetch", "imgenv_debug_set_min_jerk", "imgenv_set_ped_yaw_mode", "imgenv_debug_counters"]
+           "imgenv_record_enable", "imgenv_record_fetch", "imgenv_debug_set_min_jerk", "imgenv_set_ped_yaw_mode", "imgenv_debug_counters", "imgenv_debug_rvo_tree", "imgenv_host_rvo_tree"]
 
 
 def load_library(path=None):
@@ -275,6 +275,24 @@ class BatchedSim:
         out = np.zeros(4, np.int64)
         self._check(self.lib.imgenv_debug_counters(self.h, _ptr(out, C.c_int64), self._stream()))
         return tuple(int(x) for x in out)
+
+    def debug_rvo_tree(self, scene=0):
+        """-> dict(n, root, verts[n,8], nodes[n,4], corners[max_obs,4]) of the device-built RVO obstacle set of `scene`."""
+        mv = 16 * max(self.spec["max_obstacles"], 1) + 16
+        verts = np.zeros((mv, 8), np.float32); nodes = np.zeros((mv, 4), np.int32); corners = np.zeros((max(self.spec["max_obstacles"], 1), 4))
+        n, root = C.c_int32(), C.c_int32()
+        self._check(self.lib.imgenv_debug_rvo_tree(self.h, int(scene), C.byref(n), C.byref(root), _ptr(verts, C.c_float), _ptr(nodes, C.c_int32),
+                                                   _ptr(corners), self._stream()))
+        return dict(n=n.value, root=root.value, verts=verts[: n.value], nodes=nodes[: n.value], corners=corners)
+
+    def host_rvo_tree(self, corners, n_obj):
+        """The host restatement of the same construction on `corners[:n_obj]` -> dict(n, root, verts, nodes)."""
+        mv = 16 * max(self.spec["max_obstacles"], 1) + 16
+        verts = np.zeros((mv, 8), np.float32); nodes = np.zeros((mv, 4), np.int32)
+        root = C.c_int32()
+        cc = np.ascontiguousarray(corners, dtype=np.float64)
+        n = self.lib.imgenv_host_rvo_tree(_ptr(cc), int(n_obj), mv, C.byref(root), _ptr(verts, C.c_float), _ptr(nodes, C.c_int32))
+        return dict(n=n, root=root.value, verts=verts[: max(n, 0)], nodes=nodes[: max(n, 0)])
 
     def debug_set_min_jerk(self, min_jerk):
         """min_jerk[R,2] (linear, angular): the value the node's unassigned SpeedLimiter::min_jerk holds (tests)."""

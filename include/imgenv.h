@@ -160,6 +160,12 @@ int imgenv_set_ped_yaw_mode(imgenv_t* h, int mode);
 /* Diagnostic counters since creation: out4[0] = times an ORCA agent had more facing obstacle edges in range than the solver's
  * per-agent table holds (it then keeps the nearest; the reference keeps all).  Tests assert 0. */
 int imgenv_debug_counters(imgenv_t* h, int64_t* out4, void* stream);
+/* Tests: the RVO obstacle set of one scene as the reset kernels built it on the device (vertex ring verts[max_verts][8] = px, py,
+ * edge dir x, y, convex, next, prev, 0; BSP nodes[max_verts][4] = edge, left, right, parent; max_verts = 16 * max_obstacles + 16;
+ * corners[max_obstacles][4] = the two rotated corners per reset object the ring was built from), and the host restatement of the
+ * same construction (RVOSimulator.cpp:130-168, KdTree.cpp:119-257; no CUDA), returning the vertex count or -1. */
+int imgenv_debug_rvo_tree(imgenv_t* h, int32_t scene, int32_t* n, int32_t* root, float* verts, int32_t* nodes, double* corners, void* stream);
+int imgenv_host_rvo_tree(const double* corners, int32_t n_obj, int32_t max_verts, int32_t* root, float* verts, int32_t* nodes);
 /* ped_min_dists persistence (NearbyPed, reset_helper.py:85-99) and dones are library state. */
 int imgenv_solver_agents(const imgenv_t* h);   /* P + R' */
 int imgenv_view_dims(const imgenv_t* h, int32_t* vh, int32_t* vw);

@@ -157,3 +157,32 @@ def test_orca_dense_obstacle_field_no_truncation():
     The reference keeps ALL of them (Agent.cpp:820-838); the solver must not truncate."""
     cfg = base_cfg(R=2, P=16, scene="rvoscene", n_obj=40, max_ped=16)
     run_lockstep(cfg, seed=47, steps=5, lo=3.5, hi=7.5)
+
+
+@pytest.mark.parametrize("n_obj,seed", [(4, 61), (40, 62), (200, 63)])
+def test_device_built_rvo_obstacle_tree(n_obj, seed):
+    """The RVO vertex ring + BSP built by the reset kernel (rvotree.cuh) == the host restatement of RVOSimulator::addObstacle /
+    KdTree::buildObstacleTreeRecursive bit for bit (split vertices, pre-order node ids, links), and its vertex ring == the
+    reference node's own obstacles_ after processObstacles."""
+    from img_env_b200.lib import BatchedSim
+    from img_env_b200.scenarios import make_reset
+    from oracle.pyref import RefEnv, have_ref
+    cfg = base_cfg(R=1, P=2, scene="rvoscene", n_obj=n_obj, map_px=110 if n_obj < 100 else 400)
+    spec = build_spec(cfg)
+    rng = np.random.default_rng(seed)
+    sim = BatchedSim(spec, 2, ped_yaw_mode=1)
+    hi = 8.5 if n_obj < 100 else 30.0
+    resets = [make_reset(spec, rng, lo=2.5, hi=hi), make_reset(spec, rng, lo=2.5, hi=hi)]
+    sim.reset(resets)
+    for sc in range(2):
+        dev = sim.debug_rvo_tree(sc)
+        host = sim.host_rvo_tree(dev["corners"], n_obj)
+        assert dev["n"] == host["n"] and dev["root"] == host["root"] and dev["n"] >= 4 * n_obj
+        assert np.array_equal(dev["verts"].view(np.uint32), host["verts"].view(np.uint32)), "vertex ring differs from the host restatement"
+        assert np.array_equal(dev["nodes"], host["nodes"]), "BSP differs from the host restatement"
+        if have_ref() and n_obj <= 40:
+            ref = RefEnv(spec); ref.reset(resets[sc])
+            rv = ref.rvo_obstacles()
+            assert rv.shape[0] == dev["n"] and np.array_equal(rv.view(np.uint32), dev["verts"].view(np.uint32)), "vertex ring differs from the node's obstacles_"
+    assert sim.debug_counters()[1] == 0
+    sim.close()
