@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(FOOT_WARPS * 32) k_footprints(Dev d, const int
     const Cfg& c = d.c;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gq = blockIdx.x * FOOT_WARPS + warp;
-    if (gq >= n_scenes * c.NPA) return;
+    if (gq >= n_scenes * c.NPA || (d.n_dev && gq >= *d.n_dev * c.NPA)) return;
     const int sl = gq / c.NPA, a = gq - sl * c.NPA;
     const int s = scene_ids ? scene_ids[sl] : sl;
     if (bump_step && a == 0 && lane == 0) d.step_no[s] += 1;      // step_++ (img_env.cpp:518): the dynamics stage of this step is done
@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) k_object_footprints(Dev d, const 
     extern __shared__ uint32_t foot_sm[];             // obj_cap words
     const Cfg& c = d.c;
     const int sl = blockIdx.x / c.max_obs, o = blockIdx.x % c.max_obs;
+    if (d.n_dev && sl >= *d.n_dev) return;
     const int s = scene_ids ? scene_ids[sl] : sl;
     const int q = c.NPA + o;
     int4* hdr = d.foot_hdr + (size_t)s * c.NP + q;

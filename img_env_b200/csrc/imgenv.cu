@@ -32,6 +32,18 @@ struct imgenv {
     bool outputs_bound = false;
     int ped_yaw_mode = 0;
     unsigned solve_calls = 0;
+    // Episode queue for device-side auto-reset (imgenv_autoreset_*): per scene a ring of pre-sampled ResetEnv records in device
+    // memory.  The host sampler runs AHEAD of the simulation (same per-scene generator streams, hence the same episodes as
+    // synchronous resets), so a reset selected by a device-side mask never waits for the host.
+    struct AutoReset {
+        bool on = false; int depth = 0; imgenv_sampler* smp = nullptr; int ignore_obstacle = 0;
+        double* q_dbl = nullptr; int* q_int = nullptr; int* q_head = nullptr; int* q_tail = nullptr;   // device: [S][depth][dper], [S][depth][iper], [S], [S]
+        int* ids_d = nullptr; int* n_dev = nullptr;
+        std::vector<int> produced, seen;         // host: episodes uploaded per scene / consumed as last seen
+        int* head_h = nullptr; cudaEvent_t ev_head = nullptr; bool head_pending = false; int head_age = 0;
+        double* up_dbl = nullptr; int* up_int = nullptr; int up_cap = 0; cudaEvent_t ev_up = nullptr;   // pinned upload staging
+    } ar;
+    double* ar_up_dbl_d = nullptr; int* ar_up_int_d = nullptr;      // device landing area of a refill batch
     // reset staging (pinned host + device)
     // two sets used alternately: a reset only waits (on the set's event) for the reset before the previous one
     struct Stage { double* h = nullptr; double* d = nullptr; int* ih = nullptr; int* id = nullptr; float* fh = nullptr; float* fd = nullptr; cudaEvent_t ev = nullptr; };
@@ -132,6 +144,11 @@ extern "C" int imgenv_destroy(imgenv_t* h) {
     if (h->ev_moved) cudaEventDestroy(h->ev_moved);
     if (h->ev_tree) cudaEventDestroy(h->ev_tree);
     if (h->ev_ped) cudaEventDestroy(h->ev_ped);
+    if (h->ar.up_dbl) cudaFreeHost(h->ar.up_dbl);
+    if (h->ar.up_int) cudaFreeHost(h->ar.up_int);
+    if (h->ar.head_h) cudaFreeHost(h->ar.head_h);
+    if (h->ar.ev_head) cudaEventDestroy(h->ar.ev_head);
+    if (h->ar.ev_up) cudaEventDestroy(h->ar.ev_up);
     for (auto& g : h->stage) {
         if (g.h) cudaFreeHost(g.h);
         if (g.ih) cudaFreeHost(g.ih);
@@ -484,11 +501,24 @@ extern "C" int imgenv_bind_outputs(imgenv_t* h, const imgenv_outputs* o) {
 // staged reset record layout (per listed scene), doubles:
 //   obs[max_obs][8] | robots[R][5] x,y,yaw,gx,gy | peds[P][5] x,y,yaw,gx,gy | traj[P][max_traj][3] | segs[max_obs][4] | traj_v[P][max_traj][3]
 // ints: scene_id, n_obs, n_segs, 0, 0 | traj_len[P]      (the RVO obstacle ring + BSP are built on the device: rvotree.cuh)
-__global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, const float* stf, size_t dper, size_t iper, size_t fper) {
+// Records come either from the staged list of an imgenv_reset call (queue_depth == 0: record sl of st / sti) or from the
+// episode queues (queue_depth > 0: the listed scene's next queued record; an empty queue re-plays the newest record and is
+// counted in counters[2]).
+__global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, size_t dper, size_t iper,
+                              int queue_depth, const int* ids, int* q_head, const int* q_tail) {
     const Cfg& c = d.c;
     int sl = blockIdx.x;
-    if (sl >= n) return;
+    if (sl >= n || (d.n_dev && sl >= *d.n_dev)) return;
     const double* D = st + dper * sl; const int* I = sti + iper * sl;
+    if (queue_depth > 0) {
+        const int sc = ids[sl];
+        int e = q_head[sc];
+        if (e >= q_tail[sc]) { e = q_tail[sc] - 1; if (threadIdx.x == 0) atomicAdd(d.counters + 2, 1ull); }
+        const size_t slot = (size_t)sc * queue_depth + (size_t)(e % queue_depth);
+        D = st + dper * slot; I = sti + iper * slot;
+        __syncthreads();
+        if (threadIdx.x == 0) q_head[sc] = e + 1;
+    }
     int s = I[0];
     const double* obs = D; const double* rob = obs + 8 * (size_t)c.max_obs; const double* ped = rob + 5 * (size_t)c.R;
     const double* traj = ped + 5 * (size_t)c.P; const double* segs = traj + 3 * (size_t)c.max_traj * c.P;
@@ -545,8 +575,9 @@ __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, co
     }
 }
 
-static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int is_reset, cudaStream_t st, cudaEvent_t* ev = nullptr) {
-    Dev& d = h->d; const Cfg& c = d.c;
+static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int is_reset, cudaStream_t st, cudaEvent_t* ev = nullptr, const int* n_dev = nullptr) {
+    Dev d = h->d; const Cfg& c = d.c;
+    d.n_dev = n_dev;
     // fork: pedestrian observation (+ SFM quadtree maintenance, ped_scene.cpp:167-182 moveAgent) on the side stream
     CK(cudaEventRecord(h->ev_moved, st));
     CK(cudaStreamWaitEvent(h->side, h->ev_moved, 0));
@@ -567,44 +598,17 @@ static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int i
     return 0;
 }
 
-extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, const int32_t* n_obs, const double* obs,
-                            const double* robots, const double* peds, const int32_t* traj_len, const double* traj,
-                            const double* traj_v, int32_t ignore_obstacle, void* stream) {
-    if (!h) return fail("imgenv_reset: null handle");
-    if (!h->outputs_bound) return fail("imgenv_reset: outputs not bound (imgenv_bind_outputs)");
+// One ResetEnv record in the staging layout k_apply_reset reads (see above): request arrays of ONE scene -> D[dper], I[iper].
+static const char* pack_reset_record(imgenv* h, int s, int no, const double* obs, const double* robots, const double* peds, const int32_t* traj_len,
+                                     const double* traj, const double* traj_v, int ignore_obstacle, double* D, int* I) {
     Dev& d = h->d; const Cfg& c = d.c;
-    if (n < 1 || n > c.S) return fail("imgenv_reset: bad scene count");
-    CK(cudaSetDevice(h->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    if (h->tree_pending) { CK(cudaStreamWaitEvent(st, h->ev_tree, 0)); h->tree_pending = false; }
-    {   // staging is double-buffered: wait only until the reset that last used this set has consumed it
-        imgenv::Stage& g = h->stage[h->stage_i ^= 1];
-        CK(cudaEventSynchronize(g.ev));
-        h->st_h = g.h; h->st_d = g.d; h->sti_h = g.ih; h->sti_d = g.id; h->stf_h = g.fh; h->stf_d = g.fd;
-    }
     using ht::f32;
-    if (c.scene_type == 4 && !traj_v) return fail("imgenv_reset: dataset replay needs traj_v");
-    if (scene_ids) {   // two records for one scene would race in k_apply_reset / the object stamps
-        std::vector<char> seen(c.S, 0);
-        for (int sl = 0; sl < n; sl++) {
-            const int s = scene_ids[sl];
-            if (s < 0 || s >= c.S) return fail("imgenv_reset: scene id out of range");
-            if (seen[s]) return fail("imgenv_reset: duplicate scene id");
-            seen[s] = 1;
-        }
-    }
-    size_t dper = (size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 6 * (size_t)c.max_traj * c.P + 4 * c.max_obs;
-    size_t iper = (size_t)5 + c.P;
-    size_t fper = 0;
-    memset(h->st_h, 0, dper * n * 8); memset(h->sti_h, 0, iper * n * 4);
-    auto pack_scene = [&](int sl) -> const char* {
-        int s = scene_ids ? scene_ids[sl] : sl;
+    const int sl = 0;
+
         if (s < 0 || s >= c.S) return "imgenv_reset: scene id out of range";
-        double* D = h->st_h + dper * sl; int* I = h->sti_h + iper * sl;
         double* o_obs = D; double* o_rob = o_obs + 8 * (size_t)c.max_obs; double* o_ped = o_rob + 5 * (size_t)c.R;
         double* o_traj = o_ped + 5 * (size_t)c.P; double* o_seg = o_traj + 3 * (size_t)c.max_traj * c.P;
         double* o_trajv = o_seg + 4 * (size_t)c.max_obs;
-        int no = n_obs ? n_obs[sl] : 0;
         if (no < 0 || no > c.max_obs) return "imgenv_reset: too many obstacles for max_obstacles";
         I[0] = s; I[1] = no;
         int nseg = 0;
@@ -643,8 +647,46 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
             if (c.scene_type == 4) for (int k = 0; k < 3 * tl; k++) o_trajv[(size_t)p * c.max_traj * 3 + k] = traj_v[((size_t)sl * c.P + p) * c.max_traj * 3 + k];
         }
         return nullptr;
-    };
-    if (const char* e = for_scenes(n, pack_scene)) return fail(e);
+    }
+static size_t reset_dper(const Cfg& c) { return (size_t)8 * c.max_obs + 5 * c.R + 5 * c.P + 6 * (size_t)c.max_traj * c.P + 4 * c.max_obs; }
+static size_t reset_iper(const Cfg& c) { return (size_t)5 + c.P; }
+
+extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, const int32_t* n_obs, const double* obs,
+                            const double* robots, const double* peds, const int32_t* traj_len, const double* traj,
+                            const double* traj_v, int32_t ignore_obstacle, void* stream) {
+    if (!h) return fail("imgenv_reset: null handle");
+    if (!h->outputs_bound) return fail("imgenv_reset: outputs not bound (imgenv_bind_outputs)");
+    Dev& d = h->d; const Cfg& c = d.c;
+    if (n < 1 || n > c.S) return fail("imgenv_reset: bad scene count");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->tree_pending) { CK(cudaStreamWaitEvent(st, h->ev_tree, 0)); h->tree_pending = false; }
+    {   // staging is double-buffered: wait only until the reset that last used this set has consumed it
+        imgenv::Stage& g = h->stage[h->stage_i ^= 1];
+        CK(cudaEventSynchronize(g.ev));
+        h->st_h = g.h; h->st_d = g.d; h->sti_h = g.ih; h->sti_d = g.id; h->stf_h = g.fh; h->stf_d = g.fd;
+    }
+    using ht::f32;
+    if (c.scene_type == 4 && !traj_v) return fail("imgenv_reset: dataset replay needs traj_v");
+    if (scene_ids) {   // two records for one scene would race in k_apply_reset / the object stamps
+        std::vector<char> seen(c.S, 0);
+        for (int sl = 0; sl < n; sl++) {
+            const int s = scene_ids[sl];
+            if (s < 0 || s >= c.S) return fail("imgenv_reset: scene id out of range");
+            if (seen[s]) return fail("imgenv_reset: duplicate scene id");
+            seen[s] = 1;
+        }
+    }
+    const size_t dper = reset_dper(c), iper = reset_iper(c);
+    memset(h->st_h, 0, dper * n * 8); memset(h->sti_h, 0, iper * n * 4);
+    for (int sl = 0; sl < n; sl++) {
+        const int sc = scene_ids ? scene_ids[sl] : sl;
+        const char* e = pack_reset_record(h, sc, n_obs ? n_obs[sl] : 0, obs ? obs + (size_t)sl * c.max_obs * 11 : nullptr, robots + (size_t)sl * c.R * 8,
+                                          peds ? peds + (size_t)sl * c.P * 8 : nullptr, traj_len ? traj_len + (size_t)sl * c.P : nullptr,
+                                          traj ? traj + (size_t)sl * c.P * c.max_traj * 3 : nullptr, traj_v ? traj_v + (size_t)sl * c.P * c.max_traj * 3 : nullptr,
+                                          ignore_obstacle, h->st_h + dper * sl, h->sti_h + iper * sl);
+        if (e) return fail(e);
+    }
     CK(cudaMemcpyAsync(h->st_d, h->st_h, dper * n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->sti_d, h->sti_h, iper * n * 4, cudaMemcpyHostToDevice, st));
     // the scene-id list lives at the head of each int record; build a compact list after the records
@@ -653,7 +695,7 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     for (int sl = 0; sl < n; sl++) ids_h[sl] = h->sti_h[iper * sl];
     int* ids_d = h->sti_d + iper * n;
     CK(cudaMemcpyAsync(ids_d, ids_h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    k_apply_reset<<<n, 128, 0, st>>>(d, n, h->st_d, h->sti_d, h->stf_d, dper, iper, fper);
+    k_apply_reset<<<n, 128, 0, st>>>(d, n, h->st_d, h->sti_d, dper, iper, 0, nullptr, nullptr, nullptr);
     k_object_footprints<<<n * c.max_obs, OBJ_THREADS, h->obj_smem, st>>>(d, ids_d);     // obs.draw(obs_map_, 0, ...) img_env.cpp:187
     if (c.scene_type == 2 || c.scene_type == 3) k_rvo_build<<<n, 32, 0, st>>>(d, ids_d, ignore_obstacle);   // processObstacles (KdTree.cpp:119-128)
     if (launch_observe(h, ids_d, n, 1, st)) return -1;                 // view_agent(); get_states() img_env.cpp:285-286
@@ -835,6 +877,133 @@ extern "C" int imgenv_reset_sampled(imgenv_t* h, imgenv_sampler_t* w, int32_t n,
     return imgenv_reset(h, n, scene_ids, w->n_obs.data(), w->obs.data(), w->robots.data(), w->peds.data(), w->traj_len.data(), w->traj.data(), nullptr, ignore_obstacle, stream);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Device-side auto-reset: episode queues + resets selected by a device mask.
+// scene list of a device mask, in scene order; one warp
+__global__ void __launch_bounds__(32) k_compact_mask(const uint8_t* mask, int S, int* ids, int* n_out) {
+    int base = 0;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int s = s0 + threadIdx.x;
+        const bool on = s < S && mask[s] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (on) ids[base + __popc(m & ((1u << threadIdx.x) - 1u))] = s;
+        base += __popc(m);
+    }
+    if (threadIdx.x == 0) *n_out = base;
+}
+// uploaded records -> their queue slots (I[3] = slot, I[4] = episodes of that scene produced so far)
+__global__ void k_queue_scatter(int n, const double* up_dbl, const int* up_int, size_t dper, size_t iper, double* q_dbl, int* q_int, int* q_tail) {
+    const int k = blockIdx.x;
+    if (k >= n) return;
+    const int* I = up_int + iper * k;
+    const size_t slot = (size_t)I[3];
+    for (size_t i = threadIdx.x; i < dper; i += blockDim.x) q_dbl[slot * dper + i] = up_dbl[dper * k + i];
+    for (size_t i = threadIdx.x; i < iper; i += blockDim.x) q_int[slot * iper + i] = I[i];
+    if (threadIdx.x == 0) atomicMax(q_tail + I[0], I[4]);
+}
+extern "C" int imgenv_autoreset_refill(imgenv_t* h, void* stream) {
+    if (!h || !h->ar.on) return fail("imgenv_autoreset_refill: auto-reset is not enabled (imgenv_autoreset_enable)");
+    imgenv::AutoReset& a = h->ar; const Cfg& c = h->d.c;
+    cudaStream_t st = (cudaStream_t)stream;
+    // Consumption counters travel back asynchronously.  A scene consumes at most one episode per call, so the queues cannot run
+    // empty while the newest counters the host has seen are younger than `depth` calls: only when the host has run that far
+    // ahead of the device does it wait for the copy (an RL loop whose policy reads the observations never gets there).
+    if (a.head_pending) {
+        a.head_age++;
+        if (a.head_age >= a.depth - 2) CK(cudaEventSynchronize(a.ev_head));
+        if (cudaEventQuery(a.ev_head) == cudaSuccess) {
+            for (int s = 0; s < c.S; s++) a.seen[s] = a.head_h[s];
+            a.head_pending = false;
+        }
+    }
+    const size_t dper = reset_dper(c), iper = reset_iper(c);
+    sampler::Sampler& S = a.smp->s;
+    const size_t mo = std::max(c.max_obs, 1), mt = std::max(c.max_traj, 1), P1 = std::max(c.P, 1);
+    std::vector<double>& obs = a.smp->obs; std::vector<double>& rob = a.smp->robots; std::vector<double>& ped = a.smp->peds; std::vector<double>& trj = a.smp->traj;
+    std::vector<int32_t>& tl = a.smp->traj_len;
+    obs.assign(mo * 11, 0.0); rob.resize((size_t)c.R * 8); ped.resize(P1 * 8); tl.resize(P1); trj.assign(P1 * mt * 3, 0.0);
+    int s = 0;
+    while (s < c.S) {
+        // one upload batch: as many records as the pinned staging holds
+        int k = 0;
+        bool waited = false;
+        for (; s < c.S; s++) {
+            while (a.produced[s] - a.seen[s] < a.depth) {
+                if (k == a.up_cap) break;
+                if (!waited) { CK(cudaEventSynchronize(a.ev_up)); waited = true; }      // the previous batch has left the staging
+                std::fill(obs.begin(), obs.end(), 0.0); std::fill(trj.begin(), trj.end(), 0.0);
+                sampler::sample_scene(S, S.rng[s], obs.data(), rob.data(), ped.data(), tl.data(), trj.data(), c.max_traj);
+                double* D = a.up_dbl + dper * k; int* I = a.up_int + iper * k;
+                memset(D, 0, dper * 8); memset(I, 0, iper * 4);
+                if (const char* e = pack_reset_record(h, s, (int)S.objects.size(), obs.data(), rob.data(), ped.data(), tl.data(), trj.data(), nullptr,
+                                                      a.ignore_obstacle, D, I)) return fail(e);
+                I[3] = s * a.depth + a.produced[s] % a.depth; I[4] = ++a.produced[s];
+                k++;
+            }
+            if (k == a.up_cap && a.produced[s] - a.seen[s] < a.depth) break;
+        }
+        if (k > 0) {
+            CK(cudaMemcpyAsync(h->ar_up_dbl_d, a.up_dbl, dper * k * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(h->ar_up_int_d, a.up_int, iper * k * 4, cudaMemcpyHostToDevice, st));
+            k_queue_scatter<<<k, 128, 0, st>>>(k, h->ar_up_dbl_d, h->ar_up_int_d, dper, iper, a.q_dbl, a.q_int, a.q_tail);
+            CK(cudaEventRecord(a.ev_up, st));
+        }
+        if (k < a.up_cap) break;
+    }
+    if (!a.head_pending) {      // consumption counters back to the host, for the next top-up
+        CK(cudaMemcpyAsync(a.head_h, a.q_head, (size_t)c.S * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(a.ev_head, st));
+        a.head_pending = true; a.head_age = 0;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int imgenv_autoreset_enable(imgenv_t* h, imgenv_sampler_t* w, int32_t depth, int32_t ignore_obstacle, void* stream) {
+    if (!h || !w) return fail("imgenv_autoreset_enable: null argument");
+    const Cfg& c = h->d.c;
+    if (h->ar.on) return fail("imgenv_autoreset_enable: already enabled");
+    if (w->s.R != c.R || w->s.P != c.P || (int)w->s.rng.size() != c.S) return fail("imgenv_autoreset_enable: the sampler does not match the simulator (robots / pedestrians / scenes)");
+    if ((int)w->s.objects.size() > c.max_obs) return fail("imgenv_autoreset_enable: more objects than max_obstacles");
+    if (c.scene_type == 4) return fail("imgenv_autoreset_enable: dataset replay takes recorded trajectories (imgenv_reset)");
+    if (depth < 2 || depth > 64) return fail("imgenv_autoreset_enable: depth must be in [2, 64]");
+    imgenv::AutoReset& a = h->ar;
+    CK(cudaSetDevice(h->device));
+    const size_t dper = reset_dper(c), iper = reset_iper(c), S = c.S;
+    a.depth = depth; a.smp = w; a.ignore_obstacle = ignore_obstacle;
+    if (dalloc(h, &a.q_dbl, S * depth * dper) || dalloc(h, &a.q_int, S * depth * iper) || dalloc(h, &a.q_head, S) || dalloc(h, &a.q_tail, S) ||
+        dalloc(h, &a.ids_d, S + 8) || dalloc(h, &a.n_dev, 1)) return -1;
+    const size_t rec_bytes = dper * 8 + iper * 4;
+    a.up_cap = (int)std::max<size_t>(1, std::min<size_t>(S * depth, ((size_t)64 << 20) / rec_bytes));
+    CK(cudaMallocHost((void**)&a.up_dbl, (size_t)a.up_cap * dper * 8));
+    CK(cudaMallocHost((void**)&a.up_int, (size_t)a.up_cap * iper * 4));
+    CK(cudaMallocHost((void**)&a.head_h, S * 4));
+    if (dalloc(h, &h->ar_up_dbl_d, (size_t)a.up_cap * dper) || dalloc(h, &h->ar_up_int_d, (size_t)a.up_cap * iper)) return -1;
+    CK(cudaEventCreateWithFlags(&a.ev_head, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&a.ev_up, cudaEventDisableTiming));
+    a.produced.assign(S, 0); a.seen.assign(S, 0);
+    a.on = true;
+    return imgenv_autoreset_refill(h, stream);
+}
+// Resets the scenes whose mask byte is non-zero (device pointer, uint8 [S]) from their episode queues: EnvPos.reset + ResetEnv.srv
+// without any host involvement in the selection.  Stream-ordered, no host synchronisation.  refill != 0 also tops the queues up
+// (host sampler, non-blocking); pass 0 inside a CUDA graph capture and call imgenv_autoreset_refill between replays.
+extern "C" int imgenv_reset_masked(imgenv_t* h, const uint8_t* d_mask, int32_t refill, void* stream) {
+    if (!h || !d_mask) return fail("imgenv_reset_masked: null argument");
+    if (!h->ar.on) return fail("imgenv_reset_masked: auto-reset is not enabled (imgenv_autoreset_enable)");
+    if (!h->outputs_bound) return fail("imgenv_reset_masked: outputs not bound (imgenv_bind_outputs)");
+    imgenv::AutoReset& a = h->ar; Dev d = h->d; const Cfg& c = d.c;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (refill && imgenv_autoreset_refill(h, stream)) return -1;
+    if (h->tree_pending) { CK(cudaStreamWaitEvent(st, h->ev_tree, 0)); h->tree_pending = false; }
+    d.n_dev = a.n_dev;
+    k_compact_mask<<<1, 32, 0, st>>>(d_mask, c.S, a.ids_d, a.n_dev);
+    k_apply_reset<<<c.S, 128, 0, st>>>(d, c.S, a.q_dbl, a.q_int, reset_dper(c), reset_iper(c), a.depth, a.ids_d, a.q_head, a.q_tail);
+    k_object_footprints<<<c.S * c.max_obs, OBJ_THREADS, h->obj_smem, st>>>(d, a.ids_d);
+    if (c.scene_type == 2 || c.scene_type == 3) k_rvo_build<<<c.S, 32, 0, st>>>(d, a.ids_d, a.ignore_obstacle);
+    if (launch_observe(h, a.ids_d, c.S, 1, st, nullptr, a.n_dev)) return -1;
+    CK(cudaGetLastError());
+    return 0;
+}
 // Diagnostic counters since creation: out4[0] = ORCA obstacle-neighbour table overflows (an agent had more than ORCA_OBST_CAP
 // facing obstacle edges in range and kept the nearest; the reference keeps all of them), out4[1..3] reserved.
 extern "C" int imgenv_debug_counters(imgenv_t* h, int64_t* out4, void* stream) {

@@ -23,6 +23,7 @@ __device__ __forceinline__ V2 rvo_pt(const float* verts, int i) { return v2(vert
 
 __global__ void __launch_bounds__(32) k_rvo_build(Dev d, const int* scene_ids, int ignore_obstacle) {
     const Cfg& c = d.c;
+    if (d.n_dev && (int)blockIdx.x >= *d.n_dev) return;
     const int s = scene_ids ? scene_ids[blockIdx.x] : blockIdx.x;
     const int lane = threadIdx.x;
     float* verts = d.rvo_verts + (size_t)s * d.max_verts * 8;

@@ -170,6 +170,7 @@ struct Dev {
     // outputs
     float* o_vec; uint16_t* o_sensor; int8_t* o_coll; uint8_t* o_arr; float* o_laser;
     float* o_pvs; float* o_pmap; float* o_stepd; float* o_mind;
+    const int* n_dev;             // optional: number of listed scenes, on the device (masked resets launch for S scenes; blocks beyond *n_dev exit)
     uint8_t* dbg_view;            // optional [S][R][vh][vw]
     int* dbg_stats;               // optional [S][R][4]: active raster tiles, boundary cells, heavy cells, marching fallback
 };

@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
     const Cfg& c = d.c;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sl = blockIdx.x / c.R, r = blockIdx.x % c.R;
+    if (d.n_dev && sl >= *d.n_dev) return;
     const int s = scene_ids ? scene_ids[sl] : sl;
     const int idx = s * c.R + r;
     const RobotType ty = d.types[d.type_of[r]];
@@ -853,6 +854,7 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
     const Cfg& c = d.c;
     const int tid = threadIdx.x;
     const int sl = blockIdx.x / c.R, r = blockIdx.x % c.R;
+    if (d.n_dev && sl >= *d.n_dev) return;
     const int s = scene_ids ? scene_ids[sl] : sl;
     const int idx = s * c.R + r;
     const RobotType& ty = d.types[d.type_of[r]];

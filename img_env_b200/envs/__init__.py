@@ -7,6 +7,9 @@ from .reset_helper import EnvPos, NearbyPed                      # noqa: F401
 from .state import ImageState                                    # noqa: F401
 
 
+from .wrappers import GraphedStep                                # noqa: F401,E402
+
+
 def read_yaml(file: str) -> dict:
     with open(file, "r", encoding="utf-8") as f:
         return yaml.load(f.read(), Loader=yaml.FullLoader)

@@ -39,6 +39,11 @@ class ImageEnv:
             self.sampler = NativeSampler(sampler_desc(cfg), num_scenes=self.num_scenes, seed=int(cfg.get("sampler_seed", random.getrandbits(62))),
                                          max_obs=self.spec["max_obstacles"], max_traj=self.spec["max_traj"])
         self._ignore_obstacle = int(bool(cfg["ped_sim"].get("ignore_obstacle", False)))
+        # Device-side auto-reset (default with the native sampler): every scene holds a queue of pre-sampled episodes in device
+        # memory, so reset(scene_mask=<device bool tensor>) -- what NeverStopWrapper calls every step -- costs no host sync.
+        self.masked_reset = self.sampler is not None and not numpy_state and bool(cfg.get("device_autoreset", True))
+        if self.masked_reset:
+            self.sim.autoreset_enable(self.sampler, depth=int(cfg.get("autoreset_depth", 4)), ignore_obstacle=self._ignore_obstacle)
         self._record_steps = int(cfg.get("record_steps", 0))
         if self._record_steps:
             self.sim.record_enable(self._record_steps)
@@ -101,7 +106,25 @@ class ImageEnv:
             out.append(rs)
         return out
 
-    def reset(self, scene_ids=None, **kwargs):
+    def reset(self, scene_ids=None, scene_mask=None, **kwargs):
+        """scene_ids: list of scenes to reset (None = all).  scene_mask: bool / uint8 DEVICE tensor [num_scenes] instead of
+        scene_ids (device-side auto-reset: no host synchronisation; needs the native sampler)."""
+        torch = self.torch
+        if self.masked_reset:
+            # every sampled reset goes through the scenes' episode queues, so that a scene sees the same episode sequence
+            # whether it is reset by list or by mask
+            everything = scene_mask is None and scene_ids is None
+            if scene_mask is None:
+                scene_mask = torch.ones(self.num_scenes, dtype=torch.uint8, device=self.sim.device)
+                if scene_ids is not None:
+                    scene_mask.zero_(); scene_mask[torch.as_tensor(list(scene_ids), dtype=torch.long, device=self.sim.device)] = 1
+            self.sim.reset_masked(scene_mask, refill=not getattr(self, "_capturing", False))
+            state = self._state()
+            if self.dones is None or everything:
+                self.dones = torch.zeros(len(self), dtype=torch.int64, device=self.sim.device)
+            return state
+        if scene_mask is not None:
+            raise ValueError("reset(scene_mask=...) needs the device-side auto-reset (native sampler, torch state)")
         ids = list(range(self.num_scenes)) if scene_ids is None else list(scene_ids)
         if self.spec["scene_type"] == "dataset":
             self.sim.reset(self._dataset_resets(ids, kwargs.get("cur_ped_pos_v_datas")), scene_ids=ids)

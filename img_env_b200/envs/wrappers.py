@@ -76,6 +76,16 @@ class Wrapper:
     def step(self, action):
         return self.env.step(action)
 
+    # State carried between steps is normally REBOUND to fresh arrays (a caller may keep what a step returned).  Under CUDA-graph
+    # capture (GraphedStep) it has to live at fixed addresses instead: _keep() then updates the old tensor in place.
+    _inplace = False
+
+    def _keep(self, old, new):
+        if self._inplace and old is not None and _is_torch(old) and old.shape == new.shape and old.dtype == new.dtype:
+            old.copy_(new)
+            return old
+        return new
+
     # helpers for batched scenes
     def _robots_per_scene(self):
         return int(self.cfg["robot"]["total"])
@@ -213,14 +223,14 @@ class MultiRobotCleanWrapper(Wrapper):
                 if _is_torch(sp) and sp.device != clean.device:
                     sp = sp.to(clean.device)
                 info["speeds"] = _where(clean[:, None], sp, _zeros_like(sp))
-        self.is_clean = _where(done > 0, _zeros_like(clean), clean)
+        self.is_clean = self._keep(clean, _where(done > 0, _zeros_like(clean), clean))
         return state, reward, done, info
 
     def reset(self, **kwargs):
         state = self.env.reset(**kwargs)
         if self.is_clean is not None:
             m = self._row_mask(self.is_clean, kwargs)
-            self.is_clean = (self.is_clean | m) if m is not None else (_zeros_like(self.is_clean) == 0)
+            self.is_clean = self._keep(self.is_clean, (self.is_clean | m) if m is not None else (_zeros_like(self.is_clean) == 0))
         return state
 
 
@@ -248,8 +258,9 @@ class StateBatchWrapper(Wrapper):
         else:
             m = reset_mask.reshape((-1,) + (1,) * (q.ndim - 1))
             q = _where(m, _cat([_zeros_like(q[:, 1:]), t1], 1), q)
-        self.q[name] = q               # a fresh array every call (cat / where): the caller may keep the returned one
-        return q
+        old = self.q[name]
+        self.q[name] = self._keep(old, q)          # normally a fresh array every call (cat / where): the caller may keep the returned one
+        return self.q[name].clone() if self.q[name] is old and self._inplace else q
 
     def batch_state(self, state, reset_mask=None):
         state.sensor_maps = self._concate("sensor_maps", state.sensor_maps, reset_mask)
@@ -310,6 +321,11 @@ class NeverStopWrapper(Wrapper):
         ad = info["all_down"]
         r = self._robots_per_scene()
         per_scene = ad.reshape(-1, r)[:, 0]
+        if _is_torch(per_scene) and getattr(self.env, "masked_reset", False):
+            # device-side auto-reset: the scenes to restart are selected by a device mask, every step, without reading it
+            # (an all-false mask is a few empty launches); the stack below restarts its per-row state from the same mask
+            states = self.env.reset(scene_mask=per_scene, row_mask=ad)
+            return states, reward, done, info
         if _is_torch(per_scene):        # one small read per step; the scene list is only fetched when something ended
             scenes = per_scene.nonzero().flatten().tolist() if bool(per_scene.any()) else []
         else:
@@ -334,7 +350,7 @@ class TimeLimitWrapper(Wrapper):
         observation, reward, done, info = self.env.step(ac)
         if self._elapsed_steps is None:
             self._elapsed_steps = _i64(_zeros_like(done))
-        self._elapsed_steps = self._elapsed_steps + 1
+        self._elapsed_steps = self._keep(self._elapsed_steps, self._elapsed_steps + 1)
         over = self._elapsed_steps > self._max_episode_steps
         done = _where(over, _zeros_like(done) + 1, done)
         info["dones_info"] = _where(over, _zeros_like(info["dones_info"]) + 10, info["dones_info"])
@@ -343,7 +359,8 @@ class TimeLimitWrapper(Wrapper):
     def reset(self, **kwargs):
         if self._elapsed_steps is not None:
             m = self._row_mask(self._elapsed_steps, kwargs)
-            self._elapsed_steps = _zeros_like(self._elapsed_steps) if m is None else _where(m, _zeros_like(self._elapsed_steps), self._elapsed_steps)
+            self._elapsed_steps = self._keep(self._elapsed_steps, _zeros_like(self._elapsed_steps) if m is None else
+                                             _where(m, _zeros_like(self._elapsed_steps), self._elapsed_steps))
         return self.env.reset(**kwargs)
 
 
@@ -422,3 +439,49 @@ wrapper_dict = {
     "RealTestRecoderWrapper": _PassThrough,
     "PedTrajectoryDatasetWrapper": _PassThrough,
 }
+
+
+class GraphedStep:
+    """One env.step() of a wrapper stack captured into a CUDA graph and replayed: the ~100 small launches of the simulator and of
+    the vectorised wrappers cost one graph launch.  Needs the device-side auto-reset (ImageEnv.masked_reset: no host decision
+    inside a step) and torch actions of a fixed shape.  Everything step() returns lives in static buffers that the next replay
+    overwrites.  Between replays the episode queues are topped up (host sampler, non-blocking).
+
+        env = make_env(cfg, num_scenes=S); env.reset()
+        fast = GraphedStep(env, example_actions)
+        obs, reward, done, info = fast.step(actions)
+    """
+
+    def __init__(self, env, example_actions, warmup=3):
+        import torch
+        self.torch = torch
+        self.env = env
+        base = env
+        while isinstance(base, Wrapper):
+            base._inplace = True
+            base = base.env
+        self.base = base
+        if not getattr(base, "masked_reset", False):
+            raise RuntimeError("GraphedStep needs the device-side auto-reset (native sampler, torch state)")
+        if base.copy_state is False:
+            raise RuntimeError("GraphedStep needs copy_state=True (captured steps must not alias the library's output buffers)")
+        self.actions = example_actions.detach().clone().to(base.sim.device)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):              # lazily created wrapper state comes into being before the capture
+            for _ in range(warmup):
+                env.step(self.actions)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        base.sim.autoreset_refill()
+        base._capturing = True
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = env.step(self.actions)
+        base._capturing = False
+
+    def step(self, actions):
+        self.actions.copy_(actions, non_blocking=True)
+        self.base.sim.autoreset_refill()           # host sampler tops the episode queues up; never blocks on the device
+        self.graph.replay()
+        return self.out

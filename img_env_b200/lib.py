@@ -40,7 +40,8 @@ EXPORTS = ["imgenv_create", "imgenv_destroy", "imgenv_bind_outputs", "imgenv_res
            "imgenv_algorithmic_bytes_per_robot_step", "imgenv_last_error", "imgenv_version",
            "imgenv_sampler_create", "imgenv_sampler_destroy", "imgenv_sampler_seed", "imgenv_sampler_sample", "imgenv_sampler_draw",
            "imgenv_reset_sampled", "imgenv_debug_check_footprints",
-           "imgenv_record_enable", "imgenv_record_fetch", "imgenv_debug_set_min_jerk", "imgenv_set_ped_yaw_mode", "imgenv_debug_counters", "imgenv_debug_rvo_tree", "imgenv_host_rvo_tree"]
+           "imgenv_record_enable", "imgenv_record_fetch", "imgenv_debug_set_min_jerk", "imgenv_set_ped_yaw_mode", "imgenv_debug_counters", "imgenv_debug_rvo_tree", "imgenv_host_rvo_tree", "imgenv_autoreset_enable", "imgenv_autoreset_refill",
+           "imgenv_reset_masked"]
 
 
 def load_library(path=None):
@@ -224,6 +225,22 @@ class BatchedSim:
         """EnvPos.reset + reset service for the listed scenes without leaving native code."""
         ids = np.ascontiguousarray(scene_ids if scene_ids is not None else np.arange(self.S), dtype=np.int32)
         self._check(self.lib.imgenv_reset_sampled(self.h, sampler.h, ids.size, _ptr(ids, C.c_int32), int(ignore_obstacle), self._stream()))
+        return self.out
+
+    def autoreset_enable(self, sampler, depth=4, ignore_obstacle=0):
+        """Episode queues for device-side auto-reset: `depth` pre-sampled episodes per scene (see include/imgenv.h)."""
+        self._check(self.lib.imgenv_autoreset_enable(self.h, sampler.h, int(depth), int(ignore_obstacle), self._stream()))
+        self._autoreset_sampler = sampler          # keep it alive: the library samples from it
+
+    def autoreset_refill(self):
+        self._check(self.lib.imgenv_autoreset_refill(self.h, self._stream()))
+
+    def reset_masked(self, mask, refill=True):
+        """Resets the scenes with a non-zero mask byte (uint8 / bool CUDA tensor [S]) from their episode queues; no host sync."""
+        torch = self.torch
+        m = mask if mask.dtype == torch.uint8 else mask.to(torch.uint8)
+        assert m.is_cuda and m.is_contiguous() and m.numel() == self.S
+        self._check(self.lib.imgenv_reset_masked(self.h, C.c_void_p(m.data_ptr()), int(bool(refill)), self._stream()))
         return self.out
 
     def record_enable(self, max_steps):

@@ -120,6 +120,17 @@ int imgenv_sampler_draw(imgenv_sampler_t* s, int32_t scene, int32_t kind, double
 /* EnvPos.reset + ResetEnv.srv for the listed scenes in one call (yaml_env.py:232-262 without the Python loop). */
 int imgenv_reset_sampled(imgenv_t* h, imgenv_sampler_t* s, int32_t n, const int32_t* scene_ids, int32_t ignore_obstacle, void* stream);
 
+/* Device-side auto-reset.  imgenv_autoreset_enable gives every scene a queue of `depth` PRE-SAMPLED episodes in device memory (the
+ * host sampler runs ahead on the scenes' own generator streams, so each scene sees exactly the episode sequence synchronous
+ * imgenv_reset_sampled calls would give it).  imgenv_reset_masked then resets the scenes selected by a DEVICE mask (uint8 [S]) from
+ * their queues -- reset objects, RVO obstacle ring + BSP, poses, first observation -- stream-ordered and without any host
+ * synchronisation, so an RL loop (NeverStopWrapper, envs/wrapper/base.py:193-211) never leaves the device.  refill != 0 also tops
+ * the queues up (non-blocking); inside a CUDA graph pass 0 and call imgenv_autoreset_refill between replays.  A scene whose queue
+ * ran empty replays its newest episode and is counted in imgenv_debug_counters out4[2]. */
+int imgenv_autoreset_enable(imgenv_t* h, imgenv_sampler_t* s, int32_t depth, int32_t ignore_obstacle, void* stream);
+int imgenv_autoreset_refill(imgenv_t* h, void* stream);
+int imgenv_reset_masked(imgenv_t* h, const uint8_t* d_mask, int32_t refill, void* stream);
+
 /* StepEnv.srv for all S scenes. d_actions[S][R][3] = v, w, v_y(beep) float32 DEVICE pointer;
  * d_alive[S][R] uint8 DEVICE pointer, or NULL to use the library's own dones bookkeeping
  * (yaml_env.py:319-331,373-377: alive = not (collided or arrived) after the previous call). */
@@ -158,7 +169,8 @@ int imgenv_debug_set_min_jerk(imgenv_t* h, const double* min_jerk);
 /* Pedestrian yaw the node reads from an unassigned local (img_env.cpp:346-349): 0 keep, 1 zero (this build of the node), 2 heading. */
 int imgenv_set_ped_yaw_mode(imgenv_t* h, int mode);
 /* Diagnostic counters since creation: out4[0] = times an ORCA agent had more facing obstacle edges in range than the solver's
- * per-agent table holds (it then keeps the nearest; the reference keeps all).  Tests assert 0. */
+ * per-agent table holds (it then keeps the nearest; the reference keeps all); out4[1] = obstacle BSP builds that ran out of space;
+ * out4[2] = masked resets that found an empty episode queue.  Tests assert 0. */
 int imgenv_debug_counters(imgenv_t* h, int64_t* out4, void* stream);
 /* Tests: the RVO obstacle set of one scene as the reset kernels built it on the device (vertex ring verts[max_verts][8] = px, py,
  * edge dir x, y, convex, next, prev, 0; BSP nodes[max_verts][4] = edge, left, right, parent; max_verts = 16 * max_obstacles + 16;

@@ -192,7 +192,8 @@ def test_make_env_rejects_unknown_wrapper_and_reset_rejects_duplicate_scenes():
     with pytest.raises(ValueError, match="NoSuchWrapper"):
         make_env(cfg, num_scenes=1)
     random.seed(8)
-    env = ImageEnv(_cfg(), num_scenes=3)
+    cfg = _cfg(); cfg["device_autoreset"] = False          # (the device-mask path cannot list a scene twice)
+    env = ImageEnv(cfg, num_scenes=3)
     env.reset()
     with pytest.raises(RuntimeError, match="duplicate scene id"):
         env.reset(scene_ids=[1, 1])
@@ -225,3 +226,69 @@ def test_dataset_scenes_through_the_gym_api():
         assert np.allclose(pd[0][:, :2], datas[:, t, :2]) and np.allclose(pd[1][:, 6:8], datas[:, t, 3:5])
     env.close()
     del torch
+
+
+def test_device_side_auto_reset_equals_host_driven_resets():
+    """The episode-queue / device-mask reset path (imgenv_reset_masked, no host sync) gives every scene exactly the episodes and
+    observations the host-driven per-scene reset path gives it: same wrapper stack, same seeds, two envs, bit-equal for 60 steps."""
+    import torch
+    from img_env_b200.envs import make_env
+    outs = []
+    for device_autoreset in (True, False):
+        random.seed(5)
+        cfg = _cfg()
+        cfg.update(agent_num_per_env=1, image_batch=1, state_batch=3, laser_batch=0, time_max=5, continuous_actions=[[0, 0.6], [-0.9, 0.9]],
+                   sampler_seed=1234, device_autoreset=device_autoreset)
+        cfg["wrapper"] = ["VelActionWrapper", "TimeLimitWrapper", "SensorsPaperRewardWrapper", "InfoLogWrapper", "MultiRobotCleanWrapper",
+                          "TestEpisodeWrapper", "StateBatchWrapper", "ObsLaserStateTmp", "NeverStopWrapper"]
+        env = make_env(cfg, num_scenes=6)
+        assert env.masked_reset == device_autoreset
+        rec = [[x.clone() for x in env.reset()]]
+        g = torch.Generator(device="cpu"); g.manual_seed(3)
+        n_resets = 0
+        for t in range(60):
+            a = torch.randint(0, 4, (6,), generator=g).cuda()
+            obs, r, done, info = env.step(a)
+            rec.append([x.clone() for x in obs] + [r.clone(), done.clone()])
+            n_resets += int(info["all_down"].sum())
+        assert n_resets >= 20
+        if device_autoreset:
+            assert env.sim.debug_counters()[2] == 0, "an episode queue ran empty"
+        outs.append(rec)
+        env.close()
+    for t, (a, b) in enumerate(zip(*outs)):
+        for k, (x, y) in enumerate(zip(a, b)):
+            assert torch.equal(x, y), "step %d, output %d differs between device-side and host-driven resets" % (t, k)
+
+
+def test_graphed_step_equals_eager_step():
+    """GraphedStep (the whole wrapper stack + simulator + device-side auto-reset replayed as one CUDA graph) returns what the eager
+    loop returns, step for step."""
+    import torch
+    from img_env_b200.envs import make_env, GraphedStep
+    outs = []
+    for graphed in (False, True):
+        random.seed(6)
+        cfg = _cfg()
+        cfg.update(agent_num_per_env=1, image_batch=1, state_batch=3, laser_batch=0, time_max=5, continuous_actions=[[0, 0.6], [-0.9, 0.9]], sampler_seed=77)
+        cfg["wrapper"] = ["VelActionWrapper", "TimeLimitWrapper", "SensorsPaperRewardWrapper", "InfoLogWrapper", "MultiRobotCleanWrapper",
+                          "TestEpisodeWrapper", "StateBatchWrapper", "ObsLaserStateTmp", "NeverStopWrapper"]
+        env = make_env(cfg, num_scenes=5)
+        env.reset()
+        g = torch.Generator(device="cpu"); g.manual_seed(4)
+        acts = [torch.randint(0, 4, (5,), generator=g).cuda() for _ in range(43)]
+        rec = []
+        step = env.step
+        for t in range(3):                       # eager steps first: the wrappers create their per-row state lazily
+            env.step(acts[t])
+        if graphed:
+            step = GraphedStep(env, acts[0], warmup=0).step
+        for t in range(3, 43):
+            obs, r, done, info = step(acts[t])
+            rec.append([x.clone() for x in obs] + [r.clone(), done.clone(), info["all_down"].clone()])
+        assert env.sim.debug_counters()[2] == 0
+        outs.append(rec)
+        env.close()
+    for t, (a, b) in enumerate(zip(*outs)):
+        for k, (x, y) in enumerate(zip(a, b)):
+            assert torch.equal(x, y), "step %d, output %d differs between the graphed and the eager loop" % (t, k)
