@@ -78,6 +78,88 @@ __device__ __forceinline__ unsigned foot_cand_word(const uint32_t* bm, int nrow,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Pose-dependent constants of one robot's observation: the transforms Agent::view builds (get_base_world / get_view_world,
+// agent.cpp:118-131), the pixel -> world-cell map in fixed point, its inverse and the world bounding box of the field of
+// view.  Computed once per step by the robot's footprint warp (below) and bulk-copied (cp.async.bulk) into the observation
+// kernel's shared memory, so that kernel starts without a serial fp64 prologue.
+// ---------------------------------------------------------------------------------------------------------------------
+#define FX_ONE 4294967296.0            // 2^32: fixed-point scale of cell coordinates
+struct __align__(16) ViewConst {
+    Tf2 base_world, view_world;
+    long long ax, bx, cx, ay, by, cy;   // fixed-point (2^-32 cell) affine view pixel -> world cell, rounding offset folded in
+    double inv[4], org[2];              // inverse (world cell -> view pixel): pixel = inv * (cell - org)
+    int blk[4];                         // first block row / col, number of block rows / cols covering the FOV's world bounding box
+    int wbb[4];                         // world bounding box of the FOV in cells (x0, x1, y0, y1), clamped to the map
+    int4 own_hdr;                       // box of the observer's own footprint (header of the record k_footprints gives it)
+    int frozen, pad[3];                 // Agent::view early-out (agent.cpp:358-360)
+};
+static_assert(sizeof(ViewConst) % 16 == 0, "ViewConst is moved with 16-byte bulk copies");
+
+__device__ __forceinline__ void view_const_compute(const Dev& d, int idx, int r, ViewConst* k) {
+    const Cfg& c = d.c;
+    const RobotType& ty = d.types[d.type_of[r]];
+    const double x = RBF(d, RB_X, idx), y = RBF(d, RB_Y, idx), yaw = RBF(d, RB_YAW, idx);
+    const Tf2 B = tf_from_pose(x, y, yaw);
+    const Tf2 A = tf_mul(B, c.view_base);                        // get_view_world(), agent.cpp:128-131
+    k->base_world = B; k->view_world = A;
+    const long long ax = llrint(A.m00 * FX_ONE), bx = llrint(A.m01 * FX_ONE), cx = llrint((A.ox / c.res) * FX_ONE) + (1ll << 31);
+    const long long ay = llrint(A.m10 * FX_ONE), by = llrint(A.m11 * FX_ONE), cy = llrint((A.oy / c.res) * FX_ONE) + (1ll << 31);
+    k->ax = ax; k->bx = bx; k->cx = cx; k->ay = ay; k->by = by; k->cy = cy;
+    // stale view_map_/hits_/is_collision_ are re-sent for robots that collided or arrived
+    k->frozen = (RBF(d, RB_COLL, idx) != 0.0) || (RBF(d, RB_ARR, idx) != 0.0);
+    k->pad[0] = k->pad[1] = k->pad[2] = 0;
+    {   // the box of the robot's own footprint (the record itself may be culled when no other robot is near)
+        double bwx, bwy;
+        tf_apply(B, ty.stamp_cx, ty.stamp_cy, bwx, bwy);
+        k->own_hdr = foot_pack(foot_box(bwx, bwy, ty.stamp_rad, c.res), FK_ROBOT, r);
+    }
+    const double det = A.m00 * A.m11 - A.m01 * A.m10;
+    k->inv[0] = A.m11 / det; k->inv[1] = -A.m01 / det; k->inv[2] = -A.m10 / det; k->inv[3] = A.m00 / det;
+    k->org[0] = A.ox / c.res; k->org[1] = A.oy / c.res;
+    int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
+    for (int q = 0; q < 4; q++) {
+        const int ii = (q & 1) ? ty.fov_r1 : ty.fov_r0, jj = (q & 2) ? ty.fov_c1 : ty.fov_c0;
+        const int px = (int)((cx + (long long)ii * ax + (long long)jj * bx) >> 32);
+        const int py = (int)((cy + (long long)ii * ay + (long long)jj * by) >> 32);
+        xmin = min(xmin, px); xmax = max(xmax, px); ymin = min(ymin, py); ymax = max(ymax, py);
+    }
+    xmin = max(xmin - 1, 0); ymin = max(ymin - 1, 0); xmax = min(xmax + 1, c.H - 1); ymax = min(ymax + 1, c.W - 1);
+    k->wbb[0] = xmin; k->wbb[1] = xmax; k->wbb[2] = ymin; k->wbb[3] = ymax;
+    const bool empty = xmin > xmax || ymin > ymax || ty.fov_r1 < ty.fov_r0;
+    k->blk[0] = xmin >> 5; k->blk[1] = ymin >> 5;
+    k->blk[2] = empty ? 0 : (xmax >> 5) - (xmin >> 5) + 1; k->blk[3] = empty ? 0 : (ymax >> 5) - (ymin >> 5) + 1;
+}
+
+// mbarrier + 1-D bulk copy (TMA unit, global -> shared) helpers; sizes and addresses are multiples of 16 bytes
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// one thread per robot (a serial fp64 routine: small CTAs spread it over the SMs); grid = ceil(n_scenes * R / VC_THREADS)
+#define VC_THREADS 64
+__global__ void __launch_bounds__(VC_THREADS) k_view_consts(Dev d, const int* scene_ids, int n_scenes) {
+    const Cfg& c = d.c;
+    const int g = blockIdx.x * VC_THREADS + threadIdx.x;
+    const int sl = g / c.R, a = g - sl * c.R;
+    if (sl >= n_scenes || (d.n_dev && sl >= *d.n_dev)) return;
+    const int idx = (scene_ids ? scene_ids[sl] : sl) * c.R + a;
+    view_const_compute(d, idx, a, d.vconst + idx);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // robots and pedestrians: grid = ceil(n_scenes * NPA / FOOT_WARPS) CTAs, one warp per part
 // ---------------------------------------------------------------------------------------------------------------------
 #define FOOT_WARPS 8

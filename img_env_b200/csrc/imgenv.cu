@@ -251,8 +251,11 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     std::vector<RobotType> rts;
     for (auto& T : types) {
         T.t.pts_off = (int)lattice.size() / 2; lattice.insert(lattice.end(), T.lattice.begin(), T.lattice.end());
+        // (ray ends, spans and need_idx are bulk-copied into shared memory in 16-byte units: every segment starts on one and is padded to one)
         T.t.ray_off = (int)ray_end.size() / 2; ray_end.insert(ray_end.end(), T.ray_end.begin(), T.ray_end.end());
+        while (ray_end.size() % 8) ray_end.push_back(0);
         T.t.span_off = (int)spans.size(); spans.insert(spans.end(), T.spans.begin(), T.spans.end());
+        while (spans.size() % 8) spans.push_back(-1);
         T.t.khi_off = (int)khi.size(); khi.insert(khi.end(), T.khi.begin(), T.khi.end()); klo.insert(klo.end(), T.klo.begin(), T.klo.end());
         T.t.own_mask_off = (int)own_mask.size(); own_mask.insert(own_mask.end(), T.own_mask.begin(), T.own_mask.end());
         T.t.tile_off = (int)tile_fov.size(); tile_fov.insert(tile_fov.end(), T.tile_fov.begin(), T.tile_fov.end());
@@ -280,15 +283,22 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
             // interval of the source pixels' top rays and the float16 value the pixel takes when none of those rays hits
             // anything (free / own footprint / outside every ray), evaluated with the arithmetic of view.cuh phase F.
             const int npx = c.img * c.img;
-            T.ostat.assign((size_t)npx + (npx + 1) / 2, 0u);
+            const size_t half = (size_t)npx + (npx + 1) / 2;
+            T.ostat.assign(2 * half, 0u);
             uint16_t* oval = reinterpret_cast<uint16_t*>(T.ostat.data() + npx);
+            // second half: the all-shadow test of an output (interval of ALL rays through its source pixels | floor(smallest
+            // Chebyshev distance of such a pixel to the laser origin / 4) << 24) and its value when every one of those rays is
+            // stopped in front of the pixels (each source pixel "unknown" = 200, own footprint 100)
+            uint32_t* oshad = T.ostat.data() + half;
+            uint16_t* oshval = reinterpret_cast<uint16_t*>(T.ostat.data() + half + npx);
             const float scale = 1.f / (2048.f * 2048.f);
             for (int orow = 0; orow < c.img; orow++)
                 for (int oc = 0; oc < c.img; oc++) {
-                    uint32_t kmin = 0xFFFu, kmax = 0, imax = 0; bool any = false; float sv[4];
+                    uint32_t kmin = 0xFFFu, kmax = 0, imax = 0; bool any = false; float sv[4], ss[4];
+                    uint32_t amin = 0xFFFu, amax = 0, imin = 1023;
                     for (int t = 0; t < 4; t++) {
                         const int rr = tap[4 * orow + t];
-                        int sum = 0;
+                        int sum = 0, sum_sh = 0;
                         for (int k = 0; k < 4; k++) {
                             const int w = coef[4 * oc + k];
                             if (w == 0) continue;
@@ -299,13 +309,15 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
                                 if (coef[4 * orow + t] != 0) {
                                     kmin = std::min(kmin, kh); kmax = std::max(kmax, kh); any = true;
                                     const int pr = need_idx[rr], pc = need_idx[tap[4 * oc + k]];
-                                    imax = std::max(imax, (uint32_t)std::max(abs(pr - T.t.org_x), abs(pc - T.t.org_y)));
+                                    const uint32_t cheb = (uint32_t)std::max(abs(pr - T.t.org_x), abs(pc - T.t.org_y));
+                                    imax = std::max(imax, cheb); imin = std::min(imin, cheb);
+                                    amax = std::max(amax, kh); amin = std::min(amin, (uint32_t)(T.klo[(size_t)pr * c.vw + pc] & 0x7FFFu));
                                 }
                             }
                             if (e >> 31) val = 100;                          // own footprint
-                            sum += val * w;
+                            sum += val * w; sum_sh += ((e >> 31) ? 100 : 200) * w;
                         }
-                        sv[t] = (float)sum;
+                        sv[t] = (float)sum; ss[t] = (float)sum_sh;
                     }
                     if (!any) { kmin = 1; kmax = 0; }
                     const float b0 = coef[4 * orow + 0] * scale, b1 = coef[4 * orow + 1] * scale, b2 = coef[4 * orow + 2] * scale, b3 = coef[4 * orow + 3] * scale;
@@ -314,9 +326,15 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
                     iv = std::min(255, std::max(0, iv));
                     T.ostat[(size_t)orow * c.img + oc] = kmin | (kmax << 12) | (((imax + 3) / 4) << 24);
                     oval[(size_t)orow * c.img + oc] = lut[iv];
+                    if (!any) { amin = 1; amax = 0; }
+                    const float vs = fmaf(ss[0], b0, fmaf(ss[1], b1, fmaf(ss[2], b2, ss[3] * b3)));
+                    const int is = std::min(255, std::max(0, (int)lrintf(vs)));
+                    oshad[(size_t)orow * c.img + oc] = amin | (amax << 12) | ((imin / 4) << 24);
+                    oshval[(size_t)orow * c.img + oc] = lut[is];
                 }
         }
         T.t.ostat_off = (int)ostat.size(); ostat.insert(ostat.end(), T.ostat.begin(), T.ostat.end());
+        while (ostat.size() % 4) ostat.push_back(0u);      // (bulk-copied in 16-byte units)
         T.t.dtab_off = (int)dtab.size(); dtab.insert(dtab.end(), T.dtab.begin(), T.dtab.end());
         rts.push_back(T.t);
     }
@@ -367,6 +385,9 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     }
     c.scene_words = part_off[c.NP];
     Dev& d = h->d;
+    while (need_idx.size() % 8) need_idx.push_back(0);
+    while (tap.size() % 8) tap.push_back(0);
+    while (coef.size() % 8) coef.push_back(0);
 #define UP(field, vec) if (dupload(h, &d.field, vec)) return -1;
     std::vector<uint32_t> kpack(khi.size());
     for (size_t k = 0; k < khi.size(); k++) kpack[k] = (uint32_t)khi[k] | ((uint32_t)klo[k] << 16);
@@ -380,11 +401,11 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     size_t S = c.S;
     d.max_verts = 16 * c.max_obs + 16;
 #define AL(field, n) if (dalloc(h, &d.field, (size_t)(n))) return -1;
-    AL(foot_hdr, S * c.NP) AL(foot_words, S * (size_t)c.scene_words)
+    AL(foot_hdr, S * c.NP) AL(foot_words, S * (size_t)c.scene_words) AL(vconst, S * c.R)
     AL(rb, (size_t)RB_FIELDS * S * c.R) AL(pd, (size_t)PD_FIELDS * S * c.P)
     AL(traj, S * c.P * c.max_traj * 3) AL(traj_v, c.scene_type == 4 ? S * c.P * c.max_traj * 3 : 1) AL(traj_len, S * c.P) AL(obs, S * c.max_obs * 8) AL(n_obs, S) AL(step_no, S)
     AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_nvel, S * c.NA * 2) AL(sfm_force, c.scene_type == 1 ? S * c.NA * 12 : 1)
-    AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 4) AL(rvo_nodeseg, S * d.max_verts * 4) AL(counters, 4) AL(orca_cursor, 2)
+    AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 4) AL(rvo_nodeseg, S * d.max_verts * 4) AL(counters, 20) AL(orca_cursor, 2)
     d.rvo_arena_len = (c.scene_type == 2 || c.scene_type == 3) ? 32 * d.max_verts : 1;
     AL(rvo_arena, S * (size_t)d.rvo_arena_len)
     AL(rvo_counts, S * 2) AL(sfm, S * c.NA * SFM_REC) AL(sfm_obs, S * c.max_obs * 4) AL(sfm_nobs, S)
@@ -588,6 +609,7 @@ static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int i
         CK(cudaEventRecord(h->ev_tree, h->side));
         h->tree_pending = true;
     }
+    k_view_consts<<<(n_scenes * c.R + VC_THREADS - 1) / VC_THREADS, VC_THREADS, 0, st>>>(d, d_scene_ids, n_scenes);
     k_footprints<<<(n_scenes * c.NPA + FOOT_WARPS - 1) / FOOT_WARPS, FOOT_WARPS * 32, h->foot_smem, st>>>(d, d_scene_ids, n_scenes, is_reset ? 0 : 1);
     if (ev) cudaEventRecord(ev[2], st);
     if (c.inverse_ok) k_view<false, false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
@@ -703,8 +725,8 @@ extern "C" int imgenv_reset(imgenv_t* h, int32_t n, const int32_t* scene_ids, co
     return 0;
 }
 
-// k_dyn_solve (if a solver runs), k_dyn_apply, k_footprints, k_view, k_ped_obs (+ k_sfm_tree)
-extern "C" int imgenv_launches_per_step(const imgenv_t* h) { return !h ? 4 : (h->d.c.scene_type == 1 ? 6 : (h->d.c.NA > 0 ? 5 : 4)); }
+// k_dyn_solve (if a solver runs), k_dyn_apply, k_view_consts, k_footprints, k_view, k_ped_obs (+ k_sfm_tree)
+extern "C" int imgenv_launches_per_step(const imgenv_t* h) { return !h ? 5 : (h->d.c.scene_type == 1 ? 7 : (h->d.c.NA > 0 ? 6 : 5)); }
 
 extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d_alive, void* stream) {
     if (!h) return fail("imgenv_step: null handle");
@@ -1006,6 +1028,17 @@ extern "C" int imgenv_reset_masked(imgenv_t* h, const uint8_t* d_mask, int32_t r
 }
 // Diagnostic counters since creation: out4[0] = ORCA obstacle-neighbour table overflows (an agent had more than ORCA_OBST_CAP
 // facing obstacle edges in range and kept the nearest; the reference keeps all of them), out4[1..3] reserved.
+// Work counters of the observation kernel, summed over robots since creation -- only an instrumented build (-DVIEW_STATS=1)
+// writes them: out16[0] robots observed, [1] footprint records near the FOV, [2] their bitmap words, [3] static candidate
+// blocks, [4] candidate cells, [5] raster cells that updated rays, [6] outputs evaluated in full, [7] outputs settled by the
+// all-shadow test, [8] robots that ran the collision lattice, [9] robots that ran the FOV-edge pixels, [10] heavy cells,
+// [11] robots with any ray hit.
+extern "C" int imgenv_debug_view_stats(imgenv_t* h, int64_t* out16, void* stream) {
+    if (!h || !out16) return fail("imgenv_debug_view_stats: null argument");
+    CK(cudaMemcpyAsync(out16, h->d.counters + 4, 128, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
 extern "C" int imgenv_debug_counters(imgenv_t* h, int64_t* out4, void* stream) {
     if (!h || !out4) return fail("imgenv_debug_counters: null argument");
     unsigned long long r[4];
@@ -1143,6 +1176,7 @@ extern "C" int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* 
     if (host_out) CK(cudaMalloc((void**)&buf, n));
     if (stats_out) { CK(cudaMalloc((void**)&sbuf, (size_t)c.S * c.R * 16)); CK(cudaMemsetAsync(sbuf, 0, (size_t)c.S * c.R * 16, st)); }
     d.dbg_view = buf; d.dbg_stats = sbuf;
+    k_view_consts<<<(c.S * c.R + VC_THREADS - 1) / VC_THREADS, VC_THREADS, 0, st>>>(d, nullptr, c.S);
     k_footprints<<<(c.S * c.NPA + FOOT_WARPS - 1) / FOOT_WARPS, FOOT_WARPS * 32, h->foot_smem, st>>>(d, nullptr, c.S, 0);
     if (c.inverse_ok) k_view<true, false><<<c.S * c.R, VIEW_THREADS, h->view_smem, st>>>(d, nullptr, 0);
     else k_view<true, true><<<c.S * c.R, VIEW_THREADS, h->view_smem, st>>>(d, nullptr, 0);

@@ -89,6 +89,7 @@ struct Cfg {
     int scene_words;              // u32 words of record bitmaps per scene
 };
 
+struct ViewConst;
 struct Dev {
     Cfg c;
     // static, shared
@@ -129,6 +130,7 @@ struct Dev {
     int4* foot_hdr;               // [S][NP] first row (world cell x), first 32-cell word column, rows | words per row << 16, kind | id << 4
     uint32_t* foot_words;         // [S][scene_words] per part: cap occupancy words, then cap candidate words
     const int* part_off;          // [NP + 1] word offset of a part's bitmaps inside its scene's slice (cap = (off[q+1] - off[q]) / 2)
+    struct ViewConst* vconst;     // [S][R] pose-dependent constants of every robot's observation (foot.cuh), rewritten by k_footprints
     // dynamic state
     double* rb;                   // [RB_FIELDS][S*R]
     double* pd;                   // [PD_FIELDS][S*P]

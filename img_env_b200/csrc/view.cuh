@@ -10,28 +10,28 @@
 #include "kin.cuh"
 #include "foot.cuh"
 
+#ifndef VIEW_THREADS
 #define VIEW_THREADS 256
+#endif
+#ifndef VIEW_STATS
+#define VIEW_STATS 0          // instrumented build (tools/view_stats.py): work counters per robot in Dev::counters[4..]
+#endif
 #ifndef VIEW_MIN_CTAS
 #define VIEW_MIN_CTAS 4
 #endif
 //               // 64 registers per thread: the register file holds 32 warps per SM either way
-#define FX_ONE 4294967296.0            // 2^32: fixed-point scale of cell coordinates
 #define FX_GUARD 8192u                 // |frac - 0.5| below 2^-19 cells -> exact fp64 fallback
 
 struct ViewShared {
-    Tf2 base_world, view_world, world_base;
-    long long ax, bx, cx, ay, by, cy;   // fixed-point (2^-32 cell) affine view pixel -> world cell
-    int frozen;
+    ViewConst k;             // pose-dependent constants (foot.cuh), bulk-copied from d.vconst
+    unsigned long long bar[2];      // mbarriers: [0] constants landed, [1] static tables landed
     int red[8];              // counters / per-warp partial sums
     int coll_key;
-    // inverse (world cell -> view pixel) search: pixel = inv * (cell - org), in double; world block range of the FOV
-    double inv[4], org[2];
-    int blk[4];              // first block row / col, number of block rows / cols covering the FOV's world bounding box
-    int wbb[4];              // world bounding box of the FOV in cells (x0, x1, y0, y1), clamped to the map
     int n_cnear, n_dirty;
     unsigned long long near_pack;   // number of near records << 32 | their words so far (one atomic hands out slot and word offset)
     int hmin[64];            // per block of rays: smallest hit step (Chebyshev distance of the hit cell), NOHIT >> 22 if none
-    int4 own_hdr;            // the observer's own footprint record header
+    int stat[4];             // VIEW_STATS only: candidates, raster cells pushed, all-shadow outputs
+    int hmax[64];            // per block of rays: largest hit step, NOHIT >> 22 (1023) when a ray of the block has no hit
 };
 
 // python float floor division (Objects/floatobject.c float_floor_div) used by yaml_env.py:414-415
@@ -118,12 +118,13 @@ __device__ __noinline__ void cell_rays_inline(unsigned* hitkey, const short* ren
 #define BL_HEAVY 24
 #define NOHIT 0xFFFFFFFFu
 #define CN_CAP 32            // footprint records that overlap the observer's own footprint box (collision candidates)
+#define NEAR_CACHE 64        // near records whose header and word offset are kept in shared memory for phase B
 #define NEAR_ALL 0x8000u     // near-list flag: read the part's occupancy words (it may touch the FOV edge), not its candidates
 #define ET_SHIFT 4           // edge tiles are 16x16 view pixels
 
 #define INV_EPS 0.004f       // band around a cell edge inside which the inverse rasterisation runs the exact forward map
 #define INV_MAX_BLOCKS 512   // 32x32-cell world blocks under the FOV; more -> forward (tile) rasterisation
-struct ViewLayout { size_t sh, regA, regB, hpre, hitkey, rays, need, spans, blocks, near, npre, chdr, coff, total; };
+struct ViewLayout { size_t sh, regA, regB, hpre, hitkey, rays, need, spans, blocks, near, npre, chdr, coff, nhdr, noff, total; };
 __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     ViewLayout L;
     size_t off = 0;
@@ -143,6 +144,8 @@ __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     L.npre = off; off += ((size_t)(c.NP + 1) * 4 + 15) & ~(size_t)15;
     L.chdr = off; off += (size_t)CN_CAP * 16;
     L.coff = off; off += (size_t)CN_CAP * 4;
+    L.nhdr = off; off += (size_t)NEAR_CACHE * 16;
+    L.noff = off; off += (size_t)NEAR_CACHE * 4;
     L.total = off + 16;
     return L;
 }
@@ -156,48 +159,6 @@ __device__ __noinline__ void exact_cell(const Tf2& view_world, double res, int i
     double wx, wy;
     tf_apply(view_world, i * res, j * res, wx, wy);
     cx = world2cell(wx, res); cy = world2cell(wy, res);
-}
-// pose-dependent constants of one robot's observation (one thread per CTA)
-__device__ __forceinline__ void view_prologue(const Dev& d, ViewShared* sh, int idx, int r) {
-    const Cfg& c = d.c;
-    const RobotType& ty = d.types[d.type_of[r]];
-    double x = RBF(d, RB_X, idx), y = RBF(d, RB_Y, idx), yaw = RBF(d, RB_YAW, idx);
-    sh->base_world = tf_from_pose(x, y, yaw);
-    sh->view_world = tf_mul(sh->base_world, c.view_base);       // get_view_world(), agent.cpp:128-131
-    sh->world_base = tf_inv(sh->base_world);
-    const Tf2& A = sh->view_world;
-    sh->ax = llrint(A.m00 * FX_ONE); sh->bx = llrint(A.m01 * FX_ONE);
-    sh->cx = llrint((A.ox / c.res) * FX_ONE) + (1ll << 31);
-    sh->ay = llrint(A.m10 * FX_ONE); sh->by = llrint(A.m11 * FX_ONE);
-    sh->cy = llrint((A.oy / c.res) * FX_ONE) + (1ll << 31);
-    // Agent::view early-out (agent.cpp:358-360): stale view_map_/hits_/is_collision_ are re-sent
-    sh->frozen = (RBF(d, RB_COLL, idx) != 0.0) || (RBF(d, RB_ARR, idx) != 0.0);
-    sh->coll_key = 0;
-    sh->red[0] = 0; sh->red[1] = 0; sh->red[2] = 0; sh->red[3] = 0; sh->red[4] = 0;
-    sh->near_pack = 0ull; sh->n_cnear = 0; sh->n_dirty = 0;
-    {   // the box of the robot's own footprint (the same box k_footprints gives its record; the record itself may be
-        // culled when no other robot is near, so it is not read here)
-        double bwx, bwy;
-        tf_apply(sh->base_world, ty.stamp_cx, ty.stamp_cy, bwx, bwy);
-        sh->own_hdr = foot_pack(foot_box(bwx, bwy, ty.stamp_rad, c.res), FK_ROBOT, r);
-    }
-    {   // inverse map and the FOV's world bounding box (for the world->view rasterisation)
-        const double det = A.m00 * A.m11 - A.m01 * A.m10;
-        sh->inv[0] = A.m11 / det; sh->inv[1] = -A.m01 / det; sh->inv[2] = -A.m10 / det; sh->inv[3] = A.m00 / det;
-        sh->org[0] = A.ox / c.res; sh->org[1] = A.oy / c.res;
-        int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
-        for (int k = 0; k < 4; k++) {
-            const int ii = (k & 1) ? ty.fov_r1 : ty.fov_r0, jj = (k & 2) ? ty.fov_c1 : ty.fov_c0;
-            const int cx = (int)((sh->cx + (long long)ii * sh->ax + (long long)jj * sh->bx) >> 32);
-            const int cy = (int)((sh->cy + (long long)ii * sh->ay + (long long)jj * sh->by) >> 32);
-            xmin = min(xmin, cx); xmax = max(xmax, cx); ymin = min(ymin, cy); ymax = max(ymax, cy);
-        }
-        xmin = max(xmin - 1, 0); ymin = max(ymin - 1, 0); xmax = min(xmax + 1, c.H - 1); ymax = min(ymax + 1, c.W - 1);
-        sh->wbb[0] = xmin; sh->wbb[1] = xmax; sh->wbb[2] = ymin; sh->wbb[3] = ymax;
-        const bool empty = xmin > xmax || ymin > ymax || ty.fov_r1 < ty.fov_r0;
-        sh->blk[0] = xmin >> 5; sh->blk[1] = ymin >> 5;
-        sh->blk[2] = empty ? 0 : (xmax >> 5) - (xmin >> 5) + 1; sh->blk[3] = empty ? 0 : (ymax >> 5) - (ymin >> 5) + 1;
-    }
 }
 // Phase G: state vector and the episode bookkeeping (img_env.cpp:547-587, yaml_env.py:316, 374-376, 467-471)
 __device__ __forceinline__ void view_state_vector(const Dev& d, int idx, int is_reset) {
@@ -247,23 +208,40 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
     unsigned* npre = reinterpret_cast<unsigned*>(smem_raw + L.npre);
     int4* chdr = reinterpret_cast<int4*>(smem_raw + L.chdr);
     int* coff = reinterpret_cast<int*>(smem_raw + L.coff);
+    int4* nhdr = reinterpret_cast<int4*>(smem_raw + L.nhdr);
+    int* noff = reinterpret_cast<int*>(smem_raw + L.noff);
+    const int npx = c.img * c.img;
+    // [npx] u32: lowest | highest top ray over the source pixels of an output | farthest source pixel, then [npx] u16: the
+    // output's float16 value when none of those rays hits anything
+    const uint32_t* okk = d.ostat + (size_t)ty.ostat_off;
+    const uint16_t* oval = reinterpret_cast<const uint16_t*>(okk + npx);
+    const short* ctap = d.cubic_tap;
+    const short* ccoef = d.cubic_coef;
+    const uint16_t* lut16 = d.f16_lut;
 
     const int4* fhdr = d.foot_hdr + (size_t)s * c.NP;
     const uint32_t* fwords = d.foot_words + (size_t)s * c.scene_words;
 
-    if (tid == 0) view_prologue(d, sh, idx, r);
-    {   // static tables into shared memory
-        // one ray end = 2 shorts, one row of FOV spans = 4 shorts: copied as 4- and 8-byte words
-        const int* g_rend = reinterpret_cast<const int*>(d.ray_end + 2 * (size_t)ty.ray_off);
-        for (int k = tid; k < c.range_total; k += VIEW_THREADS) reinterpret_cast<int*>(rend)[k] = __ldg(g_rend + k);
-        for (int k = tid; k < c.ns; k += VIEW_THREADS) need[k] = d.need_idx[k];
-        const int2* g_spans = reinterpret_cast<const int2*>(d.fov_spans + (size_t)ty.span_off);
-        for (int k = tid; k < vh; k += VIEW_THREADS) reinterpret_cast<int2*>(spans)[k] = __ldg(g_spans + k);
-        for (int k = tid; k < c.range_total; k += VIEW_THREADS) hitkey[k] = NOHIT;
-        if (tid < 64) sh->hmin[tid] = 1023;
+    // Prologue: the robot's pose constants (written by k_footprints) and the static tables of its type arrive by bulk copies
+    // (one thread issues them, the TMA unit moves the data) while the CTA initialises its ray table and gathers footprints.
+    if (tid == 0) {
+        mbar_init(&sh->bar[0], 1); mbar_init(&sh->bar[1], 1); mbar_init_fence();
+        mbar_expect_tx(&sh->bar[0], (unsigned)sizeof(ViewConst));
+        bulk_g2s(&sh->k, d.vconst + idx, (unsigned)sizeof(ViewConst), &sh->bar[0]);
+        const unsigned nb_r = ((unsigned)c.range_total * 4u + 15u) & ~15u, nb_s = ((unsigned)vh * 8u + 15u) & ~15u, nb_n = ((unsigned)c.ns * 2u + 15u) & ~15u;
+        mbar_expect_tx(&sh->bar[1], nb_r + nb_s + nb_n);
+        bulk_g2s(rend, d.ray_end + 2 * (size_t)ty.ray_off, nb_r, &sh->bar[1]);          // ray end cells (agent.cpp:414-430)
+        bulk_g2s(spans, d.fov_spans + (size_t)ty.span_off, nb_s, &sh->bar[1]);          // FOV column spans per view row
+        bulk_g2s(need, d.need_idx, nb_n, &sh->bar[1]);                                  // source rows / columns the resize reads
+        sh->coll_key = 0;
+        sh->red[0] = 0; sh->red[1] = 0; sh->red[2] = 0; sh->red[3] = 0; sh->red[4] = 0; sh->red[5] = 0; sh->red[6] = 0; sh->stat[0] = 0; sh->stat[1] = 0; sh->stat[2] = 0;
+        sh->near_pack = 0ull; sh->n_cnear = 0; sh->n_dirty = 0;
     }
+    for (int k = tid; k < c.range_total; k += VIEW_THREADS) hitkey[k] = NOHIT;
+    if (tid < 64) { sh->hmin[tid] = 1023; sh->hmax[tid] = 0; }
     __syncthreads();
-    const bool frozen = DEBUG_FULL ? false : sh->frozen != 0;
+    mbar_wait(&sh->bar[0], 0);
+    const bool frozen = DEBUG_FULL ? false : sh->k.frozen != 0;
 
     if (!frozen) {
         const unsigned H = c.H, W = c.W, Wb = c.Wb;
@@ -271,22 +249,24 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
         const uint32_t* kpack = d.kpack + (size_t)ty.khi_off;
         const bool use_inverse = !FWD;
         const bool use_laser = FWD ? c.use_laser != 0 : true;
-        const int X0 = sh->wbb[0], X1 = sh->wbb[1], Y0 = sh->wbb[2], Y1 = sh->wbb[3];
-        const float i00 = (float)sh->inv[0], i01 = (float)sh->inv[1], i10 = (float)sh->inv[2], i11 = (float)sh->inv[3];
-        const int orgi0 = (int)floor(sh->org[0]), orgi1 = (int)floor(sh->org[1]);
-        const float orgf0 = (float)(sh->org[0] - orgi0), orgf1 = (float)(sh->org[1] - orgi1);
+        const int X0 = sh->k.wbb[0], X1 = sh->k.wbb[1], Y0 = sh->k.wbb[2], Y1 = sh->k.wbb[3];
+        const float i00 = (float)sh->k.inv[0], i01 = (float)sh->k.inv[1], i10 = (float)sh->k.inv[2], i11 = (float)sh->k.inv[3];
+        const int orgi0 = (int)floor(sh->k.org[0]), orgi1 = (int)floor(sh->k.org[1]);
+        const float orgf0 = (float)(sh->k.org[0] - orgi0), orgf1 = (float)(sh->k.org[1] - orgi1);
 
         // ---- Gather: footprint records of the scene whose box meets (a) the world bounding box of the field of view
         //      -> `near` (raster / ray candidates), (b) the robot's own footprint box -> `chdr` (collision candidates).
         //      A part that comes close to the FOV edge (or to the laser origin) contributes ALL of its cells, the others
         //      only their candidate cells (see phase B).
         {
-            const int4 own = sh->own_hdr;
+            const int4 own = sh->k.own_hdr;
             const uint32_t* etiles = d.edge_tiles + ty.etile_off;
             const int etw = (vw + (1 << ET_SHIFT) - 1) >> ET_SHIFT, eth = (vh + (1 << ET_SHIFT) - 1) >> ET_SHIFT;
+            int4 h_next = tid < c.NP ? __ldg(fhdr + tid) : make_int4(0, 0, 0, 0);
             for (int q = tid; q < c.NP; q += VIEW_THREADS) {
+                const int4 h = h_next;
+                if (q + VIEW_THREADS < c.NP) h_next = __ldg(fhdr + q + VIEW_THREADS);      // (next header in flight while this one is tested)
                 if (q == r) continue;                                   // the robot never sees itself (img_env.cpp:624-628)
-                const int4 h = __ldg(fhdr + q);
                 const int nrow = foot_nrow(h);
                 if (nrow == 0) continue;
                 const int bx0 = h.x, bx1 = h.x + nrow - 1, by0 = h.y, by1 = h.y + nrow - 1;
@@ -320,49 +300,62 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 }
                 {   // slot in the near list and offset of the part's words among the work items of phase B, from one atomic
                     const unsigned long long t = atomicAdd(&sh->near_pack, (1ull << 32) | (unsigned long long)(nrow * foot_wpr(h)));
-                    near[t >> 32] = (unsigned short)(q | all); npre[t >> 32] = (unsigned)t;
+                    const int slot = (int)(t >> 32);
+                    near[slot] = (unsigned short)(q | all); npre[slot] = (unsigned)t;
+                    if (slot < NEAR_CACHE) {      // phase B then needs no dependent global loads to find the part's words
+                        const int po = __ldg(d.part_off + q);
+                        nhdr[slot] = h; noff[slot] = all ? po : po + ((__ldg(d.part_off + q + 1) - po) >> 1);
+                    }
                 }
             }
             if (use_inverse) {      // 32x32-cell world blocks under the FOV that hold static candidates
                 const uint32_t* crow = d.static_crow;
-                const int nbj = sh->blk[3], nb = sh->blk[2] * nbj;
+                const uint32_t* orow = d.static_orow;
+                const int nbj = sh->k.blk[3], nb = sh->k.blk[2] * nbj;
                 for (int t = tid; t < nb; t += VIEW_THREADS) {
-                    const int bi = sh->blk[0] + t / nbj, bj = sh->blk[1] + t % nbj;
+                    const int bi = sh->k.blk[0] + t / nbj, bj = sh->k.blk[1] + t % nbj;
                     if (__ldg(crow + (unsigned)bi * c.Wb + bj)) blocks[atomicAdd(&sh->red[3], 1)] = ((unsigned)bi << 16) | (unsigned)bj;
+                    if (__ldg(orow + (unsigned)bi * c.Wb + bj)) sh->red[5] = 1;      // the static map is not empty under the FOV
                 }
-            }
+                if (tid >= VIEW_THREADS - 4) {      // ... nor under the robot's own footprint box (+1 cell; <= 2 x 2 blocks)
+                    const int u = tid - (VIEW_THREADS - 4);
+                    const int bi = min(max((u & 1) ? own.x + own.z : own.x - 1, 0), (int)H - 1) >> 5;
+                    const int bj = min(max((u & 2) ? own.y + own.z : own.y - 1, 0), (int)W - 1) >> 5;
+                    if (__ldg(orow + (unsigned)bi * c.Wb + bj)) sh->red[6] = 1;
+                }
+            } else if (tid == 0) { sh->red[5] = 1; sh->red[6] = 1; }
         }
         __syncthreads();
+        mbar_wait(&sh->bar[1], 0);
         const int n_near = (int)(sh->near_pack >> 32);
         const unsigned n_near_words = (unsigned)sh->near_pack;
         const int n_cnear = sh->n_cnear;
-        // ---- Phase A: collision code = code of the LAST colliding lattice point (agent.cpp:294-326)
+        // ---- Phase A: collision code = code of the LAST colliding lattice point (agent.cpp:294-326).
+        // No footprint record overlaps the robot's own box and the static map is free under it -> no point can collide.
         int best = 0;
-        if (!DEBUG_FULL) {
-            const double* pts = d.lattice_xy + 2 * (size_t)ty.pts_off;
-            const uint8_t* grid = d.grid;
-            for (int k = tid; k < ty.n_pts; k += VIEW_THREADS) {
-                double wx, wy;
-                const double2 pt = __ldg(reinterpret_cast<const double2*>(pts) + k);
-                tf_apply(sh->base_world, pt.x, pt.y, wx, wy);
-                const int cx = world2cell_fast(wx, c.res, c.inv_res), cy = world2cell_fast(wy, c.res, c.inv_res);
-                if ((unsigned)cx < H && (unsigned)cy < W) {
-                    unsigned f = 0;
-                    if (n_cnear <= CN_CAP) {
-                        for (int e = 0; e < n_cnear; e++) { const int4 h = chdr[e]; if (foot_covers(h, fwords + coff[e], cx, cy)) f |= foot_flag(foot_kind(h)); }
-                    } else {     // (more colliding parts than the list holds: scan every record of the scene)
-                        for (int q = 0; q < c.NP; q++) {
-                            if (q == r) continue;
-                            const int4 h = __ldg(fhdr + q);
-                            if (foot_nrow(h) && foot_covers(h, fwords + d.part_off[q], cx, cy)) f |= foot_flag(foot_kind(h));
-                        }
+        const bool need_A = !DEBUG_FULL && (n_cnear > 0 || sh->red[6] != 0);
+        const double* pts = d.lattice_xy + 2 * (size_t)ty.pts_off;
+        auto lattice_point = [&](int k) {
+            double wx, wy;
+            const double2 pt = __ldg(reinterpret_cast<const double2*>(pts) + k);
+            tf_apply(sh->k.base_world, pt.x, pt.y, wx, wy);
+            const int cx = world2cell_fast(wx, c.res, c.inv_res), cy = world2cell_fast(wy, c.res, c.inv_res);
+            if ((unsigned)cx < H && (unsigned)cy < W) {
+                unsigned f = 0;
+                if (n_cnear <= CN_CAP) {
+                    for (int e = 0; e < n_cnear; e++) { const int4 h = chdr[e]; if (foot_covers(h, fwords + coff[e], cx, cy)) f |= foot_flag(foot_kind(h)); }
+                } else {     // (more colliding parts than the list holds: scan every record of the scene)
+                    for (int q = 0; q < c.NP; q++) {
+                        if (q == r) continue;
+                        const int4 h = __ldg(fhdr + q);
+                        if (foot_nrow(h) && foot_covers(h, fwords + d.part_off[q], cx, cy)) f |= foot_flag(foot_kind(h));
                     }
-                    const int v = composed_value(__ldg(grid + (size_t)cx * W + cy), f);
-                    if (v <= 2) best = max(best, ((k + 1) << 2) | (v + 1));
                 }
+                const int v = composed_value(__ldg(d.grid + (size_t)cx * W + cy), f);
+                if (v <= 2) best = max(best, ((k + 1) << 2) | (v + 1));
             }
-            for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-        }
+        };
+        if (FWD && need_A) for (int k = tid; k < ty.n_pts; k += VIEW_THREADS) lattice_point(k);
         // ---- Phase B: egocentric occupancy raster (agent.cpp:373-404), 1 bit per view cell:
         // set <=> in FOV && in map && the robot's global_map_ value < 250.  FOV = static column spans per row; the pixel ->
         // world cell map is affine and evaluated in 2^-32-cell fixed point with an exact fp64 fallback inside a guard
@@ -407,6 +400,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
             const unsigned kp = __ldg(kpack + pr * vw + pc);
             const int kh = kp & 0xFFFF, kl = (kp >> 16) & 0x7FFF;
             if (kh == 0xFFFF) return;                                      // no ray passes through this cell
+            if (VIEW_STATS) atomicAdd(&sh->stat[1], 1);
             if (kh - kl + 1 > BL_HEAVY) {
                 const int p = atomicAdd(n_list2, 1);
                 if (p < BL2_CAP) { blist2[p] = ((unsigned)pr << 16) | (unsigned)pc; return; }
@@ -433,8 +427,8 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         const int ii = (k & 1) ? i1 : i0, jj = (k & 2) ? j1 : j0;
-                        const int cx = (int)((sh->cx + (long long)ii * sh->ax + (long long)jj * sh->bx) >> 32);
-                        const int cy = (int)((sh->cy + (long long)ii * sh->ay + (long long)jj * sh->by) >> 32);
+                        const int cx = (int)((sh->k.cx + (long long)ii * sh->k.ax + (long long)jj * sh->k.bx) >> 32);
+                        const int cy = (int)((sh->k.cy + (long long)ii * sh->k.ay + (long long)jj * sh->k.by) >> 32);
                         xmin = min(xmin, cx); xmax = max(xmax, cx); ymin = min(ymin, cy); ymax = max(ymax, cy);
                     }
                     xmin = max(xmin - 1, 0); ymin = max(ymin - 1, 0); xmax = min(xmax + 1, (int)H - 1); ymax = min(ymax + 1, (int)W - 1);
@@ -445,12 +439,11 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 if (active) { const int ti = t / vwb; tile_list[atomicAdd(n_active, 1)] = (unsigned short)((ti << 8) | (t - ti * vwb)); }
             }
         }
-        if (!DEBUG_FULL && lane == 0) atomicMax(&sh->coll_key, best);
         if (!use_inverse) __syncthreads();       // (world->view mode: block list and near list were finished before the last barrier)
         if (!use_inverse) {
             const int n_items = sh->red[2] * 32;
-            const long long lbx = sh->cx + (long long)lane * sh->bx, lby = sh->cy + (long long)lane * sh->by;
-            const long long bx32 = sh->bx * 32, by32 = sh->by * 32;
+            const long long lbx = sh->k.cx + (long long)lane * sh->k.bx, lby = sh->k.cy + (long long)lane * sh->k.by;
+            const long long bx32 = sh->k.bx * 32, by32 = sh->k.by * 32;
 #pragma unroll 2
             for (int item = warp; item < n_items; item += VIEW_THREADS / 32) {
                 const int t = reinterpret_cast<unsigned short*>(blist2)[item >> 5];
@@ -462,12 +455,12 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 const bool in_fov = (j >= a0 && j < a1) || (j >= b0 && j < b1);     // empty spans are (-1,-1)
                 bool o = false, kn = false;
                 if (in_fov) {
-                    const long long tx = lbx + (long long)i * sh->ax + (long long)wj * bx32;
-                    const long long tyy = lby + (long long)i * sh->ay + (long long)wj * by32;
+                    const long long tx = lbx + (long long)i * sh->k.ax + (long long)wj * bx32;
+                    const long long tyy = lby + (long long)i * sh->k.ay + (long long)wj * by32;
                     int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
                     const unsigned lx = (unsigned)tx, ly = (unsigned)tyy;
                     if (lx + FX_GUARD < 2 * FX_GUARD || ly + FX_GUARD < 2 * FX_GUARD) {
-                        exact_cell(sh->view_world, c.res, i, j, cx, cy);
+                        exact_cell(sh->k.view_world, c.res, i, j, cx, cy);
                     }
                     if ((unsigned)cx < H && (unsigned)cy < W) {
                         kn = true;
@@ -479,24 +472,23 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 if (lane == 0) occ[i * vwb + wj] = wo;
             }
             __syncthreads();      // the footprint records below OR into the words written above
-        } else {
-            // FOV-edge pixels (and the laser origin): forward, static map only -- footprint records near them come in whole below
-            const uint32_t* edge = d.edge_px + ty.edge_off;
-            for (int e = tid; e < ty.n_edge; e += VIEW_THREADS) {
-                const unsigned ep = __ldg(edge + e);
-                const int i = ep >> 16, j = ep & 0xFFFF;
-                const long long tx = sh->cx + (long long)i * sh->ax + (long long)j * sh->bx;
-                const long long tyy = sh->cy + (long long)i * sh->ay + (long long)j * sh->by;
-                int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
-                if ((unsigned)tx + FX_GUARD < 2 * FX_GUARD || (unsigned)tyy + FX_GUARD < 2 * FX_GUARD) {
-                    exact_cell(sh->view_world, c.res, i, j, cx, cy);
-                }
-                if ((unsigned)cx < H && (unsigned)cy < W) {
-                    const bool o = (__ldg(static_occ + (unsigned)cx * Wb + ((unsigned)cy >> 5)) >> (cy & 31)) & 1u;
-                    if (o) push_cell(i, j);
-                }
-            }
         }
+        // FOV-edge pixels (and the laser origin): forward, static map only -- footprint records near them come in whole below
+        const uint32_t* edge = d.edge_px + ty.edge_off;
+        auto edge_pixel = [&](int e) {
+            const unsigned ep = __ldg(edge + e);
+            const int i = ep >> 16, j = ep & 0xFFFF;
+            const long long tx = sh->k.cx + (long long)i * sh->k.ax + (long long)j * sh->k.bx;
+            const long long tyy = sh->k.cy + (long long)i * sh->k.ay + (long long)j * sh->k.by;
+            int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
+            if ((unsigned)tx + FX_GUARD < 2 * FX_GUARD || (unsigned)tyy + FX_GUARD < 2 * FX_GUARD) {
+                exact_cell(sh->k.view_world, c.res, i, j, cx, cy);
+            }
+            if ((unsigned)cx < H && (unsigned)cy < W) {
+                const bool o = (__ldg(static_occ + (unsigned)cx * Wb + ((unsigned)cy >> 5)) >> (cy & 31)) & 1u;
+                if (o) push_cell(i, j);
+            }
+        };
         {
             // candidate words -> candidate cells -> view pixels.  Work items: 32 rows per listed static block, then every
             // word of every near footprint record.  Each warp takes 32 items (one word per lane) from a shared counter --
@@ -504,13 +496,21 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
             const uint32_t* static_cand = d.static_cand;
             const int n_static = use_inverse ? sh->red[3] * 32 : 0;
             const int n_items = n_static + (int)n_near_words;
-            const float f00 = (float)sh->view_world.m00, f01 = (float)sh->view_world.m01, f10 = (float)sh->view_world.m10, f11 = (float)sh->view_world.m11;
+            // World->view mode: ONE work queue for the whole phase -- the heavy, uneven batches first (candidate words), then
+            // the light, even ones (FOV-edge pixels when the static map is not empty under the FOV, then the collision lattice),
+            // so the warps reach the barrier below together.
+            const int q_edge = (n_items + 31) & ~31;
+            const int q_pts = q_edge + ((use_inverse && sh->red[5]) ? (ty.n_edge + 31) & ~31 : 0);
+            const int q_end = q_pts + ((use_inverse && need_A) ? (ty.n_pts + 31) & ~31 : 0);
+            const float f00 = (float)sh->k.view_world.m00, f01 = (float)sh->k.view_world.m01, f10 = (float)sh->k.view_world.m10, f11 = (float)sh->k.view_world.m11;
             const float fr0 = (float)ty.fov_r0 - 1.5f, fr1 = (float)ty.fov_r1 + 1.5f, fc0 = (float)ty.fov_c0 - 1.5f, fc1 = (float)ty.fov_c1 + 1.5f;
             for (;;) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(&sh->red[4], 32);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= n_items) break;
+                if (base >= q_end) break;
+                if (base >= q_pts) { if (base - q_pts + lane < ty.n_pts) lattice_point(base - q_pts + lane); continue; }
+                if (base >= q_edge) { if (base - q_edge + lane < ty.n_edge) edge_pixel(base - q_edge + lane); continue; }
                 const int item = base + lane;
                 unsigned cand = 0; int X = 0, bj = 0;
                 if (item < n_static) {
@@ -521,14 +521,19 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                     const unsigned di = (unsigned)(item - n_static);
                     int lo = 0, hi = n_near - 1;                       // last k with npre[k] <= di
                     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (npre[mid] <= di) lo = mid; else hi = mid - 1; }
-                    const unsigned e = near[lo];
-                    const int q = e & 0x7FFF;
-                    const int4 h = __ldg(fhdr + q);
+                    int4 h; int wbase;
+                    if (lo < NEAR_CACHE) { h = nhdr[lo]; wbase = noff[lo]; }
+                    else {
+                        const unsigned e = near[lo];
+                        const int q = e & 0x7FFF;
+                        h = __ldg(fhdr + q);
+                        const int po = __ldg(d.part_off + q);
+                        wbase = (e & NEAR_ALL) ? po : po + ((__ldg(d.part_off + q + 1) - po) >> 1);
+                    }
                     const int wpr = foot_wpr(h), wi = (int)(di - npre[lo]);
                     const int rr = wi / wpr;
                     X = h.x + rr; bj = foot_wj0(h) + (wi - rr * wpr);
-                    const int po = __ldg(d.part_off + q), cap = (__ldg(d.part_off + q + 1) - po) >> 1;
-                    if (X >= X0 && X <= X1) cand = __ldg(fwords + po + ((e & NEAR_ALL) ? 0 : cap) + wi);
+                    if (X >= X0 && X <= X1) cand = __ldg(fwords + wbase + wi);
                 }
                 if (cand) {     // only columns under the FOV's bounding box
                     const int lo = max(Y0 - bj * 32, 0), hi = min(Y1 - bj * 32, 31);
@@ -539,6 +544,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
                 const int total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - cnt;
+                if (VIEW_STATS && lane == 0) atomicAdd(&sh->stat[0], total);
                 for (int k0 = 0; k0 < total; k0 += 32) {
                     const int k = k0 + lane;
                     int src = 0;
@@ -578,11 +584,11 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                         const int a0 = spans[i * 4 + 0], a1 = spans[i * 4 + 1], b0 = spans[i * 4 + 2], b1 = spans[i * 4 + 3];
                         if (!((j >= a0 && j < a1) || (j >= b0 && j < b1))) continue;
                         if (em > 0.5f - INV_EPS) {
-                            const long long tx = sh->cx + (long long)i * sh->ax + (long long)j * sh->bx;
-                            const long long tyy = sh->cy + (long long)i * sh->ay + (long long)j * sh->by;
+                            const long long tx = sh->k.cx + (long long)i * sh->k.ax + (long long)j * sh->k.bx;
+                            const long long tyy = sh->k.cy + (long long)i * sh->k.ay + (long long)j * sh->k.by;
                             int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
                             if ((unsigned)tx + FX_GUARD < 2 * FX_GUARD || (unsigned)tyy + FX_GUARD < 2 * FX_GUARD) {
-                                exact_cell(sh->view_world, c.res, i, j, cx, cy);
+                                exact_cell(sh->k.view_world, c.res, i, j, cx, cy);
                             }
                             if (cx != cX || cy != cY) continue;
                         }
@@ -594,6 +600,10 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                     }
                 }
             }
+        }
+        if (!DEBUG_FULL && need_A) {
+            for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (lane == 0 && best) atomicMax(&sh->coll_key, best);
         }
         __syncthreads();
         if (!DEBUG_FULL && tid == 0) {
@@ -651,30 +661,34 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 // laser ranges out; one bit per ray "hit something" (ballots: a warp's 32 rays are one word) and, per block of
                 // rays, the nearest hit -- the output classification below asks both about ray intervals
                 int any_local = 0;
+                const float nohit_out = c.laser_norm ? (float)(6.0 / c.laser_max) : 6.f;     // hit = 6 without a hit (agent.cpp:513)
                 for (int k0 = 0; k0 < c.range_total; k0 += VIEW_THREADS) {
                     const int k = k0 + tid;
                     const bool valid = k < c.range_total;
                     const unsigned key = valid ? hitkey[k] : NOHIT;
                     const bool hit_any = key != NOHIT;
                     if (valid) {
-                        double hit = 6;   // agent.cpp:513
+                        float out = nohit_out;
                         if (hit_any) {
                             const int hx = (key >> 11) & 2047, hy = key & 2047;
                             double x0 = ox * c.res, y0 = oy * c.res, xc = hx * c.res, yc = hy * c.res;
-                            hit = sqrt((x0 - xc) * (x0 - xc) + (y0 - yc) * (y0 - yc));
+                            const float wire = (float)sqrt((x0 - xc) * (x0 - xc) + (y0 - yc) * (y0 - yc));   // AgentState.laser is float32[]
+                            out = c.laser_norm ? (float)((double)wire / c.laser_max) : wire;            // yaml_env.py:440-444
                         }
-                        const float wire = (float)hit;                         // AgentState.laser is float32[]
-                        d.o_laser[(size_t)idx * c.range_total + k] = c.laser_norm ? (float)((double)wire / c.laser_max) : wire;   // yaml_env.py:440-444
+                        d.o_laser[(size_t)idx * c.range_total + k] = out;
                     }
                     const unsigned word = __ballot_sync(0xffffffffu, hit_any);
                     if (lane == 0 && (k >> 5) <= ((c.range_total - 1) >> 5)) hbits[k >> 5] = word;
                     any_local |= word != 0u;
-                    if (c.hb_shift == 4) {      // blocks of 16 rays = half warps: shuffle minimum, no atomics
-                        int hp = (int)(key >> 22);
+                    if (c.hb_shift == 4) {      // blocks of 16 rays = half warps: shuffle minimum / maximum, no atomics
+                        int hp = (int)(key >> 22), hq = valid ? hp : 0;
 #pragma unroll
-                        for (int o = 8; o; o >>= 1) hp = min(hp, __shfl_xor_sync(0xffffffffu, hp, o));
-                        if ((lane & 15) == 0 && valid) sh->hmin[k >> 4] = hp;
-                    } else if (hit_any) atomicMin(&sh->hmin[k >> c.hb_shift], (int)(key >> 22));
+                        for (int o = 8; o; o >>= 1) { hp = min(hp, __shfl_xor_sync(0xffffffffu, hp, o)); hq = max(hq, __shfl_xor_sync(0xffffffffu, hq, o)); }
+                        if ((lane & 15) == 0 && valid) { sh->hmin[k >> 4] = hp; sh->hmax[k >> 4] = hq; }
+                    } else if (valid) {
+                        if (hit_any) atomicMin(&sh->hmin[k >> c.hb_shift], (int)(key >> 22));
+                        atomicMax(&sh->hmax[k >> c.hb_shift], (int)(key >> 22));
+                    }
                 }
                 any_hit_all = __syncthreads_or(any_local);
             }
@@ -755,10 +769,9 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 }
             }
         } else {
-            const int npx = c.img * c.img;
             uint16_t* o_img = d.o_sensor + (size_t)idx * npx;
-            const uint32_t* okk = d.ostat + (size_t)ty.ostat_off;                                   // [npx] kmin | kmax << 16
-            const uint16_t* oval = reinterpret_cast<const uint16_t*>(d.ostat + (size_t)ty.ostat_off + npx);   // [npx] hit-free float16
+            const uint32_t* oshad = d.ostat + (size_t)ty.ostat_off + npx + (npx + 1) / 2;               // [npx] all-shadow test: ray interval | nearest source pixel
+            const uint16_t* oshval = reinterpret_cast<const uint16_t*>(oshad + npx);                    // [npx] all-shadow float16
             const bool any_hit = !use_laser || any_hit_all != 0;
             // any ray of [a, b] with a hit?  (a, b at most a few words apart)
             auto range_hit = [&](int a, int b) -> bool {
@@ -776,10 +789,27 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                     const int kmin = kk & 0xFFFu, kmax = (kk >> 12) & 0xFFFu;
                     if (kmax >= kmin && range_hit(kmin, kmax)) {
                         // some of the rays hit something: still clean if every hit lies beyond all of the output's source pixels
-                        // (they are then all "free", as in the hit-free value) -- nearest hit over the covering ray blocks
-                        int hm = 1023;
-                        for (int b = kmin >> c.hb_shift; b <= (kmax >> c.hb_shift); b++) hm = min(hm, sh->hmin[b]);
-                        is_dirty = hm <= (int)(kk >> 24) * 4;
+                        // (they are then all "free", as in the hit-free value) -- nearest hit over the covering ray blocks.
+                        // (Outputs next to the origin see hundreds of rays: evaluated in full without asking.)
+                        const int b0 = kmin >> c.hb_shift, b1 = kmax >> c.hb_shift;
+                        is_dirty = true;
+                        if (b1 - b0 < 8) {
+                            int hm = 1023;
+                            for (int b = b0; b <= b1; b++) hm = min(hm, sh->hmin[b]);
+                            is_dirty = hm <= (int)(kk >> 24) * 4;
+                        }
+                        if (is_dirty) {
+                            // ... or if EVERY ray through a source pixel was stopped in front of it: each source pixel is then
+                            // "unknown" (200: shadow-written or never written, agent.cpp:557-558) whatever the rays' order -> the
+                            // output takes its all-shadow value, another table entry
+                            const unsigned ks = __ldg(oshad + q);
+                            const int r0 = (int)(ks & 0xFFFu), r1 = (int)((ks >> 12) & 0xFFFu), a0 = r0 >> c.hb_shift, a1 = r1 >> c.hb_shift;
+                            if (r1 >= r0 && a1 - a0 < 8) {
+                                int hx = 0;
+                                for (int b = a0; b <= a1; b++) hx = max(hx, sh->hmax[b]);
+                                if (hx < (int)(ks >> 24) * 4) { if (VIEW_STATS) atomicAdd(&sh->stat[2], 1); o_img[q] = __ldg(oshval + q); continue; }
+                            }
+                        }
                     }
                 }
                 if (is_dirty) dirty[atomicAdd(&sh->n_dirty, 1)] = (unsigned short)q;
@@ -787,6 +817,13 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
             }
             __syncthreads();
             const int n4 = sh->n_dirty * 4;
+            if (VIEW_STATS && tid == 0) {
+                unsigned long long* st = d.counters + 4;
+                atomicAdd(st + 0, 1ull); atomicAdd(st + 1, (unsigned long long)(sh->near_pack >> 32)); atomicAdd(st + 2, (unsigned long long)(unsigned)sh->near_pack);
+                atomicAdd(st + 3, (unsigned long long)sh->red[3]); atomicAdd(st + 4, (unsigned long long)sh->stat[0]); atomicAdd(st + 5, (unsigned long long)sh->stat[1]);
+                atomicAdd(st + 6, (unsigned long long)sh->n_dirty); atomicAdd(st + 7, (unsigned long long)sh->stat[2]); atomicAdd(st + 8, (unsigned long long)(sh->n_cnear > 0 || sh->red[6]));
+                atomicAdd(st + 9, (unsigned long long)sh->red[5]); atomicAdd(st + 10, (unsigned long long)sh->red[1]); atomicAdd(st + 11, (unsigned long long)(any_hit_all != 0));
+            }
             const float scale = 1.f / (2048.f * 2048.f);
             for (int base = warp * 32; base < n4; base += VIEW_THREADS) {
                 const int it = base + lane;
@@ -795,9 +832,9 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 const int orow = (int)__umulhi((unsigned)q, c.img_inv), oc = q - orow * c.img;
                 float sv = 0.f;
                 if (act) {
-                    const short* tp = d.cubic_tap + 4 * oc;
-                    const short4 cf = __ldg(reinterpret_cast<const short4*>(d.cubic_coef) + oc);
-                    const int rr = d.cubic_tap[4 * orow + t];
+                    const short* tp = ctap + 4 * oc;
+                    const short4 cf = __ldg(reinterpret_cast<const short4*>(ccoef) + oc);
+                    const int rr = ctap[4 * orow + t];
                     uint4 e4 = make_uint4(0u, 0u, 0u, 0u);
                     if (use_laser) e4 = __ldg(reinterpret_cast<const uint4*>(dtab) + rr * c.img + oc);
                     int acc = 0;
@@ -809,16 +846,17 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 }
                 const float s1 = __shfl_down_sync(0xffffffffu, sv, 1), s2 = __shfl_down_sync(0xffffffffu, sv, 2), s3 = __shfl_down_sync(0xffffffffu, sv, 3);
                 if (act && t == 0) {
-                    const short4 cv = __ldg(reinterpret_cast<const short4*>(d.cubic_coef) + orow);
+                    const short4 cv = __ldg(reinterpret_cast<const short4*>(ccoef) + orow);
                     const float b0 = cv.x * scale, b1 = cv.y * scale, b2 = cv.z * scale, b3 = cv.w * scale;
                     const float v = fmaf(sv, b0, fmaf(s1, b1, fmaf(s2, b2, s3 * b3)));
                     int iv = __float2int_rn(v);
                     iv = min(255, max(0, iv));
-                    o_img[q] = d.f16_lut[iv];
+                    o_img[q] = __ldg(lut16 + iv);
                 }
             }
         }
     }
+    if (frozen) mbar_wait(&sh->bar[1], 0);       // (a CTA must not exit with bulk copies in flight)
     if (DEBUG_FULL) return;
 
     // ---- Phase G: state vector and the episode bookkeeping.  The pedestrian observation does not depend on the raster:

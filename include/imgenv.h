@@ -172,6 +172,12 @@ int imgenv_set_ped_yaw_mode(imgenv_t* h, int mode);
  * per-agent table holds (it then keeps the nearest; the reference keeps all); out4[1] = obstacle BSP builds that ran out of space;
  * out4[2] = masked resets that found an empty episode queue.  Tests assert 0. */
 int imgenv_debug_counters(imgenv_t* h, int64_t* out4, void* stream);
+/* Work counters of the observation kernel summed over robots since creation; written only by an instrumented build of the
+ * library (-DVIEW_STATS=1, tools/view_stats.py), all zero otherwise.  out16: [0] robots observed, [1] footprint records near
+ * the field of view, [2] their bitmap words, [3] static candidate blocks, [4] candidate cells, [5] raster cells that updated
+ * rays, [6] outputs evaluated in full, [7] outputs settled by the all-shadow test, [8] robots that ran the collision lattice,
+ * [9] robots that ran the FOV-edge pixels, [10] heavy cells, [11] robots with any ray hit. */
+int imgenv_debug_view_stats(imgenv_t* h, int64_t* out16, void* stream);
 /* Tests: the RVO obstacle set of one scene as the reset kernels built it on the device (vertex ring verts[max_verts][8] = px, py,
  * edge dir x, y, convex, next, prev, 0; BSP nodes[max_verts][4] = edge, left, right, parent; max_verts = 16 * max_obstacles + 16;
  * corners[max_obstacles][4] = the two rotated corners per reset object the ring was built from), and the host restatement of the
