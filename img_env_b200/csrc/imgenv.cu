@@ -284,7 +284,8 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
             // anything (free / own footprint / outside every ray), evaluated with the arithmetic of view.cuh phase F.
             const int npx = c.img * c.img;
             const size_t half = (size_t)npx + (npx + 1) / 2;
-            T.ostat.assign(2 * half, 0u);
+            const int n_seg = (npx + 7) / 8;
+            T.ostat.assign(2 * half + n_seg, 0u);
             uint16_t* oval = reinterpret_cast<uint16_t*>(T.ostat.data() + npx);
             // second half: the all-shadow test of an output (interval of ALL rays through its source pixels | floor(smallest
             // Chebyshev distance of such a pixel to the laser origin / 4) << 24) and its value when every one of those rays is
@@ -332,6 +333,17 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
                     oshad[(size_t)orow * c.img + oc] = amin | (amax << 12) | ((imin / 4) << 24);
                     oshval[(size_t)orow * c.img + oc] = lut[is];
                 }
+            // third part: the same interval | farthest pixel per SEGMENT of 8 consecutive outputs
+            for (int sg = 0; sg < n_seg; sg++) {
+                uint32_t kmin = 1, kmax = 0, far4 = 0; bool any = false;
+                for (int q = 8 * sg; q < std::min(8 * sg + 8, npx); q++) {
+                    const uint32_t kk = T.ostat[q], a = kk & 0xFFFu, b = (kk >> 12) & 0xFFFu;
+                    if (b < a) continue;
+                    if (!any) { kmin = a; kmax = b; any = true; } else { kmin = std::min(kmin, a); kmax = std::max(kmax, b); }
+                    far4 = std::max(far4, kk >> 24);
+                }
+                T.ostat[2 * half + sg] = kmin | (kmax << 12) | (far4 << 24);
+            }
         }
         T.t.ostat_off = (int)ostat.size(); ostat.insert(ostat.end(), T.ostat.begin(), T.ostat.end());
         while (ostat.size() % 4) ostat.push_back(0u);      // (bulk-copied in 16-byte units)

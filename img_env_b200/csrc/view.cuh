@@ -27,7 +27,7 @@ struct ViewShared {
     unsigned long long bar[2];      // mbarriers: [0] constants landed, [1] static tables landed
     int red[8];              // counters / per-warp partial sums
     int coll_key;
-    int n_cnear, n_dirty;
+    int n_cnear, n_dirty, n_seglist;
     unsigned long long near_pack;   // number of near records << 32 | their words so far (one atomic hands out slot and word offset)
     int hmin[64];            // per block of rays: smallest hit step (Chebyshev distance of the hit cell), NOHIT >> 22 if none
     int stat[4];             // VIEW_STATS only: candidates, raster cells pushed, all-shadow outputs
@@ -119,12 +119,13 @@ __device__ __noinline__ void cell_rays_inline(unsigned* hitkey, const short* ren
 #define NOHIT 0xFFFFFFFFu
 #define CN_CAP 32            // footprint records that overlap the observer's own footprint box (collision candidates)
 #define NEAR_CACHE 64        // near records whose header and word offset are kept in shared memory for phase B
+#define CAND_CHUNK (2 * VIEW_THREADS)   // candidate words per pass of phase B (two per thread)
 #define NEAR_ALL 0x8000u     // near-list flag: read the part's occupancy words (it may touch the FOV edge), not its candidates
 #define ET_SHIFT 4           // edge tiles are 16x16 view pixels
 
 #define INV_EPS 0.004f       // band around a cell edge inside which the inverse rasterisation runs the exact forward map
 #define INV_MAX_BLOCKS 512   // 32x32-cell world blocks under the FOV; more -> forward (tile) rasterisation
-struct ViewLayout { size_t sh, regA, regB, hpre, hitkey, rays, need, spans, blocks, near, npre, chdr, coff, nhdr, noff, total; };
+struct ViewLayout { size_t sh, regA, regB, hpre, hitkey, rays, need, spans, blocks, near, npre, chdr, coff, nhdr, noff, cword, cmeta, cpre, cwsum, seglist, total; };
 __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     ViewLayout L;
     size_t off = 0;
@@ -146,6 +147,11 @@ __host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
     L.coff = off; off += (size_t)CN_CAP * 4;
     L.nhdr = off; off += (size_t)NEAR_CACHE * 16;
     L.noff = off; off += (size_t)NEAR_CACHE * 4;
+    L.cword = off; off += (size_t)CAND_CHUNK * 4;
+    L.cmeta = off; off += (size_t)CAND_CHUNK * 4;
+    L.cpre = off; off += (size_t)CAND_CHUNK * 2;
+    L.cwsum = off; off += (size_t)(VIEW_THREADS / 32) * 4;
+    L.seglist = off; off += (((size_t)c.img * c.img + 7) / 8 * 2 + 15) & ~(size_t)15;
     L.total = off + 16;
     return L;
 }
@@ -210,6 +216,11 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
     int* coff = reinterpret_cast<int*>(smem_raw + L.coff);
     int4* nhdr = reinterpret_cast<int4*>(smem_raw + L.nhdr);
     int* noff = reinterpret_cast<int*>(smem_raw + L.noff);
+    uint32_t* cword = reinterpret_cast<uint32_t*>(smem_raw + L.cword);
+    uint32_t* cmeta = reinterpret_cast<uint32_t*>(smem_raw + L.cmeta);
+    unsigned short* cpre = reinterpret_cast<unsigned short*>(smem_raw + L.cpre);
+    int* cwsum = reinterpret_cast<int*>(smem_raw + L.cwsum);
+    unsigned short* seglist = reinterpret_cast<unsigned short*>(smem_raw + L.seglist);   // phase D: segments of 8 outputs that need a closer look
     const int npx = c.img * c.img;
     // [npx] u32: lowest | highest top ray over the source pixels of an output | farthest source pixel, then [npx] u16: the
     // output's float16 value when none of those rays hits anything
@@ -235,7 +246,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
         bulk_g2s(need, d.need_idx, nb_n, &sh->bar[1]);                                  // source rows / columns the resize reads
         sh->coll_key = 0;
         sh->red[0] = 0; sh->red[1] = 0; sh->red[2] = 0; sh->red[3] = 0; sh->red[4] = 0; sh->red[5] = 0; sh->red[6] = 0; sh->stat[0] = 0; sh->stat[1] = 0; sh->stat[2] = 0;
-        sh->near_pack = 0ull; sh->n_cnear = 0; sh->n_dirty = 0;
+        sh->near_pack = 0ull; sh->n_cnear = 0; sh->n_dirty = 0; sh->n_seglist = 0;
     }
     for (int k = tid; k < c.range_total; k += VIEW_THREADS) hitkey[k] = NOHIT;
     if (tid < 64) { sh->hmin[tid] = 1023; sh->hmax[tid] = 0; }
@@ -489,116 +500,134 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 if (o) push_cell(i, j);
             }
         };
+        // the light, even parts of the phase (world->view mode): FOV-edge pixels when the static map is not empty under the
+        // FOV, and the collision lattice
+        if (use_inverse && sh->red[5]) for (int e = tid; e < ty.n_edge; e += VIEW_THREADS) edge_pixel(e);
+        if (use_inverse && need_A) for (int k = tid; k < ty.n_pts; k += VIEW_THREADS) lattice_point(k);
         {
             // candidate words -> candidate cells -> view pixels.  Work items: 32 rows per listed static block, then every
-            // word of every near footprint record.  Each warp takes 32 items (one word per lane) from a shared counter --
-            // dense words make the work per batch very uneven -- and expands their candidate bits over all lanes.
+            // word of every near footprint record.  Dense words make the work per word very uneven, so the CTA takes the
+            // items in chunks of two per thread: (1) every thread decodes and loads its two words into shared memory, (2) a
+            // block-wide prefix sum numbers the candidate bits of the chunk, (3) the candidates are split EVENLY over the
+            // threads -- each thread finds the word holding its first candidate by bisection and then walks on bit by bit.
             const uint32_t* static_cand = d.static_cand;
             const int n_static = use_inverse ? sh->red[3] * 32 : 0;
             const int n_items = n_static + (int)n_near_words;
-            // World->view mode: ONE work queue for the whole phase -- the heavy, uneven batches first (candidate words), then
-            // the light, even ones (FOV-edge pixels when the static map is not empty under the FOV, then the collision lattice),
-            // so the warps reach the barrier below together.
-            const int q_edge = (n_items + 31) & ~31;
-            const int q_pts = q_edge + ((use_inverse && sh->red[5]) ? (ty.n_edge + 31) & ~31 : 0);
-            const int q_end = q_pts + ((use_inverse && need_A) ? (ty.n_pts + 31) & ~31 : 0);
             const float f00 = (float)sh->k.view_world.m00, f01 = (float)sh->k.view_world.m01, f10 = (float)sh->k.view_world.m10, f11 = (float)sh->k.view_world.m11;
             const float fr0 = (float)ty.fov_r0 - 1.5f, fr1 = (float)ty.fov_r1 + 1.5f, fc0 = (float)ty.fov_c0 - 1.5f, fc1 = (float)ty.fov_c1 + 1.5f;
-            for (;;) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&sh->red[4], 32);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= q_end) break;
-                if (base >= q_pts) { if (base - q_pts + lane < ty.n_pts) lattice_point(base - q_pts + lane); continue; }
-                if (base >= q_edge) { if (base - q_edge + lane < ty.n_edge) edge_pixel(base - q_edge + lane); continue; }
-                const int item = base + lane;
-                unsigned cand = 0; int X = 0, bj = 0;
-                if (item < n_static) {
-                    const unsigned bb = blocks[item >> 5];
-                    X = (int)(bb >> 16) * 32 + (item & 31); bj = (int)(bb & 0xFFFF);
-                    if (X >= X0 && X <= X1) cand = __ldg(static_cand + (unsigned)X * Wb + bj);
-                } else if (item < n_items) {
-                    const unsigned di = (unsigned)(item - n_static);
-                    int lo = 0, hi = n_near - 1;                       // last k with npre[k] <= di
-                    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (npre[mid] <= di) lo = mid; else hi = mid - 1; }
-                    int4 h; int wbase;
-                    if (lo < NEAR_CACHE) { h = nhdr[lo]; wbase = noff[lo]; }
-                    else {
-                        const unsigned e = near[lo];
-                        const int q = e & 0x7FFF;
-                        h = __ldg(fhdr + q);
-                        const int po = __ldg(d.part_off + q);
-                        wbase = (e & NEAR_ALL) ? po : po + ((__ldg(d.part_off + q + 1) - po) >> 1);
+            auto candidate = [&](int cX, int cY) {
+                const float u = (float)(cX - orgi0) - orgf0, v = (float)(cY - orgi1) - orgf1;      // cell - org, exact integer part
+                const float qi = i00 * u + i01 * v, qj = i10 * u + i11 * v;
+                // Pixel (i,j) maps to this cell iff M*((i,j) - q) lies in the unit square around the cell centre (M =
+                // rotation of view_world).  The float test decides all pixels farther than INV_EPS from the square's
+                // edge; only the others run the exact forward map.  |q| < 2^10 so the float error is < 1e-3 cell.
+                if (qi < fr0 || qi > fr1 || qj < fc0 || qj > fc1) return;       // (pixel box of the FOV, 1.5 px margin)
+                const int ia = (int)ceilf(qi - 0.72f), ja = (int)ceilf(qj - 0.72f);
+                // cheap part for the 2 x 2 window at once (M*d is linear: the four offsets share two products), ...
+                const float du0 = (float)ia - qi, dv0 = (float)ja - qj;
+                const float x00 = f00 * du0 + f01 * dv0, y00 = f10 * du0 + f11 * dv0;
+                float e4[4];
+                e4[0] = fmaxf(fabsf(x00), fabsf(y00));
+                e4[1] = fmaxf(fabsf(x00 + f01), fabsf(y00 + f11));
+                e4[2] = fmaxf(fabsf(x00 + f00), fabsf(y00 + f10));
+                e4[3] = fmaxf(fabsf(x00 + f00 + f01), fabsf(y00 + f10 + f11));
+                unsigned live = (e4[0] <= 0.5f + INV_EPS ? 1u : 0u) | (e4[1] <= 0.5f + INV_EPS ? 2u : 0u) |
+                                (e4[2] <= 0.5f + INV_EPS ? 4u : 0u) | (e4[3] <= 0.5f + INV_EPS ? 8u : 0u);
+                // ... then the (usually one) surviving pixel
+                while (live) {
+                    const int t = __ffs(live) - 1; live &= live - 1;
+                    const int i = ia + (t >> 1), j = ja + (t & 1);
+                    const float em = t == 0 ? e4[0] : t == 1 ? e4[1] : t == 2 ? e4[2] : e4[3];
+                    if ((unsigned)i >= (unsigned)vh || (unsigned)j >= (unsigned)vw) continue;
+                    const int a0 = spans[i * 4 + 0], a1 = spans[i * 4 + 1], b0 = spans[i * 4 + 2], b1 = spans[i * 4 + 3];
+                    if (!((j >= a0 && j < a1) || (j >= b0 && j < b1))) continue;
+                    if (em > 0.5f - INV_EPS) {
+                        const long long tx = sh->k.cx + (long long)i * sh->k.ax + (long long)j * sh->k.bx;
+                        const long long tyy = sh->k.cy + (long long)i * sh->k.ay + (long long)j * sh->k.by;
+                        int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
+                        if ((unsigned)tx + FX_GUARD < 2 * FX_GUARD || (unsigned)tyy + FX_GUARD < 2 * FX_GUARD) {
+                            exact_cell(sh->k.view_world, c.res, i, j, cx, cy);
+                        }
+                        if (cx != cX || cy != cY) continue;
                     }
-                    const int wpr = foot_wpr(h), wi = (int)(di - npre[lo]);
-                    const int rr = wi / wpr;
-                    X = h.x + rr; bj = foot_wj0(h) + (wi - rr * wpr);
-                    if (X >= X0 && X <= X1) cand = __ldg(fwords + wbase + wi);
+                    // World->view mode: no raster is kept -- a view pixel has ONE world cell, so it can only be found twice when
+                    // two records (or a record and the static map) cover that cell; it is then listed twice, which is harmless.
+                    // Forward mode: into the raster; its boundary cells are listed by the scan below.
+                    if (use_inverse) push_cell(i, j);
+                    else atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31));
                 }
-                if (cand) {     // only columns under the FOV's bounding box
-                    const int lo = max(Y0 - bj * 32, 0), hi = min(Y1 - bj * 32, 31);
-                    cand = lo <= hi ? cand & ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo)) : 0u;
+            };
+            for (int c0 = 0; c0 < n_items; c0 += CAND_CHUNK) {
+                const int n_ch = min(CAND_CHUNK, n_items - c0);
+                int cnt2[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int it = 2 * tid + u, item = c0 + it;
+                    unsigned cand = 0; int X = 0, bj = 0;
+                    if (it < n_ch) {
+                        if (item < n_static) {
+                            const unsigned bb = blocks[item >> 5];
+                            X = (int)(bb >> 16) * 32 + (item & 31); bj = (int)(bb & 0xFFFF);
+                            if (X >= X0 && X <= X1) cand = __ldg(static_cand + (unsigned)X * Wb + bj);
+                        } else {
+                            const unsigned di = (unsigned)(item - n_static);
+                            int lo = 0, hi = n_near - 1;                       // last k with npre[k] <= di
+                            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (npre[mid] <= di) lo = mid; else hi = mid - 1; }
+                            int4 h; int wbase;
+                            if (lo < NEAR_CACHE) { h = nhdr[lo]; wbase = noff[lo]; }
+                            else {
+                                const unsigned e = near[lo];
+                                const int q = e & 0x7FFF;
+                                h = __ldg(fhdr + q);
+                                const int po = __ldg(d.part_off + q);
+                                wbase = (e & NEAR_ALL) ? po : po + ((__ldg(d.part_off + q + 1) - po) >> 1);
+                            }
+                            const int wpr = foot_wpr(h), wi = (int)(di - npre[lo]);
+                            const int rr = wi / wpr;
+                            X = h.x + rr; bj = foot_wj0(h) + (wi - rr * wpr);
+                            if (X >= X0 && X <= X1) cand = __ldg(fwords + wbase + wi);
+                        }
+                        if (cand) {     // only columns under the FOV's bounding box
+                            const int lo = max(Y0 - bj * 32, 0), hi = min(Y1 - bj * 32, 31);
+                            cand = lo <= hi ? cand & ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo)) : 0u;
+                        }
+                    }
+                    cword[it] = cand; cmeta[it] = ((unsigned)X << 12) | (unsigned)bj;
+                    cnt2[u] = __popc(cand);
                 }
-                const int cnt = __popc(cand);
-                int incl = cnt;
+                const int mine = cnt2[0] + cnt2[1];
+                int incl = mine;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                const int total = __shfl_sync(0xffffffffu, incl, 31), excl = incl - cnt;
-                if (VIEW_STATS && lane == 0) atomicAdd(&sh->stat[0], total);
-                for (int k0 = 0; k0 < total; k0 += 32) {
-                    const int k = k0 + lane;
-                    int src = 0;
+                if (lane == 31) cwsum[warp] = incl;
+                __syncthreads();
+                int woff = 0, total = 0;
 #pragma unroll
-                    for (int step = 16; step; step >>= 1) {
-                        const int e = __shfl_sync(0xffffffffu, excl, (src + step) & 31);
-                        if (src + step < 32 && e <= k) src += step;
+                for (int w = 0; w < VIEW_THREADS / 32; w++) { const int v = cwsum[w]; total += v; if (w < warp) woff += v; }
+                const int excl = woff + incl - mine;
+                cpre[2 * tid] = (unsigned short)excl; cpre[2 * tid + 1] = (unsigned short)(excl + cnt2[0]);
+                __syncthreads();
+                if (VIEW_STATS && tid == 0) atomicAdd(&sh->stat[0], total);
+                const int per = (total + VIEW_THREADS - 1) / VIEW_THREADS;
+                int k = tid * per;
+                const int k_end = min(k + per, total);
+                if (k < k_end) {
+                    int lo = 0, hi = n_ch - 1;                                 // last word with cpre[w] <= k (empty words share their successor's count)
+                    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int)cpre[mid] <= k) lo = mid; else hi = mid - 1; }
+                    int wi = lo;
+                    unsigned m = cword[wi];
+                    {   // drop the candidates of this word that belong to the thread before
+                        const int skip = k - (int)cpre[wi];
+                        if (skip) m &= 0xFFFFFFFEu << nth_set_bit(m, skip - 1);
                     }
-                    const int n = k - __shfl_sync(0xffffffffu, excl, src);
-                    const unsigned m = __shfl_sync(0xffffffffu, cand, src);
-                    const int cX = __shfl_sync(0xffffffffu, X, src), cbj = __shfl_sync(0xffffffffu, bj, src);
-                    if (k >= total) continue;
-                    const int cY = cbj * 32 + nth_set_bit(m, n);
-                    const float u = (float)(cX - orgi0) - orgf0, v = (float)(cY - orgi1) - orgf1;      // cell - org, exact integer part
-                    const float qi = i00 * u + i01 * v, qj = i10 * u + i11 * v;
-                    // Pixel (i,j) maps to this cell iff M*((i,j) - q) lies in the unit square around the cell centre (M =
-                    // rotation of view_world).  The float test decides all pixels farther than INV_EPS from the square's
-                    // edge; only the others run the exact forward map.  |q| < 2^10 so the float error is < 1e-3 cell.
-                    if (qi < fr0 || qi > fr1 || qj < fc0 || qj > fc1) continue;       // (pixel box of the FOV, 1.5 px margin)
-                    const int ia = (int)ceilf(qi - 0.72f), ja = (int)ceilf(qj - 0.72f);
-                    // cheap part for the 2 x 2 window at once (M*d is linear: the four offsets share two products), ...
-                    const float du0 = (float)ia - qi, dv0 = (float)ja - qj;
-                    const float x00 = f00 * du0 + f01 * dv0, y00 = f10 * du0 + f11 * dv0;
-                    float e4[4];
-                    e4[0] = fmaxf(fabsf(x00), fabsf(y00));
-                    e4[1] = fmaxf(fabsf(x00 + f01), fabsf(y00 + f11));
-                    e4[2] = fmaxf(fabsf(x00 + f00), fabsf(y00 + f10));
-                    e4[3] = fmaxf(fabsf(x00 + f00 + f01), fabsf(y00 + f10 + f11));
-                    unsigned live = (e4[0] <= 0.5f + INV_EPS ? 1u : 0u) | (e4[1] <= 0.5f + INV_EPS ? 2u : 0u) |
-                                    (e4[2] <= 0.5f + INV_EPS ? 4u : 0u) | (e4[3] <= 0.5f + INV_EPS ? 8u : 0u);
-                    // ... then the (usually one) surviving pixel
-                    while (live) {
-                        const int t = __ffs(live) - 1; live &= live - 1;
-                        const int i = ia + (t >> 1), j = ja + (t & 1);
-                        const float em = t == 0 ? e4[0] : t == 1 ? e4[1] : t == 2 ? e4[2] : e4[3];
-                        if ((unsigned)i >= (unsigned)vh || (unsigned)j >= (unsigned)vw) continue;
-                        const int a0 = spans[i * 4 + 0], a1 = spans[i * 4 + 1], b0 = spans[i * 4 + 2], b1 = spans[i * 4 + 3];
-                        if (!((j >= a0 && j < a1) || (j >= b0 && j < b1))) continue;
-                        if (em > 0.5f - INV_EPS) {
-                            const long long tx = sh->k.cx + (long long)i * sh->k.ax + (long long)j * sh->k.bx;
-                            const long long tyy = sh->k.cy + (long long)i * sh->k.ay + (long long)j * sh->k.by;
-                            int cx = (int)(tx >> 32), cy = (int)(tyy >> 32);
-                            if ((unsigned)tx + FX_GUARD < 2 * FX_GUARD || (unsigned)tyy + FX_GUARD < 2 * FX_GUARD) {
-                                exact_cell(sh->k.view_world, c.res, i, j, cx, cy);
-                            }
-                            if (cx != cX || cy != cY) continue;
-                        }
-                        // World->view mode: no raster is kept -- a view pixel has ONE world cell, so it can only be found twice when
-                        // two records (or a record and the static map) cover that cell; it is then listed twice, which is harmless.
-                        // Forward mode: into the raster; its boundary cells are listed by the scan below.
-                        if (use_inverse) push_cell(i, j);
-                        else atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31));
+                    unsigned meta = cmeta[wi];
+                    for (; k < k_end; k++) {
+                        while (m == 0u) { wi++; m = cword[wi]; meta = cmeta[wi]; }
+                        const int bit = __ffs(m) - 1; m &= m - 1;
+                        candidate((int)(meta >> 12), (int)(meta & 0xFFFu) * 32 + bit);
                     }
                 }
+                if (c0 + CAND_CHUNK < n_items) __syncthreads();       // the chunk arrays are rewritten
             }
         }
         if (!DEBUG_FULL && need_A) {
@@ -782,9 +811,34 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 for (int w = wa + 1; w < wb; w++) acc |= hbits[w];
                 return acc != 0u;
             };
-            for (int q = tid; q < npx; q += VIEW_THREADS) {
+            // (1) Segments of 8 consecutive outputs (one 16-byte store): a segment none of whose rays was stopped in front of
+            //     its farthest source pixel keeps its hit-free values -- one table load, one store.  The others are listed.
+            const int n_seg = (npx + 7) >> 3;
+            const bool seg_ok = use_laser && (npx & 7) == 0 && (reinterpret_cast<size_t>(d.o_sensor) & 15) == 0;     // (16-byte stores)
+            const uint32_t* oseg = oshad + npx + (npx + 1) / 2;        // [n_seg] like okk, over the segment's outputs
+            for (int sg = tid; sg < n_seg; sg += VIEW_THREADS) {
+                bool flagged = !seg_ok;
+                if (seg_ok && any_hit) {
+                    const unsigned kk = __ldg(oseg + sg);
+                    const int kmin = kk & 0xFFFu, kmax = (kk >> 12) & 0xFFFu;
+                    if (kmax >= kmin) {
+                        const int b0 = kmin >> c.hb_shift, b1 = kmax >> c.hb_shift;
+                        int hm = b1 - b0 < 16 ? 1023 : 0;                 // (segments next to the origin: listed without asking)
+                        if (hm) for (int b = b0; b <= b1; b++) hm = min(hm, sh->hmin[b]);
+                        flagged = hm <= (int)(kk >> 24) * 4;
+                    }
+                }
+                if (!flagged) reinterpret_cast<uint4*>(o_img)[sg] = __ldg(reinterpret_cast<const uint4*>(oval) + sg);
+                else seglist[atomicAdd(&sh->n_seglist, 1)] = (unsigned short)sg;
+            }
+            __syncthreads();
+            // (2) the outputs of the listed segments, one per thread
+            const int n_listed = sh->n_seglist * 8;
+            for (int it = tid; it < n_listed; it += VIEW_THREADS) {
+                const int q = (int)seglist[it >> 3] * 8 + (it & 7);
+                if (q >= npx) continue;
                 bool is_dirty = !use_laser;
-                if (use_laser && any_hit) {
+                if (use_laser) {
                     const unsigned kk = __ldg(okk + q);
                     const int kmin = kk & 0xFFFu, kmax = (kk >> 12) & 0xFFFu;
                     if (kmax >= kmin && range_hit(kmin, kmax)) {
@@ -871,7 +925,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
 // It only reads poses, so it runs beside the stamp / view kernels on the library's side stream.
 // ---------------------------------------------------------------------------------------------
 #define PED_THREADS 128
-struct PedLayout { size_t winner, keys, idx, pobs, row, total; int n_sort; };
+struct PedLayout { size_t winner, keys, dkeys, pobs, row, total; int n_sort; };
 __host__ __device__ inline PedLayout ped_layout(const Cfg& c) {
     PedLayout L;
     int n = 1; while (n < c.P) n <<= 1;
@@ -881,7 +935,7 @@ __host__ __device__ inline PedLayout ped_layout(const Cfg& c) {
     L.keys = off; off += ((size_t)n * 8 + 15) & ~(size_t)15;
     L.pobs = off; off += (size_t)(c.P > 0 ? c.P : 1) * 16;
     L.row = off; off += ((size_t)c.pvs_len * 4 + 15) & ~(size_t)15;
-    L.idx = off; off += ((size_t)n * 2 + 15) & ~(size_t)15;
+    L.dkeys = off; off += ((size_t)n * 8 + 15) & ~(size_t)15;
     L.total = off + 16;
     return L;
 }
@@ -898,8 +952,11 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
     const RobotType& ty = d.types[d.type_of[r]];
     const PedLayout L = ped_layout(c);
     int* winner = reinterpret_cast<int*>(smem_raw + L.winner);
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + L.keys);     // bit pattern of the (non-negative) double key
-    unsigned short* order = reinterpret_cast<unsigned short*>(smem_raw + L.idx);            // pedestrian index, sorted along with the keys
+    // Sort keys: python sorts by the float64 x*x + y*y, stably.  The network sorts ONE 64-bit word per pedestrian, float32(key)
+    // << 32 | index (rounding to float32 is monotone, so the order can only be wrong inside a run of equal float32 keys: such
+    // runs -- rare -- are re-sorted by (float64 key, index) afterwards).
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + L.keys);     // float32 bits of the key << 32 | pedestrian index
+    double* dkeys = reinterpret_cast<double*>(smem_raw + L.dkeys);                           // float64 key, by pedestrian index
     float4* pobs = reinterpret_cast<float4*>(smem_raw + L.pobs);                             // px, py, vx, vy in the robot frame (float32 like PedInfo)
     float* row = reinterpret_cast<float*>(smem_raw + L.row);                                 // this robot's ped_vector_states row
     __shared__ Tf2 s_world_base;
@@ -910,7 +967,7 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
     const Tf2 world_base = s_world_base;
     for (int k = tid; k < c.pvs_len; k += PED_THREADS) row[k] = k == 0 ? (float)c.P : 0.f;
     for (int j = tid; j < L.n_sort; j += PED_THREADS) {
-        unsigned long long key = 0x7FF0000000000000ull;        // +inf: padding sorts last
+        unsigned fk = 0x7F800000u;        // +inf: padding sorts last
         if (j < c.P) {
             const int pi = s * c.P + j;
             double bx, by, bvx, bvy;
@@ -918,59 +975,74 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
             tf_rotate(world_base, PDF(d, PD_VX, pi), PDF(d, PD_VY, pi), bvx, bvy);
             const float px = (float)bx, py = (float)by;
             pobs[j] = make_float4(px, py, (float)bvx, (float)bvy);
-            key = (unsigned long long)__double_as_longlong((double)px * (double)px + (double)py * (double)py);   // python: float(x)**2 + float(y)**2
+            const double dk = (double)px * (double)px + (double)py * (double)py;   // python: float(x)**2 + float(y)**2
+            dkeys[j] = dk;
+            fk = __float_as_uint(__double2float_rn(dk));
         }
-        keys[j] = key; order[j] = (unsigned short)j;
+        keys[j] = ((unsigned long long)fk << 32) | (unsigned)j;
     }
     __syncthreads();
-    // stable nearest-first order == python's list.sort(key=...): bitonic network on (key, index) pairs.
+    // bitonic network on the packed words (all distinct: the index is part of the word)
     if (L.n_sort == 2 * PED_THREADS) {
         // 2 elements per thread in registers (2t, 2t+1): partners inside a warp are reached with shuffles, only the last
         // stages (partner thread >= 32 lanes away) go through shared memory
         unsigned long long k0 = keys[2 * tid], k1 = keys[2 * tid + 1];
-        unsigned i0 = order[2 * tid], i1 = order[2 * tid + 1];
-        auto after = [](unsigned long long ka, unsigned ia, unsigned long long kb, unsigned ib) { return ka > kb || (ka == kb && ia > ib); };
         for (int k = 2; k <= 2 * PED_THREADS; k <<= 1)
             for (int jj = k >> 1; jj > 0; jj >>= 1) {
                 const bool up = ((2 * tid) & k) == 0;
                 if (jj == 1) {
-                    if (after(k0, i0, k1, i1) == up) { const unsigned long long tk = k0; k0 = k1; k1 = tk; const unsigned ti = i0; i0 = i1; i1 = ti; }
+                    if ((k0 > k1) == up) { const unsigned long long tk = k0; k0 = k1; k1 = tk; }
                     continue;
                 }
                 const int tj = jj >> 1;                       // partner thread = tid ^ tj holds the partners of both elements
-                unsigned long long p0, p1; unsigned q0, q1;
+                unsigned long long p0, p1;
                 if (tj < 32) {
                     p0 = __shfl_xor_sync(0xffffffffu, k0, tj); p1 = __shfl_xor_sync(0xffffffffu, k1, tj);
-                    q0 = __shfl_xor_sync(0xffffffffu, i0, tj); q1 = __shfl_xor_sync(0xffffffffu, i1, tj);
                 } else {
                     __syncthreads();
-                    keys[2 * tid] = k0; keys[2 * tid + 1] = k1; order[2 * tid] = (unsigned short)i0; order[2 * tid + 1] = (unsigned short)i1;
+                    keys[2 * tid] = k0; keys[2 * tid + 1] = k1;
                     __syncthreads();
                     const int pt = tid ^ tj;
-                    p0 = keys[2 * pt]; p1 = keys[2 * pt + 1]; q0 = order[2 * pt]; q1 = order[2 * pt + 1];
+                    p0 = keys[2 * pt]; p1 = keys[2 * pt + 1];
                 }
                 const bool take_min = (((2 * tid) & jj) == 0) == up;
-                if (after(k0, i0, p0, q0) == take_min) { k0 = p0; i0 = q0; }
-                if (after(k1, i1, p1, q1) == take_min) { k1 = p1; i1 = q1; }
+                if ((k0 > p0) == take_min) k0 = p0;
+                if ((k1 > p1) == take_min) k1 = p1;
             }
         __syncthreads();
-        order[2 * tid] = (unsigned short)i0; order[2 * tid + 1] = (unsigned short)i1;
-        __syncthreads();
+        keys[2 * tid] = k0; keys[2 * tid + 1] = k1;
     } else
     for (int k = 2; k <= L.n_sort; k <<= 1)
         for (int jj = k >> 1; jj > 0; jj >>= 1) {
             for (int t = tid; t < (L.n_sort >> 1); t += PED_THREADS) {
                 const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1)), p = i | jj;      // the pair (i, i + jj) of this stage
                 const unsigned long long ka = keys[i], kb = keys[p];
-                const unsigned short ia = order[i], ib = order[p];
                 const bool up = (i & k) == 0;
-                const bool a_after_b = ka > kb || (ka == kb && ia > ib);
-                if (a_after_b == up) { keys[i] = kb; keys[p] = ka; order[i] = ib; order[p] = ia; }
+                if ((ka > kb) == up) { keys[i] = kb; keys[p] = ka; }
             }
             __syncthreads();
         }
+    {   // runs of equal float32 keys: order by (float64 key, index) like the stable python sort
+        bool tie = false;
+        __syncthreads();
+        for (int i = tid; i + 1 < c.P; i += PED_THREADS) tie |= (keys[i] >> 32) == (keys[i + 1] >> 32);
+        if (__syncthreads_or(tie)) {
+            if (tid == 0)
+                for (int i = 1; i < c.P; i++) {          // insertion inside each run
+                    const unsigned long long w = keys[i];
+                    const int ji = (int)(unsigned)w; const double di = dkeys[ji];
+                    int p = i;
+                    while (p > 0 && (keys[p - 1] >> 32) == (w >> 32)) {
+                        const int jp = (int)(unsigned)keys[p - 1]; const double dp = dkeys[jp];
+                        if (dp > di || (dp == di && jp > ji)) { keys[p] = keys[p - 1]; p--; } else break;
+                    }
+                    keys[p] = w;
+                }
+            __syncthreads();
+        }
+    }
     for (int q = tid; q < c.P; q += PED_THREADS) {       // q = rank (0 = nearest), j = pedestrian
-        const int j = order[q];
+        const int j = (int)(unsigned)keys[q];
         const float4 o = pobs[j];
         const double px = o.x, py = o.y;
         const double ped_r = d.ped_r_round[j];

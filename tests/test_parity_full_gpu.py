@@ -186,3 +186,39 @@ def test_device_built_rvo_obstacle_tree(n_obj, seed):
             assert rv.shape[0] == dev["n"] and np.array_equal(rv.view(np.uint32), dev["verts"].view(np.uint32)), "vertex ring differs from the node's obstacles_"
     assert sim.debug_counters()[1] == 0
     sim.close()
+
+
+def test_ped_order_ties():
+    """Nearest-first order of ped_vector_states / ped_maps (yaml_env.py:446-466: a stable python sort on float64 keys) when keys
+    collide: k_ped_obs sorts float32(key) << 32 | index and re-sorts runs of equal float32 keys by (float64 key, index).
+    Robot at (4, 4) with yaw 0, so pedestrian offsets are exact in the robot frame:
+    peds 0/1: equal float32 keys, different float64 keys, the farther one has the lower index (the run must be re-sorted);
+    peds 2/3: exactly equal float64 keys (mirror images): index order; peds 4/5: the same nearer to the robot."""
+    import torch
+    from img_env_b200.lib import BatchedSim
+    from img_env_b200.spec import rpy_to_q
+    from helpers import make_reset
+    from oracle.pyref import RefEnv, PyPost, have_ref
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    cfg = base_cfg(R=1, P=6, scene="rvoscene", n_obj=0, max_ped=6)
+    spec = build_spec(cfg)
+    rng = np.random.default_rng(5)
+    e = 2.0 ** -6
+    offs = [(e * (1 + 2.0 ** -23), 1.0), (e, 1.0), (1.5, 0.75), (1.5, -0.75), (0.5, -0.5), (0.5, 0.5)]
+    rs = make_reset(spec, rng, n_obj=0, robots_xy=[(4.0, 4.0)], peds_xy=[(4.0 + a, 4.0 + b) for a, b in offs])
+    rs["robots"][0, 2:6] = rpy_to_q(0.0)
+    sim = BatchedSim(spec, num_scenes=1, ped_yaw_mode=1)
+    out = sim.reset([rs])
+    torch.cuda.synchronize()
+    ref = RefEnv(spec); post = PyPost(spec); post.on_reset()
+    want = post.get_states(ref.reset(rs))
+    got = {k: v[0].cpu().numpy() for k, v in out.items()}
+    pv = want["ped_vector_states"].reshape(-1)[1:].reshape(6, 7)
+    keys32 = (pv[:, 0].astype(np.float64) ** 2 + pv[:, 1].astype(np.float64) ** 2).astype(np.float32)
+    assert (np.diff(keys32) == 0).sum() >= 3, "the scenario must produce runs of equal float32 keys"
+    assert abs(pv[2, 0] - e) < 1e-9 and pv[3, 0] > pv[2, 0], "the node orders the float32-equal pair by its float64 keys"
+    errs = compare_state(got, want, spec, where="ties: ")
+    assert not errs, "\n".join(errs)
+    assert np.array_equal(got["ped_vector_states"], want["ped_vector_states"].astype(np.float32).reshape(got["ped_vector_states"].shape))
+    sim.close()
