@@ -20,6 +20,7 @@
 // kernel gathers the records whose box meets its field of view and composes them on the fly.
 #pragma once
 #include "state.cuh"
+#include "kin.cuh"
 
 inline __host__ __device__ int stamp_rad_cells(double ext, double res) { return (int)ceil(ext / res) + 1; }
 inline __host__ __device__ int stamp_bitmap_words(int rad_cells) { return (2 * rad_cells + 1) * ((2 * rad_cells) / 32 + 2); }
@@ -148,15 +149,32 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                  ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Phase G of the observation: state vector and the episode bookkeeping that does not depend on the raster
+// (img_env.cpp:547-587, yaml_env.py:467-471); the collision code / done flag follow in k_view.
+__device__ __forceinline__ void view_state_vector(const Dev& d, int idx) {
+    const Cfg& c = d.c;
+    double st[5];
+    robot_state_vec(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx), RBF(d, RB_GX, idx), RBF(d, RB_GY, idx),
+                    RBF(d, RB_GYAW, idx), RBF(d, RB_L0V, idx), RBF(d, RB_L0W, idx), c.state_dim, st);
+    float s0 = (float)st[0], s1 = (float)st[1];
+    for (int k = 0; k < c.state_dim; k++) d.o_vec[(size_t)idx * c.state_dim + k] = (float)st[k];
+    double dist = sqrt((double)s0 * (double)s0 + (double)s1 * (double)s1);   // yaml_env.py:467
+    double prev = RBF(d, RB_PREVD, idx);
+    d.o_stepd[idx] = isnan(prev) ? 0.f : (float)(prev - dist);
+    RBF(d, RB_PREVD, idx) = dist;
+    d.o_arr[idx] = (uint8_t)(RBF(d, RB_ARR, idx) != 0.0);
+}
+
 // one thread per robot (a serial fp64 routine: small CTAs spread it over the SMs); grid = ceil(n_scenes * R / VC_THREADS)
 #define VC_THREADS 64
-__global__ void __launch_bounds__(VC_THREADS) k_view_consts(Dev d, const int* scene_ids, int n_scenes) {
+__global__ void __launch_bounds__(VC_THREADS) k_view_consts(Dev d, const int* scene_ids, int n_scenes, int debug_only) {
     const Cfg& c = d.c;
     const int g = blockIdx.x * VC_THREADS + threadIdx.x;
     const int sl = g / c.R, a = g - sl * c.R;
     if (sl >= n_scenes || (d.n_dev && sl >= *d.n_dev)) return;
     const int idx = (scene_ids ? scene_ids[sl] : sl) * c.R + a;
     view_const_compute(d, idx, a, d.vconst + idx);
+    if (!debug_only) view_state_vector(d, idx);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

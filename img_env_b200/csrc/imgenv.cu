@@ -621,7 +621,7 @@ static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int i
         CK(cudaEventRecord(h->ev_tree, h->side));
         h->tree_pending = true;
     }
-    k_view_consts<<<(n_scenes * c.R + VC_THREADS - 1) / VC_THREADS, VC_THREADS, 0, st>>>(d, d_scene_ids, n_scenes);
+    k_view_consts<<<(n_scenes * c.R + VC_THREADS - 1) / VC_THREADS, VC_THREADS, 0, st>>>(d, d_scene_ids, n_scenes, 0);
     k_footprints<<<(n_scenes * c.NPA + FOOT_WARPS - 1) / FOOT_WARPS, FOOT_WARPS * 32, h->foot_smem, st>>>(d, d_scene_ids, n_scenes, is_reset ? 0 : 1);
     if (ev) cudaEventRecord(ev[2], st);
     if (c.inverse_ok) k_view<false, false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
@@ -1188,7 +1188,7 @@ extern "C" int imgenv_debug_view_maps2(imgenv_t* h, uint8_t* host_out, int32_t* 
     if (host_out) CK(cudaMalloc((void**)&buf, n));
     if (stats_out) { CK(cudaMalloc((void**)&sbuf, (size_t)c.S * c.R * 16)); CK(cudaMemsetAsync(sbuf, 0, (size_t)c.S * c.R * 16, st)); }
     d.dbg_view = buf; d.dbg_stats = sbuf;
-    k_view_consts<<<(c.S * c.R + VC_THREADS - 1) / VC_THREADS, VC_THREADS, 0, st>>>(d, nullptr, c.S);
+    k_view_consts<<<(c.S * c.R + VC_THREADS - 1) / VC_THREADS, VC_THREADS, 0, st>>>(d, nullptr, c.S, 1);
     k_footprints<<<(c.S * c.NPA + FOOT_WARPS - 1) / FOOT_WARPS, FOOT_WARPS * 32, h->foot_smem, st>>>(d, nullptr, c.S, 0);
     if (c.inverse_ok) k_view<true, false><<<c.S * c.R, VIEW_THREADS, h->view_smem, st>>>(d, nullptr, 0);
     else k_view<true, true><<<c.S * c.R, VIEW_THREADS, h->view_smem, st>>>(d, nullptr, 0);

@@ -166,22 +166,12 @@ __device__ __noinline__ void exact_cell(const Tf2& view_world, double res, int i
     tf_apply(view_world, i * res, j * res, wx, wy);
     cx = world2cell(wx, res); cy = world2cell(wy, res);
 }
-// Phase G: state vector and the episode bookkeeping (img_env.cpp:547-587, yaml_env.py:316, 374-376, 467-471)
-__device__ __forceinline__ void view_state_vector(const Dev& d, int idx, int is_reset) {
-    const Cfg& c = d.c;
-    double st[5];
-    robot_state_vec(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx), RBF(d, RB_GX, idx), RBF(d, RB_GY, idx),
-                    RBF(d, RB_GYAW, idx), RBF(d, RB_L0V, idx), RBF(d, RB_L0W, idx), c.state_dim, st);
-    float s0 = (float)st[0], s1 = (float)st[1];
-    for (int k = 0; k < c.state_dim; k++) d.o_vec[(size_t)idx * c.state_dim + k] = (float)st[k];
-    double dist = sqrt((double)s0 * (double)s0 + (double)s1 * (double)s1);   // yaml_env.py:467
-    double prev = RBF(d, RB_PREVD, idx);
-    d.o_stepd[idx] = isnan(prev) ? 0.f : (float)(prev - dist);
-    RBF(d, RB_PREVD, idx) = dist;
-    int coll = (int)RBF(d, RB_COLL, idx), arr = RBF(d, RB_ARR, idx) != 0.0;
-    d.o_coll[idx] = (int8_t)coll;
-    d.o_arr[idx] = (uint8_t)arr;
-    RBF(d, RB_DONE, idx) = is_reset ? 0.0 : (double)min(1, min(coll, 1) + arr);   // yaml_env.py:316, 374-376
+// Collision code and done flag of one robot, once its code of this step is known (img_env.cpp:547-587, yaml_env.py:316, 374-376);
+// the rest of the state vector is written by k_view_consts.
+__device__ __forceinline__ void view_publish_code(const Dev& d, int idx, int code, int is_reset) {
+    const int arr = RBF(d, RB_ARR, idx) != 0.0;
+    d.o_coll[idx] = (int8_t)code;
+    RBF(d, RB_DONE, idx) = is_reset ? 0.0 : (double)min(1, min(code, 1) + arr);   // yaml_env.py:316, 374-376
 }
 
 // FWD = false: lasers on and a FOV of ordinary size -> world->view rasterisation, no raster in shared memory (the hot variant);
@@ -638,6 +628,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
         if (!DEBUG_FULL && tid == 0) {
             int code = sh->coll_key & 3;
             RBF(d, RB_COLL, idx) = (double)code;
+            view_publish_code(d, idx, code, is_reset);
         }
 
         // ---- Phase C: first occupied cell of every laser ray (agent.cpp:405-438, 511-624).
@@ -710,9 +701,9 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                     if (lane == 0 && (k >> 5) <= ((c.range_total - 1) >> 5)) hbits[k >> 5] = word;
                     any_local |= word != 0u;
                     if (c.hb_shift == 4) {      // blocks of 16 rays = half warps: shuffle minimum / maximum, no atomics
-                        int hp = (int)(key >> 22), hq = valid ? hp : 0;
-#pragma unroll
-                        for (int o = 8; o; o >>= 1) { hp = min(hp, __shfl_xor_sync(0xffffffffu, hp, o)); hq = max(hq, __shfl_xor_sync(0xffffffffu, hq, o)); }
+                        const unsigned half = lane < 16 ? 0x0000FFFFu : 0xFFFF0000u;
+                        const int hp0 = (int)(key >> 22);
+                        const int hp = __reduce_min_sync(half, hp0), hq = __reduce_max_sync(half, valid ? hp0 : 0);      // redux.sync over the half warp
                         if ((lane & 15) == 0 && valid) { sh->hmin[k >> 4] = hp; sh->hmax[k >> 4] = hq; }
                     } else if (valid) {
                         if (hit_any) atomicMin(&sh->hmin[k >> c.hb_shift], (int)(key >> 22));
@@ -910,12 +901,11 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
             }
         }
     }
-    if (frozen) mbar_wait(&sh->bar[1], 0);       // (a CTA must not exit with bulk copies in flight)
-    if (DEBUG_FULL) return;
-
-    // ---- Phase G: state vector and the episode bookkeeping.  The pedestrian observation does not depend on the raster:
-    //      k_ped_obs below, on its own stream.
-    if (tid == 0) view_state_vector(d, idx, is_reset);
+    if (frozen) {
+        mbar_wait(&sh->bar[1], 0);       // (a CTA must not exit with bulk copies in flight)
+        if (!DEBUG_FULL && tid == 0) view_publish_code(d, idx, (int)RBF(d, RB_COLL, idx), is_reset);      // stale code re-sent (agent.cpp:358-360)
+    }
+    // (Phase G, the state vector, is written by k_view_consts; the pedestrian observation by k_ped_obs on its own stream.)
 }
 
 // ---------------------------------------------------------------------------------------------
