@@ -9,7 +9,9 @@
 #pragma once
 #include "state.cuh"
 #include "kin.cuh"
+#ifndef DYN_THREADS
 #define DYN_THREADS 64
+#endif
 #include "orca.cuh"
 #include "sfmtree.cuh"
 

@@ -161,8 +161,10 @@ inline std::string build_type(const Cfg& c, const double* desc, double view_angl
         // 16x16-pixel view tiles that hold such a pixel: a footprint record whose view-space bounding box (+3 px) touches one
         // of them contributes all of its cells to the raster, not only its candidate cells (view.cuh, phase B)
         const int etw = (c.vw + 15) / 16, eth = (c.vh + 15) / 16;
-        T.edge_tiles.assign(((size_t)etw * eth + 31) / 32, 0u);
-        for (uint32_t ep : T.edge_px) { const int t = (int)(ep >> 16) / 16 * etw + (int)(ep & 0xFFFF) / 16; T.edge_tiles[t >> 5] |= 1u << (t & 31); }
+        // (one 64-bit column mask per tile row, as two u32 words: the view raster is at most 1022 pixels = 64 tiles wide)
+        T.edge_tiles.assign((size_t)eth * 2, 0u);
+        (void)etw;
+        for (uint32_t ep : T.edge_px) { const int ti = (int)(ep >> 16) / 16, tj = (int)(ep & 0xFFFF) / 16; T.edge_tiles[2 * ti + (tj >> 5)] |= 1u << (tj & 31); }
     }
     // own footprint cells in the view raster: draw(view_map_, 100, "view_map", bbox_) agent.cpp:503
     size_t npx = (size_t)c.vh * c.vw;

@@ -484,14 +484,14 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     CK(cudaEventCreateWithFlags(&h->ev_moved, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_ped, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_tree, cudaEventDisableTiming));
-    h->ped_smem = ped_smem_bytes(c);
+    h->ped_smem = ped_smem_bytes(c); h->d.pl = ped_layout(c);
     if (h->ped_smem > 200 * 1024) return fail("imgenv_create: too many pedestrians for the pedestrian observation kernel's shared memory");
     CK(cudaFuncSetAttribute(k_ped_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ped_smem));
     h->foot_smem = (size_t)FOOT_WARPS * c.ag_cap * 4; h->obj_smem = (size_t)c.obj_cap * 4;
     if (h->foot_smem > 200 * 1024 || h->obj_smem > 200 * 1024) return fail("imgenv_create: an agent / object footprint is too large for the footprint kernels");
     CK(cudaFuncSetAttribute(k_footprints, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->foot_smem));
     CK(cudaFuncSetAttribute(k_object_footprints, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->obj_smem));
-    h->view_smem = view_smem_bytes(c);
+    h->view_smem = view_smem_bytes(c); h->d.vl = view_layout(c);
     h->dyn_smem = dyn_smem_bytes(d);
     if (h->view_smem > 227 * 1024) return fail("imgenv_create: view kernel needs too much shared memory for this configuration");
     CK(cudaFuncSetAttribute(k_view<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));

@@ -27,10 +27,14 @@
 
 #define RVO_EPS 0.00001f
 #define ORCA_NEIGH_CAP 10
+#ifndef ORCA_FAST
 #define ORCA_FAST 16                    // obstacle neighbours / lines per agent kept in shared memory
+#endif
 #define ORCA_OBST_CAP 256               // obstacle neighbours per agent in total (beyond ORCA_FAST: in a pool slab)
 #define ORCA_LINE_CAP (ORCA_NEIGH_CAP + ORCA_OBST_CAP)
+#ifndef ORCA_NODE_CACHE
 #define ORCA_NODE_CACHE 1024             // BSP nodes (32 bytes each) staged in shared memory per CTA
+#endif
 #define ORCA_SLAB_BYTES ((ORCA_LINE_CAP - ORCA_FAST) * 16 + (ORCA_OBST_CAP - ORCA_FAST) * 8)
 #ifndef DYN_THREADS
 #define DYN_THREADS 64

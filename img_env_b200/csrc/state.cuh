@@ -49,7 +49,7 @@ struct RobotType {
     int own_mask_off;     // offset into own_mask (vh*vw bits, u32 words)
     int tile_off;         // offset into tile_fov (u32 words): bit per 32x32 view tile that contains FOV pixels
     int edge_off, n_edge; // FOV pixels with an 8-neighbour outside the FOV (u32 row<<16|col), always evaluated forward
-    int etile_off;        // offset into edge_tiles (u32 words): bit per 16x16 view tile that holds (or touches) an edge pixel
+    int etile_off;        // offset into edge_tiles (u32 words, even): per row of 16x16 view tiles a 64-bit mask of the tiles that hold an edge pixel
     int fov_r0, fov_r1, fov_c0, fov_c1;   // bounding box (inclusive) of the FOV pixels in the view raster
     int dtab_off;         // offset into dtab (ns*img*4 u32)
     int ostat_off;        // offset into ostat (img*img uint2)
@@ -89,9 +89,13 @@ struct Cfg {
     int scene_words;              // u32 words of record bitmaps per scene
 };
 
+// shared-memory plans of k_view / k_ped_obs (byte offsets; view.cuh computes them once on the host)
+struct ViewLayout { unsigned sh, regA, regB, hpre, hitkey, rays, need, spans, blocks, near, npre, chdr, coff, nhdr, noff, cword, cmeta, cpre, cwsum, seglist, total; };
+struct PedLayout { unsigned winner, keys, dkeys, pobs, row, total; int n_sort; };
 struct ViewConst;
 struct Dev {
     Cfg c;
+    ViewLayout vl; PedLayout pl;
     // static, shared
     const uint8_t* grid;          // [H][W]
     const uint32_t* static_occ;   // [H][Wb]  bit = grid < 250

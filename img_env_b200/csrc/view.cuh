@@ -125,8 +125,7 @@ __device__ __noinline__ void cell_rays_inline(unsigned* hitkey, const short* ren
 
 #define INV_EPS 0.004f       // band around a cell edge inside which the inverse rasterisation runs the exact forward map
 #define INV_MAX_BLOCKS 512   // 32x32-cell world blocks under the FOV; more -> forward (tile) rasterisation
-struct ViewLayout { size_t sh, regA, regB, hpre, hitkey, rays, need, spans, blocks, near, npre, chdr, coff, nhdr, noff, cword, cmeta, cpre, cwsum, seglist, total; };
-__host__ __device__ inline ViewLayout view_layout(const Cfg& c) {
+inline ViewLayout view_layout(const Cfg& c) {
     ViewLayout L;
     size_t off = 0;
     L.sh = off; off += (sizeof(ViewShared) + 15) & ~(size_t)15;
@@ -186,7 +185,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
     const int s = scene_ids ? scene_ids[sl] : sl;
     const int idx = s * c.R + r;
     const RobotType ty = d.types[d.type_of[r]];
-    const ViewLayout L = view_layout(c);
+    const ViewLayout& L = d.vl;          // (computed once on the host)
     const int vwb = c.vwb, vh = c.vh, vw = c.vw;
 
     ViewShared* sh = reinterpret_cast<ViewShared*>(smem_raw + L.sh);
@@ -290,13 +289,17 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                   if (!all) {
                     const int ti0 = max((int)floorf(imin - 3.f) >> ET_SHIFT, 0), ti1 = min((int)floorf(imax + 3.f) >> ET_SHIFT, eth - 1);
                     const int tj0 = max((int)floorf(jmin - 3.f) >> ET_SHIFT, 0), tj1 = min((int)floorf(jmax + 3.f) >> ET_SHIFT, etw - 1);
-                    if ((ti1 - ti0 + 1) * (tj1 - tj0 + 1) > 64) all = NEAR_ALL;        // huge part: do not bother
-                    else
-                        for (int ti = ti0; ti <= ti1 && !all; ti++)
-                            for (int tj = tj0; tj <= tj1; tj++) {
-                                const int t = ti * etw + tj;
-                                if ((__ldg(etiles + (t >> 5)) >> (t & 31)) & 1u) { all = NEAR_ALL; break; }
-                            }
+                    if (ti1 - ti0 >= 8) all = NEAR_ALL;        // huge part: do not bother
+                    else if (ti0 <= ti1 && tj0 <= tj1) {
+                        // one 64-bit column mask per tile row (independent loads, no early exit)
+                        const unsigned long long cols = (~0ull >> (63 - tj1)) & (~0ull << tj0);
+                        unsigned long long acc = 0ull;
+                        for (int ti = ti0; ti <= ti1; ti++) {
+                            const uint2 row = __ldg(reinterpret_cast<const uint2*>(etiles) + ti);
+                            acc |= ((unsigned long long)row.y << 32 | row.x) & cols;
+                        }
+                        if (acc) all = NEAR_ALL;
+                    }
                   }
                 }
                 {   // slot in the near list and offset of the part's words among the work items of phase B, from one atomic
@@ -397,8 +400,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
         };
         // An occupied raster cell updates the rays through it on the spot (phase C); only cells crossed by many rays (close
         // to the origin) are listed and shared out over a warp after the barrier.
-        auto push_cell = [&](int pr, int pc) {
-            const unsigned kp = __ldg(kpack + pr * vw + pc);
+        auto push_cell_kp = [&](int pr, int pc, unsigned kp) {           // kp = the cell's ray interval (kpack entry)
             const int kh = kp & 0xFFFF, kl = (kp >> 16) & 0x7FFF;
             if (kh == 0xFFFF) return;                                      // no ray passes through this cell
             if (VIEW_STATS) atomicAdd(&sh->stat[1], 1);
@@ -410,6 +412,14 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 const unsigned key = hit_key(max(abs(pr - ox), abs(pc - oy)), pr, pc);
                 for (int k = kl; k <= kh; k++) atomicMin(&hitkey[k], key);
             } else cell_rays_inline(hitkey, rend, ox, oy, pr, pc, kl, kh);
+        };
+        auto push_cell = [&](int pr, int pc) { push_cell_kp(pr, pc, __ldg(kpack + pr * vw + pc)); };
+        // The same one cell late: the table load of a cell is in flight while the thread works out its next candidate.
+        unsigned pend_cell = 0xFFFFFFFFu, pend_kp = 0u;
+        auto push_cell_deferred = [&](int pr, int pc) {
+            const unsigned kp = __ldg(kpack + pr * vw + pc);
+            if (pend_cell != 0xFFFFFFFFu) push_cell_kp((int)(pend_cell >> 16), (int)(pend_cell & 0xFFFFu), pend_kp);
+            pend_cell = ((unsigned)pr << 16) | (unsigned)pc; pend_kp = kp;
         };
         const int n_trow = (vh + 31) >> 5, n_tiles = n_trow * vwb;
         if (!use_inverse) for (int q = tid; q < vh * vwb; q += VIEW_THREADS) { occ[q] = 0u; if (!use_laser) known[q] = 0u; }
@@ -543,7 +553,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                     // World->view mode: no raster is kept -- a view pixel has ONE world cell, so it can only be found twice when
                     // two records (or a record and the static map) cover that cell; it is then listed twice, which is harmless.
                     // Forward mode: into the raster; its boundary cells are listed by the scan below.
-                    if (use_inverse) push_cell(i, j);
+                    if (use_inverse) push_cell_deferred(i, j);
                     else atomicOr(&occ[i * vwb + (j >> 5)], 1u << (j & 31));
                 }
             };
@@ -619,6 +629,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 }
                 if (c0 + CAND_CHUNK < n_items) __syncthreads();       // the chunk arrays are rewritten
             }
+            if (pend_cell != 0xFFFFFFFFu) push_cell_kp((int)(pend_cell >> 16), (int)(pend_cell & 0xFFFFu), pend_kp);
         }
         if (!DEBUG_FULL && need_A) {
             for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -915,8 +926,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
 // It only reads poses, so it runs beside the stamp / view kernels on the library's side stream.
 // ---------------------------------------------------------------------------------------------
 #define PED_THREADS 128
-struct PedLayout { size_t winner, keys, dkeys, pobs, row, total; int n_sort; };
-__host__ __device__ inline PedLayout ped_layout(const Cfg& c) {
+inline PedLayout ped_layout(const Cfg& c) {
     PedLayout L;
     int n = 1; while (n < c.P) n <<= 1;
     L.n_sort = n;
@@ -940,7 +950,7 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
     const int s = scene_ids ? scene_ids[sl] : sl;
     const int idx = s * c.R + r;
     const RobotType& ty = d.types[d.type_of[r]];
-    const PedLayout L = ped_layout(c);
+    const PedLayout& L = d.pl;
     int* winner = reinterpret_cast<int*>(smem_raw + L.winner);
     // Sort keys: python sorts by the float64 x*x + y*y, stably.  The network sorts ONE 64-bit word per pedestrian, float32(key)
     // << 32 | index (rounding to float32 is monotone, so the order can only be wrong inside a run of equal float32 keys: such
