@@ -297,6 +297,11 @@ def run_b200(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     nprof, kms = sim.profile_end()
+    # an ORCA agent that found neither a table slot nor a pool slab would keep only its nearest obstacle edges (the reference
+    # keeps all): a number measured with such a truncation is not a parity-grade number
+    overflows = sim.debug_counters()[0]
+    if overflows:
+        raise RuntimeError("bench: %d ORCA table overflows during the timed run" % overflows)
     clocks = sampler.stop() if rank == 0 else None
     if dist:
         tms = torch.tensor([ms], device="cuda"); dist.all_reduce(tms, op=dist.ReduceOp.MAX); ms = float(tms.item())
@@ -394,6 +399,7 @@ def run_b200(args):
                                    "note": "the same call with ALL nine State tensors copied to pinned host memory every step (what a "
                                            "CPU-side learner would need); PCIe-bound"},
         "gpu_launches": int(K * launches_per_step),
+        "solver_table_overflows": int(overflows),
         "kernel_ms": {k: round(v, 4) for k, v in kms.items()},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "kernel": "k_view", "bytes_per_robot_step": B, "robot_steps_per_launch": S * R,

@@ -9,9 +9,6 @@
 #pragma once
 #include "state.cuh"
 #include "kin.cuh"
-#ifndef DYN_THREADS
-#define DYN_THREADS 64
-#endif
 #include "orca.cuh"
 #include "sfmtree.cuh"
 
@@ -205,7 +202,7 @@ __device__ inline void ped_gait(const Dev& d, int pi, int p) {
 
 // The dynamics stage runs as two kernels so that a scene's agents spread over several CTAs:
 //   k_dyn_solve : grid = S * nblk CTAs; every CTA loads the scene's agents (pre-step pos/vel) into shared
-//                 memory and solves its slice of DYN_THREADS agents (ORCA/ERVO new velocity, or the SFM forces),
+//                 memory and solves its slice of Cfg::dyn_threads agents (ORCA/ERVO new velocity, or the SFM forces),
 //                 writing only scratch (new velocities / forces) and per-agent waypoint bookkeeping;
 //   k_dyn_apply : grid = S * nblk CTAs; Agent::update / Tagent::move, pedestrian pose + gait, then the robots
 //                 (limiter, cmd, arrival) and setRobotPos.
@@ -213,10 +210,15 @@ __device__ inline void ped_gait(const Dev& d, int pi, int p) {
 __device__ __forceinline__ bool robot_alive(const Dev& d, const uint8_t* alive, int idx) {
     return alive ? alive[idx] != 0 : RBF(d, RB_DONE, idx) == 0.0;
 }
-__host__ __device__ __forceinline__ int dyn_nblk(const Cfg& c) {
+__host__ __device__ __forceinline__ int dyn_nblk(const Cfg& c) { return c.dyn_nblk; }
+// Agents per CTA and CTAs per scene: as few CTAs per scene as DYN_MAX_THREADS allows (every CTA of a scene stages the same
+// agents, hash and BSP nodes), threads rounded up to whole warps.  C4: 400 agents -> 2 CTAs x 224; C3: 21 -> 1 x 32.
+inline void dyn_pick_block(Cfg& c) {
     int n = c.NA > c.R ? c.NA : c.R;
     if (c.scene_type == 4 && c.P > n) n = c.P;
-    return (n + DYN_THREADS - 1) / DYN_THREADS;
+    if (n < 1) n = 1;
+    c.dyn_nblk = (n + DYN_MAX_THREADS - 1) / DYN_MAX_THREADS;
+    c.dyn_threads = ((n + c.dyn_nblk - 1) / c.dyn_nblk + 31) / 32 * 32;
 }
 
 // shared memory of k_dyn_solve: agents' pos + vel, beeps, spatial hash (head table + chain), per-thread ORCA tables
@@ -227,14 +229,14 @@ __host__ __device__ inline size_t dyn_scratch_offset(const Cfg& c) {
 __host__ __device__ inline int dyn_node_cache(const Dev& d) { return d.max_verts < ORCA_NODE_CACHE ? d.max_verts : ORCA_NODE_CACHE; }
 inline size_t dyn_smem_bytes(const Dev& d) {
     const Cfg& c = d.c;
-    return dyn_scratch_offset(c) + ((c.scene_type == 2 || c.scene_type == 3) ? orca_scratch_bytes() + (size_t)dyn_node_cache(d) * 32 : 0) + 16;
+    return dyn_scratch_offset(c) + ((c.scene_type == 2 || c.scene_type == 3) ? orca_scratch_bytes(c.dyn_threads) + (size_t)dyn_node_cache(d) * 32 : 0) + 16;
 }
 
-__global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* actions, const uint8_t* alive, int parity) {
+__global__ void __launch_bounds__(DYN_MAX_THREADS, 2) k_dyn_solve(Dev d, const float* actions, const uint8_t* alive, int parity) {
     extern __shared__ __align__(16) unsigned char dsm[];
     const Cfg& c = d.c;
     const int nblk = dyn_nblk(c);
-    const int s = blockIdx.x / nblk, blk = blockIdx.x % nblk, tid = threadIdx.x;
+    const int s = blockIdx.x / nblk, blk = blockIdx.x % nblk, tid = threadIdx.x, DT = c.dyn_threads;
     if (!(c.P > 0 && c.scene_type != 0 && c.scene_type != 4)) return;
     // shared memory: the scene's agents (position, velocity), beeps, spatial hash, then the per-thread ORCA tables
     V2* pos = reinterpret_cast<V2*>(dsm);
@@ -246,11 +248,11 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* a
     hash.head = reinterpret_cast<unsigned short*>(beep_r + c.R + (c.R & 1));
     hash.next = hash.head + hash.mask + 1;
     unsigned char* scratch = dsm + dyn_scratch_offset(c);
-    int4* node_cache = reinterpret_cast<int4*>(scratch + orca_scratch_bytes());
+    int4* node_cache = reinterpret_cast<int4*>(scratch + orca_scratch_bytes(DT));
     float4* seg_cache = reinterpret_cast<float4*>(node_cache + dyn_node_cache(d));
     const unsigned long long step = d.step_no[s];
     // beeps (img_env.cpp:323-342): robots' PRE-step poses; recomputed identically by every CTA of the scene
-    for (int j = tid; j < c.R; j += DYN_THREADS) {
+    for (int j = tid; j < c.R; j += DT) {
         int idx = s * c.R + j;
         bool is_beep = false;
         float v_y = robot_alive(d, alive, idx) ? actions[(size_t)idx * 3 + 2] : 0.f;
@@ -281,9 +283,9 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* a
         if (tid == 0) s_nbeep = base;
     }
     __syncthreads();
-    const int a = blk * DYN_THREADS + tid;
+    const int a = blk * DT + tid;
     if (c.scene_type == 2 || c.scene_type == 3) {
-        for (int k = tid; k < c.NA; k += DYN_THREADS) {
+        for (int k = tid; k < c.NA; k += DT) {
             pos[k] = v2(d.rvo_pos[((size_t)s * c.NA + k) * 2], d.rvo_pos[((size_t)s * c.NA + k) * 2 + 1]);
             vel[k] = v2(d.rvo_vel[((size_t)s * c.NA + k) * 2], d.rvo_vel[((size_t)s * c.NA + k) * 2 + 1]);
         }
@@ -294,12 +296,12 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* a
         ob.root = d.rvo_counts[2 * s + 1];
         ob.n_cached = min(d.rvo_counts[2 * s], dyn_node_cache(d));
         ob.cache_nodes = node_cache; ob.cache_seg = seg_cache;
-        for (int k = tid; k < ob.n_cached; k += DYN_THREADS) {     // the obstacle BSP is walked by every agent: stage it
+        for (int k = tid; k < ob.n_cached; k += DT) {     // the obstacle BSP is walked by every agent: stage it
             node_cache[k] = __ldg(reinterpret_cast<const int4*>(ob.nodes) + k);
             seg_cache[k] = __ldg(reinterpret_cast<const float4*>(ob.node_seg) + k);
         }
         __syncthreads();
-        agent_hash_build(hash, pos, c.NA, tid, DYN_THREADS);
+        agent_hash_build(hash, pos, c.NA, tid, DT);
         const unsigned warp_mask = __ballot_sync(0xffffffffu, a < c.NA);
         if (a >= c.NA) return;
         if (blockIdx.x == 0 && tid == 0) d.orca_cursor[parity ^ 1] = 0u;       // the next call's slab cursor
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* a
             pref = goalVector;
             maxSpeed = (float)d.ped_maxspeed[a];
         }
-        OrcaScratch sc = orca_scratch(scratch, tid);
+        OrcaScratch sc = orca_scratch(scratch, tid, DT);
         OrcaPool pool;
         pool.slabs = d.orca_pool; pool.n_slabs = d.orca_nslabs; pool.cursor = d.orca_cursor + parity; pool.overflow = d.counters;
         V2 nv = orca_new_velocity(a, pos, vel, hash, pref, maxSpeed, (float)c.step_hz, ob, sc, pool, warp_mask, c.scene_type == 3, s_nbeep, beep_p, beep_r);
@@ -349,11 +351,11 @@ __global__ void __launch_bounds__(DYN_THREADS) k_dyn_solve(Dev d, const float* a
     }
 }
 
-__global__ void __launch_bounds__(DYN_THREADS) k_dyn_apply(Dev d, const float* actions, const uint8_t* alive, int ped_yaw_mode) {
+__global__ void __launch_bounds__(DYN_MAX_THREADS) k_dyn_apply(Dev d, const float* actions, const uint8_t* alive, int ped_yaw_mode) {
     const Cfg& c = d.c;
     const int nblk = dyn_nblk(c);
-    const int s = blockIdx.x / nblk, blk = blockIdx.x % nblk, tid = threadIdx.x;
-    const int a = blk * DYN_THREADS + tid;
+    const int s = blockIdx.x / nblk, blk = blockIdx.x % nblk, tid = threadIdx.x, DT = c.dyn_threads;
+    const int a = blk * DT + tid;
     if (c.P > 0 && c.scene_type != 0 && a < c.NA) {
         if (c.scene_type == 2 || c.scene_type == 3) {   // Agent::update
             const size_t o = ((size_t)s * c.NA + a) * 2;

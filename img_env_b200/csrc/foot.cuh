@@ -201,11 +201,13 @@ __global__ void __launch_bounds__(FOOT_WARPS * 32) k_footprints(Dev d, const int
     int kind, id, n_pts, rad;
     const double* pts;
     double offx = 0, offy = 0, ccx, ccy;
+    int ring_n = -1; const double* ring = nullptr; double dcx = 0, dcy = 0, r_in = 0;      // circle parts: rim points + sure-covered disc
     if (is_robot) {
         const int idx = s * c.R + a;
         const RobotType& ty = d.types[d.type_of[a]];
         x = RBF(d, RB_X, idx); y = RBF(d, RB_Y, idx); yaw = RBF(d, RB_YAW, idx); ext = ty.zone_rad * c.res;
         kind = FK_ROBOT; id = a; n_pts = ty.n_pts; pts = d.lattice_xy + 2 * (size_t)ty.pts_off; rad = ty.stamp_rad; ccx = ty.stamp_cx; ccy = ty.stamp_cy;
+        ring_n = ty.ring_n; ring = d.lattice_xy + 2 * (size_t)ty.ring_off; dcx = ty.disc_cx; dcy = ty.disc_cy; r_in = ty.disc_rin;
     } else {
         const int idx = s * c.P + p;
         const int shape = d.ped_shape[p];
@@ -215,6 +217,8 @@ __global__ void __launch_bounds__(FOOT_WARPS * 32) k_footprints(Dev d, const int
         const double* pc = d.ped_part + 6 * (size_t)p + 3 * leg;
         kind = shape == 0 ? FK_CIRC : (leg ? FK_RIGHT : FK_LEFT); id = p;
         n_pts = d.ped_pts_n[2 * p + leg]; pts = d.lattice_xy + 2 * (size_t)d.ped_pts_off[2 * p + leg]; rad = (int)pc[2]; ccx = pc[0]; ccy = pc[1];
+        ring_n = d.ped_ring_n[2 * p + leg]; ring = d.lattice_xy + 2 * (size_t)d.ped_ring_off[2 * p + leg];
+        { const double* dz = d.ped_disc + 6 * (size_t)p + 3 * leg; dcx = dz[0]; dcy = dz[1]; r_in = dz[2]; }
         if (shape == 2) {   // leg2base: identity rotation + leg origin (agent.cpp:815-837)
             offx = leg ? PDF(d, PD_RLX, idx) : PDF(d, PD_LLX, idx); offy = leg ? PDF(d, PD_RLY, idx) : PDF(d, PD_LLY, idx);
         }
@@ -239,6 +243,27 @@ __global__ void __launch_bounds__(FOOT_WARPS * 32) k_footprints(Dev d, const int
     const int nw = bx.nrow * bx.wpr;                    // <= cap by construction of stamp_bitmap_words
     for (int k = lane; k < nw; k += 32) bm[k] = 0u;
     __syncwarp();
+    if (ring_n >= 0) {
+        // Circle lattice: every cell whose centre lies within r_in of the disc centre holds a lattice point for sure
+        // (host_tables.h, lattice_circle_ring) -- those cells are set row by row, and only the rim points are evaluated.
+        double wcx, wcy;
+        tf_apply(t, dcx + offx, dcy + offy, wcx, wcy);
+        for (int rr = lane; rr < bx.nrow; rr += 32) {
+            const int X = bx.cx0 + rr;
+            if ((unsigned)X >= (unsigned)c.H) continue;
+            const double dx = X * c.res - wcx, h2 = r_in * r_in - dx * dx;
+            if (h2 <= 0.0) continue;
+            const double half = sqrt(h2);
+            int y_lo = (int)ceil((wcy - half) * c.inv_res + 1e-9), y_hi = (int)floor((wcy + half) * c.inv_res - 1e-9);
+            y_lo = max(y_lo, 0); y_hi = min(y_hi, c.W - 1);
+            for (int w = 0; w < bx.wpr; w++) {
+                const int lo = max(y_lo - (bx.wj0 + w) * 32, 0), hi = min(y_hi - (bx.wj0 + w) * 32, 31);
+                if (lo <= hi) bm[rr * bx.wpr + w] = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+            }
+        }
+        __syncwarp();
+        pts = ring; n_pts = ring_n;
+    }
     for (int k = lane; k < n_pts; k += 32) {
         const double2 pt = __ldg(reinterpret_cast<const double2*>(pts) + k);
         double wx, wy;

@@ -46,6 +46,26 @@ inline void lattice_circle(double s0, double s1, double s2, std::vector<double>&
                 out.push_back(n * resolution + s1);
             }
 }
+// Ring of a circle lattice.  A grid cell (side res) whose centre lies within r_in = r - cover - eps of the disc centre holds a
+// lattice point for sure -- every point of the plane is within cover = 0.01 * sqrt(2) / 2 of a point of the 0.01 m lattice, which
+// then lies strictly inside the cell's square (res / 2 > cover) and inside the disc -- so only the lattice points that can fall
+// into OTHER cells have to be evaluated one by one: those farther than r_in - res * sqrt(2) / 2 from the centre.
+// Returns r_in, or a negative number when the resolution does not allow the shortcut; ring = (x, y) pairs like the lattice.
+inline double lattice_circle_ring(double s0, double s1, double s2, double res, std::vector<double>& ring) {
+    const double cover = 0.01 * 0.70710678118654757;
+    if (res * 0.5 - cover < 2e-4) return -1.0;
+    const double r_in = s2 - cover - 5e-5;
+    if (r_in <= 0) return -1.0;
+    const double thr = r_in - res * 0.70710678118654757 - 5e-5;
+    double resolution = 0.01;
+    int bb = (int)ceil(s2 / resolution);
+    for (int m = -bb; m <= bb; m++)
+        for (int n = -bb; n <= bb; n++) {
+            const double rad = sqrt(m * resolution * m * resolution + n * resolution * n * resolution);
+            if (rad <= s2 && rad > thr) { ring.push_back(m * resolution + s0); ring.push_back(n * resolution + s1); }
+        }
+    return r_in;
+}
 inline void lattice_rect(double s0, double s1, double s2, double s3, std::vector<double>& out) {
     double resolution = 0.01;
     int x_min = (int)floor(s0 / resolution), x_max = (int)ceil(s1 / resolution);
@@ -76,6 +96,7 @@ struct TypeTables {
     std::vector<short> spans;
     std::vector<unsigned short> khi, klo;
     std::vector<uint32_t> own_mask, tile_fov, edge_px, edge_tiles, dtab, ostat;
+    std::vector<double> ring;      // circle robots: lattice points near the rim (lattice_circle_ring)
 };
 
 // desc: shape, size[4], sensor_cfg[2] (already float32-widened)
@@ -83,6 +104,12 @@ inline std::string build_type(const Cfg& c, const double* desc, double view_angl
                               double view_min_dist, double view_max_dist, TypeTables& T) {
     int shape = (int)desc[0];
     if (shape == 0) lattice_circle(desc[1], desc[2], desc[3], T.lattice);
+    T.t.ring_n = -1; T.t.disc_cx = T.t.disc_cy = T.t.disc_rin = 0;
+    if (shape == 0) {
+        const double r_in = lattice_circle_ring(desc[1], desc[2], desc[3], c.res, T.ring);
+        if (r_in > 0) { T.t.ring_n = (int)T.ring.size() / 2; T.t.disc_cx = desc[1]; T.t.disc_cy = desc[2]; T.t.disc_rin = r_in; }
+        else T.ring.clear();
+    }
     else if (shape == 1) lattice_rect(desc[1], desc[2], desc[3], desc[4], T.lattice);
     T.t.n_pts = (int)T.lattice.size() / 2;
     double sx = desc[5], sy = desc[6];

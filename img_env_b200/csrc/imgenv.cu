@@ -167,6 +167,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     c.scene_type = c.P > 0 ? cfg->scene_type : 0;
     c.relation = cfg->relation_ped_robo;
     c.NA = (c.scene_type != 0 && c.scene_type != 4) ? c.P + (c.relation == 1 ? c.R : 0) : 0;
+    dyn_pick_block(c);
     c.H = H; c.W = W; c.Wb = (W + 31) / 32; c.Hc = (H + 31) / 32;
     c.res = f32(cfg->view_resolution); c.inv_res = 1.0 / c.res;
     double vwid = f32(cfg->view_width), vhei = f32(cfg->view_height);
@@ -251,6 +252,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     std::vector<RobotType> rts;
     for (auto& T : types) {
         T.t.pts_off = (int)lattice.size() / 2; lattice.insert(lattice.end(), T.lattice.begin(), T.lattice.end());
+        T.t.ring_off = (int)lattice.size() / 2; lattice.insert(lattice.end(), T.ring.begin(), T.ring.end());
         // (ray ends, spans and need_idx are bulk-copied into shared memory in 16-byte units: every segment starts on one and is padded to one)
         T.t.ray_off = (int)ray_end.size() / 2; ray_end.insert(ray_end.end(), T.ray_end.begin(), T.ray_end.end());
         while (ray_end.size() % 8) ray_end.push_back(0);
@@ -352,6 +354,8 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     }
     // pedestrians
     std::vector<int> pshape(c.P), poff(2 * (size_t)c.P, 0), pn(2 * (size_t)c.P, 0);
+    std::vector<int> proff(2 * (size_t)std::max(c.P, 1), 0), prn(2 * (size_t)std::max(c.P, 1), -1);
+    std::vector<double> pdisc(6 * (size_t)std::max(c.P, 1), 0.0);
     std::vector<double> psize(6 * (size_t)c.P), pmax(c.P), prr(c.P);
     std::vector<float> prw(c.P);
     std::vector<double> pext(std::max(c.P, 1), 0.0), ppart(6 * (size_t)std::max(c.P, 1), 0.0);
@@ -374,6 +378,19 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         ht::bounding_circle(a, c.res, ppart.data() + 6 * p); ht::bounding_circle(b, c.res, ppart.data() + 6 * p + 3);
         poff[2 * p] = (int)lattice.size() / 2; pn[2 * p] = (int)a.size() / 2; lattice.insert(lattice.end(), a.begin(), a.end());
         poff[2 * p + 1] = (int)lattice.size() / 2; pn[2 * p + 1] = (int)b.size() / 2; lattice.insert(lattice.end(), b.begin(), b.end());
+        for (int leg = 0; leg < 2; leg++) {      // rim points of the circle lattices (foot.cuh: the interior is filled analytically)
+            const double* z = psize.data() + 6 * p;
+            double s0, s1, s2;
+            if (pshape[p] == 0 && leg == 0) { s0 = z[0]; s1 = z[1]; s2 = z[2]; }
+            else if (pshape[p] == 2) { s0 = 0; s1 = 0; s2 = leg ? z[5] : z[2]; }
+            else continue;
+            std::vector<double> ring;
+            const double r_in = ht::lattice_circle_ring(s0, s1, s2, c.res, ring);
+            if (r_in <= 0) continue;
+            proff[2 * p + leg] = (int)lattice.size() / 2; prn[2 * p + leg] = (int)ring.size() / 2;
+            lattice.insert(lattice.end(), ring.begin(), ring.end());
+            pdisc[6 * p + 3 * leg] = s0; pdisc[6 * p + 3 * leg + 1] = s1; pdisc[6 * p + 3 * leg + 2] = r_in;
+        }
     }
     h->ped_shape = pshape;
     std::vector<uint8_t> g(grid, grid + (size_t)H * W);
@@ -408,7 +425,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     UP(cubic_coef, coef) UP(f16_lut, lut) UP(lim_v, lv) UP(lim_w, lw) UP(ped_shape, pshape) UP(ped_size, psize)
     UP(tile_fov, tile_fov) UP(edge_px, edge_px) UP(edge_tiles, edge_tiles) UP(dtab, dtab) UP(ostat, ostat) UP(static_cand, scand) UP(static_crow, scrow)
     UP(static_orow, sorow) UP(part_off, part_off) UP(ped_maxspeed, pmax) UP(ped_r_round, prr) UP(ped_pts_off, poff)
-    UP(ped_pts_n, pn) UP(ped_ext, pext) UP(ped_part, ppart)
+    UP(ped_pts_n, pn) UP(ped_ext, pext) UP(ped_part, ppart) UP(ped_ring_off, proff) UP(ped_ring_n, prn) UP(ped_disc, pdisc)
 #undef UP
     size_t S = c.S;
     d.max_verts = 16 * c.max_obs + 16;
@@ -460,7 +477,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         }
         if (dupload(h, &d.sfm_vmax0, vmax0)) return -1;
     }
-    d.orca_nslabs = (c.scene_type == 2 || c.scene_type == 3) ? 4096 : 0;
+    d.orca_nslabs = (c.scene_type == 2 || c.scene_type == 3) ? 16384 : 0;
     if (dalloc(h, &d.orca_pool, (size_t)std::max(d.orca_nslabs, 1) * ORCA_SLAB_BYTES)) return -1;
     if (dalloc(h, &h->act_d, S * c.R * 3)) return -1;
     if (dalloc(h, &h->alive_d, S * c.R)) return -1;
@@ -752,8 +769,8 @@ extern "C" int imgenv_step(imgenv_t* h, const float* d_actions, const uint8_t* d
     {
         const int nblk = dyn_nblk(c);
         if (h->tree_pending) { CK(cudaStreamWaitEvent(st, h->ev_tree, 0)); h->tree_pending = false; }
-        if (c.NA > 0) k_dyn_solve<<<c.S * nblk, DYN_THREADS, h->dyn_smem, st>>>(d, d_actions, d_alive, (int)(h->solve_calls++ & 1));
-        k_dyn_apply<<<c.S * nblk, DYN_THREADS, 0, st>>>(d, d_actions, d_alive, h->ped_yaw_mode);
+        if (c.NA > 0) k_dyn_solve<<<c.S * nblk, c.dyn_threads, h->dyn_smem, st>>>(d, d_actions, d_alive, (int)(h->solve_calls++ & 1));
+        k_dyn_apply<<<c.S * nblk, c.dyn_threads, 0, st>>>(d, d_actions, d_alive, h->ped_yaw_mode);
 
     }
     if (ev) cudaEventRecord(ev[1], st);

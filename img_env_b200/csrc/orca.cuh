@@ -7,7 +7,7 @@
 // (Agent.cpp:845-1001), and for ERVO a unit "evacuation" velocity away from every beeping robot in range, added after the
 // program and not re-clipped (Agent.cpp:63-69).  float32, no FMA contraction, like the x86 build of the reference.
 //
-// How it is organised here (one thread per agent, DYN_THREADS agents per CTA, everything per-thread in SHARED memory,
+// How it is organised here (one thread per agent, Cfg::dyn_threads agents per CTA, everything per-thread in SHARED memory,
 // strided by the thread index so that a warp's accesses never conflict; no local-memory arrays):
 //   * agent neighbours: the scene's agents are binned into a shared-memory spatial hash with 0.5 m cells
 //     (= neighborDist); an agent walks the 3 x 3 cells around it and keeps its 10 nearest by (distance^2, index) --
@@ -28,16 +28,16 @@
 #define RVO_EPS 0.00001f
 #define ORCA_NEIGH_CAP 10
 #ifndef ORCA_FAST
-#define ORCA_FAST 16                    // obstacle neighbours / lines per agent kept in shared memory
+#define ORCA_FAST 12                    // obstacle neighbours / lines per agent kept in shared memory
 #endif
 #define ORCA_OBST_CAP 256               // obstacle neighbours per agent in total (beyond ORCA_FAST: in a pool slab)
 #define ORCA_LINE_CAP (ORCA_NEIGH_CAP + ORCA_OBST_CAP)
 #ifndef ORCA_NODE_CACHE
-#define ORCA_NODE_CACHE 1024             // BSP nodes (32 bytes each) staged in shared memory per CTA
+#define ORCA_NODE_CACHE 256             // BSP nodes (32 bytes each) staged in shared memory per CTA
 #endif
 #define ORCA_SLAB_BYTES ((ORCA_LINE_CAP - ORCA_FAST) * 16 + (ORCA_OBST_CAP - ORCA_FAST) * 8)
-#ifndef DYN_THREADS
-#define DYN_THREADS 64
+#ifndef DYN_MAX_THREADS
+#define DYN_MAX_THREADS 224      // agents per CTA of the dynamics kernels at most (imgenv.cu picks the count per configuration)
 #endif
 
 struct V2 { float x, y; };
@@ -79,7 +79,7 @@ struct ObstacleSet {
     __device__ __forceinline__ int prev(int i) const { return (int)verts[8 * i + 6]; }
 };
 
-// ---- per-thread tables: the first ORCA_FAST entries in shared memory (element j of thread t at [j * DYN_THREADS + t]),
+// ---- per-thread tables: the first ORCA_FAST entries in shared memory (element j of thread t at [j * threads + t]),
 //      the rest in a slab taken from a global pool on first use ---------------------------------------------------------
 struct OrcaPool { unsigned char* slabs; int n_slabs; unsigned* cursor; unsigned long long* overflow; };
 struct OrcaScratch {
@@ -89,6 +89,7 @@ struct OrcaScratch {
     float* nb_d2;         // [ORCA_NEIGH_CAP]
     int* nb_id;           // [ORCA_NEIGH_CAP]
     unsigned char* slab;  // nullptr until needed
+    int stride;           // threads per CTA
     __device__ __forceinline__ bool need_slab(const OrcaPool& pool) {
         if (slab) return true;
         const unsigned k = atomicAdd(pool.cursor, 1u);
@@ -98,31 +99,31 @@ struct OrcaScratch {
     }
     __device__ __forceinline__ float4* slab_line(int j) const { return reinterpret_cast<float4*>(slab) + (j - ORCA_FAST); }
     __device__ __forceinline__ float* slab_d2(int i) const { return reinterpret_cast<float*>(slab + (ORCA_LINE_CAP - ORCA_FAST) * 16) + 2 * (i - ORCA_FAST); }
-    __device__ __forceinline__ float4 get_line(int j) const { return j < ORCA_FAST ? line[j * DYN_THREADS] : *slab_line(j); }
+    __device__ __forceinline__ float4 get_line(int j) const { return j < ORCA_FAST ? line[j * stride] : *slab_line(j); }
     __device__ __forceinline__ bool put_line(int j, float4 v, const OrcaPool& pool) {
-        if (j < ORCA_FAST) { line[j * DYN_THREADS] = v; return true; }
+        if (j < ORCA_FAST) { line[j * stride] = v; return true; }
         if (j >= ORCA_LINE_CAP || !need_slab(pool)) return false;
         *slab_line(j) = v; return true;
     }
-    __device__ __forceinline__ float od2(int i) const { return i < ORCA_FAST ? obst_d2[i * DYN_THREADS] : slab_d2(i)[0]; }
-    __device__ __forceinline__ int oid(int i) const { return i < ORCA_FAST ? obst_id[i * DYN_THREADS] : __float_as_int(slab_d2(i)[1]); }
+    __device__ __forceinline__ float od2(int i) const { return i < ORCA_FAST ? obst_d2[i * stride] : slab_d2(i)[0]; }
+    __device__ __forceinline__ int oid(int i) const { return i < ORCA_FAST ? obst_id[i * stride] : __float_as_int(slab_d2(i)[1]); }
     __device__ __forceinline__ void oput(int i, float d2, int id) {
-        if (i < ORCA_FAST) { obst_d2[i * DYN_THREADS] = d2; obst_id[i * DYN_THREADS] = id; }
+        if (i < ORCA_FAST) { obst_d2[i * stride] = d2; obst_id[i * stride] = id; }
         else { float* q = slab_d2(i); q[0] = d2; q[1] = __int_as_float(id); }
     }
 };
-#define SLOT(j) ((j) * DYN_THREADS)
-__host__ __device__ inline size_t orca_scratch_bytes() {
-    return (size_t)DYN_THREADS * (ORCA_FAST * 16 + ORCA_FAST * 8 + ORCA_NEIGH_CAP * 8);
+#define SLOT(j) ((j) * sc.stride)
+__host__ __device__ inline size_t orca_scratch_bytes(int threads) {
+    return (size_t)threads * (ORCA_FAST * 16 + ORCA_FAST * 8 + ORCA_NEIGH_CAP * 8);
 }
-__device__ __forceinline__ OrcaScratch orca_scratch(unsigned char* base, int tid) {
+__device__ __forceinline__ OrcaScratch orca_scratch(unsigned char* base, int tid, int threads) {
     OrcaScratch s;
     s.line = reinterpret_cast<float4*>(base) + tid;
-    float* f = reinterpret_cast<float*>(base + (size_t)DYN_THREADS * ORCA_FAST * 16);
-    s.obst_d2 = f + tid; s.obst_id = reinterpret_cast<int*>(f + DYN_THREADS * ORCA_FAST) + tid;
-    f += 2 * DYN_THREADS * ORCA_FAST;
-    s.nb_d2 = f + tid; s.nb_id = reinterpret_cast<int*>(f + DYN_THREADS * ORCA_NEIGH_CAP) + tid;
-    s.slab = nullptr;
+    float* f = reinterpret_cast<float*>(base + (size_t)threads * ORCA_FAST * 16);
+    s.obst_d2 = f + tid; s.obst_id = reinterpret_cast<int*>(f + threads * ORCA_FAST) + tid;
+    f += 2 * threads * ORCA_FAST;
+    s.nb_d2 = f + tid; s.nb_id = reinterpret_cast<int*>(f + threads * ORCA_NEIGH_CAP) + tid;
+    s.slab = nullptr; s.stride = threads;
     return s;
 }
 

@@ -54,6 +54,8 @@ struct RobotType {
     int dtab_off;         // offset into dtab (ns*img*4 u32)
     int ostat_off;        // offset into ostat (img*img uint2)
     double stamp_cx, stamp_cy; int stamp_rad;   // footprint lattice: centre (base frame, m) and radius (cells, incl. margin) of its bounding circle
+    int ring_off, ring_n; // circle robots: lattice points near the rim (offset into lattice_xy, count; -1 = evaluate the whole lattice)
+    double disc_cx, disc_cy, disc_rin;   // ... and the disc (base frame, m) every cell centre inside which is covered for sure
     int zone_rad;         // bound (world cells) on the distance from the robot's position to any cell of its footprint
     double size_last;     // python: robots[i].size[-1]
     double sensor_x, sensor_y;
@@ -62,6 +64,7 @@ struct RobotType {
 struct Cfg {
     // geometry
     int S, R, P, NA;         // NA = solver agents = P + (relation ? R : 0)
+    int dyn_threads, dyn_nblk;    // dynamics kernels: agents per CTA, CTAs per scene (dyn.cuh: dyn_pick_block)
     int H, W, Wb, Hc;        // grid rows, cols, u32 words per bit-plane row, 32-row blocks
     int vh, vw, vwb;         // view raster rows/cols, words per row
     double res, inv_res;     // view resolution == grid resolution (float32 widened), 1/res
@@ -128,6 +131,9 @@ struct Dev {
     const double* ped_r_round;    // [P] python round(r_,2)
     const int* ped_pts_off;       // [P][2] lattice offsets (body or left leg, right leg)
     const int* ped_pts_n;         // [P][2]
+    const int* ped_ring_off;      // [P][2] rim points of the part's circle lattice (offset into lattice_xy)
+    const int* ped_ring_n;        // [P][2] their number, -1 = evaluate the whole lattice
+    const double* ped_disc;       // [P][2][3] disc centre (part frame, m) and the radius inside which every cell centre is covered
     const double* ped_part;       // [P][2][3] per stamped part (body / left leg, right leg): bounding circle centre x, y (m) and radius (cells)
     const double* ped_ext;        // [P] bound on the distance from the pedestrian position to any cell it stamps
     // per scene footprint records (foot.cuh)
