@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(VC_THREADS) k_view_consts(Dev d, const int* sc
 // robots and pedestrians: grid = ceil(n_scenes * NPA / FOOT_WARPS) CTAs, one warp per part
 // ---------------------------------------------------------------------------------------------------------------------
 #define FOOT_WARPS 8
-__global__ void __launch_bounds__(FOOT_WARPS * 32) k_footprints(Dev d, const int* scene_ids, int n_scenes, int bump_step) {
+__global__ void __launch_bounds__(FOOT_WARPS * 32) k_footprints(Dev d, const int* scene_ids, int n_scenes, int flags) {      // flags: 1 = step_++, 2 = evaluate whole lattices (tests)
     extern __shared__ uint32_t foot_sm[];             // FOOT_WARPS * ag_cap words
     const Cfg& c = d.c;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(FOOT_WARPS * 32) k_footprints(Dev d, const int
     if (gq >= n_scenes * c.NPA || (d.n_dev && gq >= *d.n_dev * c.NPA)) return;
     const int sl = gq / c.NPA, a = gq - sl * c.NPA;
     const int s = scene_ids ? scene_ids[sl] : sl;
-    if (bump_step && a == 0 && lane == 0) d.step_no[s] += 1;      // step_++ (img_env.cpp:518): the dynamics stage of this step is done
+    if ((flags & 1) && a == 0 && lane == 0) d.step_no[s] += 1;      // step_++ (img_env.cpp:518): the dynamics stage of this step is done
     uint32_t* bm = foot_sm + (size_t)warp * c.ag_cap;
     int4* hdr = d.foot_hdr + (size_t)s * c.NP + a;
     uint32_t* out = d.foot_words + (size_t)s * c.scene_words + d.part_off[a];
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(FOOT_WARPS * 32) k_footprints(Dev d, const int
     const int nw = bx.nrow * bx.wpr;                    // <= cap by construction of stamp_bitmap_words
     for (int k = lane; k < nw; k += 32) bm[k] = 0u;
     __syncwarp();
-    if (ring_n >= 0) {
+    if (ring_n >= 0 && !(flags & 2)) {
         // Circle lattice: every cell whose centre lies within r_in of the disc centre holds a lattice point for sure
         // (host_tables.h, lattice_circle_ring) -- those cells are set row by row, and only the rim points are evaluated.
         double wcx, wcy;

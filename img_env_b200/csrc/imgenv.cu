@@ -497,7 +497,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
         CK(cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming));
     }
 
-    CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));      // (stream priorities make no difference here: measured)
     CK(cudaEventCreateWithFlags(&h->ev_moved, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_ped, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_tree, cudaEventDisableTiming));
@@ -1328,6 +1328,21 @@ __global__ void k_debug_check_footprints(Dev d, unsigned long long* out) {
     if (nc) atomicAdd(out + 2, nc);
     if (bad) atomicAdd(out + 3, bad);
 }
+// words / headers of the agents' records that differ between two builds
+__global__ void k_debug_diff_footprints(Dev d, const uint32_t* words_b, const int4* hdr_b, unsigned long long* out) {
+    const size_t q = blockIdx.x;                                 // s * NP + part
+    const int part = (int)(q % d.c.NP);
+    if (part >= d.c.NPA) return;
+    const int4 h = d.foot_hdr[q], hb = hdr_b[q];
+    unsigned long long bad = 0;
+    if (threadIdx.x == 0 && (h.x != hb.x || h.y != hb.y || h.z != hb.z || h.w != hb.w)) bad++;
+    const int nrow = foot_nrow(h), wpr = foot_wpr(h);
+    const int po = d.part_off[part], cap = (d.part_off[part + 1] - po) >> 1;
+    const size_t base = (q / d.c.NP) * (size_t)d.c.scene_words + po;
+    for (int k = threadIdx.x; k < nrow * wpr; k += blockDim.x)
+        bad += (d.foot_words[base + k] != words_b[base + k]) + (d.foot_words[base + cap + k] != words_b[base + cap + k]);
+    if (bad) atomicAdd(out + 3, bad);
+}
 extern "C" int imgenv_debug_check_footprints(imgenv_t* h, int64_t* out4, void* stream) {
     if (!h || !out4) return fail("imgenv_debug_check_footprints: null argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1335,6 +1350,22 @@ extern "C" int imgenv_debug_check_footprints(imgenv_t* h, int64_t* out4, void* s
     CK(cudaMalloc((void**)&buf, 32));
     CK(cudaMemsetAsync(buf, 0, 32, st));
     k_debug_check_footprints<<<h->d.c.S * h->d.c.NP, 64, 0, st>>>(h->d, buf);
+    {   // the records as k_footprints builds them (circle parts: analytic interior + rim points) must equal the records the
+        // whole lattices give: rebuild them the slow way and compare word for word (differences count as violations)
+        const Cfg& c = h->d.c;
+        const size_t nw = (size_t)c.S * c.scene_words, nh = (size_t)c.S * c.NP;
+        uint32_t* wcopy = nullptr; int4* hcopy = nullptr;
+        CK(cudaMalloc((void**)&wcopy, nw * 4)); CK(cudaMalloc((void**)&hcopy, nh * 16));
+        const int grid = (c.S * c.NPA + FOOT_WARPS - 1) / FOOT_WARPS;
+        k_footprints<<<grid, FOOT_WARPS * 32, h->foot_smem, st>>>(h->d, nullptr, c.S, 0);      // (as the step builds them)
+        CK(cudaMemcpyAsync(wcopy, h->d.foot_words, nw * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(hcopy, h->d.foot_hdr, nh * 16, cudaMemcpyDeviceToDevice, st));
+        k_footprints<<<grid, FOOT_WARPS * 32, h->foot_smem, st>>>(h->d, nullptr, c.S, 2);      // whole lattices
+        k_debug_diff_footprints<<<c.S * c.NP, 64, 0, st>>>(h->d, wcopy, hcopy, buf);
+        k_footprints<<<grid, FOOT_WARPS * 32, h->foot_smem, st>>>(h->d, nullptr, c.S, 0);
+        cudaStreamSynchronize(st);
+        cudaFree(wcopy); cudaFree(hcopy);
+    }
     unsigned long long r[4];
     cudaError_t e = cudaMemcpyAsync(r, buf, 32, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

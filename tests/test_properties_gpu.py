@@ -75,3 +75,30 @@ def test_batch_invariance_determinism_and_footprint_records(wname, steps):
     assert np.isfinite(last["lasers"]).all() and last["lasers"].min() >= 0 and last["lasers"].max() <= 1.0 + 1e-6
     assert np.all(last["ped_vector_states"][..., 0] == spec["P"])
     assert set(np.unique(last["ped_maps"][:, :, 0]).tolist()) <= {0.0, 1.0}
+
+
+@pytest.mark.parametrize("robot_r,ped_shape,ped_r", [(0.17, "leg", 0.1), (0.25, "leg", 0.07), (0.4, "circle", 0.2), (0.12, "circle", 0.3)])
+def test_footprint_records_equal_whole_lattice(robot_r, ped_shape, ped_r):
+    """k_footprints sets the sure-covered interior of a circle part analytically and evaluates only the rim of its 0.01 m
+    lattice (host_tables.h lattice_circle_ring).  debug_check_footprints rebuilds every record from the WHOLE lattice
+    (agent.cpp:18-62 point by point) and counts differing words: several radii, random poses incl. the map border."""
+    import torch
+    from helpers import base_cfg, make_reset
+    from img_env_b200.lib import BatchedSim
+    cfg = base_cfg(R=6, P=10, scene="rvoscene", n_obj=3, ped_shape=ped_shape, max_ped=10)
+    cfg["robot"]["size"] = [[0, 0, robot_r] for _ in range(6)]
+    cfg["robot_radius"] = robot_r
+    cfg["ped_sim"]["size"] = [([0, ped_r, ped_r] if ped_shape == "leg" else [0, 0, ped_r]) for _ in range(10)]
+    spec = build_spec(cfg)
+    rng = np.random.default_rng(int(robot_r * 1000))
+    S = 6
+    sim = BatchedSim(spec, num_scenes=S, ped_yaw_mode=2)
+    sim.reset([make_reset(spec, rng, lo=0.2, hi=10.8) for _ in range(S)])
+    nrec, nocc, ncand, bad = sim.debug_check_footprints()
+    assert nrec > 0 and bad == 0, (nrec, nocc, ncand, bad)
+    for t in range(4):
+        a = np.stack([random_actions(spec["R"], rng) for _ in range(S)])
+        sim.step(torch.from_numpy(a).cuda())
+        nrec, nocc, ncand, bad = sim.debug_check_footprints()
+        assert bad == 0, "step %d: %d record words differ from the whole-lattice build" % (t, bad)
+    sim.close()

@@ -50,15 +50,23 @@ def main():
             for i, l in enumerate(src):
                 if p in l: return i + 1
             raise KeyError(p)
-        marks = [("prologue: static tables -> smem, pose constants", find("extern __shared__ __align__(16) unsigned char smem_raw[];")),
+        marks = [("prologue: mbarriers + bulk copies issued, ray table initialised", find("extern __shared__ __align__(16) unsigned char smem_raw[];")),
                  ("gather: footprint records near the FOV / the robot, static block list", find("// ---- Gather: footprint records")),
-                 ("A: collision code over the footprint lattice", find("// ---- Phase A: collision code")),
-                 ("B: lambdas (rays of a found cell) + forward-mode setup", find("// ---- Phase B: egocentric occupancy raster")),
-                 ("B: FOV-edge pixels (forward, static map)", find("// FOV-edge pixels (and the laser origin): forward")),
-                 ("B: candidate words -> cells -> view pixels", find("// candidate words -> candidate cells -> view pixels")),
-                 ("C: heavy cells, laser ranges, hit bitmask", find("// ---- Phase C: first occupied cell")),
-                 ("D/E/F: output classification + dirty outputs (laser_map + cubic resize + f16)", find("// ---- Phase D/E/F: laser_map reconstruction")),
-                 ("G: state vector", find("// ---- Phase G: state vector")),
+                 ("A: collision lattice (lambda; runs for robots with something under them)", find("// ---- Phase A: collision code")),
+                 ("B/C: ray update of a found cell (push_cell, heavy-cell list)", find("// ---- Phase B: egocentric occupancy raster")),
+                 ("B: forward rasteriser (not used by this variant)", find("const int n_trow = (vh + 31) >> 5")),
+                 ("B: FOV-edge pixels (lambda)", find("// FOV-edge pixels (and the laser origin): forward")),
+                 ("B: light loops (edge pixels, lattice)", find("// the light, even parts of the phase")),
+                 ("B: candidate cell -> view pixels (float pre-test, exact forward check)", find("auto candidate = [&](int cX, int cY) {")),
+                 ("B: chunk decode + block prefix sum", find("for (int c0 = 0; c0 < n_items; c0 += CAND_CHUNK) {")),
+                 ("B: even split, bisection, bit walk", find("const int per = (total + VIEW_THREADS - 1) / VIEW_THREADS;")),
+                 ("post-B barrier, code published, heavy cells", find("if (!DEBUG_FULL && need_A) {")),
+                 ("C: laser ranges out, hit bits, per-block nearest / farthest hit", find("// laser ranges out; one bit per ray")),
+                 ("E: value of a source pixel (pixel_code lambda)", find("// ---- Phase D/E/F: laser_map reconstruction")),
+                 ("debug raster (not used by this variant)", find("// whole 400x400 raster for the tests")),
+                 ("D1: segments of 8 outputs", find("uint16_t* o_img = d.o_sensor")),
+                 ("D2: outputs of the listed segments (hit-free / all-shadow / dirty)", find("// (2) the outputs of the listed segments")),
+                 ("E/F: dirty outputs (cubic resize + f16)", find("const int n4 = sh->n_dirty * 4;")),
                  ("end", find("// Pedestrian observation of every robot"))]
         rows = list(csv.reader(run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"]).splitlines()))
         ker = fname = ie = None; b = collections.Counter(); bi = collections.Counter()
@@ -71,7 +79,7 @@ def main():
                 except ValueError: continue
                 key = "inlined from other headers (tfmath, foot, intrinsics, atomics)"
                 if fname == 'view.cuh':
-                    key = "view.cuh helpers (ray_touch, nth_set_bit, exact_cell, prologue functions)"
+                    key = "view.cuh helpers (ray_touch, nth_set_bit, exact_cell, cell_rays_inline)"
                     for (nm, a), (_, bb) in zip(marks[:-1], marks[1:]):
                         if a <= ln < bb: key = nm
                 b[key] += s_; bi[key] += n
@@ -91,10 +99,12 @@ def main():
         m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", l)
         if m and fn: hist[fn][m.group(1).split(".")[0]] += 1
     out = ["cuobjdump -sass img_env_b200/libimgenv_b200.so: arch " + ", ".join(sorted(set(re.findall(r"arch = (sm_\w+)", sass)))) +
-           "; opcode histogram per kernel (no UTMALDG/UTCMMA/LDTM: nothing on this path is a contraction, BASELINE.json north_star)"]
+           "; opcode histogram per kernel (UBLKCP + SYNCS = cp.async.bulk staging + mbarriers in k_view, REDUX = redux.sync; "
+           "no UTCMMA/LDTM: nothing on this path is a contraction, BASELINE.json north_star)"]
     for f, c in sorted(hist.items(), key=lambda x: -sum(x[1].values())):
         tot = sum(c.values())
-        out.append("%s: %d instructions (%.1f KB)  " % (f, tot, tot * 16 / 1024.0) + ", ".join("%s %d" % kv for kv in c.most_common(14)))
+        special = ", ".join("%s %d" % (k, c[k]) for k in ("UBLKCP", "SYNCS", "REDUX", "ATOMS", "ATOMG", "RED") if c[k])
+        out.append("%s: %d instructions (%.1f KB)  " % (f, tot, tot * 16 / 1024.0) + ", ".join("%s %d" % kv for kv in c.most_common(14)) + (" | " + special if special else ""))
     open(os.path.join(P, "r02_sass_opcodes.txt"), "w").write("\n".join(out) + "\n")
     print("profiles refreshed;", {k: round(v["bytes_per_robot_step"]) for k, v in traffic.items()})
 
