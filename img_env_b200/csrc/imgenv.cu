@@ -57,7 +57,8 @@ struct imgenv {
     // the pedestrian observation (k_ped_obs only reads poses) runs beside the stamp / view kernels.  SFM only: the
     // sequential, latency-bound quadtree update of step t follows it there and is joined before the next reader of
     // the tree (next step's forces, reset).
-    cudaStream_t side = nullptr; cudaEvent_t ev_moved = nullptr, ev_ped = nullptr, ev_tree = nullptr; bool tree_pending = false;
+    cudaStream_t side = nullptr, side_tree = nullptr;      // pedestrian observation; SFM quadtree maintenance
+    cudaEvent_t ev_moved = nullptr, ev_consts = nullptr, ev_ped = nullptr, ev_tree = nullptr; bool tree_pending = false;
     size_t ped_smem = 0;
     // optional per-kernel CUDA-event timing (bench.py roofline): 4 events per profiled step
     std::vector<cudaEvent_t> evs; int prof_max = 0, prof_n = 0;
@@ -141,6 +142,8 @@ extern "C" int imgenv_destroy(imgenv_t* h) {
     if (h->d.rec_rb) cudaFree(h->d.rec_rb);
     if (h->d.rec_pd) cudaFree(h->d.rec_pd);
     if (h->side) { cudaStreamSynchronize(h->side); cudaStreamDestroy(h->side); }
+    if (h->side_tree) { cudaStreamSynchronize(h->side_tree); cudaStreamDestroy(h->side_tree); }
+    if (h->ev_consts) cudaEventDestroy(h->ev_consts);
     if (h->ev_moved) cudaEventDestroy(h->ev_moved);
     if (h->ev_tree) cudaEventDestroy(h->ev_tree);
     if (h->ev_ped) cudaEventDestroy(h->ev_ped);
@@ -498,7 +501,9 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     }
 
     CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));      // (stream priorities make no difference here: measured)
+    CK(cudaStreamCreateWithFlags(&h->side_tree, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_moved, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_consts, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_ped, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_tree, cudaEventDisableTiming));
     h->ped_smem = ped_smem_bytes(c); h->d.pl = ped_layout(c);
@@ -628,23 +633,32 @@ __global__ void k_apply_reset(Dev d, int n, const double* st, const int* sti, si
 static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int is_reset, cudaStream_t st, cudaEvent_t* ev = nullptr, const int* n_dev = nullptr) {
     Dev d = h->d; const Cfg& c = d.c;
     d.n_dev = n_dev;
-    // fork: pedestrian observation (+ SFM quadtree maintenance, ped_scene.cpp:167-182 moveAgent) on the side stream
-    CK(cudaEventRecord(h->ev_moved, st));
-    CK(cudaStreamWaitEvent(h->side, h->ev_moved, 0));
-    k_ped_obs<<<n_scenes * c.R, PED_THREADS, h->ped_smem, h->side>>>(d, d_scene_ids);
-    CK(cudaEventRecord(h->ev_ped, h->side));
+    // fork 1: the SFM quadtree maintenance (ped_scene.cpp:167-182 moveAgent) only needs the moved agents; a long sequential
+    // kernel of S warps, started first on its own stream and joined at the next step / reset
     if (!is_reset && c.scene_type == 1) {
-        k_sfm_tree<<<c.S, 32, 0, h->side>>>(d);
-        CK(cudaEventRecord(h->ev_tree, h->side));
+        CK(cudaEventRecord(h->ev_moved, st));
+        CK(cudaStreamWaitEvent(h->side_tree, h->ev_moved, 0));
+        k_sfm_tree<<<c.S, 32, 0, h->side_tree>>>(d);
+        CK(cudaEventRecord(h->ev_tree, h->side_tree));
         h->tree_pending = true;
     }
+    // per-robot pose constants + state vector: both observation kernels read them
     k_view_consts<<<(n_scenes * c.R + VC_THREADS - 1) / VC_THREADS, VC_THREADS, 0, st>>>(d, d_scene_ids, n_scenes, 0);
+    // fork 2: pedestrian observation on the side stream, joined before the call returns control to the caller's stream
+    CK(cudaEventRecord(h->ev_consts, st));
+    CK(cudaStreamWaitEvent(h->side, h->ev_consts, 0));
+    k_ped_obs<<<n_scenes * c.R, PED_THREADS, h->ped_smem, h->side>>>(d, d_scene_ids);
+    CK(cudaEventRecord(h->ev_ped, h->side));
     k_footprints<<<(n_scenes * c.NPA + FOOT_WARPS - 1) / FOOT_WARPS, FOOT_WARPS * 32, h->foot_smem, st>>>(d, d_scene_ids, n_scenes, is_reset ? 0 : 1);
     if (ev) cudaEventRecord(ev[2], st);
     if (c.inverse_ok) k_view<false, false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
     else k_view<false, true><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
     if (ev) cudaEventRecord(ev[3], st);
     CK(cudaStreamWaitEvent(st, h->ev_ped, 0));      // join: every output of the call is ordered on the caller's stream
+    if (h->tree_pending) {      // inside a CUDA graph capture every fork has to be joined before the capture ends
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) { CK(cudaStreamWaitEvent(st, h->ev_tree, 0)); h->tree_pending = false; }
+    }
     CK(cudaGetLastError());
     return 0;
 }

@@ -94,7 +94,7 @@ struct Cfg {
 
 // shared-memory plans of k_view / k_ped_obs (byte offsets; view.cuh computes them once on the host)
 struct ViewLayout { unsigned sh, regA, regB, hpre, hitkey, rays, need, spans, blocks, near, npre, chdr, coff, nhdr, noff, cword, cmeta, cpre, cwsum, seglist, total; };
-struct PedLayout { unsigned winner, keys, dkeys, pobs, row, total; int n_sort; };
+struct PedLayout { unsigned winner, keys, dkeys, pobs, row, total, paint; int n_sort; };
 struct ViewConst;
 struct Dev {
     Cfg c;

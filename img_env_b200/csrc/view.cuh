@@ -712,10 +712,13 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                     if (lane == 0 && (k >> 5) <= ((c.range_total - 1) >> 5)) hbits[k >> 5] = word;
                     any_local |= word != 0u;
                     if (c.hb_shift == 4) {      // blocks of 16 rays = half warps: shuffle minimum / maximum, no atomics
-                        const unsigned half = lane < 16 ? 0x0000FFFFu : 0xFFFF0000u;
-                        const int hp0 = (int)(key >> 22);
-                        const int hp = __reduce_min_sync(half, hp0), hq = __reduce_max_sync(half, valid ? hp0 : 0);      // redux.sync over the half warp
-                        if ((lane & 15) == 0 && valid) { sh->hmin[k >> 4] = hp; sh->hmax[k >> 4] = hq; }
+                        // redux.sync with the full (uniform) mask, the other half warp neutralised -- a per-lane half mask makes
+                        // the compiler fall back to a loop
+                        const bool lo_half = lane < 16;
+                        const int hp0 = (int)(key >> 22), hq0 = valid ? hp0 : 0;
+                        const int mn_lo = __reduce_min_sync(0xffffffffu, lo_half ? hp0 : 0x7fffffff), mn_hi = __reduce_min_sync(0xffffffffu, lo_half ? 0x7fffffff : hp0);
+                        const int mx_lo = __reduce_max_sync(0xffffffffu, lo_half ? hq0 : 0), mx_hi = __reduce_max_sync(0xffffffffu, lo_half ? 0 : hq0);
+                        if ((lane & 15) == 0 && valid) { sh->hmin[k >> 4] = lo_half ? mn_lo : mn_hi; sh->hmax[k >> 4] = lo_half ? mx_lo : mx_hi; }
                     } else if (valid) {
                         if (hit_any) atomicMin(&sh->hmin[k >> c.hb_shift], (int)(key >> 22));
                         atomicMax(&sh->hmax[k >> c.hb_shift], (int)(key >> 22));
@@ -820,6 +823,8 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
             const uint32_t* oseg = oshad + npx + (npx + 1) / 2;        // [n_seg] like okk, over the segment's outputs
             for (int sg = tid; sg < n_seg; sg += VIEW_THREADS) {
                 bool flagged = !seg_ok;
+                uint4 free8 = make_uint4(0u, 0u, 0u, 0u);
+                if (seg_ok) free8 = __ldg(reinterpret_cast<const uint4*>(oval) + sg);      // (in flight beside the test's own table load)
                 if (seg_ok && any_hit) {
                     const unsigned kk = __ldg(oseg + sg);
                     const int kmin = kk & 0xFFFu, kmax = (kk >> 12) & 0xFFFu;
@@ -830,7 +835,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                         flagged = hm <= (int)(kk >> 24) * 4;
                     }
                 }
-                if (!flagged) reinterpret_cast<uint4*>(o_img)[sg] = __ldg(reinterpret_cast<const uint4*>(oval) + sg);
+                if (!flagged) reinterpret_cast<uint4*>(o_img)[sg] = free8;
                 else seglist[atomicAdd(&sh->n_seglist, 1)] = (unsigned short)sg;
             }
             __syncthreads();
@@ -840,8 +845,10 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 const int q = (int)seglist[it >> 3] * 8 + (it & 7);
                 if (q >= npx) continue;
                 bool is_dirty = !use_laser;
+                // (the four table entries of the output are loaded together: one memory latency instead of three in a row)
+                const unsigned kk = use_laser ? __ldg(okk + q) : 0u, ks = use_laser ? __ldg(oshad + q) : 0u;
+                const uint16_t v_free = __ldg(oval + q), v_shadow = use_laser ? __ldg(oshval + q) : (uint16_t)0;
                 if (use_laser) {
-                    const unsigned kk = __ldg(okk + q);
                     const int kmin = kk & 0xFFFu, kmax = (kk >> 12) & 0xFFFu;
                     if (kmax >= kmin && range_hit(kmin, kmax)) {
                         // some of the rays hit something: still clean if every hit lies beyond all of the output's source pixels
@@ -858,18 +865,17 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                             // ... or if EVERY ray through a source pixel was stopped in front of it: each source pixel is then
                             // "unknown" (200: shadow-written or never written, agent.cpp:557-558) whatever the rays' order -> the
                             // output takes its all-shadow value, another table entry
-                            const unsigned ks = __ldg(oshad + q);
                             const int r0 = (int)(ks & 0xFFFu), r1 = (int)((ks >> 12) & 0xFFFu), a0 = r0 >> c.hb_shift, a1 = r1 >> c.hb_shift;
                             if (r1 >= r0 && a1 - a0 < 8) {
                                 int hx = 0;
                                 for (int b = a0; b <= a1; b++) hx = max(hx, sh->hmax[b]);
-                                if (hx < (int)(ks >> 24) * 4) { if (VIEW_STATS) atomicAdd(&sh->stat[2], 1); o_img[q] = __ldg(oshval + q); continue; }
+                                if (hx < (int)(ks >> 24) * 4) { if (VIEW_STATS) atomicAdd(&sh->stat[2], 1); o_img[q] = v_shadow; continue; }
                             }
                         }
                     }
                 }
                 if (is_dirty) dirty[atomicAdd(&sh->n_dirty, 1)] = (unsigned short)q;
-                else o_img[q] = __ldg(oval + q);
+                else o_img[q] = v_free;
             }
             __syncthreads();
             const int n4 = sh->n_dirty * 4;
@@ -936,6 +942,7 @@ inline PedLayout ped_layout(const Cfg& c) {
     L.pobs = off; off += (size_t)(c.P > 0 ? c.P : 1) * 16;
     L.row = off; off += ((size_t)c.pvs_len * 4 + 15) & ~(size_t)15;
     L.dkeys = off; off += ((size_t)n * 8 + 15) & ~(size_t)15;
+    L.paint = off; off += (size_t)(c.P > 0 ? c.P : 1) * 16;
     L.total = off + 16;
     return L;
 }
@@ -956,11 +963,14 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
     // << 32 | index (rounding to float32 is monotone, so the order can only be wrong inside a run of equal float32 keys: such
     // runs -- rare -- are re-sorted by (float64 key, index) afterwards).
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + L.keys);     // float32 bits of the key << 32 | pedestrian index
+    int4* paint = reinterpret_cast<int4*>(smem_raw + L.paint);                               // pedestrians inside the ped map: rank << 16 | index, cell window
     double* dkeys = reinterpret_cast<double*>(smem_raw + L.dkeys);                           // float64 key, by pedestrian index
     float4* pobs = reinterpret_cast<float4*>(smem_raw + L.pobs);                             // px, py, vx, vy in the robot frame (float32 like PedInfo)
     float* row = reinterpret_cast<float*>(smem_raw + L.row);                                 // this robot's ped_vector_states row
     __shared__ Tf2 s_world_base;
-    if (tid == 0) s_world_base = tf_inv(tf_from_pose(RBF(d, RB_X, idx), RBF(d, RB_Y, idx), RBF(d, RB_YAW, idx)));
+    __shared__ int s_npaint;
+    if (tid == 0) s_npaint = 0;
+    if (tid == 0) s_world_base = tf_inv(d.vconst[idx].base_world);      // (k_view_consts ran before the fork)
     const int npm = c.img * c.img;
     for (int k = tid; k < npm; k += PED_THREADS) winner[k] = -1;
     __syncthreads();
@@ -1053,20 +1063,32 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
         }
         if (q == 0) RBF(d, RB_MIND, idx) = (double)(f7 - f6);      // NearbyPed.set(i, ped_tmp[7] - ped_tmp[6]) in float32 (yaml_env.py:455-456)
         if (px > 3 || px < -3 || py > 3 || py < -3) continue;
+        // inside the 6 m x 6 m ped map: its cell window (python floor divisions, yaml_env.py:414-415) goes to a list; the few
+        // pedestrians that are painted are then shared out over the CTA instead of holding everybody up at the barrier
         const double tmx = -px + 3, tmy = -py + 3;
         const int x0 = (int)py_floordiv(tmx - c.ped_image_r, c.ped_res), x1 = (int)py_floordiv(tmx + c.ped_image_r, c.ped_res);
         const int y0 = (int)py_floordiv(tmy - c.ped_image_r, c.ped_res), y1 = (int)py_floordiv(tmy + c.ped_image_r, c.ped_res);
-        for (int jj = x0; jj < x1; jj++)
-            for (int kk = y0; kk < y1; kk++) {
-                if (jj < 0 || jj >= c.img || kk < 0 || kk >= c.img) continue;
-                const double ddx = (jj + 0.5) * c.ped_res - tmx, ddy = (kk + 0.5) * c.ped_res - tmy;
-                if (ddx * ddx + ddy * ddy < c.ped_image_r * c.ped_image_r) atomicMax(&winner[jj * c.img + kk], (q << 16) | j);   // farther pedestrians overwrite
-            }
+        const int e = atomicAdd(&s_npaint, 1);
+        paint[e] = make_int4((q << 16) | j, (max(x0, 0) << 16) | max(min(x1, c.img), 0), (max(y0, 0) << 16) | max(min(y1, c.img), 0), 0);
     }
     __syncthreads();
     if (tid == 0) d.o_mind[idx] = (float)RBF(d, RB_MIND, idx);
+    for (int e = tid >> 5; e < s_npaint; e += PED_THREADS / 32) {      // one warp per painted pedestrian, one lane per cell of its window
+        const int4 pe = paint[e];
+        const int j = pe.x & 0xFFFF, x0 = pe.y >> 16, x1 = pe.y & 0xFFFF, y0 = pe.z >> 16, y1 = pe.z & 0xFFFF;
+        const int wdt = y1 - y0, ncell = (x1 - x0) * wdt;
+        if (ncell <= 0) continue;
+        const float4 o = pobs[j];
+        const double tmx = -(double)o.x + 3, tmy = -(double)o.y + 3;
+        for (int u = tid & 31; u < ncell; u += 32) {
+            const int jj = x0 + u / wdt, kk = y0 + u % wdt;
+            const double ddx = (jj + 0.5) * c.ped_res - tmx, ddy = (kk + 0.5) * c.ped_res - tmy;
+            if (ddx * ddx + ddy * ddy < c.ped_image_r * c.ped_image_r) atomicMax(&winner[jj * c.img + kk], pe.x);   // farther pedestrians overwrite
+        }
+    }
     float* pvs = d.o_pvs + (size_t)idx * c.pvs_len;
     for (int k = tid; k < c.pvs_len; k += PED_THREADS) pvs[k] = row[k];
+    __syncthreads();
     // 3 x img x img float32, mostly zeros: 16-byte stores (each robot's block starts on a 16-byte boundary when img*img*3 % 4 == 0)
     float* pm = d.o_pmap + (size_t)idx * 3 * npm;
     auto value = [&](int ch, int cell) -> float {
