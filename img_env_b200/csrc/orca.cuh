@@ -33,7 +33,7 @@
 #define ORCA_OBST_CAP 256               // obstacle neighbours per agent in total (beyond ORCA_FAST: in a pool slab)
 #define ORCA_LINE_CAP (ORCA_NEIGH_CAP + ORCA_OBST_CAP)
 #ifndef ORCA_NODE_CACHE
-#define ORCA_NODE_CACHE 256             // BSP nodes (32 bytes each) staged in shared memory per CTA
+#define ORCA_NODE_CACHE 576             // BSP nodes (32 bytes each) staged in shared memory per CTA
 #endif
 #define ORCA_SLAB_BYTES ((ORCA_LINE_CAP - ORCA_FAST) * 16 + (ORCA_OBST_CAP - ORCA_FAST) * 8)
 #ifndef DYN_MAX_THREADS

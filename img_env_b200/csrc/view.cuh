@@ -321,11 +321,12 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                     if (__ldg(crow + (unsigned)bi * c.Wb + bj)) blocks[atomicAdd(&sh->red[3], 1)] = ((unsigned)bi << 16) | (unsigned)bj;
                     if (__ldg(orow + (unsigned)bi * c.Wb + bj)) sh->red[5] = 1;      // the static map is not empty under the FOV
                 }
-                if (tid >= VIEW_THREADS - 4) {      // ... nor under the robot's own footprint box (+1 cell; <= 2 x 2 blocks)
-                    const int u = tid - (VIEW_THREADS - 4);
-                    const int bi = min(max((u & 1) ? own.x + own.z : own.x - 1, 0), (int)H - 1) >> 5;
-                    const int bj = min(max((u & 2) ? own.y + own.z : own.y - 1, 0), (int)W - 1) >> 5;
-                    if (__ldg(orow + (unsigned)bi * c.Wb + bj)) sh->red[6] = 1;
+                if (tid >= VIEW_THREADS - 32) {     // ... nor under the robot's own footprint box (+1 cell): every block the box touches
+                    const int bi0 = min(max(own.x - 1, 0), (int)H - 1) >> 5, bi1 = min(max(own.x + own.z, 0), (int)H - 1) >> 5;
+                    const int bj0 = min(max(own.y - 1, 0), (int)W - 1) >> 5, bj1 = min(max(own.y + own.z, 0), (int)W - 1) >> 5;
+                    const int nbw = bj1 - bj0 + 1, nbb = (bi1 - bi0 + 1) * nbw;
+                    for (int u = tid - (VIEW_THREADS - 32); u < nbb; u += 32)
+                        if (__ldg(orow + (unsigned)(bi0 + u / nbw) * c.Wb + (bj0 + u % nbw))) sh->red[6] = 1;
                 }
             } else if (tid == 0) { sh->red[5] = 1; sh->red[6] = 1; }
         }
@@ -972,10 +973,12 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
     if (tid == 0) s_npaint = 0;
     if (tid == 0) s_world_base = tf_inv(d.vconst[idx].base_world);      // (k_view_consts ran before the fork)
     const int npm = c.img * c.img;
-    for (int k = tid; k < npm; k += PED_THREADS) winner[k] = -1;
+    if ((npm & 3) == 0) for (int k = tid; k < npm / 4; k += PED_THREADS) reinterpret_cast<int4*>(winner)[k] = make_int4(-1, -1, -1, -1);
+    else for (int k = tid; k < npm; k += PED_THREADS) winner[k] = -1;
     __syncthreads();
     const Tf2 world_base = s_world_base;
-    for (int k = tid; k < c.pvs_len; k += PED_THREADS) row[k] = k == 0 ? (float)c.P : 0.f;
+    for (int k = tid; k < (c.pvs_len + 3) / 4; k += PED_THREADS)      // (the row's slot is padded to 16 bytes)
+        reinterpret_cast<float4*>(row)[k] = make_float4(k == 0 ? (float)c.P : 0.f, 0.f, 0.f, 0.f);
     for (int j = tid; j < L.n_sort; j += PED_THREADS) {
         unsigned fk = 0x7F800000u;        // +inf: padding sorts last
         if (j < c.P) {
@@ -1098,13 +1101,18 @@ __global__ void __launch_bounds__(PED_THREADS) k_ped_obs(Dev d, const int* scene
         return ch == 0 ? 1.0f : (ch == 1 ? o.z : o.w);
     };
     if ((npm & 3) == 0) {
-        for (int ch = 0; ch < 3; ch++)
-            for (int v = tid; v < npm / 4; v += PED_THREADS) {
-                const int4 w4 = reinterpret_cast<const int4*>(winner)[v];
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((w4.x & w4.y & w4.z & w4.w) >= 0) o = make_float4(value(ch, 4 * v), value(ch, 4 * v + 1), value(ch, 4 * v + 2), value(ch, 4 * v + 3));   // some cell is painted
-                reinterpret_cast<float4*>(pm + (size_t)ch * npm)[v] = o;
+        for (int v = tid; v < npm / 4; v += PED_THREADS) {      // four cells of all three channels per pass
+            const int4 w4 = reinterpret_cast<const int4*>(winner)[v];
+            float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0;
+            if ((w4.x & w4.y & w4.z & w4.w) >= 0) {      // some cell is painted
+                o0 = make_float4(value(0, 4 * v), value(0, 4 * v + 1), value(0, 4 * v + 2), value(0, 4 * v + 3));
+                o1 = make_float4(value(1, 4 * v), value(1, 4 * v + 1), value(1, 4 * v + 2), value(1, 4 * v + 3));
+                o2 = make_float4(value(2, 4 * v), value(2, 4 * v + 1), value(2, 4 * v + 2), value(2, 4 * v + 3));
             }
+            reinterpret_cast<float4*>(pm)[v] = o0;
+            reinterpret_cast<float4*>(pm + (size_t)npm)[v] = o1;
+            reinterpret_cast<float4*>(pm + 2 * (size_t)npm)[v] = o2;
+        }
     } else {
         for (int v = tid; v < 3 * npm; v += PED_THREADS) { const int ch = v / npm; pm[v] = value(ch, v - ch * npm); }
     }

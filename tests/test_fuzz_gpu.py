@@ -34,7 +34,7 @@ def _random_case(seed):
     return kw
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("IMGENV_FUZZ_N", "16"))))      # IMGENV_FUZZ_N=200 for a longer hunt
+@pytest.mark.parametrize("seed", range(int(os.environ.get("IMGENV_FUZZ_N", "120"))))      # IMGENV_FUZZ_N=1000 for a longer hunt
 def test_random_configuration_matches_reference(seed):
     kw = _random_case(seed)
     cfg = _variant(**kw)

@@ -222,3 +222,15 @@ def test_ped_order_ties():
     assert not errs, "\n".join(errs)
     assert np.array_equal(got["ped_vector_states"], want["ped_vector_states"].astype(np.float32).reshape(got["ped_vector_states"].shape))
     sim.close()
+
+
+@pytest.mark.parametrize("shape,size", [("rectangle", [-0.45, 0.45, -0.3, 0.3]), ("circle", [0, 0, 0.5]), ("rectangle", [-0.2, 0.2, -0.15, 0.15])])
+def test_big_robots_against_walls_and_greys(shape, size):
+    """Collision codes of robots whose footprint box spans three 32-cell blocks, alone next to walls / grey cells: the
+    observation kernel skips the collision lattice when nothing is under the robot's own box, so EVERY block under that box
+    has to be looked at (a fuzz case found the 2 x 2 corner check of an earlier version wanting)."""
+    from test_parity_gpu import _variant
+    cfg = _variant(R=4, P=0, scene="rvoscene", n_obj=0, robot_shape=shape, grey_map=True, view=(0.02, 4.0) if size[-1] < 0.3 else (0.015, 6.0))
+    cfg["robot"]["size"] = [list(size) for _ in range(4)]
+    # poses spread over the whole room incl. the 0.5 m wall band (robots inside / touching walls collide with code 3)
+    run_lockstep(cfg, seed=71, steps=6, S=3, lo=0.3, hi=10.7)
