@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(VC_THREADS) k_view_consts(Dev d, const int* sc
 // robots and pedestrians: grid = ceil(n_scenes * NPA / FOOT_WARPS) CTAs, one warp per part
 // ---------------------------------------------------------------------------------------------------------------------
 #define FOOT_WARPS 8
-__global__ void __launch_bounds__(FOOT_WARPS * 32) k_footprints(Dev d, const int* scene_ids, int n_scenes, int flags) {      // flags: 1 = step_++, 2 = evaluate whole lattices (tests)
+__global__ void __launch_bounds__(FOOT_WARPS * 32, 4) k_footprints(Dev d, const int* scene_ids, int n_scenes, int flags) {      // flags: 1 = step_++, 2 = evaluate whole lattices (tests)
     extern __shared__ uint32_t foot_sm[];             // FOOT_WARPS * ag_cap words
     const Cfg& c = d.c;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -227,14 +227,18 @@ __global__ void __launch_bounds__(FOOT_WARPS * 32) k_footprints(Dev d, const int
     // (view half-diagonal + own extent) from every (other) robot get an empty record.
     {
         const double reach = c.cull_reach + ext;
-        bool rel = false;
-        for (int j = lane; j < c.R; j += 32) {
-            if (is_robot && j == a) continue;
-            const int idx = s * c.R + j;
-            const double dx = RBF(d, RB_X, idx) - x, dy = RBF(d, RB_Y, idx) - y;
-            rel |= dx * dx + dy * dy <= reach * reach;
+        bool any = false;
+        for (int j0 = 0; j0 < c.R && !any; j0 += 32) {      // 32 robots at a time, stop at the first batch with a robot in reach
+            const int j = j0 + lane;
+            bool rel = false;
+            if (j < c.R && !(is_robot && j == a)) {
+                const int idx = s * c.R + j;
+                const double dx = RBF(d, RB_X, idx) - x, dy = RBF(d, RB_Y, idx) - y;
+                rel = dx * dx + dy * dy <= reach * reach;
+            }
+            any = __any_sync(0xffffffffu, rel);
         }
-        if (!__any_sync(0xffffffffu, rel)) { if (lane == 0) *hdr = make_int4(0, 0, 0, 0); return; }
+        if (!any) { if (lane == 0) *hdr = make_int4(0, 0, 0, 0); return; }
     }
     const Tf2 t = tf_from_pose(x, y, yaw);
     double bwx, bwy;

@@ -40,3 +40,32 @@ def test_random_configuration_matches_reference(seed):
     cfg = _variant(**kw)
     extra = dict(lo=3.0, hi=8.0) if kw["scene"] == "pedscene" else dict(lo=2.5, hi=8.0)
     run_lockstep(cfg, seed=500 + seed, steps=4, **extra)
+
+
+def _crowded_case(seed):
+    """More agents in less space, bigger and smaller bodies, several scenes per handle: overlapping footprints, robots that
+    see each other at close range, collision candidates from many records, near-origin (heavy) raster cells."""
+    rng = np.random.default_rng(7000 + seed)
+    R = int(rng.integers(3, 13)); P = int(rng.integers(2, 17))
+    robot_shape = ["circle", "rectangle"][int(rng.integers(0, 2))]
+    kw = dict(R=R, P=P, scene=["rvoscene", "ervoscene"][seed % 2], n_obj=int(rng.integers(0, 7)), max_ped=P + int(rng.integers(0, 3)),      # (the reference's _draw_ped_map indexes out of bounds with max_ped < P)
+             
+              ped_shape=["leg", "circle"][int(rng.integers(0, 2))], robot_shape=robot_shape, relation=int(rng.integers(0, 2)),
+              range_total=int(rng.choice([360, 1000])))
+    cfg = _variant(**kw)
+    if robot_shape == "circle":
+        cfg["robot"]["size"] = [[0, 0, float(rng.choice([0.1, 0.17, 0.3, 0.45]))] for _ in range(R)]
+    else:
+        a, b = float(rng.uniform(0.1, 0.5)), float(rng.uniform(0.1, 0.35))
+        cfg["robot"]["size"] = [[-a, a, -b, b] for _ in range(R)]
+    pr = float(rng.choice([0.07, 0.1, 0.2]))
+    cfg["ped_sim"]["size"] = [([0, pr, pr] if kw["ped_shape"] == "leg" else [0, 0, pr]) for _ in range(P)]
+    span = float(rng.choice([1.5, 3.0, 6.0]))
+    lo = float(rng.uniform(0.6, 10.4 - span))
+    return cfg, dict(lo=lo, hi=lo + span, S=int(rng.integers(1, 4)), beep=bool(seed % 2), opt_in_beep=bool(seed % 2))
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("IMGENV_FUZZ_CROWDED_N", "40"))))
+def test_random_crowded_configuration_matches_reference(seed):
+    cfg, extra = _crowded_case(seed)
+    run_lockstep(cfg, seed=900 + seed, steps=3, **extra)
