@@ -115,7 +115,9 @@ __device__ __noinline__ void cell_rays_inline(unsigned* hitkey, const short* ren
 //             footprint records near the robot: NP*2 (part ids) + (NP+1)*4 (running word counts) + colliding parts
 //   (no 400x400 pixel buffer: the laser_map values are evaluated per output pixel of the resize)
 #define BL2_CAP 512          // cells touched by many rays (close to the origin): listed, then processed warp-cooperatively
+#ifndef BL_HEAVY
 #define BL_HEAVY 24
+#endif
 #define NOHIT 0xFFFFFFFFu
 #define CN_CAP 32            // footprint records that overlap the observer's own footprint box (collision candidates)
 #define NEAR_CACHE 64        // near records whose header and word offset are kept in shared memory for phase B
@@ -886,6 +888,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
                 atomicAdd(st + 3, (unsigned long long)sh->red[3]); atomicAdd(st + 4, (unsigned long long)sh->stat[0]); atomicAdd(st + 5, (unsigned long long)sh->stat[1]);
                 atomicAdd(st + 6, (unsigned long long)sh->n_dirty); atomicAdd(st + 7, (unsigned long long)sh->stat[2]); atomicAdd(st + 8, (unsigned long long)(sh->n_cnear > 0 || sh->red[6]));
                 atomicAdd(st + 9, (unsigned long long)sh->red[5]); atomicAdd(st + 10, (unsigned long long)sh->red[1]); atomicAdd(st + 11, (unsigned long long)(any_hit_all != 0));
+                atomicAdd(st + 12, (unsigned long long)sh->n_seglist);
             }
             const float scale = 1.f / (2048.f * 2048.f);
             for (int base = warp * 32; base < n4; base += VIEW_THREADS) {

@@ -176,7 +176,7 @@ int imgenv_debug_counters(imgenv_t* h, int64_t* out4, void* stream);
  * library (-DVIEW_STATS=1, tools/view_stats.py), all zero otherwise.  out16: [0] robots observed, [1] footprint records near
  * the field of view, [2] their bitmap words, [3] static candidate blocks, [4] candidate cells, [5] raster cells that updated
  * rays, [6] outputs evaluated in full, [7] outputs settled by the all-shadow test, [8] robots that ran the collision lattice,
- * [9] robots that ran the FOV-edge pixels, [10] heavy cells, [11] robots with any ray hit. */
+ * [9] robots that ran the FOV-edge pixels, [10] heavy cells, [11] robots with any ray hit, [12] segments of 8 outputs listed. */
 int imgenv_debug_view_stats(imgenv_t* h, int64_t* out16, void* stream);
 /* Tests: the RVO obstacle set of one scene as the reset kernels built it on the device (vertex ring verts[max_verts][8] = px, py,
  * edge dir x, y, convex, next, prev, 0; BSP nodes[max_verts][4] = edge, left, right, parent; max_verts = 16 * max_obstacles + 16;

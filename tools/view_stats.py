@@ -8,7 +8,7 @@ from img_env_b200.scenarios import WORKLOADS, make_cfg, make_resets, random_acti
 from img_env_b200.spec import build_spec
 from img_env_b200.lib import BatchedSim
 NAMES = ["robots", "near records", "near words", "static blocks", "candidates", "cells pushed", "dirty outputs", "shadow outputs",
-         "ran lattice", "ran edge px", "heavy cells", "any hit"]
+         "ran lattice", "ran edge px", "heavy cells", "any hit", "listed segments"]
 for wn in sys.argv[1:] or ["c4"]:
     w = WORKLOADS[wn]; S = min(w["scenes"], 64)
     spec = build_spec(make_cfg(w))
@@ -22,5 +22,5 @@ for wn in sys.argv[1:] or ["c4"]:
     torch.cuda.synchronize()
     st = sim.debug_view_stats() - base
     n = max(int(st[0]), 1)
-    print(wn, "robot observations", n, "|", ", ".join("%s %.1f" % (NAMES[k], st[k] / n) for k in range(1, 12)))
+    print(wn, "robot observations", n, "|", ", ".join("%s %.1f" % (NAMES[k], st[k] / n) for k in range(1, 13)))
     sim.close()
