@@ -116,7 +116,7 @@ __device__ __noinline__ void cell_rays_inline(unsigned* hitkey, const short* ren
 //   (no 400x400 pixel buffer: the laser_map values are evaluated per output pixel of the resize)
 #define BL2_CAP 512          // cells touched by many rays (close to the origin): listed, then processed warp-cooperatively
 #ifndef BL_HEAVY
-#define BL_HEAVY 24
+#define BL_HEAVY 12
 #endif
 #define NOHIT 0xFFFFFFFFu
 #define CN_CAP 32            // footprint records that overlap the observer's own footprint box (collision candidates)
