@@ -261,9 +261,11 @@ def test_device_side_auto_reset_equals_host_driven_resets():
             assert torch.equal(x, y), "step %d, output %d differs between device-side and host-driven resets" % (t, k)
 
 
-def test_graphed_step_equals_eager_step():
+@pytest.mark.parametrize("scene", ["rvoscene", "pedscene"])
+def test_graphed_step_equals_eager_step(scene):
     """GraphedStep (the whole wrapper stack + simulator + device-side auto-reset replayed as one CUDA graph) returns what the eager
-    loop returns, step for step."""
+    loop returns, step for step.  pedscene: the SFM quadtree update runs on its own stream and is normally joined at the NEXT
+    call -- inside a capture it has to be joined before the call ends."""
     import torch
     from img_env_b200.envs import make_env, GraphedStep
     outs = []
@@ -271,6 +273,7 @@ def test_graphed_step_equals_eager_step():
         random.seed(6)
         cfg = _cfg()
         cfg.update(agent_num_per_env=1, image_batch=1, state_batch=3, laser_batch=0, time_max=5, continuous_actions=[[0, 0.6], [-0.9, 0.9]], sampler_seed=77)
+        cfg["ped_sim"] = dict(cfg["ped_sim"], type=scene)
         cfg["wrapper"] = ["VelActionWrapper", "TimeLimitWrapper", "SensorsPaperRewardWrapper", "InfoLogWrapper", "MultiRobotCleanWrapper",
                           "TestEpisodeWrapper", "StateBatchWrapper", "ObsLaserStateTmp", "NeverStopWrapper"]
         env = make_env(cfg, num_scenes=5)
