@@ -13,9 +13,6 @@
 #ifndef VIEW_THREADS
 #define VIEW_THREADS 256
 #endif
-#ifndef VIEW_REND_GLOBAL
-#define VIEW_REND_GLOBAL 0        // experiment: ray end cells read from global memory (rare paths only) instead of staged
-#endif
 #ifndef VIEW_STATS
 #define VIEW_STATS 0          // instrumented build (tools/view_stats.py): work counters per robot in Dev::counters[4..]
 #endif
@@ -141,7 +138,7 @@ inline ViewLayout view_layout(const Cfg& c) {
     if (!c.inverse_ok) bl = bl > (size_t)((c.vh + 31) / 32) * c.vwb * 2 ? bl : (size_t)((c.vh + 31) / 32) * c.vwb * 2;   // forward mode: tile list
     L.regB = off; L.hpre = off + dl; off += ((bl > hb ? bl : hb) + 15) & ~(size_t)15;
     L.hitkey = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
-    L.rays = off; if (!VIEW_REND_GLOBAL) off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
+    L.rays = off; off += ((size_t)c.range_total * 4 + 15) & ~(size_t)15;
     L.need = off; off += ((size_t)c.ns * 2 + 15) & ~(size_t)15;
     L.spans = off; off += ((size_t)c.vh * 8 + 15) & ~(size_t)15;
     L.blocks = off; off += (size_t)INV_MAX_BLOCKS * 4;
@@ -202,7 +199,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
     short* spans = reinterpret_cast<short*>(smem_raw + L.spans);
     uint32_t* blocks = reinterpret_cast<uint32_t*>(smem_raw + L.blocks);
     unsigned* hitkey = reinterpret_cast<unsigned*>(smem_raw + L.hitkey);
-    const short* rend = VIEW_REND_GLOBAL ? d.ray_end + 2 * (size_t)ty.ray_off : reinterpret_cast<const short*>(smem_raw + L.rays);
+    short* rend = reinterpret_cast<short*>(smem_raw + L.rays);
     short* need = reinterpret_cast<short*>(smem_raw + L.need);
     unsigned short* near = reinterpret_cast<unsigned short*>(smem_raw + L.near);
     unsigned* npre = reinterpret_cast<unsigned*>(smem_raw + L.npre);
@@ -234,8 +231,8 @@ __global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, con
         mbar_expect_tx(&sh->bar[0], (unsigned)sizeof(ViewConst));
         bulk_g2s(&sh->k, d.vconst + idx, (unsigned)sizeof(ViewConst), &sh->bar[0]);
         const unsigned nb_r = ((unsigned)c.range_total * 4u + 15u) & ~15u, nb_s = ((unsigned)vh * 8u + 15u) & ~15u, nb_n = ((unsigned)c.ns * 2u + 15u) & ~15u;
-        mbar_expect_tx(&sh->bar[1], (VIEW_REND_GLOBAL ? 0u : nb_r) + nb_s + nb_n);
-        if (!VIEW_REND_GLOBAL) bulk_g2s(smem_raw + L.rays, d.ray_end + 2 * (size_t)ty.ray_off, nb_r, &sh->bar[1]);          // ray end cells (agent.cpp:414-430)
+        mbar_expect_tx(&sh->bar[1], nb_r + nb_s + nb_n);
+        bulk_g2s(rend, d.ray_end + 2 * (size_t)ty.ray_off, nb_r, &sh->bar[1]);          // ray end cells (agent.cpp:414-430)
         bulk_g2s(spans, d.fov_spans + (size_t)ty.span_off, nb_s, &sh->bar[1]);          // FOV column spans per view row
         bulk_g2s(need, d.need_idx, nb_n, &sh->bar[1]);                                  // source rows / columns the resize reads
         sh->coll_key = 0;
