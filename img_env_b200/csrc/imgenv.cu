@@ -53,6 +53,7 @@ struct imgenv {
     float* stf_h = nullptr; float* stf_d = nullptr; size_t st_floats = 0;
     float* act_d = nullptr; uint8_t* alive_d = nullptr;
     size_t view_smem = 0, dyn_smem = 0, foot_smem = 0, obj_smem = 0;
+    bool view_ctas5 = false;
     // Side stream, forked after the agents have moved and joined before the call returns to the caller's stream:
     // the pedestrian observation (k_ped_obs only reads poses) runs beside the stamp / view kernels.  SFM only: the
     // sequential, latency-bound quadtree update of step t follows it there and is joined before the next reader of
@@ -517,6 +518,8 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     h->dyn_smem = dyn_smem_bytes(d);
     if (h->view_smem > 227 * 1024) return fail("imgenv_create: view kernel needs too much shared memory for this configuration");
     CK(cudaFuncSetAttribute(k_view<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
+    CK(cudaFuncSetAttribute(k_view<false, false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
+    h->view_ctas5 = c.NP <= 256 && !getenv("IMGENV_VIEW_CTAS4");      // (view.cuh: occupancy variant, measured per workload)
     CK(cudaFuncSetAttribute(k_view<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
     CK(cudaFuncSetAttribute(k_view<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
     CK(cudaFuncSetAttribute(k_view<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->view_smem));
@@ -651,7 +654,8 @@ static int launch_observe(imgenv* h, const int* d_scene_ids, int n_scenes, int i
     CK(cudaEventRecord(h->ev_ped, h->side));
     k_footprints<<<(n_scenes * c.NPA + FOOT_WARPS - 1) / FOOT_WARPS, FOOT_WARPS * 32, h->foot_smem, st>>>(d, d_scene_ids, n_scenes, is_reset ? 0 : 1);
     if (ev) cudaEventRecord(ev[2], st);
-    if (c.inverse_ok) k_view<false, false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
+    if (c.inverse_ok && h->view_ctas5) k_view<false, false, 5><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
+    else if (c.inverse_ok) k_view<false, false><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
     else k_view<false, true><<<n_scenes * c.R, VIEW_THREADS, h->view_smem, st>>>(d, d_scene_ids, is_reset);
     if (ev) cudaEventRecord(ev[3], st);
     CK(cudaStreamWaitEvent(st, h->ev_ped, 0));      // join: every output of the call is ordered on the caller's stream

@@ -177,8 +177,10 @@ __device__ __forceinline__ void view_publish_code(const Dev& d, int idx, int cod
 
 // FWD = false: lasers on and a FOV of ordinary size -> world->view rasterisation, no raster in shared memory (the hot variant);
 // FWD = true: lasers off (the "known" plane needs every FOV pixel) or a huge FOV -> forward rasterisation into a raster.
-template <bool DEBUG_FULL, bool FWD>
-__global__ void __launch_bounds__(VIEW_THREADS, VIEW_MIN_CTAS) k_view(Dev d, const int* scene_ids, int is_reset) {
+// MINB = CTAs per SM the kernel is compiled for: 4 (64 registers) or 5 (48 registers, a few more spills, 25 % more warps in
+// flight).  Measured: 5 wins on scenes with few parts (C1 +2 %, C5 +5 %), 4 on C4's 800 parts per scene (+1.2 %); imgenv.cu picks.
+template <bool DEBUG_FULL, bool FWD, int MINB = VIEW_MIN_CTAS>
+__global__ void __launch_bounds__(VIEW_THREADS, MINB) k_view(Dev d, const int* scene_ids, int is_reset) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Cfg& c = d.c;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
