@@ -438,7 +438,7 @@ static int create_impl(imgenv* h, const imgenv_config* cfg, const uint8_t* grid,
     AL(rb, (size_t)RB_FIELDS * S * c.R) AL(pd, (size_t)PD_FIELDS * S * c.P)
     AL(traj, S * c.P * c.max_traj * 3) AL(traj_v, c.scene_type == 4 ? S * c.P * c.max_traj * 3 : 1) AL(traj_len, S * c.P) AL(obs, S * c.max_obs * 8) AL(n_obs, S) AL(step_no, S)
     AL(rvo_pos, S * c.NA * 2) AL(rvo_vel, S * c.NA * 2) AL(rvo_nvel, S * c.NA * 2) AL(sfm_force, c.scene_type == 1 ? S * c.NA * 12 : 1)
-    AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 4) AL(rvo_nodeseg, S * d.max_verts * 4) AL(counters, 20) AL(orca_cursor, 2)
+    AL(rvo_verts, S * d.max_verts * 8) AL(rvo_nodes, S * d.max_verts * 4) AL(rvo_nodeseg, S * d.max_verts * 4) AL(counters, 32) AL(orca_cursor, 2)
     d.rvo_arena_len = (c.scene_type == 2 || c.scene_type == 3) ? 32 * d.max_verts : 1;
     AL(rvo_arena, S * (size_t)d.rvo_arena_len)
     AL(rvo_counts, S * 2) AL(sfm, S * c.NA * SFM_REC) AL(sfm_obs, S * c.max_obs * 4) AL(sfm_nobs, S)
@@ -1082,7 +1082,15 @@ extern "C" int imgenv_reset_masked(imgenv_t* h, const uint8_t* d_mask, int32_t r
 // [11] robots with any ray hit.
 extern "C" int imgenv_debug_view_stats(imgenv_t* h, int64_t* out16, void* stream) {
     if (!h || !out16) return fail("imgenv_debug_view_stats: null argument");
-    CK(cudaMemcpyAsync(out16, h->d.counters + 4, 128, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaMemcpyAsync(out16, h->d.counters + 4, 128, cudaMemcpyDeviceToHost, (cudaStream_t)stream));      // (+ imgenv_debug_view_phases)
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+// Instrumented builds: SM cycles thread 0 of the observation CTAs spent between phase boundaries, summed over robots:
+// out8[0] prologue, [1] gather, [2] phase B (+ A), [3] heavy cells + laser ranges, [4] D1, [5] D2, [6] dirty outputs.
+extern "C" int imgenv_debug_view_phases(imgenv_t* h, int64_t* out8, void* stream) {
+    if (!h || !out8) return fail("imgenv_debug_view_phases: null argument");
+    CK(cudaMemcpyAsync(out8, h->d.counters + 20, 64, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }

@@ -177,6 +177,12 @@ __device__ __forceinline__ void view_publish_code(const Dev& d, int idx, int cod
 
 // FWD = false: lasers on and a FOV of ordinary size -> world->view rasterisation, no raster in shared memory (the hot variant);
 // FWD = true: lasers off (the "known" plane needs every FOV pixel) or a huge FOV -> forward rasterisation into a raster.
+// VIEW_STATS builds: cycles between phase boundaries of a CTA (thread 0's clock), summed into Dev::counters[20 + phase]
+#if VIEW_STATS
+#define VIEW_MARK(ph) do { if (tid == 0) { const long long t_now = clock64(); atomicAdd(d.counters + 20 + (ph), (unsigned long long)(t_now - t_mark)); t_mark = t_now; } } while (0)
+#else
+#define VIEW_MARK(ph) do { } while (0)
+#endif
 // MINB = CTAs per SM the kernel is compiled for: 4 (64 registers) or 5 (48 registers, a few more spills, 25 % more warps in
 // flight).  Measured: 5 wins on scenes with few parts (C1 +2 %, C5 +5 %), 4 on C4's 800 parts per scene (+1.2 %); imgenv.cu picks.
 template <bool DEBUG_FULL, bool FWD, int MINB = VIEW_MIN_CTAS>
@@ -184,6 +190,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, MINB) k_view(Dev d, const int* s
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Cfg& c = d.c;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long t_mark = VIEW_STATS ? clock64() : 0; (void)t_mark;
     const int sl = blockIdx.x / c.R, r = blockIdx.x % c.R;
     if (d.n_dev && sl >= *d.n_dev) return;
     const int s = scene_ids ? scene_ids[sl] : sl;
@@ -245,6 +252,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, MINB) k_view(Dev d, const int* s
     if (tid < 64) { sh->hmin[tid] = 1023; sh->hmax[tid] = 0; }
     __syncthreads();
     mbar_wait(&sh->bar[0], 0);
+    VIEW_MARK(0);      // prologue
     const bool frozen = DEBUG_FULL ? false : sh->k.frozen != 0;
 
     if (!frozen) {
@@ -336,6 +344,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, MINB) k_view(Dev d, const int* s
         }
         __syncthreads();
         mbar_wait(&sh->bar[1], 0);
+        VIEW_MARK(1);      // gather
         const int n_near = (int)(sh->near_pack >> 32);
         const unsigned n_near_words = (unsigned)sh->near_pack;
         const int n_cnear = sh->n_cnear;
@@ -641,6 +650,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, MINB) k_view(Dev d, const int* s
             if (lane == 0 && best) atomicMax(&sh->coll_key, best);
         }
         __syncthreads();
+        VIEW_MARK(2);      // phase B (+ A, edge pixels)
         if (!DEBUG_FULL && tid == 0) {
             int code = sh->coll_key & 3;
             RBF(d, RB_COLL, idx) = (double)code;
@@ -730,6 +740,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, MINB) k_view(Dev d, const int* s
                     }
                 }
                 any_hit_all = __syncthreads_or(any_local);
+                VIEW_MARK(3);      // heavy cells + laser ranges
             }
         }
 
@@ -844,6 +855,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, MINB) k_view(Dev d, const int* s
                 else seglist[atomicAdd(&sh->n_seglist, 1)] = (unsigned short)sg;
             }
             __syncthreads();
+            VIEW_MARK(4);      // D1 segments
             // (2) the outputs of the listed segments, one per thread
             const int n_listed = sh->n_seglist * 8;
             for (int it = tid; it < n_listed; it += VIEW_THREADS) {
@@ -883,6 +895,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, MINB) k_view(Dev d, const int* s
                 else o_img[q] = v_free;
             }
             __syncthreads();
+            VIEW_MARK(5);      // D2 listed outputs
             const int n4 = sh->n_dirty * 4;
             if (VIEW_STATS && tid == 0) {
                 unsigned long long* st = d.counters + 4;
@@ -924,6 +937,7 @@ __global__ void __launch_bounds__(VIEW_THREADS, MINB) k_view(Dev d, const int* s
             }
         }
     }
+    VIEW_MARK(6);          // dirty outputs (thread 0's share)
     if (frozen) {
         mbar_wait(&sh->bar[1], 0);       // (a CTA must not exit with bulk copies in flight)
         if (!DEBUG_FULL && tid == 0) view_publish_code(d, idx, (int)RBF(d, RB_COLL, idx), is_reset);      // stale code re-sent (agent.cpp:358-360)

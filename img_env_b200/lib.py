@@ -40,7 +40,7 @@ EXPORTS = ["imgenv_create", "imgenv_destroy", "imgenv_bind_outputs", "imgenv_res
            "imgenv_algorithmic_bytes_per_robot_step", "imgenv_last_error", "imgenv_version",
            "imgenv_sampler_create", "imgenv_sampler_destroy", "imgenv_sampler_seed", "imgenv_sampler_sample", "imgenv_sampler_draw",
            "imgenv_reset_sampled", "imgenv_debug_check_footprints",
-           "imgenv_record_enable", "imgenv_record_fetch", "imgenv_debug_set_min_jerk", "imgenv_set_ped_yaw_mode", "imgenv_debug_counters", "imgenv_debug_view_stats", "imgenv_debug_rvo_tree", "imgenv_host_rvo_tree", "imgenv_autoreset_enable", "imgenv_autoreset_refill",
+           "imgenv_record_enable", "imgenv_record_fetch", "imgenv_debug_set_min_jerk", "imgenv_set_ped_yaw_mode", "imgenv_debug_counters", "imgenv_debug_view_stats", "imgenv_debug_view_phases", "imgenv_debug_rvo_tree", "imgenv_host_rvo_tree", "imgenv_autoreset_enable", "imgenv_autoreset_refill",
            "imgenv_reset_masked"]
 
 
@@ -297,6 +297,12 @@ class BatchedSim:
         """Work counters of the observation kernel (instrumented builds only, see include/imgenv.h)."""
         out = np.zeros(16, np.int64)
         self._check(self.lib.imgenv_debug_view_stats(self.h, _ptr(out, C.c_int64), self._stream()))
+        return out
+
+    def debug_view_phases(self):
+        """Cycles per phase of the observation CTAs (instrumented builds only, see include/imgenv.h)."""
+        out = np.zeros(8, np.int64)
+        self._check(self.lib.imgenv_debug_view_phases(self.h, _ptr(out, C.c_int64), self._stream()))
         return out
 
     def debug_rvo_tree(self, scene=0):

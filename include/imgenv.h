@@ -178,6 +178,10 @@ int imgenv_debug_counters(imgenv_t* h, int64_t* out4, void* stream);
  * rays, [6] outputs evaluated in full, [7] outputs settled by the all-shadow test, [8] robots that ran the collision lattice,
  * [9] robots that ran the FOV-edge pixels, [10] heavy cells, [11] robots with any ray hit, [12] segments of 8 outputs listed. */
 int imgenv_debug_view_stats(imgenv_t* h, int64_t* out16, void* stream);
+/* Instrumented builds only: SM cycles between the phase boundaries of the observation CTAs (thread 0's clock), summed over
+ * robots: out8[0] prologue, [1] gather, [2] phase B (+ collision lattice), [3] heavy cells + laser ranges, [4] segment
+ * classification, [5] listed outputs, [6] dirty outputs, [7] 0. */
+int imgenv_debug_view_phases(imgenv_t* h, int64_t* out8, void* stream);
 /* Tests: the RVO obstacle set of one scene as the reset kernels built it on the device (vertex ring verts[max_verts][8] = px, py,
  * edge dir x, y, convex, next, prev, 0; BSP nodes[max_verts][4] = edge, left, right, parent; max_verts = 16 * max_obstacles + 16;
  * corners[max_obstacles][4] = the two rotated corners per reset object the ring was built from), and the host restatement of the
