@@ -309,7 +309,10 @@ __device__ __forceinline__ void solve_relaxed(const OrcaScratch* table, int n, i
         if (cross(li.d, li.p - result) > worst) {
             const RelaxedLines R{table, n_obst, li};
             const V2 keep = result;
-            if (solve_plane(R, i, radius, perp_ccw(li.d), true, result) < i) result = keep;
+            // the relaxed program holds ALL obstacle lines (also when line i is itself an obstacle line that the disc of
+            // admissible speeds cannot meet) and the bisectors of the agent lines before i (Agent.cpp:960-987)
+            const int n_proj = i > n_obst ? i : n_obst;
+            if (solve_plane(R, n_proj, radius, perp_ccw(li.d), true, result) < n_proj) result = keep;
             worst = cross(li.d, li.p - result);
         }
     }

@@ -31,6 +31,8 @@ def _random_case(seed):
         kw["grey_map"] = True
     if scene == "pedscene":          # keep the reference node inside the region where its quadtree terminates
         kw["R"] = min(R, 3); kw["P"] = min(P, 5)
+    if rng.integers(0, 8) == 0:      # (drawn last: the cases of earlier seeds keep their other parameters)
+        kw["use_laser"] = False      # the forward rasteriser: view_map_ is the raster, no rays (agent.cpp:439-441)
     return kw
 
 
